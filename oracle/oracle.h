@@ -1,0 +1,119 @@
+/* oracle/oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * C interface of the CPU oracle (liboracle_scan.so).  Only tests/, the
+ * __graft_entry__.smoke() check and bench.py's cpu_baseline / --impl reference legs
+ * may load this library.  The product (librplidar_b200.so) never links or calls it.
+ *
+ * Part 1 (scan_oracle.cpp) restates the reference's per-scan hot path:
+ *   - ascendScanData_<hq>              reference src/sdk/src/sl_lidar_driver.cpp:128-184
+ *   - RPlidarNode::publish_scan body   reference src/rplidar_node.cpp:556-680
+ * PARITY PINNED: orc_ascend_scan is checked node-for-node against the reference's own
+ * compiled ascendScanData (oracle/_ref, built by oracle/Makefile) in
+ * tests/test_oracle_vs_ref.py, and both are checked against golden vectors captured
+ * from the reference's DummyLidarDriver (tests/golden/, made by
+ * tests/golden/make_golden.py).  publish_scan itself needs rclcpp (absent here), so its
+ * restatement is pinned by line-by-line citation plus the golden LaserScan arrays.
+ *
+ * Part 2 (cloud_oracle.cpp) defines the north-star extensions that have NO reference
+ * implementation (polar->xyz, PointCloud2 packing, range/intensity window, voxel grid,
+ * statistical outlier removal).  PARITY UNPINNED: self-authored definitions; see the
+ * header of cloud_oracle.cpp.
+ */
+#ifndef RPL_ORACLE_H_
+#define RPL_ORACLE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* reference src/sdk/include/sl_lidar_cmd.h:272-278 : 8 bytes, dist at unaligned offset 2 */
+typedef struct __attribute__((packed)) orc_node_hq {
+  uint16_t angle_z_q14;
+  uint32_t dist_mm_q2;
+  uint8_t quality;
+  uint8_t flag;
+} orc_node_hq;
+
+#define ORC_RESULT_OK 0u
+#define ORC_RESULT_OPERATION_FAIL 0x80008001u /* reference sl_types.h: SL_RESULT_OPERATION_FAIL */
+
+/* LaserScan scalar fields filled by publish_scan (reference rplidar_node.cpp:616-625,
+ * :632-636, :664-668). */
+typedef struct orc_scan_header {
+  float angle_min;
+  float angle_max;
+  float angle_increment;
+  float time_increment;
+  float scan_time;
+  float range_min;
+  float range_max;
+  uint32_t beam_count; /* ranges.size() */
+  uint32_t published;  /* 0 when the reference returns early (no valid point) */
+} orc_scan_header;
+
+typedef struct orc_scan_params {
+  uint8_t is_new_protocol; /* reference rplidar_node.cpp:575-579 */
+  uint8_t scan_processing; /* Mode A (1) / Mode B (0), :630 */
+  uint8_t inverted;        /* :644, :673 */
+  uint8_t apply_ascend;    /* angle_compensate -> profile_.apply_geometric_correction,
+                              reference lidar_driver_wrapper.cpp:107,:328 */
+  float range_max;         /* cached_current_max_range_, :389-394 */
+  double scan_duration;    /* seconds, :442 */
+} orc_scan_params;
+
+/* ---- part 1: the reference path ------------------------------------------------ */
+
+/* In place.  stable=0: std::sort exactly as the reference (tie order = libstdc++
+ * introsort).  stable=1: std::stable_sort -- the documented tie rule of the CUDA path. */
+uint32_t orc_ascend_scan(orc_node_hq* nodes, size_t count, int stable);
+
+/* ranges/intensities must hold `count` floats.  Returns header.published. */
+uint32_t orc_publish_scan(const orc_node_hq* nodes, size_t count, const orc_scan_params* p,
+                          int stable, float* ranges, float* intensities, orc_scan_header* hdr);
+
+/* grab_scan_data glue + publish_scan for a batch (one scan per task, `threads` workers):
+ * nodes are modified in place when p->apply_ascend (like the wrapper's buffer).
+ * Outputs are strided like the inputs.  Returns wall seconds of the timed region. */
+double orc_pipeline_batch(orc_node_hq* nodes, const uint32_t* counts, uint32_t n_scans,
+                          uint32_t stride, const orc_scan_params* p, int stable, float* ranges,
+                          float* intensities, uint32_t* beam_counts, float* angle_increment,
+                          uint32_t* status, int threads);
+
+/* Restatement of DummyLidarDriver::grab_scan_data's generator for call number
+ * `call_index` (1-based: the reference pre-increments phase by 0.1f per call).
+ * reference src/lidar_driver_wrapper.cpp:441-471.  Writes 360 nodes. */
+void orc_dummy_scan(uint32_t call_index, orc_node_hq* out360);
+
+/* Deterministic synthetic scans of SURVEY.md 8(d) (splitmix64, seed 0x5EED0000+scan_id).
+ * variant: 0 = C2 tie-free rotated (5% invalid, quality 188), 1 = same with U[0,255]
+ * quality, 2 = tie variant (iid U[0,65535] keys), 3 = C4 (tie-free keys, iid shuffled). */
+void orc_synth_scan(uint64_t scan_id, uint32_t n, int variant, orc_node_hq* out);
+void orc_synth_batch(uint64_t first_scan_id, uint32_t n_scans, uint32_t n, uint32_t stride,
+                     int variant, orc_node_hq* out, int threads);
+
+/* ---- part 2: extensions (parity unpinned) --------------------------------------- */
+
+typedef struct orc_cloud_params {
+  float range_min;      /* keep range_min <= r <= range_max */
+  float range_max;
+  float intensity_min;  /* keep intensity >= intensity_min */
+  float voxel_size;     /* metres; 0 = no voxel grid */
+  uint32_t sor_k;       /* 0 = no statistical outlier removal */
+  float sor_alpha;
+  uint8_t is_new_protocol;
+  uint8_t pad[3];
+} orc_cloud_params;
+
+/* One scan -> filtered, angle-sorted polar points -> xyz (+intensity), optionally SOR,
+ * optionally voxel-grid centroids.  xyzi holds 4 floats per output point (PointCloud2
+ * point_step 16: x,y,z,intensity).  Returns the number of output points. */
+uint32_t orc_cloud_scan(const orc_node_hq* nodes, size_t count, const orc_cloud_params* p,
+                        float* xyzi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPL_ORACLE_H_ */

@@ -1,0 +1,223 @@
+"""ctypes loader for the CPU oracle -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module (see oracle/oracle.h).  The product package
+rplidar_ros2_driver_b200 never does.
+
+liboracle_scan.so  : the restatement (oracle/scan_oracle.cpp, oracle/cloud_oracle.cpp)
+_ref/libref_rplidar.so : the UNMODIFIED reference SDK + wrapper compiled in place
+                         (oracle/Makefile, oracle/ref_shim.cpp); optional.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "liboracle_scan.so")
+REF_SO = os.path.join(HERE, "_ref", "libref_rplidar.so")
+
+NODE_DTYPE = np.dtype(
+    {
+        "names": ["angle_z_q14", "dist_mm_q2", "quality", "flag"],
+        "formats": ["<u2", "<u4", "u1", "u1"],
+        "offsets": [0, 2, 6, 7],
+        "itemsize": 8,
+    }
+)
+
+RESULT_OK = 0
+RESULT_OPERATION_FAIL = 0x80008001
+
+
+class ScanHeader(C.Structure):
+    _fields_ = [
+        ("angle_min", C.c_float),
+        ("angle_max", C.c_float),
+        ("angle_increment", C.c_float),
+        ("time_increment", C.c_float),
+        ("scan_time", C.c_float),
+        ("range_min", C.c_float),
+        ("range_max", C.c_float),
+        ("beam_count", C.c_uint32),
+        ("published", C.c_uint32),
+    ]
+
+
+class ScanParams(C.Structure):
+    _fields_ = [
+        ("is_new_protocol", C.c_uint8),
+        ("scan_processing", C.c_uint8),
+        ("inverted", C.c_uint8),
+        ("apply_ascend", C.c_uint8),
+        ("range_max", C.c_float),
+        ("scan_duration", C.c_double),
+    ]
+
+
+class CloudParams(C.Structure):
+    _fields_ = [
+        ("range_min", C.c_float),
+        ("range_max", C.c_float),
+        ("intensity_min", C.c_float),
+        ("voxel_size", C.c_float),
+        ("sor_k", C.c_uint32),
+        ("sor_alpha", C.c_float),
+        ("is_new_protocol", C.c_uint8),
+        ("pad", C.c_uint8 * 3),
+    ]
+
+
+def build(ref: bool = True) -> None:
+    """Compile the oracle (and, when /root/reference exists, oracle/_ref)."""
+    subprocess.run(["make", "-C", HERE, "oracle"], check=True, capture_output=True)
+    if ref and os.path.isdir("/root/reference/src/sdk/src"):
+        subprocess.run(["make", "-C", HERE, "ref"], check=True, capture_output=True)
+
+
+_lib = None
+_ref = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        L = C.CDLL(ORACLE_SO)
+        vp, sz, u32, i32 = C.c_void_p, C.c_size_t, C.c_uint32, C.c_int
+        L.orc_ascend_scan.argtypes = [vp, sz, i32]
+        L.orc_ascend_scan.restype = u32
+        L.orc_publish_scan.argtypes = [vp, sz, C.POINTER(ScanParams), i32, vp, vp, C.POINTER(ScanHeader)]
+        L.orc_publish_scan.restype = u32
+        L.orc_pipeline_batch.argtypes = [vp, vp, u32, u32, C.POINTER(ScanParams), i32, vp, vp, vp, vp, vp, i32]
+        L.orc_pipeline_batch.restype = C.c_double
+        L.orc_dummy_scan.argtypes = [u32, vp]
+        L.orc_dummy_scan.restype = None
+        L.orc_synth_scan.argtypes = [C.c_uint64, u32, i32, vp]
+        L.orc_synth_scan.restype = None
+        L.orc_synth_batch.argtypes = [C.c_uint64, u32, u32, u32, i32, vp, i32]
+        L.orc_synth_batch.restype = None
+        L.orc_cloud_scan.argtypes = [vp, sz, C.POINTER(CloudParams), vp]
+        L.orc_cloud_scan.restype = u32
+        _lib = L
+    return _lib
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def ref() -> C.CDLL:
+    global _ref
+    if _ref is None:
+        L = C.CDLL(REF_SO)
+        L.ref_ascend_scan.argtypes = [C.c_void_p, C.c_size_t]
+        L.ref_ascend_scan.restype = C.c_uint32
+        L.ref_dummy_grab.argtypes = [C.c_void_p, C.c_size_t]
+        L.ref_dummy_grab.restype = C.c_int
+        L.ref_sizeof_node.restype = C.c_size_t
+        _ref = L
+    return _ref
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+def make_nodes(angle, dist, quality=None, flag=None) -> np.ndarray:
+    angle = np.asarray(angle)
+    n = np.zeros(angle.shape, dtype=NODE_DTYPE)
+    n["angle_z_q14"] = angle
+    n["dist_mm_q2"] = dist
+    n["quality"] = 0 if quality is None else quality
+    n["flag"] = 0 if flag is None else flag
+    return n
+
+
+def ascend(nodes: np.ndarray, stable: bool = False):
+    """Returns (sl_result, ascended copy)."""
+    buf = np.ascontiguousarray(nodes).copy()
+    rc = lib().orc_ascend_scan(_ptr(buf), buf.shape[0], int(stable))
+    return rc, buf
+
+
+def ref_ascend(nodes: np.ndarray):
+    buf = np.ascontiguousarray(nodes).copy()
+    rc = ref().ref_ascend_scan(_ptr(buf), buf.shape[0])
+    return rc, buf
+
+
+def ref_dummy_grab() -> np.ndarray:
+    buf = np.zeros(360, dtype=NODE_DTYPE)
+    n = ref().ref_dummy_grab(_ptr(buf), 360)
+    assert n == 360
+    return buf
+
+
+def dummy_scan(call_index: int) -> np.ndarray:
+    buf = np.zeros(360, dtype=NODE_DTYPE)
+    lib().orc_dummy_scan(call_index, _ptr(buf))
+    return buf
+
+
+def scan_params(is_new_protocol=0, scan_processing=1, inverted=0, apply_ascend=1, range_max=40.0,
+                scan_duration=0.1) -> ScanParams:
+    return ScanParams(int(is_new_protocol), int(scan_processing), int(inverted), int(apply_ascend),
+                      float(range_max), float(scan_duration))
+
+
+def publish(nodes: np.ndarray, params: ScanParams, stable: bool = False):
+    """Returns (header, ranges[beam_count], intensities[beam_count])."""
+    nodes = np.ascontiguousarray(nodes)
+    n = nodes.shape[0]
+    ranges = np.full(max(n, 1), np.nan, dtype=np.float32)
+    inten = np.full(max(n, 1), np.nan, dtype=np.float32)
+    hdr = ScanHeader()
+    lib().orc_publish_scan(_ptr(nodes), n, C.byref(params), int(stable), _ptr(ranges), _ptr(inten),
+                           C.byref(hdr))
+    m = hdr.beam_count
+    return hdr, ranges[:m].copy(), inten[:m].copy()
+
+
+def pipeline_batch(nodes: np.ndarray, counts: np.ndarray, params: ScanParams, stable=False, threads=1):
+    """nodes [n_scans, stride] (modified in place when apply_ascend).  Returns dict."""
+    assert nodes.dtype == NODE_DTYPE and nodes.ndim == 2 and nodes.flags.c_contiguous
+    n_scans, stride = nodes.shape
+    counts = np.ascontiguousarray(counts, dtype=np.uint32)
+    ranges = np.zeros((n_scans, stride), dtype=np.float32)
+    inten = np.zeros((n_scans, stride), dtype=np.float32)
+    beams = np.zeros(n_scans, dtype=np.uint32)
+    inc = np.zeros(n_scans, dtype=np.float32)
+    status = np.zeros(n_scans, dtype=np.uint32)
+    secs = lib().orc_pipeline_batch(_ptr(nodes), _ptr(counts), n_scans, stride, C.byref(params),
+                                    int(stable), _ptr(ranges), _ptr(inten), _ptr(beams), _ptr(inc),
+                                    _ptr(status), int(threads))
+    return dict(seconds=secs, ranges=ranges, intensities=inten, beam_counts=beams,
+                angle_increment=inc, status=status)
+
+
+def synth_batch(first_scan_id: int, n_scans: int, n: int, variant: int = 0, stride: int | None = None,
+                threads: int = 0) -> np.ndarray:
+    stride = n if stride is None else stride
+    out = np.zeros((n_scans, stride), dtype=NODE_DTYPE)
+    if threads <= 0:
+        threads = min(os.cpu_count() or 1, 32)
+    lib().orc_synth_batch(first_scan_id, n_scans, n, stride, variant, _ptr(out), threads)
+    return out
+
+
+def cloud_params(range_min=0.15, range_max=40.0, intensity_min=0.0, voxel_size=0.0, sor_k=0,
+                 sor_alpha=1.0, is_new_protocol=0) -> CloudParams:
+    return CloudParams(float(range_min), float(range_max), float(intensity_min), float(voxel_size),
+                       int(sor_k), float(sor_alpha), int(is_new_protocol), (C.c_uint8 * 3)(0, 0, 0))
+
+
+def cloud(nodes: np.ndarray, params: CloudParams) -> np.ndarray:
+    nodes = np.ascontiguousarray(nodes)
+    out = np.zeros((max(nodes.shape[0], 1), 4), dtype=np.float32)
+    m = lib().orc_cloud_scan(_ptr(nodes), nodes.shape[0], C.byref(params), _ptr(out))
+    return out[:m].copy()
