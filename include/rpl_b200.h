@@ -1,0 +1,177 @@
+/* include/rpl_b200.h -- C-ABI of librplidar_b200.so (the drop-in boundary).
+ *
+ * B200-native (sm_100a) replacement for the per-scan point-processing hot path of
+ * frozenreboot/rplidar_ros2_driver.  Every entry point is extern "C", POD-only, caller owns
+ * all memory, nothing throws across the boundary, and results are sl_result-style uint32_t
+ * (reference src/sdk/include/sl_types.h:70-81).  There is NO CPU fallback: without a CUDA
+ * device rpl_ctx_create fails and nothing else can be called.
+ *
+ * What each entry point replaces in the reference:
+ *
+ *   rpl_ascend_scan          sl::ILidarDriver::ascendScanData(node*, count)
+ *                              src/sdk/include/sl_lidar_driver.h:477
+ *                              (body src/sdk/src/sl_lidar_driver.cpp:128-184, entry :957-960)
+ *   rpl_laserscan            the compute body of RPlidarNode::publish_scan
+ *                              src/rplidar_node.cpp:581-677 (filter+unpack :581-600, sort
+ *                              :605-607, Mode A :630-660, Mode B :661-677)
+ *   rpl_scan                 both, fused: RealLidarDriver::grab_scan_data's "ascend if the
+ *                              profile asks" (src/lidar_driver_wrapper.cpp:328-329) followed by
+ *                              publish_scan -- one host<->device round trip per scan
+ *   rpl_*_batch              the same per scan over [n_scans][stride] buffers (the reference
+ *                              has no batched form: one scan thread per node,
+ *                              src/rplidar_node.cpp:220)
+ *   rpl_*_batch_dev          the batched forms on buffers already resident in HBM
+ *   rpl_cloud_batch[_dev]    north-star extensions with no reference counterpart (polar->xyz
+ *                              PointCloud2 packing, range/intensity window, statistical
+ *                              outlier removal, voxel grid); defined by oracle/cloud_oracle.cpp
+ *   rpl_synth_batch_dev      synthetic scan streams of SURVEY.md 8(d) generated in HBM
+ *
+ * Tie rule.  The reference sorts with std::sort (unstable); on equal angle_z_q14 its order
+ * is whatever libstdc++'s introsort produces.  This library defines the order: equal keys
+ * keep buffer order (stable).  On tie-free scans results are bit-identical to the reference.
+ *
+ * Threading (reference: one scan thread holding driver_mutex_, src/rplidar_node.cpp:420-439):
+ * a context is single-threaded; use one context per thread.  No global state.
+ */
+#ifndef RPL_B200_H_
+#define RPL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RPL_ABI_VERSION 1u
+
+typedef uint32_t rpl_result;
+/* reference src/sdk/include/sl_types.h:72-81 */
+#define RPL_RESULT_OK 0u
+#define RPL_RESULT_FAIL_BIT 0x80000000u
+#define RPL_RESULT_INVALID_DATA 0x80008000u
+#define RPL_RESULT_OPERATION_FAIL 0x80008001u
+#define RPL_RESULT_OPERATION_TIMEOUT 0x80008002u
+#define RPL_RESULT_OPERATION_NOT_SUPPORT 0x80008004u
+#define RPL_RESULT_INSUFFICIENT_MEMORY 0x80008006u
+#define RPL_IS_OK(x) (((x) & RPL_RESULT_FAIL_BIT) == 0u)
+
+/* reference src/sdk/include/sl_lidar_cmd.h:272-278 (sizeof 8, offsets 0/2/6/7) */
+typedef struct __attribute__((packed)) rpl_node_hq {
+  uint16_t angle_z_q14; /* 90 deg / 16384 per unit; 65536 = 360 deg */
+  uint32_t dist_mm_q2;  /* quarter millimetres; 0 = no measurement   */
+  uint8_t quality;
+  uint8_t flag;         /* bit0 = scan start sync (sl_lidar_cmd.h:178) */
+} rpl_node_hq;
+
+typedef struct rpl_scan_params {
+  uint8_t is_new_protocol; /* intensity = quality (1) or quality>>2 (0); rplidar_node.cpp:575-590 */
+  uint8_t scan_processing; /* 1 = Mode A resample, 0 = Mode B raw map; rplidar_node.cpp:630 */
+  uint8_t inverted;        /* rplidar_node.cpp:644,673 */
+  uint8_t apply_ascend;    /* angle_compensate; lidar_driver_wrapper.cpp:107,328 */
+  uint32_t flags;          /* RPL_FLAG_* */
+} rpl_scan_params;
+
+#define RPL_FLAG_FORCE_GENERAL 1u /* route every scan through the general (radix-sort) kernel */
+
+/* per-scan path report (optional output) */
+#define RPL_PATH_FAST 0u    /* tie-free scan: bitmap-rank kernel */
+#define RPL_PATH_GENERAL 1u /* duplicate keys (or forced): stable radix-sort kernel */
+
+typedef struct rpl_cloud_params {
+  float range_min;     /* keep range_min <= r <= range_max */
+  float range_max;
+  float intensity_min; /* keep intensity >= intensity_min */
+  float voxel_size;    /* metres; 0 disables the voxel grid */
+  uint32_t sor_k;      /* 0 disables statistical outlier removal; <= 32 */
+  float sor_alpha;
+  uint8_t is_new_protocol;
+  uint8_t pad[3];
+} rpl_cloud_params;
+
+typedef struct rpl_ctx rpl_ctx;
+
+/* ---- context -------------------------------------------------------------------------- */
+uint32_t rpl_abi_version(void);
+/* device: CUDA ordinal.  max_nodes: largest scan (nodes) the context will see; max_scans:
+ * largest batch for the HOST-buffer entry points (device staging is sized from these). */
+rpl_result rpl_ctx_create(int device, uint32_t max_nodes, uint32_t max_scans, rpl_ctx** out);
+void rpl_ctx_destroy(rpl_ctx* ctx);
+const char* rpl_last_error(const rpl_ctx* ctx);
+/* Block until everything queued by this context has finished. */
+rpl_result rpl_ctx_synchronize(rpl_ctx* ctx);
+/* Pinned host memory for the host-buffer entry points (optional; pageable works, slower). */
+rpl_result rpl_host_alloc(size_t bytes, void** out);
+void rpl_host_free(void* p);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t rpl_ctx_launch_count(const rpl_ctx* ctx);
+
+/* ---- single scan, host buffers (the reference-shaped calls) --------------------------- */
+/* In place, like ascendScanData.  RPL_RESULT_OPERATION_FAIL when no node is measured
+ * (buffer untouched) or count == 0. */
+rpl_result rpl_ascend_scan(rpl_ctx* ctx, rpl_node_hq* nodes, size_t count);
+/* ranges / intensities: `count` floats each; the first *beam_count are written.
+ * *beam_count == 0 means the reference would not publish (no measured node). */
+rpl_result rpl_laserscan(rpl_ctx* ctx, const rpl_node_hq* nodes, size_t count,
+                         const rpl_scan_params* params, float* ranges, float* intensities,
+                         uint32_t* beam_count, float* angle_increment);
+/* Fused grab_scan_data glue + publish_scan: nodes are ascended in place when
+ * params->apply_ascend (its sl_result goes to *ascend_status, may be NULL), then converted. */
+rpl_result rpl_scan(rpl_ctx* ctx, rpl_node_hq* nodes, size_t count, const rpl_scan_params* params,
+                    float* ranges, float* intensities, uint32_t* beam_count,
+                    float* angle_increment, rpl_result* ascend_status);
+
+/* ---- batches, host buffers ------------------------------------------------------------ */
+/* nodes: [n_scans][stride]; counts[s] <= stride nodes are live in scan s.
+ * nodes_out (may be NULL, may equal nodes): ascended node buffers, same layout.
+ * ranges/intensities: [n_scans][stride] floats; beam_counts/angle_increment/status/path:
+ * [n_scans] (each may be NULL).  status[s] = ascendScanData's sl_result when apply_ascend,
+ * else RPL_RESULT_OK. */
+rpl_result rpl_scan_batch(rpl_ctx* ctx, const rpl_node_hq* nodes, const uint32_t* counts,
+                          uint32_t n_scans, uint32_t stride, const rpl_scan_params* params,
+                          rpl_node_hq* nodes_out, float* ranges, float* intensities,
+                          uint32_t* beam_counts, float* angle_increment, uint32_t* status,
+                          uint32_t* path);
+rpl_result rpl_ascend_scan_batch(rpl_ctx* ctx, rpl_node_hq* nodes, const uint32_t* counts,
+                                 uint32_t n_scans, uint32_t stride, uint32_t* status);
+rpl_result rpl_laserscan_batch(rpl_ctx* ctx, const rpl_node_hq* nodes, const uint32_t* counts,
+                               uint32_t n_scans, uint32_t stride, const rpl_scan_params* params,
+                               float* ranges, float* intensities, uint32_t* beam_counts,
+                               float* angle_increment);
+
+/* ---- batches, device buffers (asynchronous on `stream`, a cudaStream_t; NULL = the
+ * context's own stream).  Same layout as above; nodes_out must not alias nodes. ---------- */
+rpl_result rpl_scan_batch_dev(rpl_ctx* ctx, const rpl_node_hq* nodes, const uint32_t* counts,
+                              uint32_t n_scans, uint32_t stride, const rpl_scan_params* params,
+                              rpl_node_hq* nodes_out, float* ranges, float* intensities,
+                              uint32_t* beam_counts, float* angle_increment, uint32_t* status,
+                              uint32_t* path, void* stream);
+
+/* ---- PointCloud2 path (extensions; oracle/cloud_oracle.cpp is the definition) --------- */
+/* xyzi: [n_scans][stride][4] floats (x, y, z, intensity = PointCloud2 point_step 16);
+ * point_counts[s] = points written for scan s. */
+rpl_result rpl_cloud_batch_dev(rpl_ctx* ctx, const rpl_node_hq* nodes, const uint32_t* counts,
+                               uint32_t n_scans, uint32_t stride, const rpl_cloud_params* params,
+                               float* xyzi, uint32_t* point_counts, void* stream);
+rpl_result rpl_cloud_batch(rpl_ctx* ctx, const rpl_node_hq* nodes, const uint32_t* counts,
+                           uint32_t n_scans, uint32_t stride, const rpl_cloud_params* params,
+                           float* xyzi, uint32_t* point_counts);
+/* Packs the per-scan clouds of a batch into one dense cloud (the per-GPU "fused cloud" that
+ * is all-gathered across ranks): fused[0..*total) points, 16 B each; offsets[s] = first point
+ * of scan s.  fused must hold n_scans*stride points. */
+rpl_result rpl_cloud_fuse_dev(rpl_ctx* ctx, const float* xyzi, const uint32_t* point_counts,
+                              uint32_t n_scans, uint32_t stride, float* fused, uint32_t* offsets,
+                              uint32_t* total, void* stream);
+
+/* ---- synthetic scan streams ------------------------------------------ */
+/* variant 0: tie-free rotated revolution, 5% unmeasured, quality 188; 1: same, quality
+ * U[0,255]; 2: iid U[0,65535] keys (ties); 3: tie-free keys in pseudo-random order.
+ * Also writes counts[s] = n when counts != NULL. */
+rpl_result rpl_synth_batch_dev(rpl_ctx* ctx, uint64_t first_scan_id, uint32_t n_scans, uint32_t n,
+                               uint32_t stride, int variant, rpl_node_hq* nodes, uint32_t* counts,
+                               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPL_B200_H_ */

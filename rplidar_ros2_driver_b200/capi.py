@@ -1,0 +1,283 @@
+"""ctypes binding of librplidar_b200.so (include/rpl_b200.h) -- used by tests/ and bench.py.
+
+This is a thin mirror of the C-ABI, not a second implementation: every call goes to the CUDA
+library.  Loading fails loudly when the library has not been built (`build()` compiles it
+in-tree with nvcc for sm_100a); creating a Context fails when no CUDA device is present.
+There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librplidar_b200.so")
+
+RESULT_OK = 0
+RESULT_INVALID_DATA = 0x80008000
+RESULT_OPERATION_FAIL = 0x80008001
+RESULT_OPERATION_NOT_SUPPORT = 0x80008004
+FLAG_FORCE_GENERAL = 1
+PATH_FAST, PATH_GENERAL = 0, 1
+
+# reference src/sdk/include/sl_lidar_cmd.h:272-278
+NODE_DTYPE = np.dtype(
+    {
+        "names": ["angle_z_q14", "dist_mm_q2", "quality", "flag"],
+        "formats": ["<u2", "<u4", "u1", "u1"],
+        "offsets": [0, 2, 6, 7],
+        "itemsize": 8,
+    }
+)
+
+EXPORTS = [
+    "rpl_abi_version", "rpl_ctx_create", "rpl_ctx_destroy", "rpl_last_error", "rpl_ctx_synchronize",
+    "rpl_host_alloc", "rpl_host_free", "rpl_ctx_launch_count", "rpl_ascend_scan", "rpl_laserscan",
+    "rpl_scan", "rpl_scan_batch", "rpl_ascend_scan_batch", "rpl_laserscan_batch", "rpl_scan_batch_dev",
+    "rpl_cloud_batch_dev", "rpl_cloud_batch", "rpl_cloud_fuse_dev", "rpl_synth_batch_dev",
+]
+
+
+class ScanParams(C.Structure):
+    _fields_ = [
+        ("is_new_protocol", C.c_uint8),
+        ("scan_processing", C.c_uint8),
+        ("inverted", C.c_uint8),
+        ("apply_ascend", C.c_uint8),
+        ("flags", C.c_uint32),
+    ]
+
+
+class CloudParams(C.Structure):
+    _fields_ = [
+        ("range_min", C.c_float),
+        ("range_max", C.c_float),
+        ("intensity_min", C.c_float),
+        ("voxel_size", C.c_float),
+        ("sor_k", C.c_uint32),
+        ("sor_alpha", C.c_float),
+        ("is_new_protocol", C.c_uint8),
+        ("pad", C.c_uint8 * 3),
+    ]
+
+
+class RplError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"rpl_result 0x{code:08x}: {msg}")
+        self.code = code
+
+
+def build(verbose: bool = False) -> str:
+    """Compile librplidar_b200.so in-tree (nvcc, sm_100a)."""
+    r = subprocess.run(["bash", os.path.join(HERE, "build.sh")], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building librplidar_b200.so failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The loaded library.  Raises if it is not built: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: run rplidar_ros2_driver_b200/build.sh (or __graft_entry__.build()). "
+            "The CUDA library is the only implementation of this path."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, sz, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_size_t, C.c_int
+    PSP, PCP = C.POINTER(ScanParams), C.POINTER(CloudParams)
+    sig = {
+        "rpl_abi_version": ([], u32),
+        "rpl_ctx_create": ([i32, u32, u32, C.POINTER(vp)], u32),
+        "rpl_ctx_destroy": ([vp], None),
+        "rpl_last_error": ([vp], C.c_char_p),
+        "rpl_ctx_synchronize": ([vp], u32),
+        "rpl_host_alloc": ([sz, C.POINTER(vp)], u32),
+        "rpl_host_free": ([vp], None),
+        "rpl_ctx_launch_count": ([vp], u64),
+        "rpl_ascend_scan": ([vp, vp, sz], u32),
+        "rpl_laserscan": ([vp, vp, sz, PSP, vp, vp, C.POINTER(u32), C.POINTER(C.c_float)], u32),
+        "rpl_scan": ([vp, vp, sz, PSP, vp, vp, C.POINTER(u32), C.POINTER(C.c_float), C.POINTER(u32)], u32),
+        "rpl_scan_batch": ([vp, vp, vp, u32, u32, PSP, vp, vp, vp, vp, vp, vp, vp], u32),
+        "rpl_ascend_scan_batch": ([vp, vp, vp, u32, u32, vp], u32),
+        "rpl_laserscan_batch": ([vp, vp, vp, u32, u32, PSP, vp, vp, vp, vp], u32),
+        "rpl_scan_batch_dev": ([vp, vp, vp, u32, u32, PSP, vp, vp, vp, vp, vp, vp, vp, vp], u32),
+        "rpl_cloud_batch_dev": ([vp, vp, vp, u32, u32, PCP, vp, vp, vp], u32),
+        "rpl_cloud_batch": ([vp, vp, vp, u32, u32, PCP, vp, vp], u32),
+        "rpl_cloud_fuse_dev": ([vp, vp, vp, u32, u32, vp, vp, vp, vp], u32),
+        "rpl_synth_batch_dev": ([vp, u64, u32, u32, u32, i32, vp, vp, vp], u32),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(L, name)  # AttributeError here = the library does not export the ABI
+        fn.argtypes = args
+        fn.restype = res
+    _lib = L
+    return L
+
+
+def scan_params(is_new_protocol=0, scan_processing=1, inverted=0, apply_ascend=1, flags=0) -> ScanParams:
+    return ScanParams(int(is_new_protocol), int(scan_processing), int(inverted), int(apply_ascend), int(flags))
+
+
+def cloud_params(range_min=0.15, range_max=40.0, intensity_min=0.0, voxel_size=0.0, sor_k=0,
+                 sor_alpha=1.0, is_new_protocol=0) -> CloudParams:
+    return CloudParams(float(range_min), float(range_max), float(intensity_min), float(voxel_size),
+                       int(sor_k), float(sor_alpha), int(is_new_protocol), (C.c_uint8 * 3)(0, 0, 0))
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(int(a))  # raw device / host address
+
+
+class Context:
+    """rpl_ctx wrapper.  One per thread (the reference has one scan thread per node)."""
+
+    def __init__(self, device: int = 0, max_nodes: int = 8192, max_scans: int = 1):
+        self._L = lib()
+        h = C.c_void_p()
+        rc = self._L.rpl_ctx_create(device, max_nodes, max_scans, C.byref(h))
+        if rc != RESULT_OK:
+            raise RplError(rc, "rpl_ctx_create failed (no CUDA device / not a B200?) -- there is no CPU fallback")
+        self._h = h
+        self.device, self.max_nodes, self.max_scans = device, max_nodes, max_scans
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.rpl_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != RESULT_OK:
+            raise RplError(rc, (self._L.rpl_last_error(self._h) or b"").decode())
+
+    def synchronize(self):
+        self._check(self._L.rpl_ctx_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.rpl_ctx_launch_count(self._h))
+
+    # ---- single scan (reference-shaped) ---------------------------------------------------
+    def ascend_scan(self, nodes: np.ndarray):
+        """ILidarDriver::ascendScanData: returns (sl_result, ascended copy)."""
+        buf = np.ascontiguousarray(nodes, dtype=NODE_DTYPE).copy()
+        rc = self._L.rpl_ascend_scan(self._h, _p(buf), buf.shape[0])
+        return rc, buf
+
+    def laserscan(self, nodes: np.ndarray, params: ScanParams):
+        nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
+        n = nodes.shape[0]
+        ranges = np.full(max(n, 1), np.nan, np.float32)
+        inten = np.full(max(n, 1), np.nan, np.float32)
+        beams, inc = C.c_uint32(0), C.c_float(0)
+        self._check(self._L.rpl_laserscan(self._h, _p(nodes), n, C.byref(params), _p(ranges), _p(inten),
+                                          C.byref(beams), C.byref(inc)))
+        m = beams.value
+        return ranges[:m].copy(), inten[:m].copy(), m, np.float32(inc.value)
+
+    def scan(self, nodes: np.ndarray, params: ScanParams):
+        """Fused grab glue + publish_scan.  Returns dict(nodes, ranges, intensities, beam_count,
+        angle_increment, ascend_status)."""
+        buf = np.ascontiguousarray(nodes, dtype=NODE_DTYPE).copy()
+        n = buf.shape[0]
+        ranges = np.full(max(n, 1), np.nan, np.float32)
+        inten = np.full(max(n, 1), np.nan, np.float32)
+        beams, inc, st = C.c_uint32(0), C.c_float(0), C.c_uint32(0)
+        self._check(self._L.rpl_scan(self._h, _p(buf), n, C.byref(params), _p(ranges), _p(inten),
+                                     C.byref(beams), C.byref(inc), C.byref(st)))
+        m = beams.value
+        return dict(nodes=buf, ranges=ranges[:m].copy(), intensities=inten[:m].copy(), beam_count=m,
+                    angle_increment=np.float32(inc.value), ascend_status=st.value)
+
+    # ---- batches, host buffers -----------------------------------------------------------------
+    def scan_batch(self, nodes: np.ndarray, counts, params: ScanParams, emit_nodes=False, want_scan=True,
+                   out=None):
+        """nodes [n_scans, stride].  `out` may carry preallocated (e.g. pinned) arrays."""
+        assert nodes.dtype == NODE_DTYPE and nodes.ndim == 2 and nodes.flags.c_contiguous
+        n_scans, stride = nodes.shape
+        counts = np.ascontiguousarray(counts, dtype=np.uint32)
+        out = dict(out or {})
+        if want_scan:
+            out.setdefault("ranges", np.full((n_scans, stride), np.nan, np.float32))
+            out.setdefault("intensities", np.full((n_scans, stride), np.nan, np.float32))
+        if emit_nodes:
+            out.setdefault("nodes", np.zeros((n_scans, stride), NODE_DTYPE))
+        for k, dt in (("beam_counts", np.uint32), ("angle_increment", np.float32), ("status", np.uint32),
+                      ("path", np.uint32)):
+            out.setdefault(k, np.zeros(n_scans, dt))
+        self._check(self._L.rpl_scan_batch(
+            self._h, _p(nodes), _p(counts), n_scans, stride, C.byref(params), _p(out.get("nodes")),
+            _p(out.get("ranges")), _p(out.get("intensities")), _p(out["beam_counts"]),
+            _p(out["angle_increment"]), _p(out["status"]), _p(out["path"])))
+        return out
+
+    # ---- batches, device buffers (addresses as ints, e.g. torch.Tensor.data_ptr()) -------------
+    def scan_batch_dev(self, nodes, counts, n_scans, stride, params: ScanParams, nodes_out=None, ranges=None,
+                       intensities=None, beam_counts=None, angle_increment=None, status=None, path=None,
+                       stream=None):
+        self._check(self._L.rpl_scan_batch_dev(
+            self._h, _p(nodes), _p(counts), n_scans, stride, C.byref(params), _p(nodes_out), _p(ranges),
+            _p(intensities), _p(beam_counts), _p(angle_increment), _p(status), _p(path), _p(stream)))
+
+    def synth_batch_dev(self, first_scan_id, n_scans, n, stride, variant, nodes, counts=None, stream=None):
+        self._check(self._L.rpl_synth_batch_dev(self._h, first_scan_id, n_scans, n, stride, variant, _p(nodes),
+                                                _p(counts), _p(stream)))
+
+    def cloud_batch_dev(self, nodes, counts, n_scans, stride, params: CloudParams, xyzi, point_counts, stream=None):
+        self._check(self._L.rpl_cloud_batch_dev(self._h, _p(nodes), _p(counts), n_scans, stride, C.byref(params),
+                                                _p(xyzi), _p(point_counts), _p(stream)))
+
+    def cloud_batch(self, nodes: np.ndarray, counts, params: CloudParams):
+        assert nodes.dtype == NODE_DTYPE and nodes.ndim == 2 and nodes.flags.c_contiguous
+        n_scans, stride = nodes.shape
+        counts = np.ascontiguousarray(counts, dtype=np.uint32)
+        xyzi = np.full((n_scans, stride, 4), np.nan, np.float32)
+        pc = np.zeros(n_scans, np.uint32)
+        self._check(self._L.rpl_cloud_batch(self._h, _p(nodes), _p(counts), n_scans, stride, C.byref(params),
+                                            _p(xyzi), _p(pc)))
+        return xyzi, pc
+
+    def cloud_fuse_dev(self, xyzi, point_counts, n_scans, stride, fused, offsets, total, stream=None):
+        self._check(self._L.rpl_cloud_fuse_dev(self._h, _p(xyzi), _p(point_counts), n_scans, stride, _p(fused),
+                                               _p(offsets), _p(total), _p(stream)))
+
+
+def host_alloc(nbytes: int) -> np.ndarray:
+    """Pinned host memory as a uint8 numpy array (kept alive by a finalizer)."""
+    L = lib()
+    p = C.c_void_p()
+    rc = L.rpl_host_alloc(nbytes, C.byref(p))
+    if rc != RESULT_OK:
+        raise RplError(rc, "rpl_host_alloc failed")
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=np.uint8, count=nbytes)
+    import weakref
+
+    weakref.finalize(buf, L.rpl_host_free, p)
+    return arr

@@ -1,0 +1,530 @@
+// rpl_capi.cu -- the C-ABI of librplidar_b200.so (include/rpl_b200.h).
+//
+// Host-side glue only: context, workspaces, streams, the chunked host<->device pipeline of
+// the host-buffer entry points, and kernel launches.  There is no CPU implementation of the
+// path in this library: every entry point either runs the CUDA kernels or fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/rpl_b200.h"
+#include "cloud_args.h"
+#include "scan_args.h"
+
+namespace rpl {
+cudaError_t launch_synth(uint64_t first_scan_id, uint32_t n_scans, uint32_t n, uint32_t stride,
+                         int variant, uint2* nodes, uint32_t* counts, cudaStream_t stream);
+}
+
+static_assert(sizeof(rpl_node_hq) == 8, "packed node must be 8 bytes");
+
+namespace {
+
+constexpr int kLanes = 2;  // host-buffer pipeline depth (copy/compute overlap)
+
+struct Lane {
+  cudaStream_t stream = nullptr;
+  uint32_t* fallback_list = nullptr;
+  uint32_t* fallback_count = nullptr;
+  rpl::FastWorkspace fws{};
+  rpl::GeneralWorkspace gws{};
+  rpl::CloudWorkspace cws{};
+  // device staging for host-buffer calls (lazy)
+  uint2* d_nodes = nullptr;
+  uint2* d_nodes_out = nullptr;
+  uint32_t* d_counts = nullptr;
+  float* d_ranges = nullptr;
+  float* d_intens = nullptr;
+  uint32_t* d_beams = nullptr;
+  float* d_inc = nullptr;
+  uint32_t* d_status = nullptr;
+  uint32_t* d_path = nullptr;
+  float* d_xyzi = nullptr;
+  uint32_t* d_pcount = nullptr;
+  size_t staged_nodes = 0;  // capacity in nodes of the staging buffers
+  uint32_t staged_scans = 0;
+};
+
+}  // namespace
+
+struct rpl_ctx {
+  int device = 0;
+  uint32_t max_nodes = 0, max_scans = 0;
+  int num_sms = 0;
+  int fast_grid = 0, general_grid = 0;
+  Lane lane[kLanes];
+  std::string err;
+  uint64_t launches = 0;
+};
+
+namespace {
+
+bool cuda_ok(rpl_ctx* c, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  char buf[256];
+  std::snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+  c->err = buf;
+  return false;
+}
+#define RPL_CUDA(c, call, code)                   \
+  do {                                            \
+    if (!cuda_ok((c), (call), #call)) return (code); \
+  } while (0)
+
+template <class P>
+cudaError_t dev_alloc(P** p, size_t count) {
+  return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(P));
+}
+
+void free_lane(Lane& l) {
+  cudaFree(l.fallback_list);
+  cudaFree(l.fallback_count);
+  cudaFree(l.fws.group);
+  cudaFree(l.gws.keyf);
+  cudaFree(l.gws.idx0);
+  cudaFree(l.gws.idx1);
+  cudaFree(l.gws.vidx);
+  cudaFree(l.gws.cell);
+  rpl::cloud_workspace_free(l.cws);
+  cudaFree(l.d_nodes);
+  cudaFree(l.d_nodes_out);
+  cudaFree(l.d_counts);
+  cudaFree(l.d_ranges);
+  cudaFree(l.d_intens);
+  cudaFree(l.d_beams);
+  cudaFree(l.d_inc);
+  cudaFree(l.d_status);
+  cudaFree(l.d_path);
+  cudaFree(l.d_xyzi);
+  cudaFree(l.d_pcount);
+  if (l.stream) cudaStreamDestroy(l.stream);
+  l = Lane{};
+}
+
+rpl_result ensure_staging(rpl_ctx* c, Lane& l, uint32_t scans, size_t nodes, bool cloud) {
+  if (l.staged_nodes < nodes || l.staged_scans < scans) {
+    cudaFree(l.d_nodes);
+    cudaFree(l.d_nodes_out);
+    cudaFree(l.d_ranges);
+    cudaFree(l.d_intens);
+    cudaFree(l.d_counts);
+    cudaFree(l.d_beams);
+    cudaFree(l.d_inc);
+    cudaFree(l.d_status);
+    cudaFree(l.d_path);
+    cudaFree(l.d_xyzi);
+    cudaFree(l.d_pcount);
+    l.d_nodes = l.d_nodes_out = nullptr;
+    l.d_ranges = l.d_intens = l.d_inc = l.d_xyzi = nullptr;
+    l.d_counts = l.d_beams = l.d_status = l.d_path = l.d_pcount = nullptr;
+    l.staged_nodes = 0;
+    l.staged_scans = 0;
+    const rpl_result oom = RPL_RESULT_INSUFFICIENT_MEMORY;
+    RPL_CUDA(c, dev_alloc(&l.d_nodes, nodes), oom);
+    RPL_CUDA(c, dev_alloc(&l.d_nodes_out, nodes), oom);
+    RPL_CUDA(c, dev_alloc(&l.d_ranges, nodes), oom);
+    RPL_CUDA(c, dev_alloc(&l.d_intens, nodes), oom);
+    RPL_CUDA(c, dev_alloc(&l.d_counts, scans), oom);
+    RPL_CUDA(c, dev_alloc(&l.d_beams, scans), oom);
+    RPL_CUDA(c, dev_alloc(&l.d_inc, scans), oom);
+    RPL_CUDA(c, dev_alloc(&l.d_status, scans), oom);
+    RPL_CUDA(c, dev_alloc(&l.d_path, scans), oom);
+    RPL_CUDA(c, dev_alloc(&l.d_pcount, scans), oom);
+    l.staged_nodes = nodes;
+    l.staged_scans = scans;
+  }
+  if (cloud && !l.d_xyzi) RPL_CUDA(c, dev_alloc(&l.d_xyzi, l.staged_nodes * 4), RPL_RESULT_INSUFFICIENT_MEMORY);
+  return RPL_RESULT_OK;
+}
+
+// queue the scan kernels for one device-resident batch on `stream`
+rpl_result enqueue_scan(rpl_ctx* c, Lane& l, const rpl_node_hq* nodes, const uint32_t* counts,
+                        uint32_t n_scans, uint32_t stride, const rpl_scan_params* p,
+                        rpl_node_hq* nodes_out, float* ranges, float* intens, uint32_t* beams,
+                        float* inc, uint32_t* status, uint32_t* path, cudaStream_t stream) {
+  if (n_scans == 0) return RPL_RESULT_OK;
+  if (!nodes || !counts || !p) {
+    c->err = "null nodes/counts/params";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if (n_scans > c->max_scans) {
+    c->err = "n_scans exceeds the context's max_scans";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if ((ranges == nullptr) != (intens == nullptr)) {
+    c->err = "ranges and intensities must be given together";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if (nodes_out && static_cast<const void*>(nodes_out) == static_cast<const void*>(nodes)) {
+    c->err = "nodes_out must not alias nodes on the device path";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  rpl::ScanBatchArgs a{};
+  a.nodes = reinterpret_cast<const uint2*>(nodes);
+  a.nodes_out = reinterpret_cast<uint2*>(nodes_out);
+  a.counts = counts;
+  a.n_scans = n_scans;
+  a.stride = stride;
+  a.ranges = ranges;
+  a.intensities = intens;
+  a.beam_counts = beams;
+  a.angle_inc = inc;
+  a.status = status;
+  a.path = path;
+  a.fallback_list = l.fallback_list;
+  a.fallback_count = l.fallback_count;
+  a.is_new_protocol = p->is_new_protocol;
+  a.mode_a = p->scan_processing;
+  a.inverted = p->inverted;
+  a.apply_ascend = p->apply_ascend;
+
+  const bool force_general = (p->flags & RPL_FLAG_FORCE_GENERAL) != 0;
+  if (!force_general) {
+    RPL_CUDA(c, cudaMemsetAsync(l.fallback_count, 0, sizeof(uint32_t), stream), RPL_RESULT_OPERATION_FAIL);
+    const int grid = (int)std::min<uint32_t>(n_scans, (uint32_t)c->fast_grid);
+    RPL_CUDA(c, rpl::launch_scan_fast(a, l.fws, grid, stream), RPL_RESULT_OPERATION_FAIL);
+    c->launches++;
+  }
+  const int ggrid = (int)std::min<uint32_t>(n_scans, (uint32_t)c->general_grid);
+  RPL_CUDA(c, rpl::launch_scan_general(a, l.gws, ggrid, force_general, stream), RPL_RESULT_OPERATION_FAIL);
+  c->launches++;
+  return RPL_RESULT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t rpl_abi_version(void) { return RPL_ABI_VERSION; }
+
+rpl_result rpl_ctx_create(int device, uint32_t max_nodes, uint32_t max_scans, rpl_ctx** out) {
+  if (!out || max_nodes == 0 || max_scans == 0) return RPL_RESULT_INVALID_DATA;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    // no CPU fallback by design
+    return RPL_RESULT_OPERATION_NOT_SUPPORT;
+  }
+  rpl_ctx* c = new (std::nothrow) rpl_ctx();
+  if (!c) return RPL_RESULT_INSUFFICIENT_MEMORY;
+  c->device = device;
+  c->max_nodes = max_nodes;
+  c->max_scans = max_scans;
+  auto fail = [&](rpl_result r) {
+    std::fprintf(stderr, "[rpl_b200] rpl_ctx_create failed: %s\n", c->err.c_str());
+    rpl_ctx_destroy(c);
+    return r;
+  };
+  if (!cuda_ok(c, cudaSetDevice(device), "cudaSetDevice")) return fail(RPL_RESULT_OPERATION_FAIL);
+  cudaDeviceProp prop{};
+  if (!cuda_ok(c, cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties"))
+    return fail(RPL_RESULT_OPERATION_FAIL);
+  if (prop.major < 10) {
+    c->err = "librplidar_b200 is built for sm_100a (B200) only";
+    return fail(RPL_RESULT_OPERATION_NOT_SUPPORT);
+  }
+  c->num_sms = prop.multiProcessorCount;
+  if (!cuda_ok(c, rpl::scan_fast_configure(), "scan_fast_configure") ||
+      !cuda_ok(c, rpl::scan_general_configure(), "scan_general_configure") ||
+      !cuda_ok(c, rpl::cloud_configure(), "cloud_configure"))
+    return fail(RPL_RESULT_OPERATION_FAIL);
+  const int occ = std::max(1, rpl::scan_fast_max_ctas_per_sm());
+  c->fast_grid = c->num_sms * occ;
+  c->general_grid = c->num_sms;
+
+  for (int i = 0; i < kLanes; ++i) {
+    Lane& l = c->lane[i];
+    const rpl_result oom = RPL_RESULT_INSUFFICIENT_MEMORY;
+    if (!cuda_ok(c, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking), "cudaStreamCreate"))
+      return fail(RPL_RESULT_OPERATION_FAIL);
+    const size_t fast_nodes = (size_t)c->fast_grid * max_nodes;
+    const size_t gen_nodes = (size_t)c->general_grid * max_nodes;
+    l.fws.max_nodes = max_nodes;
+    l.gws.max_nodes = max_nodes;
+    if (!cuda_ok(c, dev_alloc(&l.fallback_list, max_scans), "cudaMalloc") ||
+        !cuda_ok(c, dev_alloc(&l.fallback_count, 1), "cudaMalloc") ||
+        !cuda_ok(c, dev_alloc(&l.fws.group, fast_nodes), "cudaMalloc") ||
+        !cuda_ok(c, dev_alloc(&l.gws.keyf, gen_nodes), "cudaMalloc") ||
+        !cuda_ok(c, dev_alloc(&l.gws.idx0, gen_nodes), "cudaMalloc") ||
+        !cuda_ok(c, dev_alloc(&l.gws.idx1, gen_nodes), "cudaMalloc") ||
+        !cuda_ok(c, dev_alloc(&l.gws.vidx, gen_nodes), "cudaMalloc") ||
+        !cuda_ok(c, dev_alloc(&l.gws.cell, gen_nodes), "cudaMalloc") ||
+        !cuda_ok(c, rpl::cloud_workspace_alloc(l.cws, c->num_sms, max_nodes), "cloud workspace"))
+      return fail(oom);
+    if (!cuda_ok(c, cudaMemset(l.fallback_count, 0, sizeof(uint32_t)), "cudaMemset"))
+      return fail(RPL_RESULT_OPERATION_FAIL);
+  }
+  *out = c;
+  return RPL_RESULT_OK;
+}
+
+void rpl_ctx_destroy(rpl_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  for (int i = 0; i < kLanes; ++i) {
+    if (c->lane[i].stream) cudaStreamSynchronize(c->lane[i].stream);
+    free_lane(c->lane[i]);
+  }
+  delete c;
+}
+
+const char* rpl_last_error(const rpl_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+rpl_result rpl_ctx_synchronize(rpl_ctx* c) {
+  if (!c) return RPL_RESULT_INVALID_DATA;
+  for (int i = 0; i < kLanes; ++i)
+    RPL_CUDA(c, cudaStreamSynchronize(c->lane[i].stream), RPL_RESULT_OPERATION_FAIL);
+  return RPL_RESULT_OK;
+}
+
+rpl_result rpl_host_alloc(size_t bytes, void** out) {
+  if (!out) return RPL_RESULT_INVALID_DATA;
+  *out = nullptr;
+  return cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocDefault) == cudaSuccess
+             ? RPL_RESULT_OK
+             : RPL_RESULT_INSUFFICIENT_MEMORY;
+}
+void rpl_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+uint64_t rpl_ctx_launch_count(const rpl_ctx* c) { return c ? c->launches : 0; }
+
+// ---- device-resident batch ----------------------------------------------------------------
+rpl_result rpl_scan_batch_dev(rpl_ctx* c, const rpl_node_hq* nodes, const uint32_t* counts,
+                              uint32_t n_scans, uint32_t stride, const rpl_scan_params* params,
+                              rpl_node_hq* nodes_out, float* ranges, float* intensities,
+                              uint32_t* beam_counts, float* angle_increment, uint32_t* status,
+                              uint32_t* path, void* stream) {
+  if (!c) return RPL_RESULT_INVALID_DATA;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  if (stride > c->max_nodes && false) return RPL_RESULT_INVALID_DATA;
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
+  return enqueue_scan(c, c->lane[0], nodes, counts, n_scans, stride, params, nodes_out, ranges,
+                      intensities, beam_counts, angle_increment, status, path, st);
+}
+
+// ---- host-buffer batch: chunked over the two lanes so that the H2D copy of chunk i+1, the
+// kernels of chunk i and the D2H copy of chunk i-1 overlap ---------------------------------
+rpl_result rpl_scan_batch(rpl_ctx* c, const rpl_node_hq* nodes, const uint32_t* counts,
+                          uint32_t n_scans, uint32_t stride, const rpl_scan_params* params,
+                          rpl_node_hq* nodes_out, float* ranges, float* intensities,
+                          uint32_t* beam_counts, float* angle_increment, uint32_t* status,
+                          uint32_t* path) {
+  if (!c) return RPL_RESULT_INVALID_DATA;
+  if (n_scans == 0) return RPL_RESULT_OK;
+  if (!nodes || !counts || !params) {
+    c->err = "null nodes/counts/params";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if (n_scans > c->max_scans || stride == 0) {
+    c->err = "n_scans exceeds max_scans (or stride == 0)";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  for (uint32_t s = 0; s < n_scans; ++s)
+    if (counts[s] > stride || counts[s] > c->max_nodes) {
+      c->err = "counts[s] exceeds stride or the context's max_nodes";
+      return RPL_RESULT_INVALID_DATA;
+    }
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+
+  // chunk: about 32 MiB of nodes, at least one scan
+  const size_t target_nodes = (32u << 20) / sizeof(rpl_node_hq);
+  uint32_t chunk = (uint32_t)std::max<size_t>(1, target_nodes / stride);
+  chunk = std::min(chunk, n_scans);
+  const bool want_scan = ranges != nullptr;
+  for (int i = 0; i < kLanes; ++i) {
+    rpl_result r = ensure_staging(c, c->lane[i], chunk, (size_t)chunk * stride, false);
+    if (r != RPL_RESULT_OK) return r;
+  }
+  const cudaMemcpyKind h2d = cudaMemcpyHostToDevice, d2h = cudaMemcpyDeviceToHost;
+  uint32_t ci = 0;
+  for (uint32_t s0 = 0; s0 < n_scans; s0 += chunk, ++ci) {
+    Lane& l = c->lane[ci % kLanes];
+    const uint32_t ns = std::min(chunk, n_scans - s0);
+    const size_t off = (size_t)s0 * stride, cnt = (size_t)ns * stride;
+    // the lane's previous chunk (2 chunks ago) must have left its staging buffers
+    RPL_CUDA(c, cudaStreamSynchronize(l.stream), RPL_RESULT_OPERATION_FAIL);
+    RPL_CUDA(c, cudaMemcpyAsync(l.d_nodes, nodes + off, cnt * sizeof(rpl_node_hq), h2d, l.stream),
+             RPL_RESULT_OPERATION_FAIL);
+    RPL_CUDA(c, cudaMemcpyAsync(l.d_counts, counts + s0, ns * sizeof(uint32_t), h2d, l.stream),
+             RPL_RESULT_OPERATION_FAIL);
+    rpl_result r = enqueue_scan(c, l, reinterpret_cast<rpl_node_hq*>(l.d_nodes), l.d_counts, ns, stride,
+                                params, nodes_out ? reinterpret_cast<rpl_node_hq*>(l.d_nodes_out) : nullptr,
+                                want_scan ? l.d_ranges : nullptr, want_scan ? l.d_intens : nullptr,
+                                l.d_beams, l.d_inc, l.d_status, l.d_path, l.stream);
+    if (r != RPL_RESULT_OK) return r;
+    if (nodes_out)
+      RPL_CUDA(c, cudaMemcpyAsync(nodes_out + off, l.d_nodes_out, cnt * sizeof(rpl_node_hq), d2h, l.stream),
+               RPL_RESULT_OPERATION_FAIL);
+    if (want_scan) {
+      RPL_CUDA(c, cudaMemcpyAsync(ranges + off, l.d_ranges, cnt * sizeof(float), d2h, l.stream),
+               RPL_RESULT_OPERATION_FAIL);
+      RPL_CUDA(c, cudaMemcpyAsync(intensities + off, l.d_intens, cnt * sizeof(float), d2h, l.stream),
+               RPL_RESULT_OPERATION_FAIL);
+    }
+    if (beam_counts)
+      RPL_CUDA(c, cudaMemcpyAsync(beam_counts + s0, l.d_beams, ns * sizeof(uint32_t), d2h, l.stream),
+               RPL_RESULT_OPERATION_FAIL);
+    if (angle_increment)
+      RPL_CUDA(c, cudaMemcpyAsync(angle_increment + s0, l.d_inc, ns * sizeof(float), d2h, l.stream),
+               RPL_RESULT_OPERATION_FAIL);
+    if (status)
+      RPL_CUDA(c, cudaMemcpyAsync(status + s0, l.d_status, ns * sizeof(uint32_t), d2h, l.stream),
+               RPL_RESULT_OPERATION_FAIL);
+    if (path)
+      RPL_CUDA(c, cudaMemcpyAsync(path + s0, l.d_path, ns * sizeof(uint32_t), d2h, l.stream),
+               RPL_RESULT_OPERATION_FAIL);
+  }
+  return rpl_ctx_synchronize(c);
+}
+
+rpl_result rpl_ascend_scan_batch(rpl_ctx* c, rpl_node_hq* nodes, const uint32_t* counts,
+                                 uint32_t n_scans, uint32_t stride, uint32_t* status) {
+  rpl_scan_params p{};
+  p.apply_ascend = 1;
+  return rpl_scan_batch(c, nodes, counts, n_scans, stride, &p, nodes, nullptr, nullptr, nullptr,
+                        nullptr, status, nullptr);
+}
+
+rpl_result rpl_laserscan_batch(rpl_ctx* c, const rpl_node_hq* nodes, const uint32_t* counts,
+                               uint32_t n_scans, uint32_t stride, const rpl_scan_params* params,
+                               float* ranges, float* intensities, uint32_t* beam_counts,
+                               float* angle_increment) {
+  if (!params) return RPL_RESULT_INVALID_DATA;
+  rpl_scan_params p = *params;
+  p.apply_ascend = 0;  // the LaserScan never depends on the ascended buffer
+  return rpl_scan_batch(c, nodes, counts, n_scans, stride, &p, nullptr, ranges, intensities,
+                        beam_counts, angle_increment, nullptr, nullptr);
+}
+
+// ---- single scan (the reference-shaped calls) ----------------------------------------------
+rpl_result rpl_ascend_scan(rpl_ctx* c, rpl_node_hq* nodes, size_t count) {
+  if (!c) return RPL_RESULT_INVALID_DATA;
+  if (count == 0) return RPL_RESULT_OPERATION_FAIL;  // reference: i == count -> FAIL
+  if (!nodes || count > c->max_nodes) return RPL_RESULT_INVALID_DATA;
+  uint32_t cnt = (uint32_t)count, status = RPL_RESULT_OPERATION_FAIL;
+  rpl_result r = rpl_ascend_scan_batch(c, nodes, &cnt, 1, cnt, &status);
+  return r != RPL_RESULT_OK ? r : status;
+}
+
+rpl_result rpl_laserscan(rpl_ctx* c, const rpl_node_hq* nodes, size_t count,
+                         const rpl_scan_params* params, float* ranges, float* intensities,
+                         uint32_t* beam_count, float* angle_increment) {
+  if (!c || !beam_count) return RPL_RESULT_INVALID_DATA;
+  *beam_count = 0;
+  if (angle_increment) *angle_increment = 0.0f;
+  if (count == 0) return RPL_RESULT_OK;  // publish_scan: nodes.empty() -> return
+  if (!nodes || count > c->max_nodes) return RPL_RESULT_INVALID_DATA;
+  uint32_t cnt = (uint32_t)count;
+  return rpl_laserscan_batch(c, nodes, &cnt, 1, cnt, params, ranges, intensities, beam_count,
+                             angle_increment);
+}
+
+rpl_result rpl_scan(rpl_ctx* c, rpl_node_hq* nodes, size_t count, const rpl_scan_params* params,
+                    float* ranges, float* intensities, uint32_t* beam_count,
+                    float* angle_increment, rpl_result* ascend_status) {
+  if (!c || !beam_count || !params) return RPL_RESULT_INVALID_DATA;
+  *beam_count = 0;
+  if (angle_increment) *angle_increment = 0.0f;
+  if (ascend_status) *ascend_status = params->apply_ascend ? RPL_RESULT_OPERATION_FAIL : RPL_RESULT_OK;
+  if (count == 0) return RPL_RESULT_OK;
+  if (!nodes || count > c->max_nodes) return RPL_RESULT_INVALID_DATA;
+  uint32_t cnt = (uint32_t)count, status = 0;
+  rpl_result r = rpl_scan_batch(c, nodes, &cnt, 1, cnt, params, params->apply_ascend ? nodes : nullptr,
+                                ranges, intensities, beam_count, angle_increment, &status, nullptr);
+  if (ascend_status) *ascend_status = status;
+  return r;
+}
+
+// ---- synthetic streams ------------------------------------------------------------------------
+rpl_result rpl_synth_batch_dev(rpl_ctx* c, uint64_t first_scan_id, uint32_t n_scans, uint32_t n,
+                               uint32_t stride, int variant, rpl_node_hq* nodes, uint32_t* counts,
+                               void* stream) {
+  if (!c || !nodes || n > stride || variant < 0 || variant > 3) return RPL_RESULT_INVALID_DATA;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
+  RPL_CUDA(c, rpl::launch_synth(first_scan_id, n_scans, n, stride, variant,
+                                reinterpret_cast<uint2*>(nodes), counts, st),
+           RPL_RESULT_OPERATION_FAIL);
+  c->launches++;
+  return RPL_RESULT_OK;
+}
+
+// ---- PointCloud2 path ----------------------------------------------------------------------------
+rpl_result rpl_cloud_batch_dev(rpl_ctx* c, const rpl_node_hq* nodes, const uint32_t* counts,
+                               uint32_t n_scans, uint32_t stride, const rpl_cloud_params* params,
+                               float* xyzi, uint32_t* point_counts, void* stream) {
+  if (!c || !nodes || !counts || !params || !xyzi || !point_counts) return RPL_RESULT_INVALID_DATA;
+  if (n_scans == 0) return RPL_RESULT_OK;
+  if (n_scans > c->max_scans || params->sor_k > 32) {
+    c->err = "n_scans exceeds max_scans or sor_k > 32";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
+  rpl::CloudBatchArgs a{};
+  a.nodes = reinterpret_cast<const uint2*>(nodes);
+  a.counts = counts;
+  a.n_scans = n_scans;
+  a.stride = stride;
+  a.xyzi = reinterpret_cast<float4*>(xyzi);
+  a.point_counts = point_counts;
+  a.range_min = params->range_min;
+  a.range_max = params->range_max;
+  a.intensity_min = params->intensity_min;
+  a.voxel_size = params->voxel_size;
+  a.sor_k = params->sor_k;
+  a.sor_alpha = params->sor_alpha;
+  a.is_new_protocol = params->is_new_protocol;
+  int launched = 0;
+  RPL_CUDA(c, rpl::launch_cloud(a, c->lane[0].cws, c->num_sms, st, &launched), RPL_RESULT_OPERATION_FAIL);
+  c->launches += launched;
+  return RPL_RESULT_OK;
+}
+
+rpl_result rpl_cloud_batch(rpl_ctx* c, const rpl_node_hq* nodes, const uint32_t* counts,
+                           uint32_t n_scans, uint32_t stride, const rpl_cloud_params* params,
+                           float* xyzi, uint32_t* point_counts) {
+  if (!c || !nodes || !counts || !params || !xyzi || !point_counts) return RPL_RESULT_INVALID_DATA;
+  if (n_scans == 0) return RPL_RESULT_OK;
+  if (n_scans > c->max_scans) return RPL_RESULT_INVALID_DATA;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  Lane& l = c->lane[0];
+  rpl_result r = ensure_staging(c, l, n_scans, (size_t)n_scans * stride, true);
+  if (r != RPL_RESULT_OK) return r;
+  const size_t cnt = (size_t)n_scans * stride;
+  RPL_CUDA(c, cudaMemcpyAsync(l.d_nodes, nodes, cnt * sizeof(rpl_node_hq), cudaMemcpyHostToDevice, l.stream),
+           RPL_RESULT_OPERATION_FAIL);
+  RPL_CUDA(c, cudaMemcpyAsync(l.d_counts, counts, n_scans * sizeof(uint32_t), cudaMemcpyHostToDevice, l.stream),
+           RPL_RESULT_OPERATION_FAIL);
+  r = rpl_cloud_batch_dev(c, reinterpret_cast<rpl_node_hq*>(l.d_nodes), l.d_counts, n_scans, stride, params,
+                          l.d_xyzi, l.d_pcount, l.stream);
+  if (r != RPL_RESULT_OK) return r;
+  RPL_CUDA(c, cudaMemcpyAsync(xyzi, l.d_xyzi, cnt * 4 * sizeof(float), cudaMemcpyDeviceToHost, l.stream),
+           RPL_RESULT_OPERATION_FAIL);
+  RPL_CUDA(c, cudaMemcpyAsync(point_counts, l.d_pcount, n_scans * sizeof(uint32_t), cudaMemcpyDeviceToHost, l.stream),
+           RPL_RESULT_OPERATION_FAIL);
+  RPL_CUDA(c, cudaStreamSynchronize(l.stream), RPL_RESULT_OPERATION_FAIL);
+  return RPL_RESULT_OK;
+}
+
+rpl_result rpl_cloud_fuse_dev(rpl_ctx* c, const float* xyzi, const uint32_t* point_counts,
+                              uint32_t n_scans, uint32_t stride, float* fused, uint32_t* offsets,
+                              uint32_t* total, void* stream) {
+  if (!c || !xyzi || !point_counts || !fused || !offsets || !total) return RPL_RESULT_INVALID_DATA;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
+  int launched = 0;
+  RPL_CUDA(c, rpl::launch_cloud_fuse(reinterpret_cast<const float4*>(xyzi), point_counts, n_scans, stride,
+                                     reinterpret_cast<float4*>(fused), offsets, total, st, &launched),
+           RPL_RESULT_OPERATION_FAIL);
+  c->launches += launched;
+  return RPL_RESULT_OK;
+}
+
+}  // extern "C"

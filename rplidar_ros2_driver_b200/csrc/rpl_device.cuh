@@ -1,0 +1,136 @@
+// rpl_device.cuh -- device-side building blocks shared by the scan kernels.
+//
+// Everything here reproduces the reference's scalar arithmetic bit for bit; every float
+// operation is an explicit round-to-nearest intrinsic (no FMA contraction: the x86-64
+// reference build rounds the multiply and the add separately) and the library
+// is compiled without --use_fast_math.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rpl {
+
+constexpr uint32_t kKeySpace = 65536;  // angle_z_q14 is a u16: 65536 units = 360 degrees
+constexpr uint32_t kResultOk = 0u;
+constexpr uint32_t kResultOperationFail = 0x80008001u;  // SL_RESULT_OPERATION_FAIL
+
+// A packed node (reference sl_lidar_cmd.h:272-278) seen as two little-endian words:
+//   x = angle_z_q14 | dist_mm_q2[15:0] << 16
+//   y = dist_mm_q2[31:16] | quality << 16 | flag << 24
+// dist_mm_q2 sits at the unaligned byte offset 2, so it is never dereferenced directly.
+__device__ __forceinline__ uint32_t node_key(uint2 n) { return n.x & 0xFFFFu; }
+__device__ __forceinline__ uint32_t node_dist(uint2 n) { return __funnelshift_r(n.x, n.y, 16); }
+__device__ __forceinline__ uint32_t node_quality(uint2 n) { return (n.y >> 16) & 0xFFu; }
+__device__ __forceinline__ uint2 node_with_key(uint2 n, uint32_t key) {
+  n.x = (n.x & 0xFFFF0000u) | (key & 0xFFFFu);
+  return n;
+}
+
+// getAngle(hq): angle_z_q14 * 90.f / 16384.f (reference sl_lidar_driver.cpp:102-105).
+// Both operations are exact (key*90 < 2^24, then a power-of-two scale).
+__device__ __forceinline__ float key_to_deg(uint32_t key) {
+  return __fmul_rn(__fmul_rn(__uint2float_rn(key), 90.0f), 1.0f / 16384.0f);
+}
+// setAngle(hq, v): angle_z_q14 = (u16)(u32)(v * 16384.f / 90.f) (reference :107-110).
+__device__ __forceinline__ uint32_t deg_to_key(float deg) {
+  return __float2uint_rz(__fdiv_rn(__fmul_rn(deg, 16384.0f), 90.0f)) & 0xFFFFu;
+}
+// inc_origin_angle = 360.f / count (reference :130)
+__device__ __forceinline__ float ascend_step(uint32_t count) {
+  return __fdiv_rn(360.0f, __uint2float_rn(count));
+}
+// fill of an unmeasured node i >= 1 (reference :171-178)
+__device__ __forceinline__ uint32_t ascend_fill_key(float front_deg, uint32_t i, float step) {
+  float a = __fadd_rn(front_deg, __fmul_rn(__uint2float_rn(i), step));
+  if (a > 360.0f) a = __fsub_rn(a, 360.0f);
+  return deg_to_key(a);
+}
+// head tune (reference :133-147): walk back from the first measured node, re-quantising at
+// every step.  Only node 0's value survives (the fill overwrites the others), but it depends
+// on the whole chain, so it is reproduced serially.  Once the chain clamps to 0 it stays 0.
+__device__ __forceinline__ uint32_t ascend_head_key(uint32_t first_key, uint32_t first_index,
+                                                    float step) {
+  uint32_t k = first_key;
+  for (uint32_t j = first_index; j > 0 && k != 0; --j) {
+    float a = __fsub_rn(key_to_deg(k), step);
+    if (a < 0.0f) a = 0.0f;
+    k = deg_to_key(a);
+  }
+  return k;
+}
+
+// publish_scan unpack (reference rplidar_node.cpp:586-590)
+__device__ __forceinline__ float key_to_rad(uint32_t key) {
+  // float angle_rad = angle_deg * (M_PI / 180.0f): double product rounded to float
+  const double kDegToRad = 3.14159265358979323846 / 180.0;
+  return __double2float_rn(__dmul_rn((double)key_to_deg(key), kDegToRad));
+}
+__device__ __forceinline__ float dist_to_m(uint32_t dist_q2) {
+  return __fdiv_rn(__uint2float_rn(dist_q2), 4000.0f);
+}
+__device__ __forceinline__ float quality_to_intensity(uint32_t q, bool new_protocol) {
+  return __uint2float_rn(new_protocol ? q : (q >> 2));
+}
+
+// LaserScan.angle_increment (reference rplidar_node.cpp:633-634 Mode A, :664-666 Mode B)
+__device__ __forceinline__ float angle_increment(uint32_t m, bool mode_a) {
+  const double kTwoPi = 2.0 * 3.14159265358979323846;
+  const uint32_t d = mode_a ? m : (m > 1 ? m - 1 : 1);
+  return __double2float_rn(__ddiv_rn(kTwoPi, (double)d));
+}
+// Mode A bin of a measured point (reference rplidar_node.cpp:641-652); always < m for m >= 1
+// because angle_rad <= 6.28308964 < 2*pi, but the reference's bounds check is kept by callers.
+__device__ __forceinline__ int mode_a_bin(uint32_t key, float inc, bool inverted) {
+  const double kTwoPi = 2.0 * 3.14159265358979323846;
+  float a = key_to_rad(key);
+  if (inverted) {
+    a = __double2float_rn(__dsub_rn(kTwoPi, (double)a));
+    if ((double)a >= kTwoPi) a = __double2float_rn(__dsub_rn((double)a, kTwoPi));
+  }
+  return __float2int_rz(__fdiv_rn(__fsub_rn(a, 0.0f), inc));
+}
+
+// ---- counter-based splitmix64 (same definition as oracle/scan_oracle.cpp) --------------
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  uint64_t z = x + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// ---- small block-level helpers -----------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_min(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v) {
+  const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= (uint32_t)o) v += t;
+  }
+  return v;
+}
+
+// streaming global accesses: inputs are read at most twice, outputs written once
+__device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ld_stream_v2(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+
+}  // namespace rpl

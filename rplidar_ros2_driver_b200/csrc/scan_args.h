@@ -1,0 +1,58 @@
+// scan_args.h -- argument block shared by the scan kernels and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rpl {
+
+struct ScanBatchArgs {
+  const uint2* nodes;      // [n_scans][stride] packed 8-byte nodes
+  uint2* nodes_out;        // ascended nodes (nullable; must not alias nodes)
+  const uint32_t* counts;  // [n_scans]
+  uint32_t n_scans;
+  uint32_t stride;
+  float* ranges;           // [n_scans][stride] (nullable together with intensities)
+  float* intensities;
+  uint32_t* beam_counts;   // [n_scans] nullable
+  float* angle_inc;        // [n_scans] nullable
+  uint32_t* status;        // [n_scans] nullable
+  uint32_t* path;          // [n_scans] nullable
+  // fast kernel -> general kernel hand-off (device side, no host round trip)
+  uint32_t* fallback_list;   // [n_scans]
+  uint32_t* fallback_count;  // [1], zeroed before the fast kernel
+  uint8_t is_new_protocol;
+  uint8_t mode_a;
+  uint8_t inverted;
+  uint8_t apply_ascend;
+};
+
+// per-CTA global workspace of the general kernel, sized for max_nodes
+struct GeneralWorkspace {
+  uint16_t* keyf;       // [ctas][max_nodes] final key of every node
+  uint32_t* idx0;       // [ctas][max_nodes]
+  uint32_t* idx1;       // [ctas][max_nodes]
+  uint32_t* vidx;       // [ctas][max_nodes] sorted measured nodes -> buffer index
+  unsigned long long* cell;  // [ctas][max_nodes] Mode A accumulators
+  uint32_t max_nodes;
+};
+
+// per-CTA global scratch of the fast kernel (Mode A collision groups)
+struct FastWorkspace {
+  unsigned long long* group;  // [ctas][max_nodes]
+  uint32_t max_nodes;
+};
+
+constexpr int kFastThreads = 512;
+constexpr int kGeneralThreads = 128;
+
+cudaError_t launch_scan_fast(const ScanBatchArgs& a, const FastWorkspace& ws, int grid,
+                             cudaStream_t stream);
+cudaError_t launch_scan_general(const ScanBatchArgs& a, const GeneralWorkspace& ws, int grid,
+                                bool all_scans, cudaStream_t stream);
+size_t scan_fast_smem_bytes();
+size_t scan_general_smem_bytes();
+cudaError_t scan_fast_configure();     // opt-in dynamic shared memory, once per device
+cudaError_t scan_general_configure();
+int scan_fast_max_ctas_per_sm();
+
+}  // namespace rpl

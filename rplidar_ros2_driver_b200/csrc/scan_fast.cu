@@ -1,0 +1,512 @@
+// scan_fast.cu -- the hot kernel: fused ascendScanData + publish_scan for tie-free scans.
+//
+// Replaces, per scan (one CTA per scan, persistent over the batch):
+//   ascendScanData_            reference src/sdk/src/sl_lidar_driver.cpp:128-184
+//   publish_scan compute body  reference src/rplidar_node.cpp:581-677
+//
+// Idea: the sort key is the 16-bit angle_z_q14 (angle_rad is strictly monotonic in it), so
+// for a scan whose keys are distinct the two std::sort calls collapse into a RANK LOOKUP:
+//   pass 1  stream the packed nodes once from HBM (128-bit loads), mark a 65536-entry
+//           presence map in shared memory with plain byte stores (no atomics),
+//   scan    fold the byte map into a bitmap + per-word exclusive popcount prefix,
+//   pass 2  stream the nodes again (L2 hits: the tile was just read) and place every point
+//           at rank(key) = prefix[key>>5] + popc(bits[key>>5] & below(key)).
+// Mode B writes ranges[rank]; Mode A derives bin ownership (head / tail / empty-bin gaps)
+// from the same bitmap; the ascended node buffer is a second rank over all nodes' final keys.
+// A scan with duplicate keys (detected as popcount != count) is handed to the general
+// radix-sort kernel through a device-side list -- results there follow the stable tie rule.
+//
+// HBM traffic per node: 8 B read + 4 B ranges + 4 B intensities (+8 B ascended node).
+#include "rpl_device.cuh"
+#include "scan_args.h"
+
+namespace rpl {
+
+namespace {
+
+constexpr int T = kFastThreads;                 // 512 threads = 16 warps
+constexpr int kWarps = T / 32;
+constexpr uint32_t kWords = kKeySpace / 32;     // 2048 bitmap words
+constexpr uint32_t kPendingCap = 8192;          // Mode A collision-group heads kept on chip
+constexpr uint32_t kMaxFastNodes = kKeySpace;   // more nodes cannot be tie-free
+constexpr int kUnroll = 4;
+
+struct __align__(16) FastSmem {
+  uint8_t bytemap[kKeySpace];      // presence map (swizzled); reused as the pending-head list
+  uint2 rankV[kWords];             // {bits, exclusive prefix} over measured keys
+  uint2 rankA[kWords];             // same over all nodes' final keys (ascended buffer)
+  uint32_t vbE[kKeySpace / 64];    // validity ballots of even / odd nodes
+  uint32_t vbO[kKeySpace / 64];
+  uint32_t red[4 * kWarps];
+  uint32_t valid_count;
+  uint32_t first_valid;
+  uint32_t front_key;
+  uint32_t totV;
+  uint32_t totA;
+  uint32_t pending;
+  uint32_t fallback;
+};
+
+// byte map address swizzle: spreads a thread's 128-byte row over the 16-byte columns so
+// the 128-bit reads of the fold step are bank-conflict free
+__device__ __forceinline__ uint32_t swz(uint32_t key) { return key ^ ((key >> 3) & 0x70u); }
+
+__device__ __forceinline__ uint32_t gather4(uint32_t x) { return (x * 0x10204080u) >> 28; }
+
+__device__ __forceinline__ uint32_t rank_of(const uint2* rk, uint32_t key) {
+  const uint2 e = rk[key >> 5];
+  return e.y + __popc(e.x & ((1u << (key & 31)) - 1u));
+}
+// largest set key < k (or -1) / smallest set key > k (or -1)
+__device__ __forceinline__ int prev_set(const uint2* rk, uint32_t k) {
+  int w = (int)(k >> 5);
+  uint32_t m = rk[w].x & ((1u << (k & 31)) - 1u);
+  for (;;) {
+    if (m) return (w << 5) + 31 - __clz(m);
+    if (w == 0) return -1;
+    m = rk[--w].x;
+  }
+}
+__device__ __forceinline__ int next_set(const uint2* rk, uint32_t k) {
+  uint32_t w = k >> 5;
+  uint32_t m = rk[w].x & ~((2u << (k & 31)) - 1u);
+  for (;;) {
+    if (m) return (int)((w << 5) + __ffs(m) - 1);
+    if (++w == kWords) return -1;
+    m = rk[w].x;
+  }
+}
+
+struct Pair {
+  uint2 a, b;
+  bool has_a, has_b;
+};
+__device__ __forceinline__ Pair load_pair(const uint2* base, uint32_t n, bool vec, uint32_t p) {
+  Pair r;
+  const uint32_t i0 = 2 * p;
+  r.has_a = i0 < n;
+  r.has_b = i0 + 1 < n;
+  r.a = make_uint2(0, 0);
+  r.b = make_uint2(0, 0);
+  if (vec && r.has_b) {
+    const uint4 v = ld_stream_v4(base + i0);
+    r.a = make_uint2(v.x, v.y);
+    r.b = make_uint2(v.z, v.w);
+  } else {
+    if (r.has_a) r.a = ld_stream_v2(base + i0);
+    if (r.has_b) r.b = ld_stream_v2(base + i0 + 1);
+  }
+  return r;
+}
+
+
+// ---- Mode A (reference rplidar_node.cpp:630-660) ------------------------------------------
+// beam_count = M bins; every measured point goes to bin (int)(angle / angle_increment) and the
+// bin keeps the smallest dist_m (strict '<': on equal dist_m the first point in ascending
+// key order).  Bins grow with the key (for inverted scans: key 0 first, then descending
+// keys), so the points of a bin are neighbours in that order and the presence bitmap alone
+// tells a point whether it is the first (head) / last (tail) of its bin and which empty bins
+// lie before it.  Single-point bins are written directly; shared bins go through a small
+// per-CTA scratch and are resolved by their head after the pass.
+struct ModeACtx {
+  const uint2* rankV;
+  float* ranges;
+  float* intens;
+  unsigned long long* gscratch;
+  uint2* pending;
+  uint32_t* pending_count;
+  uint32_t* fallback;
+  uint32_t M;
+  float inc;
+  bool inverted, has0, new_proto;
+};
+
+__device__ __noinline__ void mode_a_place(const ModeACtx& c, uint32_t k, uint32_t r, float dm,
+                                          uint32_t q) {
+  const uint32_t M = c.M;
+  const float kInf = __int_as_float(0x7f800000);
+  int pk, nk;
+  uint32_t ru;
+  if (!c.inverted) {
+    pk = prev_set(c.rankV, k);
+    nk = next_set(c.rankV, k);
+    ru = r;
+  } else if (k == 0) {
+    pk = -1;
+    nk = (c.rankV[kWords - 1].x >> 31) ? (int)(kKeySpace - 1) : prev_set(c.rankV, kKeySpace - 1);
+    if (nk == 0) nk = -1;
+    ru = 0;
+  } else {
+    pk = next_set(c.rankV, k);
+    if (pk < 0 && c.has0) pk = 0;
+    nk = prev_set(c.rankV, k);
+    if (nk == 0) nk = -1;  // key 0 comes first in the inverted order, never after
+    ru = (M - 1 - r) + (c.has0 ? 1u : 0u);
+  }
+  const int b = mode_a_bin(k, c.inc, c.inverted);
+  if (b < 0 || b >= (int)M) {  // never taken for u16 keys; the reference's guard, kept
+    *c.fallback = 1;
+    return;
+  }
+  const int bp = pk >= 0 ? mode_a_bin((uint32_t)pk, c.inc, c.inverted) : -1;
+  const int bn = nk >= 0 ? mode_a_bin((uint32_t)nk, c.inc, c.inverted) : (int)M;
+  const bool head = bp != b, tail = bn != b;
+  if (head)
+    for (int e = bp + 1; e < b; ++e) {  // empty bins in front of this group
+      c.ranges[e] = kInf;
+      c.intens[e] = 0.0f;
+    }
+  if (nk < 0)
+    for (int e = b + 1; e < (int)M; ++e) {  // empty bins behind the last group
+      c.ranges[e] = kInf;
+      c.intens[e] = 0.0f;
+    }
+  if (head && tail) {
+    c.ranges[b] = dm;
+    c.intens[b] = quality_to_intensity(q, c.new_proto);
+    return;
+  }
+  // several points share the bin: keep the smallest (dist_m, key)
+  c.gscratch[ru] = ((unsigned long long)__float_as_uint(dm) << 32) | ((unsigned long long)k << 16) |
+                   ((unsigned long long)q << 8) | (tail ? 1ull : 0ull);
+  if (head) {
+    const uint32_t slot = atomicAdd(c.pending_count, 1u);
+    if (slot < kPendingCap) c.pending[slot] = make_uint2(ru, (uint32_t)b);
+    else *c.fallback = 1;
+  }
+}
+
+template <bool EMIT, bool MODE_A>
+__global__ void __launch_bounds__(T, 2) scan_fast_kernel(ScanBatchArgs a, FastWorkspace ws) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool new_proto = a.is_new_protocol != 0;
+  const bool inverted = a.inverted != 0;
+  const bool want_scan = a.ranges != nullptr;
+  unsigned long long* gscratch = ws.group + (size_t)blockIdx.x * ws.max_nodes;
+
+  for (uint32_t s = blockIdx.x; s < a.n_scans; s += gridDim.x) {
+    const uint32_t n = a.counts[s];
+    const uint2* base = a.nodes + (size_t)s * a.stride;
+    const bool vec = ((reinterpret_cast<uintptr_t>(base) & 15u) == 0);
+    const uint32_t npairs = (n + 1) >> 1;
+
+    if (n > a.stride || n > ws.max_nodes) {  // caller error: report, touch nothing
+      if (tid == 0) {
+        if (a.status) a.status[s] = 0x80008000u;  // SL_RESULT_INVALID_DATA
+        if (a.path) a.path[s] = 0u;
+        if (a.beam_counts) a.beam_counts[s] = 0u;
+        if (a.angle_inc) a.angle_inc[s] = 0.0f;
+      }
+      continue;
+    }
+    if (n > kMaxFastNodes) {  // cannot be tie-free: general kernel
+      if (tid == 0) a.fallback_list[atomicAdd(a.fallback_count, 1u)] = s;
+      continue;
+    }
+
+    // ---- phase 0: clear the presence map ------------------------------------------------
+    {
+      uint4* bm = reinterpret_cast<uint4*>(sm.bytemap);
+      const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (uint32_t j = 0; j < kKeySpace / 16 / T; ++j) bm[j * T + tid] = z;
+      if (tid == 0) {
+        sm.pending = 0;
+        sm.fallback = 0;
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 1: stream the scan from HBM, mark measured keys --------------------------
+    uint32_t cnt = 0, first = 0xFFFFFFFFu;
+    for (uint32_t p0 = 0; p0 < npairs; p0 += T * kUnroll) {
+      Pair pr[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) pr[u] = load_pair(base, n, vec, p0 + u * T + tid);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const uint32_t p = p0 + u * T + tid;
+        const bool va = pr[u].has_a && node_dist(pr[u].a) != 0;
+        const bool vb = pr[u].has_b && node_dist(pr[u].b) != 0;
+        if (va) sm.bytemap[swz(node_key(pr[u].a))] = 1;
+        if (vb) sm.bytemap[swz(node_key(pr[u].b))] = 1;
+        cnt += (uint32_t)va + (uint32_t)vb;
+        if (va) first = min(first, 2 * p);
+        else if (vb) first = min(first, 2 * p + 1);
+        if (EMIT) {
+          const uint32_t be = __ballot_sync(0xffffffffu, va);
+          const uint32_t bo = __ballot_sync(0xffffffffu, vb);
+          if (lane == 0 && (p >> 5) < kKeySpace / 64) {
+            sm.vbE[p >> 5] = be;
+            sm.vbO[p >> 5] = bo;
+          }
+        }
+      }
+    }
+    cnt = warp_sum(cnt);
+    first = warp_min(first);
+    if (lane == 0) {
+      sm.red[warp] = cnt;
+      sm.red[kWarps + warp] = first;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t c = lane < kWarps ? sm.red[lane] : 0u;
+      uint32_t f = lane < kWarps ? sm.red[kWarps + lane] : 0xFFFFFFFFu;
+      c = warp_sum(c);
+      f = warp_min(f);
+      if (lane == 0) {
+        sm.valid_count = c;
+        sm.first_valid = f;
+        if (EMIT) {
+          // head tune: serial, only node 0's result survives (reference :133-147)
+          const float step = ascend_step(n);
+          uint32_t fk = 0;
+          if (c != 0) {
+            const uint32_t k0 = node_key(ld_stream_v2(base + f));
+            fk = ascend_head_key(k0, f, step);
+          }
+          sm.front_key = fk;
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t M = sm.valid_count;
+
+    if (M == 0) {
+      // ascendScanData: OPERATION_FAIL, buffer untouched; publish_scan: nothing to publish
+      if (tid == 0) {
+        if (a.status) a.status[s] = a.apply_ascend ? kResultOperationFail : kResultOk;
+        if (a.path) a.path[s] = 0u;
+        if (a.beam_counts) a.beam_counts[s] = 0u;
+        if (a.angle_inc) a.angle_inc[s] = 0.0f;
+      }
+      if (a.nodes_out) {
+        uint2* out = a.nodes_out + (size_t)s * a.stride;
+        for (uint32_t i = tid; i < n; i += T) out[i] = ld_stream_v2(base + i);
+      }
+      __syncthreads();
+      continue;
+    }
+
+    const float step = ascend_step(n);
+    const uint32_t front_key = EMIT ? sm.front_key : 0u;
+    const float front_deg = key_to_deg(front_key);
+
+    // ---- phase 1c (ascended buffer): mark the filled keys of unmeasured nodes -----------
+    if (EMIT) {
+      const uint32_t nwords = (npairs + 31) >> 5;
+      for (uint32_t w = tid; w < nwords; w += T) {
+        const uint32_t pbase = w << 5;
+        // pairs in range
+        const uint32_t live = npairs - pbase >= 32 ? 0xFFFFFFFFu : ((1u << (npairs - pbase)) - 1u);
+        uint32_t ie = ~sm.vbE[w] & live;
+        uint32_t io = ~sm.vbO[w] & live;
+        while (ie) {
+          const uint32_t b = __ffs(ie) - 1;
+          ie &= ie - 1;
+          const uint32_t i = 2 * (pbase + b);
+          const uint32_t fk = (i == 0) ? front_key : ascend_fill_key(front_deg, i, step);
+          sm.bytemap[swz(fk)] = 2;
+        }
+        while (io) {
+          const uint32_t b = __ffs(io) - 1;
+          io &= io - 1;
+          const uint32_t i = 2 * (pbase + b) + 1;
+          if (i < n) sm.bytemap[swz(ascend_fill_key(front_deg, i, step))] = 2;
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- fold: byte map -> bitmaps + exclusive popcount prefix --------------------------
+    {
+      // thread t owns keys [128 t, 128 t + 128) = 4 bitmap words = 8 16-byte chunks
+      uint32_t wv[4] = {0, 0, 0, 0}, wa[4] = {0, 0, 0, 0};
+      const uint4* bm = reinterpret_cast<const uint4*>(sm.bytemap);
+#pragma unroll
+      for (uint32_t c = 0; c < 8; ++c) {
+        const uint4 q = bm[tid * 8 + (c ^ (tid & 7u))];  // physical column of logical chunk c
+        const uint32_t x[4] = {q.x, q.y, q.z, q.w};
+        uint32_t bv = 0, bi = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          bv |= gather4(x[j] & 0x01010101u) << (4 * j);
+          bi |= gather4((x[j] >> 1) & 0x01010101u) << (4 * j);
+        }
+        wv[c >> 1] |= bv << (16 * (c & 1));
+        wa[c >> 1] |= (bv | bi) << (16 * (c & 1));
+      }
+      uint32_t sv = 0, sa = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sv += __popc(wv[j]);
+        sa += __popc(wa[j]);
+      }
+      const uint32_t iv = warp_inclusive_scan(sv), ia = warp_inclusive_scan(sa);
+      if (lane == 31) {
+        sm.red[2 * kWarps + warp] = iv;
+        sm.red[3 * kWarps + warp] = ia;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        uint32_t tv = lane < kWarps ? sm.red[2 * kWarps + lane] : 0u;
+        uint32_t ta = lane < kWarps ? sm.red[3 * kWarps + lane] : 0u;
+        const uint32_t cv = warp_inclusive_scan(tv), ca = warp_inclusive_scan(ta);
+        if (lane < kWarps) {
+          sm.red[2 * kWarps + lane] = cv - tv;
+          sm.red[3 * kWarps + lane] = ca - ta;
+        }
+        if (lane == 31) {
+          sm.totV = cv;
+          sm.totA = ca;
+        }
+      }
+      __syncthreads();
+      uint32_t pv = sm.red[2 * kWarps + warp] + iv - sv;
+      uint32_t pa = sm.red[3 * kWarps + warp] + ia - sa;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sm.rankV[tid * 4 + j] = make_uint2(wv[j], pv);
+        pv += __popc(wv[j]);
+        if (EMIT) {
+          sm.rankA[tid * 4 + j] = make_uint2(wa[j], pa);
+          pa += __popc(wa[j]);
+        }
+      }
+    }
+    __syncthreads();
+
+    // duplicate keys -> general kernel (stable tie rule)
+    const bool tie = (sm.totV != M) || (EMIT && sm.totA != n);
+    if (tie) {
+      if (tid == 0) a.fallback_list[atomicAdd(a.fallback_count, 1u)] = s;
+      __syncthreads();
+      continue;
+    }
+
+    // ---- phase 2: stream again (L2), rank and place --------------------------------------
+    float* ranges = want_scan ? a.ranges + (size_t)s * a.stride : nullptr;
+    float* intens = want_scan ? a.intensities + (size_t)s * a.stride : nullptr;
+    uint2* nodes_out = a.nodes_out ? a.nodes_out + (size_t)s * a.stride : nullptr;
+    const float inc = angle_increment(M, MODE_A);
+    const bool has0 = (sm.rankV[0].x & 1u) != 0;
+    uint2* pending = reinterpret_cast<uint2*>(sm.bytemap);  // presence map is dead now
+
+    ModeACtx mc;
+    mc.rankV = sm.rankV;
+    mc.ranges = ranges;
+    mc.intens = intens;
+    mc.gscratch = gscratch;
+    mc.pending = pending;
+    mc.pending_count = &sm.pending;
+    mc.fallback = &sm.fallback;
+    mc.M = M;
+    mc.inc = inc;
+    mc.inverted = inverted;
+    mc.has0 = has0;
+    mc.new_proto = new_proto;
+
+    auto emit_point = [&](uint2 nd, uint32_t i, bool measured) {
+      const uint32_t k = node_key(nd);
+      if (nodes_out) {
+        if (EMIT) {
+          const uint32_t fk =
+              measured ? k : (i == 0 ? front_key : ascend_fill_key(front_deg, i, step));
+          nodes_out[rank_of(sm.rankA, fk)] = node_with_key(nd, fk);
+        } else {
+          nodes_out[i] = nd;  // no geometric correction requested: buffer passes through
+        }
+      }
+      if (!measured || !want_scan) return;
+      const float dm = dist_to_m(node_dist(nd));
+      const uint32_t q = node_quality(nd);
+      const uint32_t r = rank_of(sm.rankV, k);
+      if (!MODE_A) {  // Mode B: reference rplidar_node.cpp:661-677
+        const uint32_t o = inverted ? (M - 1 - r) : r;
+        ranges[o] = dm;
+        intens[o] = quality_to_intensity(q, new_proto);
+      } else {
+        mode_a_place(mc, k, r, dm, q);
+      }
+    };
+
+    for (uint32_t p0 = 0; p0 < npairs; p0 += T * kUnroll) {
+      Pair pr[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) pr[u] = load_pair(base, n, vec, p0 + u * T + tid);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const uint32_t p = p0 + u * T + tid;
+        if (pr[u].has_a) emit_point(pr[u].a, 2 * p, node_dist(pr[u].a) != 0);
+        if (pr[u].has_b) emit_point(pr[u].b, 2 * p + 1, node_dist(pr[u].b) != 0);
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 3 (Mode A): resolve bins that hold several points --------------------------
+    if (MODE_A && want_scan) {
+      const uint32_t np = min(sm.pending, kPendingCap);
+      for (uint32_t e = tid; e < np; e += T) {
+        const uint2 h = pending[e];
+        unsigned long long best = ~0ull;
+        for (uint32_t slot = h.x; slot < M; ++slot) {
+          const unsigned long long g = gscratch[slot];
+          best = min(best, g);
+          if (g & 1ull) break;
+        }
+        ranges[h.y] = __uint_as_float((uint32_t)(best >> 32));
+        intens[h.y] = quality_to_intensity((uint32_t)(best >> 8) & 0xFFu, new_proto);
+      }
+    }
+    if (tid == 0) {
+      if (sm.fallback) {
+        a.fallback_list[atomicAdd(a.fallback_count, 1u)] = s;
+      } else {
+        if (a.status) a.status[s] = kResultOk;
+        if (a.path) a.path[s] = 0u;
+        if (a.beam_counts) a.beam_counts[s] = M;
+        if (a.angle_inc) a.angle_inc[s] = inc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+size_t scan_fast_smem_bytes() { return sizeof(FastSmem); }
+
+cudaError_t launch_scan_fast(const ScanBatchArgs& a, const FastWorkspace& ws, int grid,
+                             cudaStream_t stream) {
+  const bool emit = a.nodes_out != nullptr && a.apply_ascend != 0;
+  const bool mode_a = a.mode_a != 0;
+  const size_t sh = sizeof(FastSmem);
+  if (emit && mode_a) scan_fast_kernel<true, true><<<grid, T, sh, stream>>>(a, ws);
+  else if (emit) scan_fast_kernel<true, false><<<grid, T, sh, stream>>>(a, ws);
+  else if (mode_a) scan_fast_kernel<false, true><<<grid, T, sh, stream>>>(a, ws);
+  else scan_fast_kernel<false, false><<<grid, T, sh, stream>>>(a, ws);
+  return cudaGetLastError();
+}
+
+cudaError_t scan_fast_configure() {
+  const int sh = (int)sizeof(FastSmem);
+  cudaError_t e;
+  e = cudaFuncSetAttribute(scan_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sh);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(scan_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sh);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(scan_fast_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sh);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(scan_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sh);
+}
+
+int scan_fast_max_ctas_per_sm() {
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, scan_fast_kernel<false, false>, T, sizeof(FastSmem));
+  return nb;
+}
+
+}  // namespace rpl

@@ -1,0 +1,191 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C-ABI, against the
+CPU oracle on the same inputs.  Integer / index work must be bit-exact; the only floats on
+this path (dist_m, intensity, angle_increment) are single correctly-rounded operations and
+are compared bit-for-bit too."""
+import numpy as np
+import pytest
+
+from helpers import bits
+
+pytestmark = pytest.mark.gpu
+
+ALL_MODES = [(newp, mode_a, inv) for newp in (0, 1) for mode_a in (0, 1) for inv in (0, 1)]
+
+
+@pytest.fixture(scope="module")
+def R():
+    import rplidar_ros2_driver_b200 as R
+
+    return R
+
+
+@pytest.fixture(scope="module")
+def ctx(R):
+    c = R.Context(0, 70000, 64)
+    yield c
+    c.close()
+
+
+def _nodes(a, O):
+    return np.ascontiguousarray(a).view(O.NODE_DTYPE).reshape(a.shape[:-1])
+
+
+def oracle_batch(O, nodes, counts, newp, mode_a, inv, ascend, stable=True):
+    buf = nodes.copy()
+    prm = O.scan_params(newp, mode_a, inv, ascend, 40.0, 0.1)
+    res = O.pipeline_batch(buf, counts, prm, stable=stable, threads=4)
+    res["nodes"] = buf
+    return res
+
+
+def check_batch(R, O, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=0, stable=True, expect_path=None):
+    counts = np.asarray(counts, dtype=np.uint32)
+    exp = oracle_batch(O, nodes, counts, newp, mode_a, inv, ascend, stable)
+    got = ctx.scan_batch(nodes.view(R.NODE_DTYPE), counts, R.scan_params(newp, mode_a, inv, ascend, flags),
+                         emit_nodes=True)
+    tag = (newp, mode_a, inv, ascend, flags)
+    assert (got["beam_counts"] == exp["beam_counts"]).all(), tag
+    assert (got["status"] == exp["status"]).all(), tag
+    assert (bits(got["angle_increment"]) == bits(exp["angle_increment"])).all(), tag
+    for s in range(nodes.shape[0]):
+        m, n = int(exp["beam_counts"][s]), int(counts[s])
+        assert (bits(got["ranges"][s, :m]) == bits(exp["ranges"][s, :m])).all(), (tag, s)
+        assert (bits(got["intensities"][s, :m]) == bits(exp["intensities"][s, :m])).all(), (tag, s)
+        assert (got["nodes"][s, :n].view(np.uint64) == exp["nodes"][s, :n].view(np.uint64)).all(), (tag, s)
+    if expect_path is not None:
+        assert (got["path"] == expect_path).all(), (tag, got["path"])
+    return got
+
+
+# ---- config 1: A1 single scan, golden vectors from the compiled reference ------------------
+@pytest.mark.parametrize("flags", [0, 1])
+def test_a1_golden_laserscan_bit_exact(R, oracle, ctx, golden_dir, flags):
+    g = np.load(f"{golden_dir}/laserscan_golden.npz")
+    d = np.load(f"{golden_dir}/dummy_scans.npz")
+    var = _nodes(d["variants"], oracle)
+    asc = _nodes(d["variants_ascended"], oracle)
+    for k in range(int(g["n"])):
+        vi, use_asc, newp, mode_a, inv = g[f"cfg_{k}"].tolist()
+        res = ctx.scan(var[vi].view(R.NODE_DTYPE), R.scan_params(newp, mode_a, inv, use_asc, flags))
+        assert res["beam_count"] == int(g[f"beams_{k}"]), k
+        assert (bits(res["ranges"]) == bits(g[f"ranges_{k}"])).all(), k
+        assert (bits(res["intensities"]) == bits(g[f"intens_{k}"])).all(), k
+        assert bits(res["angle_increment"]) == bits(g[f"hdr_{k}"][2]), k
+        if use_asc:
+            assert res["ascend_status"] == int(d["variants_rc"][vi])
+            assert (res["nodes"].view(np.uint64) == asc[vi].view(np.uint64)).all(), k
+        else:
+            assert (res["nodes"].view(np.uint64) == var[vi].view(np.uint64)).all(), k
+
+
+def test_a1_all_sixteen_dummy_scans(R, oracle, ctx, golden_dir):
+    d = np.load(f"{golden_dir}/dummy_scans.npz")
+    raw = _nodes(d["raw"], oracle)
+    counts = np.full(16, 360, np.uint32)
+    for newp, mode_a, inv in ALL_MODES:
+        check_batch(R, oracle, ctx, raw, counts, newp, mode_a, inv, 1, expect_path=0)
+
+
+@pytest.mark.parametrize("flags", [0, 1])
+def test_ascend_edge_cases_golden(R, oracle, ctx, golden_dir, flags):
+    g = np.load(f"{golden_dir}/ascend_cases.npz")
+    for i in range(int(g["n_cases"])):
+        inp = _nodes(g[f"in_{i}"], oracle)
+        if flags == 0:
+            rc, out = ctx.ascend_scan(inp.view(R.NODE_DTYPE))
+        else:
+            r = ctx.scan(inp.view(R.NODE_DTYPE), R.scan_params(0, 0, 0, 1, flags))
+            rc, out = r["ascend_status"], r["nodes"]
+        assert rc == int(g[f"rc_{i}"]), i
+        assert (out.view(np.uint8).reshape(-1, 8) == g[f"out_{i}"]).all(), i
+    rc, out = ctx.ascend_scan(oracle.make_nodes([3, 2, 1], [0, 0, 0]).view(R.NODE_DTYPE))
+    assert rc == R.RESULT_OPERATION_FAIL and out["angle_z_q14"].tolist() == [3, 2, 1]
+    rc, _ = ctx.ascend_scan(np.zeros(0, R.NODE_DTYPE))
+    assert rc == R.RESULT_OPERATION_FAIL
+    r, i, m, inc = ctx.laserscan(np.zeros(0, R.NODE_DTYPE), R.scan_params())
+    assert m == 0
+
+
+# ---- synthetic scans --------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 360, 3200, 8192, 32768])
+@pytest.mark.parametrize("variant", [0, 1, 3])
+def test_tie_free_synthetic_both_kernels(R, oracle, ctx, n, variant):
+    nodes = oracle.synth_batch(5000 + 10 * variant + n, 5, n, variant)
+    counts = np.full(5, n, np.uint32)
+    modes = ALL_MODES if n in (360, 3200) else [(0, 0, 0), (1, 1, 0), (0, 1, 1), (1, 0, 1)]
+    for newp, mode_a, inv in modes:
+        for ascend in (0, 1):
+            # tie-free measured keys: the reference's std::sort and the stable rule coincide
+            check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=0, stable=True)
+            check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=1, stable=True,
+                        expect_path=1)
+
+
+@pytest.mark.parametrize("n", [2, 64, 2048, 32768])
+def test_tie_variant_follows_stable_rule(R, oracle, ctx, n):
+    nodes = oracle.synth_batch(900 + n, 4, n, 2)
+    counts = np.full(4, n, np.uint32)
+    for newp, mode_a, inv in [(0, 0, 0), (0, 1, 0), (1, 1, 1), (1, 0, 1)]:
+        for ascend in (0, 1):
+            check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, stable=True)
+    # the reference itself (unstable sort) agrees wherever order is defined: Mode A ranges
+    exp = oracle_batch(oracle, nodes, counts, 0, 1, 0, 1, stable=False)
+    got = ctx.scan_batch(nodes.view(R.NODE_DTYPE), counts, R.scan_params(0, 1, 0, 1))
+    for s in range(4):
+        m = int(exp["beam_counts"][s])
+        assert (bits(got["ranges"][s, :m]) == bits(exp["ranges"][s, :m])).all()
+
+
+def test_mixed_batch_ragged_counts_and_paths(R, oracle, ctx):
+    """One batch mixing tie-free and tie scans, empty scans, all-unmeasured scans, odd counts
+    and a stride larger than every count."""
+    stride = 1000
+    rng = np.random.default_rng(3)
+    counts = np.array([0, 1, 999, 360, 513, 7, 1000, 64, 250, 2], np.uint32)
+    nodes = np.zeros((len(counts), stride), oracle.NODE_DTYPE)
+    for s, n in enumerate(counts):
+        if n == 0:
+            continue
+        variant = [0, 2, 3, 1][s % 4]
+        nodes[s, :n] = oracle.synth_batch(40 + s, 1, int(n), variant)[0]
+    nodes[3]["dist_mm_q2"][:] = 0  # a scan with no measurement at all
+    nodes[6]["dist_mm_q2"][: 37] = 0  # long unmeasured head (serial head tune)
+    nodes[8]["angle_z_q14"][:] = rng.integers(0, 8, size=stride)  # heavy ties
+    for newp, mode_a, inv in ALL_MODES:
+        for ascend in (0, 1):
+            got = check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend)
+    assert got["status"][3] == R.RESULT_OPERATION_FAIL and got["beam_counts"][3] == 0
+    assert got["path"][8] == R.PATH_GENERAL
+
+
+def test_extreme_values(R, oracle, ctx):
+    """dist_mm_q2 up to 2^32-1 (float rounding collisions in dist_m), keys 0 and 65535, a bin
+    shared by many points, more than 65536 nodes (cannot be tie-free)."""
+    mk = oracle.make_nodes
+    n = 4096
+    keys = np.arange(n) * 16
+    keys[-1] = 65535
+    dist = np.full(n, 0xFFFFFFFF, np.uint64)
+    dist[::3] = 0xFFFFFF00
+    dist[::5] = 1
+    a = mk(keys, dist, np.arange(n) % 256)
+    narrow = mk(np.arange(1000), np.random.default_rng(1).integers(1, 9000, 1000), np.arange(1000) % 256)
+    nodes = np.zeros((2, n), oracle.NODE_DTYPE)
+    nodes[0] = a
+    nodes[1, :1000] = narrow
+    counts = np.array([n, 1000], np.uint32)
+    for newp, mode_a, inv in ALL_MODES:
+        check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, 1)
+        check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, 0, flags=1)
+    big = oracle.synth_batch(1, 1, 70000, 0)
+    check_batch(R, oracle, ctx, big, np.array([70000], np.uint32), 0, 1, 0, 1, expect_path=1)
+    check_batch(R, oracle, ctx, big, np.array([70000], np.uint32), 1, 0, 1, 1, expect_path=1)
+
+
+def test_invalid_arguments_fail_loudly(R, ctx):
+    nodes = np.zeros((1, 8), R.NODE_DTYPE)
+    with pytest.raises(R.RplError):
+        ctx.scan_batch(nodes, np.array([9], np.uint32), R.scan_params())  # count > stride
+    with pytest.raises(R.RplError):
+        big = np.zeros((65, 8), R.NODE_DTYPE)
+        ctx.scan_batch(big, np.full(65, 8, np.uint32), R.scan_params())  # n_scans > max_scans
