@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path on synthetic scan streams, one JSON line on stdout.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU loop
+
+Workload (BASELINE.json configs[1]): S2 DenseBoost, 32768 nodes/scan x 4096
+scans per GPU (1.07 GB of packed nodes in, 1.07 GB of LaserScan floats out per step -- both far
+larger than the 126 MB L2, so no L2 flush is needed between iterations).  One step = one pass of
+the fused path (ascendScanData status + filter + fixed-point unpack + angle rank + LaserScan
+Mode B, the launch-file default `scan_processing: false`) over the whole batch.
+
+  value     Mpoints/s (input nodes per second), buffers resident in HBM, CUDA events on the
+            launching stream, max over ranks, whole-job aggregate over N GPUs (weak scaling:
+            every rank owns its own 4096 scans; the LaserScan path has no data-path collective)
+  e2e       the same metric through the host-buffer C-ABI call rpl_scan_batch: pinned host
+            buffers in, H2D + kernels + D2H inside the timed region
+  roofline  scan_fast_kernel: algorithmic bytes (16 B/node) / kernel time from
+            CUDA events recorded by the library around every launch, against the measured HBM
+            copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the oracle (a port of the reference loop) on this box's host cores, same buffers
+
+The oracle is used here ONLY as the cpu_baseline / --impl reference leg.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mpoints/s through unpack+filter+polar->xyz (LaserScan path: fused ascend+unpack+filter+angle-rank)"
+UNIT = "Mpoints/s"
+NODES_PER_SCAN = 32768
+SCANS_PER_GPU = 4096
+BYTES_PER_NODE_LASERSCAN = 16  # 8 B node read + 4 B ranges + 4 B intensities
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scans", type=int, default=SCANS_PER_GPU, help="scans per GPU")
+    ap.add_argument("--nodes", type=int, default=NODES_PER_SCAN, help="nodes per scan")
+    ap.add_argument("--mode", default="b", choices=["a", "b"], help="LaserScan mode of the headline")
+    ap.add_argument("--variant", type=int, default=0, help="synthetic variant (SURVEY 8(d))")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    return (f"S2 DenseBoost {args.nodes} nodes/scan x {args.scans} scans per GPU, synthetic variant "
+            f"{args.variant} (tie-free rotated revolution, 5% unmeasured), LaserScan Mode "
+            f"{'A' if args.mode == 'a' else 'B'}, angle_compensate on")
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: NVML polled from a thread DURING the timed regions
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting",
+               0x10: "sync_boost"}
+
+    def __init__(self, uuid: str | None, index: int):
+        self.samples = []  # (t, sm_mhz, reasons_mask, power_w)
+        self.windows = []
+        self._stop = threading.Event()
+        self._thr = None
+        self.max_mhz = None
+        self.ok = False
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            self.nv = nv
+            h = None
+            if uuid:
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+                except Exception:
+                    h = None
+            self.h = h if h is not None else nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def _reasons(self):
+        nv = self.nv
+        for name in ("nvmlDeviceGetCurrentClocksEventReasons", "nvmlDeviceGetCurrentClocksThrottleReasons"):
+            fn = getattr(nv, name, None)
+            if fn:
+                try:
+                    return int(fn(self.h))
+                except Exception:
+                    continue
+        return 0
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                except Exception:
+                    pw = 0.0
+                self.samples.append((time.perf_counter(), mhz, self._reasons(), pw))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.ok:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=2)
+
+    def window(self, t0, t1, name):
+        self.windows.append((t0, t1, name))
+
+    def summary(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML unavailable"}
+        used, names = [], []
+        for t0, t1, name in self.windows:
+            w = [s for s in self.samples if t0 <= s[0] <= t1]
+            if w:
+                used += w
+                names.append(name)
+            if len(used) >= 5:
+                break
+        if not used:
+            used = self.samples[-5:]
+            names = ["nearest samples"]
+        mask = 0
+        for s in used:
+            mask |= s[2]
+        reasons = [v for k, v in self.REASONS.items() if mask & k]
+        return {"sm_mhz": statistics.median([s[1] for s in used]) if used else None,
+                "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(used),
+                "power_w_max": max([s[3] for s in used]) if used else None, "window": " + ".join(names)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU loop (oracle port) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_leg(O, nodes_host, counts, mode_a, threads, reps):
+    """ascendScanData + publish_scan per scan (one scan per worker).  Returns (Mpoints/s, seconds)."""
+    prm = O.scan_params(0, mode_a, 0, 1, 40.0, 0.1)
+    total_pts = int(counts.sum())
+    secs = 0.0
+    for _ in range(reps):
+        buf = nodes_host.copy()  # ascend works in place: start every rep from the raw buffers
+        res = O.pipeline_batch(buf, counts, prm, stable=False, threads=threads)
+        secs += res["seconds"]
+    return total_pts * reps / secs / 1e6, secs
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return  # rank 0 alone runs and prints the reference arm
+    from oracle import pyoracle as O
+
+    O.build(ref=False)
+    cores = os.cpu_count() or 1
+    sample_scans = min(args.scans, 256)
+    nodes = O.synth_batch(0, sample_scans, args.nodes, args.variant)
+    counts = np.full(sample_scans, args.nodes, np.uint32)
+    mode_a = 1 if args.mode == "a" else 0
+    for _ in range(max(args.warmup, 1)):
+        cpu_leg(O, nodes, counts, mode_a, cores, 1)
+    t_total, pts = 0.0, 0
+    for _ in range(args.steps):
+        _, s = cpu_leg(O, nodes, counts, mode_a, cores, 1)
+        t_total += s
+        pts += int(counts.sum())
+    value = pts / t_total / 1e6
+    one, _ = cpu_leg(O, nodes[:32].copy(), counts[:32], mode_a, 1, 1)
+    sample = (f"{sample_scans} scans x {args.nodes} nodes per step ({sample_scans * args.nodes / 1e6:.1f} Mpoints), "
+              f"oracle port of ascendScanData+publish_scan (validated against the compiled reference), "
+              f"one scan per worker thread, {cores} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "scans_per_step": sample_scans, "nodes_per_scan": args.nodes},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "value_1thread": one},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    import rplidar_ros2_driver_b200 as R
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the CUDA library is the only implementation of this path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    S, N = args.scans, args.nodes
+    mode_a = 1 if args.mode == "a" else 0
+    ctx = R.Context(local_rank, N, S)
+    # a real (non-default) stream: the library treats a NULL stream as "use the context's own"
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sptr = stream.cuda_stream
+    assert sptr != 0
+
+    nodes = torch.empty((S, N, 8), dtype=torch.uint8, device=dev)
+    counts = torch.empty(S, dtype=torch.int32, device=dev)
+    ranges = torch.empty((S, N), dtype=torch.float32, device=dev)
+    intens = torch.empty((S, N), dtype=torch.float32, device=dev)
+    beams = torch.empty(S, dtype=torch.int32, device=dev)
+    inc = torch.empty(S, dtype=torch.float32, device=dev)
+    status = torch.empty(S, dtype=torch.int32, device=dev)
+    path = torch.empty(S, dtype=torch.int32, device=dev)
+    ctx.synth_batch_dev(rank * S, S, N, N, args.variant, nodes.data_ptr(), counts.data_ptr(), stream=sptr)
+    torch.cuda.synchronize()
+
+    def step(params, nodes_out=None):
+        ctx.scan_batch_dev(nodes.data_ptr(), counts.data_ptr(), S, N, params, nodes_out=nodes_out,
+                           ranges=ranges.data_ptr(), intensities=intens.data_ptr(), beam_counts=beams.data_ptr(),
+                           angle_increment=inc.data_ptr(), status=status.data_ptr(), path=path.data_ptr(),
+                           stream=sptr)
+
+    uuid = None
+    try:
+        uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        pass
+    sampler = ClockSampler(uuid, local_rank)
+    sampler.start()
+
+    def timed(params, K, W, nodes_out=None, profile=False):
+        for _ in range(W):
+            step(params, nodes_out)
+        torch.cuda.synchronize()
+        ctx.profile_read()
+        ctx.profile(profile)
+        l0 = ctx.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(K):
+            step(params, nodes_out)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        prof = ctx.profile_read()
+        ctx.profile(False)
+        return ms, prof, ctx.launch_count - l0, (t0, t1)
+
+    params = R.scan_params(0, mode_a, 0, 1)
+    ms, prof, launches, win = timed(params, args.steps, max(args.warmup, 3), profile=True)
+    sampler.window(win[0], win[1], "timed region")
+    pts_step = S * N
+    value = world * pts_step * args.steps / (ms * 1e-3) / 1e6
+    n_fast = int((path == 0).sum().item())
+    fast_ms = prof[0] / max(prof[1], 1)
+    peak, peak_src = measured_peak()
+    alg_bytes = BYTES_PER_NODE_LASERSCAN * pts_step
+    achieved = alg_bytes / (fast_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(f"scan_fast_kernel.mode_{args.mode}")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "scan_fast_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": fast_ms,
+                "kernel_share_of_step": prof[0] / ms if ms > 0 else None,
+                "general_kernel_ms": prof[2] / max(prof[3], 1)}
+
+    extra = {"scans_on_fast_kernel": n_fast, "scans_total": S}
+    if not args.no_extra:
+        k2 = max(5, min(args.steps, 30))
+        other = R.scan_params(0, 1 - mode_a, 0, 1)
+        ms2, prof2, _, _ = timed(other, k2, 3, profile=True)
+        extra[f"mode_{'b' if mode_a else 'a'}_mpoints_s"] = world * pts_step * k2 / (ms2 * 1e-3) / 1e6
+        nodes_out = torch.empty((S, N, 8), dtype=torch.uint8, device=dev)
+        ms3, prof3, _, _ = timed(params, k2, 3, nodes_out=nodes_out.data_ptr(), profile=True)
+        f3 = prof3[0] / max(prof3[1], 1)
+        extra["with_ascended_nodes_out"] = {
+            "mpoints_s": world * pts_step * k2 / (ms3 * 1e-3) / 1e6, "bytes_per_node": 24,
+            "achieved_gbs": 24 * pts_step / (f3 * 1e-3) / 1e9, "frac": 24 * pts_step / (f3 * 1e-3) / 1e9 / peak}
+        del nodes_out
+
+    # ---- e2e: host buffers through rpl_scan_batch ------------------------------------------------
+    e2e = None
+    h_nodes = None
+    if not args.no_e2e:
+        h_nodes_t = torch.empty((S, N, 8), dtype=torch.uint8, pin_memory=True)
+        h_nodes_t.copy_(nodes)
+        h_counts = counts.cpu().numpy().astype(np.uint32)
+        h_nodes = h_nodes_t.numpy().view(R.NODE_DTYPE).reshape(S, N)
+        out_t = {"ranges": torch.empty((S, N), dtype=torch.float32, pin_memory=True),
+                 "intensities": torch.empty((S, N), dtype=torch.float32, pin_memory=True)}
+        out = {k: v.numpy() for k, v in out_t.items()}
+        ke = max(3, min(args.steps, 10))
+        # what the host link can do on this box (plain pinned copies of the same buffers)
+        pc = []
+        for src, dst in ((h_nodes_t, nodes), (ranges, out_t["ranges"])):
+            torch.cuda.synchronize()
+            tp0 = time.perf_counter()
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            pc.append(src.numel() * src.element_size() / (time.perf_counter() - tp0) / 1e9)
+        for _ in range(2):
+            res = ctx.scan_batch(h_nodes, h_counts, params, out=out)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            res = ctx.scan_batch(h_nodes, h_counts, params, out=out)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        barrier()
+        sampler.window(t0, t1, "e2e leg")
+        dt = max_over_ranks(t1 - t0)
+        # the device-resident result and the host-path result must be the same bytes
+        step(params)
+        torch.cuda.synchronize()
+        same = True
+        for sidx in (0, S // 2, S - 1):
+            m = int(res["beam_counts"][sidx])
+            dev_r = ranges[sidx, :m].cpu().numpy().view(np.uint32)
+            dev_i = intens[sidx, :m].cpu().numpy().view(np.uint32)
+            same = same and m == int(beams[sidx].item()) and bool((dev_r == out["ranges"][sidx, :m].view(np.uint32)).all()) \
+                and bool((dev_i == out["intensities"][sidx, :m].view(np.uint32)).all())
+        e2e = {"value": world * pts_step * ke / dt / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": S * N * 8 + S * 4, "d2h_bytes_per_step": 2 * S * N * 4 + 4 * S * 4,
+               "steps": ke, "ms_per_step": dt / ke * 1e3, "api": "rpl_scan_batch (pinned host buffers)",
+               "matches_device_path": same, "beam_count_scan0": int(res["beam_counts"][0]),
+               "link_h2d_gbs": pc[0], "link_d2h_gbs": pc[1]}
+    sampler.stop()
+    clocks = sampler.summary()
+
+    # ---- cpu baseline: rank 0, N=1 only -----------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import pyoracle as O
+
+        O.build(ref=False)
+        cores = os.cpu_count() or 1
+        if h_nodes is None:
+            h_nodes = nodes.cpu().numpy().view(R.NODE_DTYPE).reshape(S, N)
+        hc = np.full(S, N, np.uint32)
+        host = np.ascontiguousarray(h_nodes).view(O.NODE_DTYPE).reshape(S, N)
+        v_all, secs = cpu_leg(O, host, hc, mode_a, cores, 2)
+        sub = min(S, 128)
+        v_one, _ = cpu_leg(O, host[:sub].copy(), hc[:sub], mode_a, 1, 1)
+        cpu = {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": (f"the bench batch itself, 2 passes x {S} scans x {N} nodes = {2 * S * N / 1e6:.0f} Mpoints "
+                          f"({secs:.1f} s wall, {cores} worker threads, one scan per task); oracle port of "
+                          f"ascendScanData+publish_scan, validated against the compiled reference"),
+               "value_1thread": v_one, "sample_1thread": f"{sub} scans x {N} nodes"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "scans_per_gpu": S, "nodes_per_scan": N,
+                       "parallelism": f"{world} x independent stream shards (no data-path collective on the LaserScan path)",
+                       "l2": "inputs 1.07 GB + outputs 1.07 GB per step exceed the 126 MB L2; no flush needed"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

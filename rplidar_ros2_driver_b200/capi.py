@@ -35,7 +35,7 @@ NODE_DTYPE = np.dtype(
 
 EXPORTS = [
     "rpl_abi_version", "rpl_ctx_create", "rpl_ctx_destroy", "rpl_last_error", "rpl_ctx_synchronize",
-    "rpl_host_alloc", "rpl_host_free", "rpl_ctx_launch_count", "rpl_ascend_scan", "rpl_laserscan",
+    "rpl_host_alloc", "rpl_host_free", "rpl_ctx_launch_count", "rpl_ctx_profile", "rpl_ctx_profile_read", "rpl_ascend_scan", "rpl_laserscan",
     "rpl_scan", "rpl_scan_batch", "rpl_ascend_scan_batch", "rpl_laserscan_batch", "rpl_scan_batch_dev",
     "rpl_cloud_batch_dev", "rpl_cloud_batch", "rpl_cloud_fuse_dev", "rpl_synth_batch_dev",
 ]
@@ -105,6 +105,8 @@ def lib() -> C.CDLL:
         "rpl_host_alloc": ([sz, C.POINTER(vp)], u32),
         "rpl_host_free": ([vp], None),
         "rpl_ctx_launch_count": ([vp], u64),
+        "rpl_ctx_profile": ([vp, i32], u32),
+        "rpl_ctx_profile_read": ([vp, C.POINTER(C.c_double), C.POINTER(u32), C.POINTER(C.c_double), C.POINTER(u32)], u32),
         "rpl_ascend_scan": ([vp, vp, sz], u32),
         "rpl_laserscan": ([vp, vp, sz, PSP, vp, vp, C.POINTER(u32), C.POINTER(C.c_float)], u32),
         "rpl_scan": ([vp, vp, sz, PSP, vp, vp, C.POINTER(u32), C.POINTER(C.c_float), C.POINTER(u32)], u32),
@@ -183,6 +185,15 @@ class Context:
     def launch_count(self) -> int:
         return int(self._L.rpl_ctx_launch_count(self._h))
 
+    def profile(self, enable: bool):
+        self._check(self._L.rpl_ctx_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        """(fast_ms, fast_launches, general_ms, general_launches) since the last read."""
+        fm, gm, fn, gn = C.c_double(0), C.c_double(0), C.c_uint32(0), C.c_uint32(0)
+        self._check(self._L.rpl_ctx_profile_read(self._h, C.byref(fm), C.byref(fn), C.byref(gm), C.byref(gn)))
+        return fm.value, fn.value, gm.value, gn.value
+
     # ---- single scan (reference-shaped) ---------------------------------------------------
     def ascend_scan(self, nodes: np.ndarray):
         """ILidarDriver::ascendScanData: returns (sl_result, ascended copy)."""
@@ -223,14 +234,17 @@ class Context:
         n_scans, stride = nodes.shape
         counts = np.ascontiguousarray(counts, dtype=np.uint32)
         out = dict(out or {})
+        # (no dict.setdefault here: it would build the default arrays even when they are given)
         if want_scan:
-            out.setdefault("ranges", np.full((n_scans, stride), np.nan, np.float32))
-            out.setdefault("intensities", np.full((n_scans, stride), np.nan, np.float32))
-        if emit_nodes:
-            out.setdefault("nodes", np.zeros((n_scans, stride), NODE_DTYPE))
+            for k in ("ranges", "intensities"):
+                if k not in out:
+                    out[k] = np.full((n_scans, stride), np.nan, np.float32)
+        if emit_nodes and "nodes" not in out:
+            out["nodes"] = np.zeros((n_scans, stride), NODE_DTYPE)
         for k, dt in (("beam_counts", np.uint32), ("angle_increment", np.float32), ("status", np.uint32),
                       ("path", np.uint32)):
-            out.setdefault(k, np.zeros(n_scans, dt))
+            if k not in out:
+                out[k] = np.zeros(n_scans, dt)
         self._check(self._L.rpl_scan_batch(
             self._h, _p(nodes), _p(counts), n_scans, stride, C.byref(params), _p(out.get("nodes")),
             _p(out.get("ranges")), _p(out.get("intensities")), _p(out["beam_counts"]),

@@ -10,6 +10,8 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/rpl_b200.h"
 #include "cloud_args.h"
@@ -59,6 +61,12 @@ struct rpl_ctx {
   Lane lane[kLanes];
   std::string err;
   uint64_t launches = 0;
+  // pinned mirrors of the small per-scan arrays of the host-buffer calls: keeps every copy of
+  // the pipeline asynchronous even when the caller's small arrays are pageable
+  uint32_t* h_counts = nullptr;
+  uint32_t* h_small = nullptr;  // [4][max_scans]: beams, angle_increment bits, status, path
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_fast, prof_general;
 };
 
 namespace {
@@ -182,15 +190,45 @@ rpl_result enqueue_scan(rpl_ctx* c, Lane& l, const rpl_node_hq* nodes, const uin
   a.inverted = p->inverted;
   a.apply_ascend = p->apply_ascend;
 
-  const bool force_general = (p->flags & RPL_FLAG_FORCE_GENERAL) != 0;
+  bool force_general = (p->flags & RPL_FLAG_FORCE_GENERAL) != 0;
+  if (a.nodes_out && !a.apply_ascend) {
+    // no geometric correction requested: the buffer passes through unchanged
+    // (reference lidar_driver_wrapper.cpp:330-337); a plain device copy, not kernel work
+    RPL_CUDA(c, cudaMemcpy2DAsync(a.nodes_out, (size_t)stride * 8, a.nodes, (size_t)stride * 8,
+                                  (size_t)stride * 8, n_scans, cudaMemcpyDeviceToDevice, stream),
+             RPL_RESULT_OPERATION_FAIL);
+    a.nodes_out = nullptr;
+  }
+  // status-only calls (no LaserScan, no ascended buffer) take the general kernel
+  if (!a.ranges && !a.nodes_out) force_general = true;
   if (!force_general) {
     RPL_CUDA(c, cudaMemsetAsync(l.fallback_count, 0, sizeof(uint32_t), stream), RPL_RESULT_OPERATION_FAIL);
     const int grid = (int)std::min<uint32_t>(n_scans, (uint32_t)c->fast_grid);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->profile) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, stream);
+    }
     RPL_CUDA(c, rpl::launch_scan_fast(a, l.fws, grid, stream), RPL_RESULT_OPERATION_FAIL);
+    if (c->profile) {
+      cudaEventRecord(e1, stream);
+      c->prof_fast.emplace_back(e0, e1);
+    }
     c->launches++;
   }
   const int ggrid = (int)std::min<uint32_t>(n_scans, (uint32_t)c->general_grid);
+  cudaEvent_t g0 = nullptr, g1 = nullptr;
+  if (c->profile) {
+    cudaEventCreate(&g0);
+    cudaEventCreate(&g1);
+    cudaEventRecord(g0, stream);
+  }
   RPL_CUDA(c, rpl::launch_scan_general(a, l.gws, ggrid, force_general, stream), RPL_RESULT_OPERATION_FAIL);
+  if (c->profile) {
+    cudaEventRecord(g1, stream);
+    c->prof_general.emplace_back(g0, g1);
+  }
   c->launches++;
   return RPL_RESULT_OK;
 }
@@ -258,6 +296,11 @@ rpl_result rpl_ctx_create(int device, uint32_t max_nodes, uint32_t max_scans, rp
     if (!cuda_ok(c, cudaMemset(l.fallback_count, 0, sizeof(uint32_t)), "cudaMemset"))
       return fail(RPL_RESULT_OPERATION_FAIL);
   }
+  if (!cuda_ok(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_counts), (size_t)max_scans * 4, cudaHostAllocDefault),
+               "cudaHostAlloc") ||
+      !cuda_ok(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_small), (size_t)max_scans * 16, cudaHostAllocDefault),
+               "cudaHostAlloc"))
+    return fail(RPL_RESULT_INSUFFICIENT_MEMORY);
   *out = c;
   return RPL_RESULT_OK;
 }
@@ -269,6 +312,8 @@ void rpl_ctx_destroy(rpl_ctx* c) {
     if (c->lane[i].stream) cudaStreamSynchronize(c->lane[i].stream);
     free_lane(c->lane[i]);
   }
+  if (c->h_counts) cudaFreeHost(c->h_counts);
+  if (c->h_small) cudaFreeHost(c->h_small);
   delete c;
 }
 
@@ -293,6 +338,34 @@ void rpl_host_free(void* p) {
 }
 
 uint64_t rpl_ctx_launch_count(const rpl_ctx* c) { return c ? c->launches : 0; }
+
+rpl_result rpl_ctx_profile(rpl_ctx* c, int enable) {
+  if (!c) return RPL_RESULT_INVALID_DATA;
+  c->profile = enable != 0;
+  return RPL_RESULT_OK;
+}
+
+rpl_result rpl_ctx_profile_read(rpl_ctx* c, double* fast_ms, uint32_t* fast_launches,
+                                double* general_ms, uint32_t* general_launches) {
+  if (!c) return RPL_RESULT_INVALID_DATA;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  auto drain = [&](std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v, double* ms, uint32_t* n) {
+    double sum = 0.0;
+    for (auto& pr : v) {
+      cudaEventSynchronize(pr.second);
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) sum += t;
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    if (ms) *ms = sum;
+    if (n) *n = (uint32_t)v.size();
+    v.clear();
+  };
+  drain(c->prof_fast, fast_ms, fast_launches);
+  drain(c->prof_general, general_ms, general_launches);
+  return RPL_RESULT_OK;
+}
 
 // ---- device-resident batch ----------------------------------------------------------------
 rpl_result rpl_scan_batch_dev(rpl_ctx* c, const rpl_node_hq* nodes, const uint32_t* counts,
@@ -342,6 +415,11 @@ rpl_result rpl_scan_batch(rpl_ctx* c, const rpl_node_hq* nodes, const uint32_t* 
     if (r != RPL_RESULT_OK) return r;
   }
   const cudaMemcpyKind h2d = cudaMemcpyHostToDevice, d2h = cudaMemcpyDeviceToHost;
+  std::memcpy(c->h_counts, counts, (size_t)n_scans * sizeof(uint32_t));
+  uint32_t* hs_beams = c->h_small;
+  uint32_t* hs_inc = c->h_small + c->max_scans;
+  uint32_t* hs_status = c->h_small + 2 * (size_t)c->max_scans;
+  uint32_t* hs_path = c->h_small + 3 * (size_t)c->max_scans;
   uint32_t ci = 0;
   for (uint32_t s0 = 0; s0 < n_scans; s0 += chunk, ++ci) {
     Lane& l = c->lane[ci % kLanes];
@@ -351,7 +429,7 @@ rpl_result rpl_scan_batch(rpl_ctx* c, const rpl_node_hq* nodes, const uint32_t* 
     RPL_CUDA(c, cudaStreamSynchronize(l.stream), RPL_RESULT_OPERATION_FAIL);
     RPL_CUDA(c, cudaMemcpyAsync(l.d_nodes, nodes + off, cnt * sizeof(rpl_node_hq), h2d, l.stream),
              RPL_RESULT_OPERATION_FAIL);
-    RPL_CUDA(c, cudaMemcpyAsync(l.d_counts, counts + s0, ns * sizeof(uint32_t), h2d, l.stream),
+    RPL_CUDA(c, cudaMemcpyAsync(l.d_counts, c->h_counts + s0, ns * sizeof(uint32_t), h2d, l.stream),
              RPL_RESULT_OPERATION_FAIL);
     rpl_result r = enqueue_scan(c, l, reinterpret_cast<rpl_node_hq*>(l.d_nodes), l.d_counts, ns, stride,
                                 params, nodes_out ? reinterpret_cast<rpl_node_hq*>(l.d_nodes_out) : nullptr,
@@ -368,19 +446,25 @@ rpl_result rpl_scan_batch(rpl_ctx* c, const rpl_node_hq* nodes, const uint32_t* 
                RPL_RESULT_OPERATION_FAIL);
     }
     if (beam_counts)
-      RPL_CUDA(c, cudaMemcpyAsync(beam_counts + s0, l.d_beams, ns * sizeof(uint32_t), d2h, l.stream),
+      RPL_CUDA(c, cudaMemcpyAsync(hs_beams + s0, l.d_beams, ns * sizeof(uint32_t), d2h, l.stream),
                RPL_RESULT_OPERATION_FAIL);
     if (angle_increment)
-      RPL_CUDA(c, cudaMemcpyAsync(angle_increment + s0, l.d_inc, ns * sizeof(float), d2h, l.stream),
+      RPL_CUDA(c, cudaMemcpyAsync(hs_inc + s0, l.d_inc, ns * sizeof(float), d2h, l.stream),
                RPL_RESULT_OPERATION_FAIL);
     if (status)
-      RPL_CUDA(c, cudaMemcpyAsync(status + s0, l.d_status, ns * sizeof(uint32_t), d2h, l.stream),
+      RPL_CUDA(c, cudaMemcpyAsync(hs_status + s0, l.d_status, ns * sizeof(uint32_t), d2h, l.stream),
                RPL_RESULT_OPERATION_FAIL);
     if (path)
-      RPL_CUDA(c, cudaMemcpyAsync(path + s0, l.d_path, ns * sizeof(uint32_t), d2h, l.stream),
+      RPL_CUDA(c, cudaMemcpyAsync(hs_path + s0, l.d_path, ns * sizeof(uint32_t), d2h, l.stream),
                RPL_RESULT_OPERATION_FAIL);
   }
-  return rpl_ctx_synchronize(c);
+  const rpl_result rs = rpl_ctx_synchronize(c);
+  if (rs != RPL_RESULT_OK) return rs;
+  if (beam_counts) std::memcpy(beam_counts, hs_beams, (size_t)n_scans * 4);
+  if (angle_increment) std::memcpy(angle_increment, hs_inc, (size_t)n_scans * 4);
+  if (status) std::memcpy(status, hs_status, (size_t)n_scans * 4);
+  if (path) std::memcpy(path, hs_path, (size_t)n_scans * 4);
+  return RPL_RESULT_OK;
 }
 
 rpl_result rpl_ascend_scan_batch(rpl_ctx* c, rpl_node_hq* nodes, const uint32_t* counts,

@@ -65,11 +65,22 @@ __device__ __forceinline__ float key_to_rad(uint32_t key) {
   const double kDegToRad = 3.14159265358979323846 / 180.0;
   return __double2float_rn(__dmul_rn((double)key_to_deg(key), kDegToRad));
 }
+// dist_m = dist_mm_q2 / 4000.0f, correctly rounded.  One multiply + two FMAs (Markstein's
+// reciprocal refinement) instead of the generic division sequence; proven bit-identical to
+// the IEEE quotient for every float a u32 converts to by oracle/check_div4000.c.
 __device__ __forceinline__ float dist_to_m(uint32_t dist_q2) {
-  return __fdiv_rn(__uint2float_rn(dist_q2), 4000.0f);
+  const float x = __uint2float_rn(dist_q2);
+  const float r = 1.0f / 4000.0f;  // RN(1/4000) = 0x1.0624dep-12
+  const float q0 = __fmul_rn(x, r);
+  const float e = __fmaf_rn(-q0, 4000.0f, x);
+  return __fmaf_rn(e, r, q0);
+}
+// (float)q for q < 2^23 without the conversion pipe: 2^23 + q is exact, minus 2^23 is exact
+__device__ __forceinline__ float small_uint_to_float(uint32_t q) {
+  return __fsub_rn(__uint_as_float(0x4B000000u | q), 8388608.0f);
 }
 __device__ __forceinline__ float quality_to_intensity(uint32_t q, bool new_protocol) {
-  return __uint2float_rn(new_protocol ? q : (q >> 2));
+  return small_uint_to_float(new_protocol ? q : (q >> 2));
 }
 
 // LaserScan.angle_increment (reference rplidar_node.cpp:633-634 Mode A, :664-666 Mode B)
@@ -117,6 +128,41 @@ __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v) {
     if (lane >= (uint32_t)o) v += t;
   }
   return v;
+}
+
+// L2 residency control.  A scan tile is read twice (mark pass, place pass): the first read
+// asks L2 to keep the lines (evict_last), the second read and all output stores mark their
+// lines evict_first so that the 1 GB/launch output stream does not push tiles out of the
+// 126 MB L2 before their second read.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ld_hint_v4(const void* p, uint64_t pol) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ uint2 ld_hint_v2(const void* p, uint64_t pol) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
+               : "=r"(r.x), "=r"(r.y)
+               : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void st_hint_f32(float* p, float v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol));
+}
+__device__ __forceinline__ void st_hint_v2(uint2* p, uint2 v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol));
 }
 
 // streaming global accesses: inputs are read at most twice, outputs written once

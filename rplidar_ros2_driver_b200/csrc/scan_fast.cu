@@ -6,17 +6,19 @@
 //
 // Idea: the sort key is the 16-bit angle_z_q14 (angle_rad is strictly monotonic in it), so
 // for a scan whose keys are distinct the two std::sort calls collapse into a RANK LOOKUP:
-//   pass 1  stream the packed nodes once from HBM (128-bit loads), mark a 65536-entry
-//           presence map in shared memory with plain byte stores (no atomics),
-//   scan    fold the byte map into a bitmap + per-word exclusive popcount prefix,
-//   pass 2  stream the nodes again (L2 hits: the tile was just read) and place every point
-//           at rank(key) = prefix[key>>5] + popc(bits[key>>5] & below(key)).
+//   mark    stream the packed nodes once from HBM (128-bit loads, L2 evict_last), mark a
+//           65536-entry presence map in shared memory with plain byte stores (no atomics),
+//   fold    turn the byte map into a bitmap + per-word exclusive popcount prefix,
+//   place   stream the nodes again (L2 hits: the tile was just read; evict_first) and put
+//           every point at rank(key) = prefix[key>>5] + popc(bits[key>>5] & below(key)).
 // Mode B writes ranges[rank]; Mode A derives bin ownership (head / tail / empty-bin gaps)
 // from the same bitmap; the ascended node buffer is a second rank over all nodes' final keys.
 // A scan with duplicate keys (detected as popcount != count) is handed to the general
 // radix-sort kernel through a device-side list -- results there follow the stable tie rule.
 //
 // HBM traffic per node: 8 B read + 4 B ranges + 4 B intensities (+8 B ascended node).
+#include <type_traits>
+
 #include "rpl_device.cuh"
 #include "scan_args.h"
 
@@ -30,13 +32,14 @@ constexpr uint32_t kWords = kKeySpace / 32;     // 2048 bitmap words
 constexpr uint32_t kPendingCap = 8192;          // Mode A collision-group heads kept on chip
 constexpr uint32_t kMaxFastNodes = kKeySpace;   // more nodes cannot be tie-free
 constexpr int kUnroll = 4;
+constexpr uint32_t kDummySlot = kKeySpace;      // where unmeasured nodes "mark"
 
 struct __align__(16) FastSmem {
   uint8_t bytemap[kKeySpace];      // presence map (swizzled); reused as the pending-head list
+  uint8_t dummy[16];
   uint2 rankV[kWords];             // {bits, exclusive prefix} over measured keys
   uint2 rankA[kWords];             // same over all nodes' final keys (ascended buffer)
-  uint32_t vbE[kKeySpace / 64];    // validity ballots of even / odd nodes
-  uint32_t vbO[kKeySpace / 64];
+  uint32_t vbits[kKeySpace / 32];  // measured flag per node index (ascended buffer only)
   uint32_t red[4 * kWarps];
   uint32_t valid_count;
   uint32_t first_valid;
@@ -48,7 +51,9 @@ struct __align__(16) FastSmem {
 };
 
 // byte map address swizzle: spreads a thread's 128-byte row over the 16-byte columns so
-// the 128-bit reads of the fold step are bank-conflict free
+// the 128-bit reads of the fold step are bank-conflict free.  Takes the raw first word of a
+// node (key in the low 16 bits).
+__device__ __forceinline__ uint32_t swz_x(uint32_t x) { return (x ^ ((x >> 3) & 0x70u)) & 0xFFFFu; }
 __device__ __forceinline__ uint32_t swz(uint32_t key) { return key ^ ((key >> 3) & 0x70u); }
 
 __device__ __forceinline__ uint32_t gather4(uint32_t x) { return (x * 0x10204080u) >> 28; }
@@ -77,28 +82,13 @@ __device__ __forceinline__ int next_set(const uint2* rk, uint32_t k) {
   }
 }
 
-struct Pair {
-  uint2 a, b;
-  bool has_a, has_b;
-};
-__device__ __forceinline__ Pair load_pair(const uint2* base, uint32_t n, bool vec, uint32_t p) {
-  Pair r;
-  const uint32_t i0 = 2 * p;
-  r.has_a = i0 < n;
-  r.has_b = i0 + 1 < n;
-  r.a = make_uint2(0, 0);
-  r.b = make_uint2(0, 0);
-  if (vec && r.has_b) {
-    const uint4 v = ld_stream_v4(base + i0);
-    r.a = make_uint2(v.x, v.y);
-    r.b = make_uint2(v.z, v.w);
-  } else {
-    if (r.has_a) r.a = ld_stream_v2(base + i0);
-    if (r.has_b) r.b = ld_stream_v2(base + i0 + 1);
-  }
-  return r;
+// predicated streaming stores (no branch around them)
+__device__ __forceinline__ void st_f32_if(float* p, float v, uint64_t pol, uint32_t pred) {
+  asm volatile(
+      "{ .reg .pred q; setp.ne.u32 q, %3, 0;\n\t"
+      "@q st.global.L1::no_allocate.L2::cache_hint.f32 [%0], %1, %2; }" ::"l"(p),
+      "f"(v), "l"(pol), "r"(pred));
 }
-
 
 // ---- Mode A (reference rplidar_node.cpp:630-660) ------------------------------------------
 // beam_count = M bins; every measured point goes to bin (int)(angle / angle_increment) and the
@@ -183,14 +173,19 @@ __global__ void __launch_bounds__(T, 2) scan_fast_kernel(ScanBatchArgs a, FastWo
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool new_proto = a.is_new_protocol != 0;
   const bool inverted = a.inverted != 0;
-  const bool want_scan = a.ranges != nullptr;
+  // launches without the ascended buffer always produce the LaserScan (host guarantees it)
+  const bool want_scan = EMIT ? (a.ranges != nullptr) : true;
   unsigned long long* gscratch = ws.group + (size_t)blockIdx.x * ws.max_nodes;
+  const uint64_t pol_keep = l2_policy_evict_last();
+  const uint64_t pol_stream = l2_policy_evict_first();
+  // intensity = quality (new protocol) or quality >> 2, taken straight from word y
+  const uint32_t q_shift = new_proto ? 16u : 18u, q_mask = new_proto ? 0xFFu : 0x3Fu;
+  using Checked = std::integral_constant<bool, true>;
+  using Unchecked = std::integral_constant<bool, false>;
 
   for (uint32_t s = blockIdx.x; s < a.n_scans; s += gridDim.x) {
     const uint32_t n = a.counts[s];
     const uint2* base = a.nodes + (size_t)s * a.stride;
-    const bool vec = ((reinterpret_cast<uintptr_t>(base) & 15u) == 0);
-    const uint32_t npairs = (n + 1) >> 1;
 
     if (n > a.stride || n > ws.max_nodes) {  // caller error: report, touch nothing
       if (tid == 0) {
@@ -212,6 +207,8 @@ __global__ void __launch_bounds__(T, 2) scan_fast_kernel(ScanBatchArgs a, FastWo
       const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
       for (uint32_t j = 0; j < kKeySpace / 16 / T; ++j) bm[j * T + tid] = z;
+      if (EMIT)
+        for (uint32_t w = tid; w < kKeySpace / 32; w += T) sm.vbits[w] = 0;
       if (tid == 0) {
         sm.pending = 0;
         sm.fallback = 0;
@@ -219,55 +216,96 @@ __global__ void __launch_bounds__(T, 2) scan_fast_kernel(ScanBatchArgs a, FastWo
     }
     __syncthreads();
 
-    // ---- phase 1: stream the scan from HBM, mark measured keys --------------------------
-    uint32_t cnt = 0, first = 0xFFFFFFFFu;
-    for (uint32_t p0 = 0; p0 < npairs; p0 += T * kUnroll) {
-      Pair pr[kUnroll];
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) pr[u] = load_pair(base, n, vec, p0 + u * T + tid);
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const uint32_t p = p0 + u * T + tid;
-        const bool va = pr[u].has_a && node_dist(pr[u].a) != 0;
-        const bool vb = pr[u].has_b && node_dist(pr[u].b) != 0;
-        if (va) sm.bytemap[swz(node_key(pr[u].a))] = 1;
-        if (vb) sm.bytemap[swz(node_key(pr[u].b))] = 1;
-        cnt += (uint32_t)va + (uint32_t)vb;
-        if (va) first = min(first, 2 * p);
-        else if (vb) first = min(first, 2 * p + 1);
-        if (EMIT) {
-          const uint32_t be = __ballot_sync(0xffffffffu, va);
-          const uint32_t bo = __ballot_sync(0xffffffffu, vb);
-          if (lane == 0 && (p >> 5) < kKeySpace / 64) {
-            sm.vbE[p >> 5] = be;
-            sm.vbO[p >> 5] = bo;
-          }
+    // ---- phase 1 (mark): stream the scan from HBM, mark measured keys --------------------
+    uint32_t cnt = 0;
+    auto mark = [&](uint32_t x, uint32_t y) -> uint32_t {
+      const uint32_t valid = __funnelshift_r(x, y, 16) != 0 ? 1u : 0u;
+      sm.bytemap[valid ? swz_x(x) : kDummySlot] = 1;
+      cnt += valid;
+      return valid;
+    };
+    if (!EMIT) {
+      // 128-bit loads, two nodes per lane; peel one node when the scan starts mid-16-bytes
+      const uint32_t head = (n != 0 && (reinterpret_cast<uintptr_t>(base) & 8u)) ? 1u : 0u;
+      const uint4* b4 = reinterpret_cast<const uint4*>(base + head);
+      const uint32_t npairs = (n - head) >> 1;
+      if (tid == 0) {
+        if (head) {
+          const uint2 nd = ld_hint_v2(base, pol_keep);
+          mark(nd.x, nd.y);
+        }
+        if ((n - head) & 1u) {
+          const uint2 nd = ld_hint_v2(base + n - 1, pol_keep);
+          mark(nd.x, nd.y);
         }
       }
+      auto block = [&](auto checked, uint32_t p0) {
+        uint4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const uint32_t p = p0 + u * T + tid;
+          if (!decltype(checked)::value || p < npairs) v[u] = ld_hint_v4(b4 + p, pol_keep);
+          else v[u] = make_uint4(0, 0, 0, 0);  // dist 0: marks the dummy slot
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          mark(v[u].x, v[u].y);
+          mark(v[u].z, v[u].w);
+        }
+      };
+      uint32_t p0 = 0;
+      for (; p0 + T * kUnroll <= npairs; p0 += T * kUnroll) block(Unchecked{}, p0);
+      if (p0 < npairs) block(Checked{}, p0);
+    } else {
+      // one node per lane so that a ballot is the measured mask of 32 consecutive nodes
+      auto block = [&](auto checked, uint32_t i0) {
+        uint2 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const uint32_t i = i0 + u * T + tid;
+          if (!decltype(checked)::value || i < n) v[u] = ld_hint_v2(base + i, pol_keep);
+          else v[u] = make_uint2(0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const uint32_t i = i0 + u * T + tid;
+          const uint32_t valid = mark(v[u].x, v[u].y);
+          const uint32_t bal = __ballot_sync(0xffffffffu, valid != 0);
+          if (lane == 0 && (i >> 5) < kKeySpace / 32) sm.vbits[i >> 5] = bal;
+        }
+      };
+      uint32_t i0 = 0;
+      for (; i0 + T * kUnroll <= n; i0 += T * kUnroll) block(Unchecked{}, i0);
+      if (i0 < n) block(Checked{}, i0);
     }
     cnt = warp_sum(cnt);
-    first = warp_min(first);
-    if (lane == 0) {
-      sm.red[warp] = cnt;
-      sm.red[kWarps + warp] = first;
-    }
+    if (lane == 0) sm.red[warp] = cnt;
     __syncthreads();
     if (warp == 0) {
       uint32_t c = lane < kWarps ? sm.red[lane] : 0u;
-      uint32_t f = lane < kWarps ? sm.red[kWarps + lane] : 0xFFFFFFFFu;
       c = warp_sum(c);
-      f = warp_min(f);
+      uint32_t f = 0xFFFFFFFFu;
+      if (EMIT) {  // first measured node = first set bit of vbits
+        const uint32_t nw = (n + 31) >> 5;
+        for (uint32_t w0 = 0; w0 < nw; w0 += 32) {
+          const uint32_t w = w0 + lane;
+          const uint32_t bits = w < nw ? sm.vbits[w] : 0u;
+          const uint32_t any = __ballot_sync(0xffffffffu, bits != 0);
+          if (any) {
+            const uint32_t src = __ffs(any) - 1;
+            const uint32_t b = __shfl_sync(0xffffffffu, bits, src);
+            f = ((w0 + src) << 5) + __ffs(b) - 1;
+            break;
+          }
+        }
+      }
       if (lane == 0) {
         sm.valid_count = c;
         sm.first_valid = f;
         if (EMIT) {
           // head tune: serial, only node 0's result survives (reference :133-147)
-          const float step = ascend_step(n);
           uint32_t fk = 0;
-          if (c != 0) {
-            const uint32_t k0 = node_key(ld_stream_v2(base + f));
-            fk = ascend_head_key(k0, f, step);
-          }
+          if (c != 0) fk = ascend_head_key(node_key(ld_stream_v2(base + f)), f, ascend_step(n));
           sm.front_key = fk;
         }
       }
@@ -297,25 +335,17 @@ __global__ void __launch_bounds__(T, 2) scan_fast_kernel(ScanBatchArgs a, FastWo
 
     // ---- phase 1c (ascended buffer): mark the filled keys of unmeasured nodes -----------
     if (EMIT) {
-      const uint32_t nwords = (npairs + 31) >> 5;
-      for (uint32_t w = tid; w < nwords; w += T) {
-        const uint32_t pbase = w << 5;
-        // pairs in range
-        const uint32_t live = npairs - pbase >= 32 ? 0xFFFFFFFFu : ((1u << (npairs - pbase)) - 1u);
-        uint32_t ie = ~sm.vbE[w] & live;
-        uint32_t io = ~sm.vbO[w] & live;
-        while (ie) {
-          const uint32_t b = __ffs(ie) - 1;
-          ie &= ie - 1;
-          const uint32_t i = 2 * (pbase + b);
+      const uint32_t nw = (n + 31) >> 5;
+      for (uint32_t w = tid; w < nw; w += T) {
+        const uint32_t left = n - (w << 5);
+        const uint32_t live = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
+        uint32_t inv = ~sm.vbits[w] & live;
+        while (inv) {
+          const uint32_t b = __ffs(inv) - 1;
+          inv &= inv - 1;
+          const uint32_t i = (w << 5) + b;
           const uint32_t fk = (i == 0) ? front_key : ascend_fill_key(front_deg, i, step);
           sm.bytemap[swz(fk)] = 2;
-        }
-        while (io) {
-          const uint32_t b = __ffs(io) - 1;
-          io &= io - 1;
-          const uint32_t i = 2 * (pbase + b) + 1;
-          if (i < n) sm.bytemap[swz(ascend_fill_key(front_deg, i, step))] = 2;
         }
       }
       __syncthreads();
@@ -334,10 +364,10 @@ __global__ void __launch_bounds__(T, 2) scan_fast_kernel(ScanBatchArgs a, FastWo
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           bv |= gather4(x[j] & 0x01010101u) << (4 * j);
-          bi |= gather4((x[j] >> 1) & 0x01010101u) << (4 * j);
+          if (EMIT) bi |= gather4((x[j] >> 1) & 0x01010101u) << (4 * j);
         }
         wv[c >> 1] |= bv << (16 * (c & 1));
-        wa[c >> 1] |= (bv | bi) << (16 * (c & 1));
+        if (EMIT) wa[c >> 1] |= (bv | bi) << (16 * (c & 1));
       }
       uint32_t sv = 0, sa = 0;
 #pragma unroll
@@ -345,7 +375,8 @@ __global__ void __launch_bounds__(T, 2) scan_fast_kernel(ScanBatchArgs a, FastWo
         sv += __popc(wv[j]);
         sa += __popc(wa[j]);
       }
-      const uint32_t iv = warp_inclusive_scan(sv), ia = warp_inclusive_scan(sa);
+      const uint32_t iv = warp_inclusive_scan(sv);
+      const uint32_t ia = EMIT ? warp_inclusive_scan(sa) : 0u;
       if (lane == 31) {
         sm.red[2 * kWarps + warp] = iv;
         sm.red[3 * kWarps + warp] = ia;
@@ -387,13 +418,15 @@ __global__ void __launch_bounds__(T, 2) scan_fast_kernel(ScanBatchArgs a, FastWo
       continue;
     }
 
-    // ---- phase 2: stream again (L2), rank and place --------------------------------------
+    // ---- phase 2 (place): stream again (L2), rank and place -------------------------------
     float* ranges = want_scan ? a.ranges + (size_t)s * a.stride : nullptr;
     float* intens = want_scan ? a.intensities + (size_t)s * a.stride : nullptr;
-    uint2* nodes_out = a.nodes_out ? a.nodes_out + (size_t)s * a.stride : nullptr;
+    uint2* nodes_out = EMIT ? a.nodes_out + (size_t)s * a.stride : nullptr;
     const float inc = angle_increment(M, MODE_A);
     const bool has0 = (sm.rankV[0].x & 1u) != 0;
     uint2* pending = reinterpret_cast<uint2*>(sm.bytemap);  // presence map is dead now
+    // Mode B output slot = ob + os * rank (reference rplidar_node.cpp:673)
+    const int ob = inverted ? (int)M - 1 : 0, os = inverted ? -1 : 1;
 
     ModeACtx mc;
     mc.rankV = sm.rankV;
@@ -409,40 +442,44 @@ __global__ void __launch_bounds__(T, 2) scan_fast_kernel(ScanBatchArgs a, FastWo
     mc.has0 = has0;
     mc.new_proto = new_proto;
 
-    auto emit_point = [&](uint2 nd, uint32_t i, bool measured) {
-      const uint32_t k = node_key(nd);
-      if (nodes_out) {
-        if (EMIT) {
-          const uint32_t fk =
-              measured ? k : (i == 0 ? front_key : ascend_fill_key(front_deg, i, step));
-          nodes_out[rank_of(sm.rankA, fk)] = node_with_key(nd, fk);
-        } else {
-          nodes_out[i] = nd;  // no geometric correction requested: buffer passes through
-        }
+    auto place = [&](uint2 nd, uint32_t i, bool live) {
+      const uint32_t k = nd.x & 0xFFFFu;
+      const uint32_t dist = __funnelshift_r(nd.x, nd.y, 16);
+      const uint32_t measured = (live && dist != 0) ? 1u : 0u;
+      if (EMIT && live) {
+        const uint32_t fk = measured ? k : (i == 0 ? front_key : ascend_fill_key(front_deg, i, step));
+        st_hint_v2(nodes_out + rank_of(sm.rankA, fk), node_with_key(nd, fk), pol_stream);
       }
-      if (!measured || !want_scan) return;
-      const float dm = dist_to_m(node_dist(nd));
-      const uint32_t q = node_quality(nd);
+      if (!want_scan) return;
       const uint32_t r = rank_of(sm.rankV, k);
+      const float dm = dist_to_m(dist);
       if (!MODE_A) {  // Mode B: reference rplidar_node.cpp:661-677
-        const uint32_t o = inverted ? (M - 1 - r) : r;
-        ranges[o] = dm;
-        intens[o] = quality_to_intensity(q, new_proto);
-      } else {
-        mode_a_place(mc, k, r, dm, q);
+        const int o = ob + os * (int)r;
+        const float it = __fsub_rn(__uint_as_float(((nd.y >> q_shift) & q_mask) | 0x4B000000u), 8388608.0f);
+        st_f32_if(ranges + o, dm, pol_stream, measured);
+        st_f32_if(intens + o, it, pol_stream, measured);
+      } else if (measured) {
+        mode_a_place(mc, k, r, dm, (nd.y >> 16) & 0xFFu);
       }
     };
-
-    for (uint32_t p0 = 0; p0 < npairs; p0 += T * kUnroll) {
-      Pair pr[kUnroll];
+    {
+      auto block = [&](auto checked, uint32_t i0) {
+        uint2 v[kUnroll];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) pr[u] = load_pair(base, n, vec, p0 + u * T + tid);
+        for (int u = 0; u < kUnroll; ++u) {
+          const uint32_t i = i0 + u * T + tid;
+          if (!decltype(checked)::value || i < n) v[u] = ld_hint_v2(base + i, pol_stream);
+          else v[u] = make_uint2(0, 0);
+        }
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const uint32_t p = p0 + u * T + tid;
-        if (pr[u].has_a) emit_point(pr[u].a, 2 * p, node_dist(pr[u].a) != 0);
-        if (pr[u].has_b) emit_point(pr[u].b, 2 * p + 1, node_dist(pr[u].b) != 0);
-      }
+        for (int u = 0; u < kUnroll; ++u) {
+          const uint32_t i = i0 + u * T + tid;
+          place(v[u], i, !decltype(checked)::value || i < n);
+        }
+      };
+      uint32_t i0 = 0;
+      for (; i0 + T * kUnroll <= n; i0 += T * kUnroll) block(Unchecked{}, i0);
+      if (i0 < n) block(Checked{}, i0);
     }
     __syncthreads();
 

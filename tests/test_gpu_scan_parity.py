@@ -189,3 +189,75 @@ def test_invalid_arguments_fail_loudly(R, ctx):
     with pytest.raises(R.RplError):
         big = np.zeros((65, 8), R.NODE_DTYPE)
         ctx.scan_batch(big, np.full(65, 8, np.uint32), R.scan_params())  # n_scans > max_scans
+
+
+# ---- synthetic generator and full-size properties ---------------------------------------------
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_device_synth_equals_oracle_synth(R, oracle, ctx, variant):
+    import torch
+
+    for n in (1, 7, 360, 3200, 32768):
+        t = torch.zeros((3, n, 8), dtype=torch.uint8, device="cuda")
+        cnt = torch.zeros(3, dtype=torch.int32, device="cuda")
+        ctx.synth_batch_dev(11 + variant, 3, n, n, variant, t.data_ptr(), cnt.data_ptr())
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        exp = oracle.synth_batch(11 + variant, 3, n, variant)
+        assert (t.cpu().numpy().reshape(3, n, 8) == exp.view(np.uint8).reshape(3, n, 8)).all(), (variant, n)
+        assert (cnt.cpu().numpy() == n).all()
+
+
+def test_full_size_batch_properties(R, oracle):
+    """BASELINE.json configs[1] at full size (4096 x 32768): size-independent properties checked
+    on the device with torch as an independent checker, plus oracle parity on sampled scans."""
+    import torch
+
+    S, N = 4096, 32768
+    ctx = R.Context(0, N, S)
+    dev = torch.device("cuda")
+    nodes = torch.empty((S, N, 8), dtype=torch.uint8, device=dev)
+    counts = torch.empty(S, dtype=torch.int32, device=dev)
+    ranges = torch.full((S, N), float("nan"), dtype=torch.float32, device=dev)
+    intens = torch.full((S, N), float("nan"), dtype=torch.float32, device=dev)
+    beams = torch.empty(S, dtype=torch.int32, device=dev)
+    inc = torch.empty(S, dtype=torch.float32, device=dev)
+    status = torch.empty(S, dtype=torch.int32, device=dev)
+    path = torch.empty(S, dtype=torch.int32, device=dev)
+    ctx.synth_batch_dev(0, S, N, N, 1, nodes.data_ptr(), counts.data_ptr())
+    ctx.scan_batch_dev(nodes.data_ptr(), counts.data_ptr(), S, N, R.scan_params(0, 0, 0, 1), ranges=ranges.data_ptr(),
+                       intensities=intens.data_ptr(), beam_counts=beams.data_ptr(), angle_increment=inc.data_ptr(),
+                       status=status.data_ptr(), path=path.data_ptr())
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    assert int((path != 0).sum()) == 0 and int((status != 0).sum()) == 0
+    w = nodes.view(torch.int32).reshape(S, N, 2)
+    x, y = w[..., 0], w[..., 1]
+    key = (x & 0xFFFF).to(torch.int32)
+    dist = ((x >> 16) & 0xFFFF) | ((y & 0xFFFF) << 16)
+    qual = (y >> 16) & 0xFF
+    valid = dist != 0
+    assert (valid.sum(1).to(torch.int32) == beams).all()
+    chunk = 512
+    for s0 in range(0, S, chunk):
+        sl = slice(s0, s0 + chunk)
+        # unmeasured nodes sort to the end: key + 65536
+        k2 = torch.where(valid[sl], key[sl], key[sl] + 65536)
+        order = torch.argsort(k2, dim=1, stable=True)
+        # divide by a CUDA tensor: `tensor / python_scalar` multiplies by the reciprocal in torch
+        four_k = torch.full((1, 1), 4000.0, dtype=torch.float32, device=dev)
+        d_sorted = torch.gather(dist[sl], 1, order).to(torch.float32) / four_k
+        q_sorted = (torch.gather(qual[sl], 1, order) >> 2).to(torch.float32)
+        m = beams[sl].to(torch.int64)
+        live = torch.arange(N, device=dev)[None, :] < m[:, None]
+        assert torch.equal(ranges[sl][live].view(torch.int32), d_sorted[live].view(torch.int32))
+        assert torch.equal(intens[sl][live].view(torch.int32), q_sorted[live].view(torch.int32))
+        assert bool(torch.isnan(ranges[sl][~live]).all())  # nothing written past beam_count
+    # oracle parity on sampled scans
+    for s in (0, 1, 2047, 4095):
+        host = nodes[s].cpu().numpy().view(oracle.NODE_DTYPE).reshape(1, N)
+        exp = oracle.pipeline_batch(host.copy(), np.array([N], np.uint32), oracle.scan_params(0, 0, 0, 1, 40.0, 0.1))
+        m = int(exp["beam_counts"][0])
+        assert m == int(beams[s])
+        assert (ranges[s, :m].cpu().numpy().view(np.uint32) == exp["ranges"][0, :m].view(np.uint32)).all()
+        assert bits(inc[s:s + 1].cpu().numpy())[0] == bits(exp["angle_increment"])[0]
+    ctx.close()
