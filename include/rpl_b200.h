@@ -73,6 +73,8 @@ typedef struct rpl_scan_params {
 } rpl_scan_params;
 
 #define RPL_FLAG_FORCE_GENERAL 1u /* route every scan through the general (radix-sort) kernel */
+#define RPL_FLAG_NO_TMA 2u        /* use the register-streamed fast kernel (scan_fast.cu) even when the
+                                     TMA-ring kernel (scan_tma.cu) applies; for A/B measurements */
 
 /* per-scan path report (optional output) */
 #define RPL_PATH_FAST 0u    /* tie-free scan: bitmap-rank kernel */

@@ -9,5 +9,5 @@ There is no CPU implementation here: the oracle lives under /oracle and is test-
 """
 from .capi import (  # noqa: F401
     NODE_DTYPE, Context, RplError, build, cloud_params, host_alloc, lib, scan_params,
-    FLAG_FORCE_GENERAL, PATH_FAST, PATH_GENERAL, RESULT_OK, RESULT_OPERATION_FAIL, RESULT_INVALID_DATA,
+    FLAG_FORCE_GENERAL, FLAG_NO_TMA, PATH_FAST, PATH_GENERAL, RESULT_OK, RESULT_OPERATION_FAIL, RESULT_INVALID_DATA,
 )

@@ -21,6 +21,7 @@ RESULT_INVALID_DATA = 0x80008000
 RESULT_OPERATION_FAIL = 0x80008001
 RESULT_OPERATION_NOT_SUPPORT = 0x80008004
 FLAG_FORCE_GENERAL = 1
+FLAG_NO_TMA = 2
 PATH_FAST, PATH_GENERAL = 0, 1
 
 # reference src/sdk/include/sl_lidar_cmd.h:272-278

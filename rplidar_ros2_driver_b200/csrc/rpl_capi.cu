@@ -57,7 +57,7 @@ struct rpl_ctx {
   int device = 0;
   uint32_t max_nodes = 0, max_scans = 0;
   int num_sms = 0;
-  int fast_grid = 0, general_grid = 0;
+  int fast_grid = 0, tma_grid = 0, general_grid = 0;
   Lane lane[kLanes];
   std::string err;
   uint64_t launches = 0;
@@ -92,6 +92,7 @@ void free_lane(Lane& l) {
   cudaFree(l.fallback_list);
   cudaFree(l.fallback_count);
   cudaFree(l.fws.group);
+  cudaFree(l.fws.pending);
   cudaFree(l.gws.keyf);
   cudaFree(l.gws.idx0);
   cudaFree(l.gws.idx1);
@@ -203,14 +204,21 @@ rpl_result enqueue_scan(rpl_ctx* c, Lane& l, const rpl_node_hq* nodes, const uin
   if (!a.ranges && !a.nodes_out) force_general = true;
   if (!force_general) {
     RPL_CUDA(c, cudaMemsetAsync(l.fallback_count, 0, sizeof(uint32_t), stream), RPL_RESULT_OPERATION_FAIL);
-    const int grid = (int)std::min<uint32_t>(n_scans, (uint32_t)c->fast_grid);
+    // the TMA-ring kernel needs every scan base 16-byte aligned
+    const bool emit = a.nodes_out != nullptr;
+    const bool use_tma = !emit && (p->flags & RPL_FLAG_NO_TMA) == 0 &&
+                         (reinterpret_cast<uintptr_t>(a.nodes) & 15u) == 0 && (stride & 1u) == 0;
+    const int grid = (int)std::min<uint32_t>(n_scans, (uint32_t)(use_tma ? c->tma_grid : c->fast_grid));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->profile) {
       cudaEventCreate(&e0);
       cudaEventCreate(&e1);
       cudaEventRecord(e0, stream);
     }
-    RPL_CUDA(c, rpl::launch_scan_fast(a, l.fws, grid, stream), RPL_RESULT_OPERATION_FAIL);
+    if (use_tma)
+      RPL_CUDA(c, rpl::launch_scan_tma(a, l.fws, grid, stream), RPL_RESULT_OPERATION_FAIL);
+    else
+      RPL_CUDA(c, rpl::launch_scan_fast(a, l.fws, grid, stream), RPL_RESULT_OPERATION_FAIL);
     if (c->profile) {
       cudaEventRecord(e1, stream);
       c->prof_fast.emplace_back(e0, e1);
@@ -267,11 +275,13 @@ rpl_result rpl_ctx_create(int device, uint32_t max_nodes, uint32_t max_scans, rp
   }
   c->num_sms = prop.multiProcessorCount;
   if (!cuda_ok(c, rpl::scan_fast_configure(), "scan_fast_configure") ||
+      !cuda_ok(c, rpl::scan_tma_configure(), "scan_tma_configure") ||
       !cuda_ok(c, rpl::scan_general_configure(), "scan_general_configure") ||
       !cuda_ok(c, rpl::cloud_configure(), "cloud_configure"))
     return fail(RPL_RESULT_OPERATION_FAIL);
   const int occ = std::max(1, rpl::scan_fast_max_ctas_per_sm());
   c->fast_grid = c->num_sms * occ;
+  c->tma_grid = c->num_sms * std::max(1, rpl::scan_tma_max_ctas_per_sm());
   c->general_grid = c->num_sms;
 
   for (int i = 0; i < kLanes; ++i) {
@@ -279,13 +289,14 @@ rpl_result rpl_ctx_create(int device, uint32_t max_nodes, uint32_t max_scans, rp
     const rpl_result oom = RPL_RESULT_INSUFFICIENT_MEMORY;
     if (!cuda_ok(c, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking), "cudaStreamCreate"))
       return fail(RPL_RESULT_OPERATION_FAIL);
-    const size_t fast_nodes = (size_t)c->fast_grid * max_nodes;
+    const size_t fast_nodes = (size_t)std::max(c->fast_grid, c->tma_grid) * max_nodes;
     const size_t gen_nodes = (size_t)c->general_grid * max_nodes;
     l.fws.max_nodes = max_nodes;
     l.gws.max_nodes = max_nodes;
     if (!cuda_ok(c, dev_alloc(&l.fallback_list, max_scans), "cudaMalloc") ||
         !cuda_ok(c, dev_alloc(&l.fallback_count, 1), "cudaMalloc") ||
         !cuda_ok(c, dev_alloc(&l.fws.group, fast_nodes), "cudaMalloc") ||
+        !cuda_ok(c, dev_alloc(&l.fws.pending, fast_nodes), "cudaMalloc") ||
         !cuda_ok(c, dev_alloc(&l.gws.keyf, gen_nodes), "cudaMalloc") ||
         !cuda_ok(c, dev_alloc(&l.gws.idx0, gen_nodes), "cudaMalloc") ||
         !cuda_ok(c, dev_alloc(&l.gws.idx1, gen_nodes), "cudaMalloc") ||

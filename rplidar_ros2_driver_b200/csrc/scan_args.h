@@ -39,6 +39,7 @@ struct GeneralWorkspace {
 // per-CTA global scratch of the fast kernel (Mode A collision groups)
 struct FastWorkspace {
   unsigned long long* group;  // [ctas][max_nodes]
+  uint2* pending;             // [ctas][max_nodes] heads of shared bins (TMA kernel)
   uint32_t max_nodes;
 };
 
@@ -54,5 +55,9 @@ size_t scan_general_smem_bytes();
 cudaError_t scan_fast_configure();     // opt-in dynamic shared memory, once per device
 cudaError_t scan_general_configure();
 int scan_fast_max_ctas_per_sm();
+// v2: TMA-ring kernel (scan_tma.cu); needs 16-byte aligned scan bases
+cudaError_t launch_scan_tma(const ScanBatchArgs& a, const FastWorkspace& ws, int grid, cudaStream_t stream);
+cudaError_t scan_tma_configure();
+int scan_tma_max_ctas_per_sm();
 
 }  // namespace rpl

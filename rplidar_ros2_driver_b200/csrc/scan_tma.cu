@@ -1,0 +1,403 @@
+// scan_tma.cu -- fast scan kernel v2: TMA-staged scan tiles (producer warp + mbarrier ring).
+//
+// Same contract and the same two passes as scan_fast.cu (mark keys, fold to a rank table,
+// place by rank; ascendScanData_ + publish_scan, reference
+// src/sdk/src/sl_lidar_driver.cpp:128-184 and src/rplidar_node.cpp:581-677), restructured so
+// that no consumer warp ever waits on a global load:
+//
+//   * a dedicated producer warp streams the scan tile through a shared-memory ring with
+//     1-D bulk TMA copies (cp.async.bulk, 8 KB chunks, mbarrier full/empty handshake).
+//     The chunk sequence is [scan s pass 1][scan s pass 2][scan s+1 pass 1]...: the producer
+//     runs ahead across pass and scan boundaries, so HBM/L2 latency is hidden behind the ring
+//     depth instead of behind resident warps.  Pass-1 copies carry an L2 evict_last hint, the
+//     pass-2 copies (L2 hits) and all output stores evict_first.
+//   * marking keeps v1's 64 KB byte map (plain byte stores, ~10 instructions per node).  A
+//     first version of this kernel ORed key bits into the bitmap with warp-aggregated
+//     shared-memory atomics instead; ncu showed ~100 instructions per node in that loop
+//     (profiles/ncu_r1_scan_tma_atomics.txt), so it was dropped.
+//
+// Serves launches without the ascended node buffer (that variant needs two more shared
+// tables and stays on scan_fast.cu).  Requires every scan base to be 16-byte aligned (nodes
+// pointer 16 B aligned, even stride); the host falls back to scan_fast.cu otherwise.
+#include <type_traits>
+
+#include "rpl_device.cuh"
+#include "scan_args.h"
+#include "scan_common.cuh"
+
+namespace rpl {
+
+namespace {
+
+constexpr int TC = 512;                // consumer threads (16 warps)
+constexpr int kCWarps = TC / 32;
+constexpr int kBlock = TC + 32;        // + one producer warp
+constexpr uint32_t CH = 1024;          // nodes per chunk (8 KB)
+constexpr int kStages = 4;             // ring depth (32 KB)
+constexpr uint32_t kDummySlot = kKeySpace;  // where unmeasured nodes "mark"
+constexpr int kRounds = CH / TC;       // nodes per consumer thread per chunk
+
+struct __align__(128) TmaSmem {
+  uint2 ring[kStages][CH];
+  uint8_t bytemap[kKeySpace];                // presence map (swizzled)
+  uint8_t dummy[16];
+  uint2 rankV[kWords];                       // {bits, exclusive prefix} over measured keys
+  unsigned long long full[kStages];
+  unsigned long long empty[kStages];
+  uint32_t red[4 * kCWarps];
+  uint32_t valid_count;
+  uint32_t totV;
+  uint32_t pending;
+  uint32_t fallback;
+};
+
+__device__ __forceinline__ uint32_t swz_x(uint32_t x) { return (x ^ ((x >> 3) & 0x70u)) & 0xFFFFu; }
+__device__ __forceinline__ uint32_t gather4(uint32_t x) { return (x * 0x10204080u) >> 28; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+// 1-D bulk TMA copy global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, void* bar,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC) : "memory"); }
+
+// which scans run through the ring (producer and consumers must agree)
+__device__ __forceinline__ bool scan_is_streamed(uint32_t n, uint32_t stride, uint32_t max_nodes) {
+  return n != 0 && n <= stride && n <= max_nodes && n <= kMaxFastNodes;
+}
+
+template <bool MODE_A>
+__global__ void __launch_bounds__(kBlock, 2) scan_tma_kernel(ScanBatchArgs a, FastWorkspace ws) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TmaSmem& sm = *reinterpret_cast<TmaSmem*>(smem_raw);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&sm.full[i], 1);         // the producer's arrive.expect_tx
+      mbar_init(&sm.empty[i], kCWarps);  // one arrive per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  // =========================== producer warp ===========================================
+  if (warp == kCWarps) {
+    if (lane == 0) {
+      const uint64_t pol_keep = l2_policy_evict_last();
+      const uint64_t pol_stream = l2_policy_evict_first();
+      uint32_t g = 0;  // chunks issued so far
+      for (uint32_t s = blockIdx.x; s < a.n_scans; s += gridDim.x) {
+        const uint32_t n = a.counts[s];
+        if (!scan_is_streamed(n, a.stride, ws.max_nodes)) continue;
+        const uint2* base = a.nodes + (size_t)s * a.stride;
+        const uint32_t nch = (n + CH - 1) / CH;
+        for (int pass = 0; pass < 2; ++pass) {
+          for (uint32_t c = 0; c < nch; ++c, ++g) {
+            const uint32_t stage = g % kStages, round = g / kStages;
+            mbar_wait(&sm.empty[stage], (round & 1u) ^ 1u);
+            // an odd tail is rounded up to a whole 16 bytes; the extra node lies inside the
+            // scan's stride (even stride, n odd => n + 1 <= stride) and is masked by consumers
+            const uint32_t cn = min(CH, n - c * CH);
+            const uint32_t bytes = ((cn + 1u) & ~1u) * 8u;
+            mbar_expect_tx(&sm.full[stage], bytes);
+            tma_load_1d(&sm.ring[stage][0], base + (size_t)c * CH, bytes, &sm.full[stage],
+                        pass == 0 ? pol_keep : pol_stream);
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // =========================== consumer warps ==========================================
+  const bool new_proto = a.is_new_protocol != 0;
+  const bool inverted = a.inverted != 0;
+  unsigned long long* gscratch = ws.group + (size_t)blockIdx.x * ws.max_nodes;
+  uint2* gpending = ws.pending + (size_t)blockIdx.x * ws.max_nodes;
+  const uint64_t pol_stream = l2_policy_evict_first();
+  const uint32_t q_shift = new_proto ? 16u : 18u, q_mask = new_proto ? 0xFFu : 0x3Fu;
+  uint32_t g = 0;  // chunks consumed so far
+
+  // hand a ring slot back to the producer.  `dep` is derived from the values just loaded from
+  // the slot, so the arrive cannot issue before those loads have returned.
+  auto release = [&](uint32_t stage, uint32_t dep) {
+    __syncwarp();
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0]; // %1" ::"r"(smem_u32(&sm.empty[stage])), "r"(dep)
+                   : "memory");
+  };
+  auto drain = [&](uint32_t nch) {  // consume chunks without looking at them
+    for (uint32_t c = 0; c < nch; ++c, ++g) {
+      const uint32_t stage = g % kStages;
+      mbar_wait(&sm.full[stage], (g / kStages) & 1u);
+      release(stage, 0u);
+    }
+  };
+
+  for (uint32_t s = blockIdx.x; s < a.n_scans; s += gridDim.x) {
+    const uint32_t n = a.counts[s];
+
+    if (n > a.stride || n > ws.max_nodes) {  // caller error: report, touch nothing
+      if (tid == 0) {
+        if (a.status) a.status[s] = 0x80008000u;  // SL_RESULT_INVALID_DATA
+        if (a.path) a.path[s] = 0u;
+        if (a.beam_counts) a.beam_counts[s] = 0u;
+        if (a.angle_inc) a.angle_inc[s] = 0.0f;
+      }
+      continue;
+    }
+    if (n > kMaxFastNodes) {  // cannot be tie-free: general kernel
+      if (tid == 0) a.fallback_list[atomicAdd(a.fallback_count, 1u)] = s;
+      continue;
+    }
+    if (n == 0) {  // ascendScanData: OPERATION_FAIL; publish_scan: nodes.empty() -> return
+      if (tid == 0) {
+        if (a.status) a.status[s] = a.apply_ascend ? kResultOperationFail : kResultOk;
+        if (a.path) a.path[s] = 0u;
+        if (a.beam_counts) a.beam_counts[s] = 0u;
+        if (a.angle_inc) a.angle_inc[s] = 0.0f;
+      }
+      continue;
+    }
+    const uint32_t nch = (n + CH - 1) / CH;
+
+    // ---- phase 0: clear the presence map ------------------------------------------------
+    {
+      uint4* bm = reinterpret_cast<uint4*>(sm.bytemap);
+      const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (uint32_t j = 0; j < kKeySpace / 16 / TC; ++j) bm[j * TC + tid] = z;
+      if (tid == 0) {
+        sm.pending = 0;
+        sm.fallback = 0;
+      }
+    }
+    consumer_sync();
+
+    // ---- phase 1 (mark): one byte store per measured key ---------------------------------
+    uint32_t cnt = 0;
+    uint8_t* const bmap = sm.bytemap;
+    for (uint32_t c = 0; c < nch; ++c, ++g) {
+      const uint32_t stage = g % kStages;
+      mbar_wait(&sm.full[stage], (g / kStages) & 1u);
+      const uint2* slot = sm.ring[stage];
+      uint2 v[kRounds];
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) v[r] = slot[r * TC + tid];
+      uint32_t dep = 0;
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) dep |= v[r].x;
+      release(stage, dep);  // the chunk lives in registers now
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        const uint32_t i = c * CH + r * TC + tid;
+        const uint32_t valid = (i < n && __funnelshift_r(v[r].x, v[r].y, 16) != 0) ? 1u : 0u;
+        bmap[valid ? swz_x(v[r].x) : kDummySlot] = 1;
+        cnt += valid;
+      }
+    }
+    cnt = warp_sum(cnt);
+    if (lane == 0) sm.red[warp] = cnt;
+    consumer_sync();
+
+    // ---- fold: byte map -> bitmap + exclusive popcount prefix ------------------------------
+    {
+      uint32_t wv[4] = {0, 0, 0, 0};
+      const uint4* bm = reinterpret_cast<const uint4*>(sm.bytemap);
+#pragma unroll
+      for (uint32_t c = 0; c < 8; ++c) {
+        const uint4 q = bm[tid * 8 + (c ^ (tid & 7u))];  // physical column of logical chunk c
+        const uint32_t x[4] = {q.x, q.y, q.z, q.w};
+        uint32_t bv = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv |= gather4(x[j] & 0x01010101u) << (4 * j);
+        wv[c >> 1] |= bv << (16 * (c & 1));
+      }
+      uint32_t sv = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sv += __popc(wv[j]);
+      const uint32_t iv = warp_inclusive_scan(sv);
+      if (lane == 31) sm.red[2 * kCWarps + warp] = iv;
+      consumer_sync();
+      if (warp == 0) {
+        uint32_t tv = lane < kCWarps ? sm.red[2 * kCWarps + lane] : 0u;
+        uint32_t cc = lane < kCWarps ? sm.red[lane] : 0u;
+        const uint32_t cv = warp_inclusive_scan(tv);
+        cc = warp_sum(cc);
+        if (lane < kCWarps) sm.red[2 * kCWarps + lane] = cv - tv;
+        if (lane == 31) {
+          sm.totV = cv;
+          sm.valid_count = cc;
+        }
+      }
+      consumer_sync();
+      uint32_t pv = sm.red[2 * kCWarps + warp] + iv - sv;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sm.rankV[tid * 4 + j] = make_uint2(wv[j], pv);
+        pv += __popc(wv[j]);
+      }
+    }
+    consumer_sync();
+    const uint32_t M = sm.valid_count;
+
+    if (M == 0) {
+      // ascendScanData: OPERATION_FAIL, buffer untouched; publish_scan: nothing to publish
+      if (tid == 0) {
+        if (a.status) a.status[s] = a.apply_ascend ? kResultOperationFail : kResultOk;
+        if (a.path) a.path[s] = 0u;
+        if (a.beam_counts) a.beam_counts[s] = 0u;
+        if (a.angle_inc) a.angle_inc[s] = 0.0f;
+      }
+      drain(nch);
+      consumer_sync();
+      continue;
+    }
+    // duplicate keys (fewer distinct keys than measured nodes) -> general kernel (stable rule)
+    if (sm.totV != M) {
+      if (tid == 0) a.fallback_list[atomicAdd(a.fallback_count, 1u)] = s;
+      drain(nch);
+      consumer_sync();
+      continue;
+    }
+
+    // ---- phase 2 (place): rank and place --------------------------------------------------
+    float* ranges = a.ranges + (size_t)s * a.stride;
+    float* intens = a.intensities + (size_t)s * a.stride;
+    const float inc = angle_increment(M, MODE_A);
+    const bool has0 = (sm.rankV[0].x & 1u) != 0;
+    // Mode B output slot = ob + os * rank (reference rplidar_node.cpp:673)
+    const int ob = inverted ? (int)M - 1 : 0, os = inverted ? -1 : 1;
+
+    ModeACtx mc;
+    mc.rankV = sm.rankV;
+    mc.ranges = ranges;
+    mc.intens = intens;
+    mc.gscratch = gscratch;
+    mc.pending = gpending;
+    mc.pending_count = &sm.pending;
+    mc.pending_cap = ws.max_nodes;
+    mc.fallback = &sm.fallback;
+    mc.M = M;
+    mc.inc = inc;
+    mc.inverted = inverted;
+    mc.has0 = has0;
+    mc.new_proto = new_proto;
+
+    for (uint32_t c = 0; c < nch; ++c, ++g) {
+      const uint32_t stage = g % kStages;
+      mbar_wait(&sm.full[stage], (g / kStages) & 1u);
+      const uint2* slot = sm.ring[stage];
+      uint2 v[kRounds];
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) v[r] = slot[r * TC + tid];
+      uint32_t dep = 0;
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) dep |= v[r].x;
+      release(stage, dep);
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        const uint2 nd = v[r];
+        const uint32_t i = c * CH + r * TC + tid;
+        const uint32_t k = nd.x & 0xFFFFu;
+        const uint32_t dist = __funnelshift_r(nd.x, nd.y, 16);
+        const uint32_t measured = (i < n && dist != 0) ? 1u : 0u;
+        const uint32_t rk = rank_of(sm.rankV, k);
+        const float dm = dist_to_m(dist);
+        if (!MODE_A) {  // Mode B: reference rplidar_node.cpp:661-677
+          const int o = ob + os * (int)rk;
+          const float it =
+              __fsub_rn(__uint_as_float(((nd.y >> q_shift) & q_mask) | 0x4B000000u), 8388608.0f);
+          st_f32_if(ranges + o, dm, pol_stream, measured);
+          st_f32_if(intens + o, it, pol_stream, measured);
+        } else if (measured) {
+          mode_a_place(mc, k, rk, dm, (nd.y >> 16) & 0xFFu);
+        }
+      }
+    }
+    consumer_sync();
+
+    // ---- phase 3 (Mode A): resolve bins that hold several points --------------------------
+    if (MODE_A) {
+      const uint32_t np = min(sm.pending, ws.max_nodes);
+      for (uint32_t e = tid; e < np; e += TC) {
+        const uint2 h = gpending[e];
+        unsigned long long best = ~0ull;
+        for (uint32_t slot = h.x; slot < M; ++slot) {
+          const unsigned long long gq = gscratch[slot];
+          best = min(best, gq);
+          if (gq & 1ull) break;
+        }
+        ranges[h.y] = __uint_as_float((uint32_t)(best >> 32));
+        intens[h.y] = quality_to_intensity((uint32_t)(best >> 8) & 0xFFu, new_proto);
+      }
+    }
+    if (tid == 0) {
+      if (sm.fallback) {
+        a.fallback_list[atomicAdd(a.fallback_count, 1u)] = s;
+      } else {
+        if (a.status) a.status[s] = kResultOk;
+        if (a.path) a.path[s] = 0u;
+        if (a.beam_counts) a.beam_counts[s] = M;
+        if (a.angle_inc) a.angle_inc[s] = inc;
+      }
+    }
+    consumer_sync();
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_scan_tma(const ScanBatchArgs& a, const FastWorkspace& ws, int grid, cudaStream_t stream) {
+  if (a.mode_a) scan_tma_kernel<true><<<grid, kBlock, sizeof(TmaSmem), stream>>>(a, ws);
+  else scan_tma_kernel<false><<<grid, kBlock, sizeof(TmaSmem), stream>>>(a, ws);
+  return cudaGetLastError();
+}
+
+cudaError_t scan_tma_configure() {
+  cudaError_t e = cudaFuncSetAttribute(scan_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(TmaSmem));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(scan_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)sizeof(TmaSmem));
+}
+
+int scan_tma_max_ctas_per_sm() {
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, scan_tma_kernel<false>, kBlock, sizeof(TmaSmem));
+  return nb;
+}
+
+}  // namespace rpl

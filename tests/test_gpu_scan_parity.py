@@ -58,7 +58,7 @@ def check_batch(R, O, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=0, st
 
 
 # ---- config 1: A1 single scan, golden vectors from the compiled reference ------------------
-@pytest.mark.parametrize("flags", [0, 1])
+@pytest.mark.parametrize("flags", [0, 1, 2])
 def test_a1_golden_laserscan_bit_exact(R, oracle, ctx, golden_dir, flags):
     g = np.load(f"{golden_dir}/laserscan_golden.npz")
     d = np.load(f"{golden_dir}/dummy_scans.npz")
@@ -86,13 +86,13 @@ def test_a1_all_sixteen_dummy_scans(R, oracle, ctx, golden_dir):
         check_batch(R, oracle, ctx, raw, counts, newp, mode_a, inv, 1, expect_path=0)
 
 
-@pytest.mark.parametrize("flags", [0, 1])
+@pytest.mark.parametrize("flags", [0, 1, 2])
 def test_ascend_edge_cases_golden(R, oracle, ctx, golden_dir, flags):
     g = np.load(f"{golden_dir}/ascend_cases.npz")
     for i in range(int(g["n_cases"])):
         inp = _nodes(g[f"in_{i}"], oracle)
         if flags == 0:
-            rc, out = ctx.ascend_scan(inp.view(R.NODE_DTYPE))
+            rc, out = ctx.ascend_scan(inp.view(R.NODE_DTYPE))  # TMA kernel when aligned
         else:
             r = ctx.scan(inp.view(R.NODE_DTYPE), R.scan_params(0, 0, 0, 1, flags))
             rc, out = r["ascend_status"], r["nodes"]
@@ -116,7 +116,9 @@ def test_tie_free_synthetic_both_kernels(R, oracle, ctx, n, variant):
     for newp, mode_a, inv in modes:
         for ascend in (0, 1):
             # tie-free measured keys: the reference's std::sort and the stable rule coincide
+            # flags 0: TMA-ring kernel, 2: register-streamed kernel, 1: general radix kernel
             check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=0, stable=True)
+            check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=2, stable=True)
             check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=1, stable=True,
                         expect_path=1)
 
@@ -128,6 +130,7 @@ def test_tie_variant_follows_stable_rule(R, oracle, ctx, n):
     for newp, mode_a, inv in [(0, 0, 0), (0, 1, 0), (1, 1, 1), (1, 0, 1)]:
         for ascend in (0, 1):
             check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, stable=True)
+            check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=2, stable=True)
     # the reference itself (unstable sort) agrees wherever order is defined: Mode A ranges
     exp = oracle_batch(oracle, nodes, counts, 0, 1, 0, 1, stable=False)
     got = ctx.scan_batch(nodes.view(R.NODE_DTYPE), counts, R.scan_params(0, 1, 0, 1))
@@ -154,6 +157,7 @@ def test_mixed_batch_ragged_counts_and_paths(R, oracle, ctx):
     for newp, mode_a, inv in ALL_MODES:
         for ascend in (0, 1):
             got = check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend)
+            check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=2)
     assert got["status"][3] == R.RESULT_OPERATION_FAIL and got["beam_counts"][3] == 0
     assert got["path"][8] == R.PATH_GENERAL
 
@@ -176,6 +180,7 @@ def test_extreme_values(R, oracle, ctx):
     counts = np.array([n, 1000], np.uint32)
     for newp, mode_a, inv in ALL_MODES:
         check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, 1)
+        check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, 1, flags=2)
         check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, 0, flags=1)
     big = oracle.synth_batch(1, 1, 70000, 0)
     check_batch(R, oracle, ctx, big, np.array([70000], np.uint32), 0, 1, 0, 1, expect_path=1)
@@ -261,3 +266,14 @@ def test_full_size_batch_properties(R, oracle):
         assert (ranges[s, :m].cpu().numpy().view(np.uint32) == exp["ranges"][0, :m].view(np.uint32)).all()
         assert bits(inc[s:s + 1].cpu().numpy())[0] == bits(exp["angle_increment"])[0]
     ctx.close()
+
+
+def test_odd_stride_takes_unaligned_path(R, oracle, ctx):
+    """An odd stride puts every second scan on an 8-byte (not 16-byte) boundary: the library must
+    fall back from the TMA kernel to the register-streamed kernel, with identical results."""
+    stride, n = 1001, 997
+    nodes = np.zeros((6, stride), oracle.NODE_DTYPE)
+    nodes[:, :n] = oracle.synth_batch(321, 6, n, 1)
+    counts = np.full(6, n, np.uint32)
+    for newp, mode_a, inv in ALL_MODES:
+        check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, 1, expect_path=0)
