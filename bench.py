@@ -317,10 +317,11 @@ def run_b200(args, rank, local_rank, world):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(f"scan_fast_kernel.mode_{args.mode}")
+            traffic = json.load(f).get(f"scan_tma_kernel.mode_{args.mode}")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "scan_fast_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "scan_tma_kernel<Mode %s> (TMA-ring fast kernel, scan_tma.cu)" % args.mode.upper(),
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": fast_ms,
                 "kernel_share_of_step": prof[0] / ms if ms > 0 else None,

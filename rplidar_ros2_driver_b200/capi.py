@@ -14,7 +14,8 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librplidar_b200.so")
+# RPL_B200_LIB: alternative build of the same library (tuning experiments only)
+LIB_PATH = os.environ.get("RPL_B200_LIB") or os.path.join(HERE, "librplidar_b200.so")
 
 RESULT_OK = 0
 RESULT_INVALID_DATA = 0x80008000

@@ -134,16 +134,17 @@ __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v) {
 // asks L2 to keep the lines (evict_last), the second read and all output stores mark their
 // lines evict_first so that the 1 GB/launch output stream does not push tiles out of the
 // 126 MB L2 before their second read.
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
+// The policies are the fixed encodings createpolicy.fractional.L2::evict_{last,first} (1.0)
+// produces (the same constants CUTLASS passes as TMA cache hints); as immediates they live in
+// uniform registers instead of being re-broadcast from a per-thread register at every access.
+#ifndef RPL_POLICY_KEEP
+#define RPL_POLICY_KEEP 0x14F0000000000000ull   /* evict_last */
+#endif
+#ifndef RPL_POLICY_STREAM
+#define RPL_POLICY_STREAM 0x12F0000000000000ull /* evict_first */
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_last() { return RPL_POLICY_KEEP; }
+__device__ __forceinline__ uint64_t l2_policy_evict_first() { return RPL_POLICY_STREAM; }
 __device__ __forceinline__ uint4 ld_hint_v4(const void* p, uint64_t pol) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"

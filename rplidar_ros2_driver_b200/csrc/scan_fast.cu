@@ -315,8 +315,10 @@ __global__ void __launch_bounds__(T, 2) scan_fast_kernel(ScanBatchArgs a, FastWo
     const float inc = angle_increment(M, MODE_A);
     const bool has0 = (sm.rankV[0].x & 1u) != 0;
     uint2* pending = reinterpret_cast<uint2*>(sm.bytemap);  // presence map is dead now
-    // Mode B output slot = ob + os * rank (reference rplidar_node.cpp:673)
-    const int ob = inverted ? (int)M - 1 : 0, os = inverted ? -1 : 1;
+    // Mode B output slot = ob + os * rank in wrapping u32 arithmetic (reference
+    // rplidar_node.cpp:673); intensities[] sits at a fixed byte distance from ranges[]
+    const uint32_t ob = inverted ? M - 1u : 0u, os = inverted ? 0xFFFFFFFFu : 1u;
+    const ptrdiff_t i_minus_r = reinterpret_cast<char*>(intens) - reinterpret_cast<char*>(ranges);
 
     ModeACtx mc;
     mc.rankV = sm.rankV;
@@ -345,10 +347,11 @@ __global__ void __launch_bounds__(T, 2) scan_fast_kernel(ScanBatchArgs a, FastWo
       const uint32_t r = rank_of(sm.rankV, k);
       const float dm = dist_to_m(dist);
       if (!MODE_A) {  // Mode B: reference rplidar_node.cpp:661-677
-        const int o = ob + os * (int)r;
+        const uint32_t o = ob + os * r;
         const float it = __fsub_rn(__uint_as_float(((nd.y >> q_shift) & q_mask) | 0x4B000000u), 8388608.0f);
-        st_f32_if(ranges + o, dm, pol_stream, measured);
-        st_f32_if(intens + o, it, pol_stream, measured);
+        float* pr = ranges + o;
+        st_f32_if(pr, dm, pol_stream, measured);
+        st_f32_if(reinterpret_cast<float*>(reinterpret_cast<char*>(pr) + i_minus_r), it, pol_stream, measured);
       } else if (measured) {
         mode_a_place(mc, k, r, dm, (nd.y >> 16) & 0xFFu);
       }

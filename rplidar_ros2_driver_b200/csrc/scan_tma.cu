@@ -29,18 +29,33 @@ namespace rpl {
 
 namespace {
 
-constexpr int TC = 512;                // consumer threads (16 warps)
+#ifndef RPL_TMA_TC
+#define RPL_TMA_TC 512
+#endif
+#ifndef RPL_TMA_CTAS
+#define RPL_TMA_CTAS 2
+#endif
+constexpr int TC = RPL_TMA_TC;         // consumer threads (512 or 1024)
+constexpr int kCtasPerSm = RPL_TMA_CTAS;
 constexpr int kCWarps = TC / 32;
+constexpr uint32_t kRowBytes = kKeySpace / TC;   // byte-map bytes folded by one thread
+constexpr uint32_t kCols = kRowBytes / 16;       // 16-byte columns per row
+constexpr uint32_t kWordsPerThread = kWords / TC;
+static_assert(TC == 512 || TC == 1024, "fold layout is written for 512 or 1024 consumer threads");
 constexpr int kBlock = TC + 32;        // + one producer warp
-constexpr uint32_t CH = 1024;          // nodes per chunk (8 KB)
-constexpr int kStages = 4;             // ring depth (32 KB)
-constexpr uint32_t kDummySlot = kKeySpace;  // where unmeasured nodes "mark"
+#ifndef RPL_TMA_CH
+#define RPL_TMA_CH 1024
+#endif
+#ifndef RPL_TMA_STAGES
+#define RPL_TMA_STAGES 4
+#endif
+constexpr uint32_t CH = RPL_TMA_CH;          // nodes per chunk (8 bytes each)
+constexpr int kStages = RPL_TMA_STAGES;      // ring depth; CH * kStages * 8 = 32 KB
 constexpr int kRounds = CH / TC;       // nodes per consumer thread per chunk
 
 struct __align__(128) TmaSmem {
-  uint2 ring[kStages][CH];
   uint8_t bytemap[kKeySpace];                // presence map (swizzled)
-  uint8_t dummy[16];
+  uint2 ring[kStages][CH];
   uint2 rankV[kWords];                       // {bits, exclusive prefix} over measured keys
   unsigned long long full[kStages];
   unsigned long long empty[kStages];
@@ -51,7 +66,12 @@ struct __align__(128) TmaSmem {
   uint32_t fallback;
 };
 
-__device__ __forceinline__ uint32_t swz_x(uint32_t x) { return (x ^ ((x >> 3) & 0x70u)) & 0xFFFFu; }
+// byte-map swizzle: within the row a thread folds, the 16-byte column is XORed with row bits so
+// that the 128-bit reads of 8 neighbouring threads hit 8 different bank groups
+__device__ __forceinline__ uint32_t swz_x(uint32_t x) {
+  if (TC == 512) return (x ^ ((x >> 3) & 0x70u)) & 0xFFFFu;  // 128-byte rows: column ^= row & 7
+  return (x ^ ((x >> 3) & 0x30u)) & 0xFFFFu;                 // 64-byte rows: column ^= (row >> 1) & 3
+}
 __device__ __forceinline__ uint32_t gather4(uint32_t x) { return (x * 0x10204080u) >> 28; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -97,7 +117,7 @@ __device__ __forceinline__ bool scan_is_streamed(uint32_t n, uint32_t stride, ui
 }
 
 template <bool MODE_A>
-__global__ void __launch_bounds__(kBlock, 2) scan_tma_kernel(ScanBatchArgs a, FastWorkspace ws) {
+__global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchArgs a, FastWorkspace ws) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TmaSmem& sm = *reinterpret_cast<TmaSmem*>(smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -117,16 +137,15 @@ __global__ void __launch_bounds__(kBlock, 2) scan_tma_kernel(ScanBatchArgs a, Fa
     if (lane == 0) {
       const uint64_t pol_keep = l2_policy_evict_last();
       const uint64_t pol_stream = l2_policy_evict_first();
-      uint32_t g = 0;  // chunks issued so far
+      uint32_t stage = 0, parity = 1;  // empty-barrier parity: first round passes at once
       for (uint32_t s = blockIdx.x; s < a.n_scans; s += gridDim.x) {
         const uint32_t n = a.counts[s];
         if (!scan_is_streamed(n, a.stride, ws.max_nodes)) continue;
         const uint2* base = a.nodes + (size_t)s * a.stride;
         const uint32_t nch = (n + CH - 1) / CH;
         for (int pass = 0; pass < 2; ++pass) {
-          for (uint32_t c = 0; c < nch; ++c, ++g) {
-            const uint32_t stage = g % kStages, round = g / kStages;
-            mbar_wait(&sm.empty[stage], (round & 1u) ^ 1u);
+          for (uint32_t c = 0; c < nch; ++c) {
+            mbar_wait(&sm.empty[stage], parity);
             // an odd tail is rounded up to a whole 16 bytes; the extra node lies inside the
             // scan's stride (even stride, n odd => n + 1 <= stride) and is masked by consumers
             const uint32_t cn = min(CH, n - c * CH);
@@ -134,6 +153,10 @@ __global__ void __launch_bounds__(kBlock, 2) scan_tma_kernel(ScanBatchArgs a, Fa
             mbar_expect_tx(&sm.full[stage], bytes);
             tma_load_1d(&sm.ring[stage][0], base + (size_t)c * CH, bytes, &sm.full[stage],
                         pass == 0 ? pol_keep : pol_stream);
+            if (++stage == kStages) {
+              stage = 0;
+              parity ^= 1u;
+            }
           }
         }
       }
@@ -148,21 +171,28 @@ __global__ void __launch_bounds__(kBlock, 2) scan_tma_kernel(ScanBatchArgs a, Fa
   uint2* gpending = ws.pending + (size_t)blockIdx.x * ws.max_nodes;
   const uint64_t pol_stream = l2_policy_evict_first();
   const uint32_t q_shift = new_proto ? 16u : 18u, q_mask = new_proto ? 0xFFu : 0x3Fu;
-  uint32_t g = 0;  // chunks consumed so far
+  uint32_t stage = 0, parity = 0;  // ring position of the next chunk to consume
+  using Checked = std::integral_constant<bool, true>;
+  using Unchecked = std::integral_constant<bool, false>;
+  auto advance = [&]() {
+    if (++stage == kStages) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  };
 
-  // hand a ring slot back to the producer.  `dep` is derived from the values just loaded from
-  // the slot, so the arrive cannot issue before those loads have returned.
-  auto release = [&](uint32_t stage, uint32_t dep) {
+  // hand the current ring slot back to the producer.  Called after the memory operations
+  // (byte-map / output stores) whose addresses depend on the values loaded from the slot, so
+  // the arrive cannot issue before those loads have returned.
+  auto release = [&]() {
     __syncwarp();
-    if (lane == 0)
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0]; // %1" ::"r"(smem_u32(&sm.empty[stage])), "r"(dep)
-                   : "memory");
+    if (lane == 0) mbar_arrive(&sm.empty[stage]);
   };
   auto drain = [&](uint32_t nch) {  // consume chunks without looking at them
-    for (uint32_t c = 0; c < nch; ++c, ++g) {
-      const uint32_t stage = g % kStages;
-      mbar_wait(&sm.full[stage], (g / kStages) & 1u);
-      release(stage, 0u);
+    for (uint32_t c = 0; c < nch; ++c) {
+      mbar_wait(&sm.full[stage], parity);
+      release();
+      advance();
     }
   };
 
@@ -209,36 +239,40 @@ __global__ void __launch_bounds__(kBlock, 2) scan_tma_kernel(ScanBatchArgs a, Fa
     // ---- phase 1 (mark): one byte store per measured key ---------------------------------
     uint32_t cnt = 0;
     uint8_t* const bmap = sm.bytemap;
-    for (uint32_t c = 0; c < nch; ++c, ++g) {
-      const uint32_t stage = g % kStages;
-      mbar_wait(&sm.full[stage], (g / kStages) & 1u);
+    auto mark_chunk = [&](auto checked, uint32_t c) {
+      mbar_wait(&sm.full[stage], parity);
       const uint2* slot = sm.ring[stage];
       uint2 v[kRounds];
 #pragma unroll
       for (int r = 0; r < kRounds; ++r) v[r] = slot[r * TC + tid];
-      uint32_t dep = 0;
-#pragma unroll
-      for (int r = 0; r < kRounds; ++r) dep |= v[r].x;
-      release(stage, dep);  // the chunk lives in registers now
 #pragma unroll
       for (int r = 0; r < kRounds; ++r) {
-        const uint32_t i = c * CH + r * TC + tid;
-        const uint32_t valid = (i < n && __funnelshift_r(v[r].x, v[r].y, 16) != 0) ? 1u : 0u;
-        bmap[valid ? swz_x(v[r].x) : kDummySlot] = 1;
-        cnt += valid;
+        bool valid = __funnelshift_r(v[r].x, v[r].y, 16) != 0;
+        if (decltype(checked)::value && c * CH + r * TC + tid >= n) valid = false;
+        if (valid) bmap[swz_x(v[r].x)] = 1;
+        cnt += valid ? 1u : 0u;
       }
-    }
+      release();
+      advance();
+    };
+    const uint32_t nfull = n / CH;
+    for (uint32_t c = 0; c < nfull; ++c) mark_chunk(Unchecked{}, c);
+    if (nfull < nch) mark_chunk(Checked{}, nfull);
     cnt = warp_sum(cnt);
     if (lane == 0) sm.red[warp] = cnt;
     consumer_sync();
 
     // ---- fold: byte map -> bitmap + exclusive popcount prefix ------------------------------
     {
-      uint32_t wv[4] = {0, 0, 0, 0};
-      const uint4* bm = reinterpret_cast<const uint4*>(sm.bytemap);
+      // thread t owns keys [kRowBytes t, kRowBytes (t+1)) = kWordsPerThread bitmap words
+      uint32_t wv[kWordsPerThread];
 #pragma unroll
-      for (uint32_t c = 0; c < 8; ++c) {
-        const uint4 q = bm[tid * 8 + (c ^ (tid & 7u))];  // physical column of logical chunk c
+      for (uint32_t j = 0; j < kWordsPerThread; ++j) wv[j] = 0;
+      const uint4* bm = reinterpret_cast<const uint4*>(sm.bytemap);
+      const uint32_t colx = (TC == 512) ? (tid & 7u) : ((tid >> 1) & 3u);
+#pragma unroll
+      for (uint32_t c = 0; c < kCols; ++c) {
+        const uint4 q = bm[tid * kCols + (c ^ colx)];  // physical column of logical chunk c
         const uint32_t x[4] = {q.x, q.y, q.z, q.w};
         uint32_t bv = 0;
 #pragma unroll
@@ -247,7 +281,7 @@ __global__ void __launch_bounds__(kBlock, 2) scan_tma_kernel(ScanBatchArgs a, Fa
       }
       uint32_t sv = 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) sv += __popc(wv[j]);
+      for (uint32_t j = 0; j < kWordsPerThread; ++j) sv += __popc(wv[j]);
       const uint32_t iv = warp_inclusive_scan(sv);
       if (lane == 31) sm.red[2 * kCWarps + warp] = iv;
       consumer_sync();
@@ -265,8 +299,8 @@ __global__ void __launch_bounds__(kBlock, 2) scan_tma_kernel(ScanBatchArgs a, Fa
       consumer_sync();
       uint32_t pv = sm.red[2 * kCWarps + warp] + iv - sv;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        sm.rankV[tid * 4 + j] = make_uint2(wv[j], pv);
+      for (uint32_t j = 0; j < kWordsPerThread; ++j) {
+        sm.rankV[tid * kWordsPerThread + j] = make_uint2(wv[j], pv);
         pv += __popc(wv[j]);
       }
     }
@@ -298,8 +332,10 @@ __global__ void __launch_bounds__(kBlock, 2) scan_tma_kernel(ScanBatchArgs a, Fa
     float* intens = a.intensities + (size_t)s * a.stride;
     const float inc = angle_increment(M, MODE_A);
     const bool has0 = (sm.rankV[0].x & 1u) != 0;
-    // Mode B output slot = ob + os * rank (reference rplidar_node.cpp:673)
-    const int ob = inverted ? (int)M - 1 : 0, os = inverted ? -1 : 1;
+    // Mode B output slot = ob + os * rank in wrapping u32 arithmetic (reference
+    // rplidar_node.cpp:673); intensities[] sits at a fixed byte distance from ranges[]
+    const uint32_t ob = inverted ? M - 1u : 0u, os = inverted ? 0xFFFFFFFFu : 1u;
+    const ptrdiff_t i_minus_r = reinterpret_cast<char*>(intens) - reinterpret_cast<char*>(ranges);
 
     ModeACtx mc;
     mc.rankV = sm.rankV;
@@ -316,37 +352,37 @@ __global__ void __launch_bounds__(kBlock, 2) scan_tma_kernel(ScanBatchArgs a, Fa
     mc.has0 = has0;
     mc.new_proto = new_proto;
 
-    for (uint32_t c = 0; c < nch; ++c, ++g) {
-      const uint32_t stage = g % kStages;
-      mbar_wait(&sm.full[stage], (g / kStages) & 1u);
+    auto place_chunk = [&](auto checked, uint32_t c) {
+      mbar_wait(&sm.full[stage], parity);
       const uint2* slot = sm.ring[stage];
       uint2 v[kRounds];
 #pragma unroll
       for (int r = 0; r < kRounds; ++r) v[r] = slot[r * TC + tid];
-      uint32_t dep = 0;
-#pragma unroll
-      for (int r = 0; r < kRounds; ++r) dep |= v[r].x;
-      release(stage, dep);
 #pragma unroll
       for (int r = 0; r < kRounds; ++r) {
         const uint2 nd = v[r];
-        const uint32_t i = c * CH + r * TC + tid;
         const uint32_t k = nd.x & 0xFFFFu;
         const uint32_t dist = __funnelshift_r(nd.x, nd.y, 16);
-        const uint32_t measured = (i < n && dist != 0) ? 1u : 0u;
+        uint32_t measured = dist != 0 ? 1u : 0u;
+        if (decltype(checked)::value && c * CH + r * TC + tid >= n) measured = 0;
         const uint32_t rk = rank_of(sm.rankV, k);
         const float dm = dist_to_m(dist);
         if (!MODE_A) {  // Mode B: reference rplidar_node.cpp:661-677
-          const int o = ob + os * (int)rk;
+          const uint32_t o = ob + os * rk;
           const float it =
               __fsub_rn(__uint_as_float(((nd.y >> q_shift) & q_mask) | 0x4B000000u), 8388608.0f);
-          st_f32_if(ranges + o, dm, pol_stream, measured);
-          st_f32_if(intens + o, it, pol_stream, measured);
+          float* pr = ranges + o;
+          st_f32_if(pr, dm, pol_stream, measured);
+          st_f32_if(reinterpret_cast<float*>(reinterpret_cast<char*>(pr) + i_minus_r), it, pol_stream, measured);
         } else if (measured) {
           mode_a_place(mc, k, rk, dm, (nd.y >> 16) & 0xFFu);
         }
       }
-    }
+      release();
+      advance();
+    };
+    for (uint32_t c = 0; c < nfull; ++c) place_chunk(Unchecked{}, c);
+    if (nfull < nch) place_chunk(Checked{}, nfull);
     consumer_sync();
 
     // ---- phase 3 (Mode A): resolve bins that hold several points --------------------------
