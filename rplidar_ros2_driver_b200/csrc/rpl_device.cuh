@@ -101,6 +101,23 @@ __device__ __forceinline__ int mode_a_bin(uint32_t key, float inc, bool inverted
   return __float2int_rz(__fdiv_rn(__fsub_rn(a, 0.0f), inc));
 }
 
+// Mode A bin without floating point for most keys.  The reference's float chain computes
+// (k * 2pi/65536) / (2pi/M) with three float roundings (angle_rad, angle_increment, the
+// quotient; the double-precision steps add < 1e-14): relative error <= 3 * 2^-24, i.e. at
+// most 0.012 bins over the whole range (0.016 for inverted scans, where 2pi - angle adds an
+// absolute 2^-24 * 2pi).  So whenever the exact ratio k*M/65536 (resp. (65536-k)*M/65536) has
+// a fractional part in [1/32, 31/32], truncation of the float result equals the integer
+// quotient; only the ~6% of keys closer than 1/32 to a bin edge, and key 0 of inverted scans
+// (the reference wraps it to 1.7e-7), take the exact chain.  tests/test_device_math_proofs.py
+// checks the claim against the float chain for every key over thousands of beam counts.
+__device__ __forceinline__ int mode_a_bin_fast(uint32_t key, uint32_t m, float inc, bool inverted) {
+  const uint32_t kk = inverted ? (65536u - key) : key;
+  const uint32_t t = kk * m;  // < 2^32: kk <= 65535 on this branch, m <= 65536
+  const uint32_t frac = t & 0xFFFFu;
+  if ((!inverted || key != 0u) && (frac - 2048u) <= (63488u - 2048u)) return (int)(t >> 16);
+  return mode_a_bin(key, inc, inverted);
+}
+
 // ---- counter-based splitmix64 (same definition as oracle/scan_oracle.cpp) --------------
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   uint64_t z = x + 0x9E3779B97F4A7C15ull;

@@ -8,7 +8,6 @@ namespace rpl {
 namespace {
 
 constexpr uint32_t kWords = kKeySpace / 32;     // 2048 bitmap words
-constexpr uint32_t kPendingCap = 8192;          // Mode A collision-group heads kept on chip
 constexpr uint32_t kMaxFastNodes = kKeySpace;   // more nodes cannot be tie-free
 
 __device__ __forceinline__ uint32_t rank_of(const uint2* rk, uint32_t key) {
@@ -50,23 +49,24 @@ __device__ __forceinline__ void st_f32_if(float* p, float v, uint64_t pol, uint3
 // keys), so the points of a bin are neighbours in that order and the presence bitmap alone
 // tells a point whether it is the first (head) / last (tail) of its bin and which empty bins
 // lie before it.  Single-point bins are written directly; shared bins go through a small
-// per-CTA scratch and are resolved by their head after the pass.
+// per-CTA scratch and are resolved after the pass by the warp that saw their head (every warp
+// keeps its own head list and count: no shared counter, no atomics).
 struct ModeACtx {
   const uint2* rankV;
   float* ranges;
   float* intens;
   unsigned long long* gscratch;
-  uint2* pending;
-  uint32_t* pending_count;
-  uint32_t pending_cap;
   uint32_t* fallback;
   uint32_t M;
   float inc;
   bool inverted, has0, new_proto;
 };
 
-__device__ __noinline__ void mode_a_place(const ModeACtx& c, uint32_t k, uint32_t r, float dm,
-                                          uint32_t q) {
+// Returns 0 for nothing left to do, 1 when this point is alone in bin b_out (the caller stores
+// it with one converged, coalesced warp store), 2 when it heads a bin shared by several
+// points ((ru_out, b_out) then name the group's first scratch slot and its bin).
+__device__ __forceinline__ uint32_t mode_a_place(const ModeACtx& c, uint32_t k, uint32_t r, float dm,
+                                                 uint32_t q, uint32_t& ru_out, uint32_t& b_out) {
   const uint32_t M = c.M;
   const float kInf = __int_as_float(0x7f800000);
   int pk, nk;
@@ -87,13 +87,13 @@ __device__ __noinline__ void mode_a_place(const ModeACtx& c, uint32_t k, uint32_
     if (nk == 0) nk = -1;  // key 0 comes first in the inverted order, never after
     ru = (M - 1 - r) + (c.has0 ? 1u : 0u);
   }
-  const int b = mode_a_bin(k, c.inc, c.inverted);
+  const int b = mode_a_bin_fast(k, M, c.inc, c.inverted);
   if (b < 0 || b >= (int)M) {  // never taken for u16 keys; the reference's guard, kept
     *c.fallback = 1;
-    return;
+    return 0u;
   }
-  const int bp = pk >= 0 ? mode_a_bin((uint32_t)pk, c.inc, c.inverted) : -1;
-  const int bn = nk >= 0 ? mode_a_bin((uint32_t)nk, c.inc, c.inverted) : (int)M;
+  const int bp = pk >= 0 ? mode_a_bin_fast((uint32_t)pk, M, c.inc, c.inverted) : -1;
+  const int bn = nk >= 0 ? mode_a_bin_fast((uint32_t)nk, M, c.inc, c.inverted) : (int)M;
   const bool head = bp != b, tail = bn != b;
   if (head)
     for (int e = bp + 1; e < b; ++e) {  // empty bins in front of this group
@@ -105,18 +105,42 @@ __device__ __noinline__ void mode_a_place(const ModeACtx& c, uint32_t k, uint32_
       c.ranges[e] = kInf;
       c.intens[e] = 0.0f;
     }
-  if (head && tail) {
-    c.ranges[b] = dm;
-    c.intens[b] = quality_to_intensity(q, c.new_proto);
-    return;
-  }
+  b_out = (uint32_t)b;
+  if (head && tail) return 1u;
   // several points share the bin: keep the smallest (dist_m, key)
   c.gscratch[ru] = ((unsigned long long)__float_as_uint(dm) << 32) | ((unsigned long long)k << 16) |
                    ((unsigned long long)q << 8) | (tail ? 1ull : 0ull);
-  if (head) {
-    const uint32_t slot = atomicAdd(c.pending_count, 1u);
-    if (slot < c.pending_cap) c.pending[slot] = make_uint2(ru, (uint32_t)b);
-    else *c.fallback = 1;
+  ru_out = ru;
+  return head ? 2u : 0u;
+}
+
+// warp-private list of shared-bin heads: converged call, one entry per lane with `is_head`
+__device__ __forceinline__ void mode_a_push_heads(uint2* wlist, uint32_t cap, uint32_t& wcount, bool is_head,
+                                                  uint32_t ru, uint32_t b, uint32_t* fallback) {
+  const uint32_t m = __ballot_sync(0xffffffffu, is_head);
+  if (m == 0) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  if (is_head) {
+    const uint32_t slot = wcount + __popc(m & ((1u << lane) - 1u));
+    if (slot < cap) wlist[slot] = make_uint2(ru, b);
+    else *fallback = 1;
+  }
+  wcount += __popc(m);
+}
+
+// resolver: the minimum (dist_m, key) of every listed group -> ranges / intensities
+__device__ __forceinline__ void mode_a_resolve(const ModeACtx& c, const uint2* wlist, uint32_t wcount) {
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t e = lane; e < wcount; e += 32) {
+    const uint2 h = wlist[e];
+    unsigned long long best = ~0ull;
+    for (uint32_t slot = h.x; slot < c.M; ++slot) {
+      const unsigned long long g = c.gscratch[slot];
+      best = min(best, g);
+      if (g & 1ull) break;
+    }
+    c.ranges[h.y] = __uint_as_float((uint32_t)(best >> 32));
+    c.intens[h.y] = quality_to_intensity((uint32_t)(best >> 8) & 0xFFu, c.new_proto);
   }
 }
 

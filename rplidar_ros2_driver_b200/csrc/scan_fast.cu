@@ -44,7 +44,6 @@ struct __align__(16) FastSmem {
   uint32_t front_key;
   uint32_t totV;
   uint32_t totA;
-  uint32_t pending;
   uint32_t fallback;
 };
 
@@ -100,7 +99,6 @@ __global__ void __launch_bounds__(T, 2) scan_fast_kernel(ScanBatchArgs a, FastWo
       if (EMIT)
         for (uint32_t w = tid; w < kKeySpace / 32; w += T) sm.vbits[w] = 0;
       if (tid == 0) {
-        sm.pending = 0;
         sm.fallback = 0;
       }
     }
@@ -314,7 +312,10 @@ __global__ void __launch_bounds__(T, 2) scan_fast_kernel(ScanBatchArgs a, FastWo
     uint2* nodes_out = EMIT ? a.nodes_out + (size_t)s * a.stride : nullptr;
     const float inc = angle_increment(M, MODE_A);
     const bool has0 = (sm.rankV[0].x & 1u) != 0;
-    uint2* pending = reinterpret_cast<uint2*>(sm.bytemap);  // presence map is dead now
+    // warp-private lists of Mode A shared-bin heads live in the (now dead) presence map
+    constexpr uint32_t wcap = kKeySpace / 8 / kWarps;
+    uint2* wlist = reinterpret_cast<uint2*>(sm.bytemap) + warp * wcap;
+    uint32_t wcount = 0;
     // Mode B output slot = ob + os * rank in wrapping u32 arithmetic (reference
     // rplidar_node.cpp:673); intensities[] sits at a fixed byte distance from ranges[]
     const uint32_t ob = inverted ? M - 1u : 0u, os = inverted ? 0xFFFFFFFFu : 1u;
@@ -325,9 +326,6 @@ __global__ void __launch_bounds__(T, 2) scan_fast_kernel(ScanBatchArgs a, FastWo
     mc.ranges = ranges;
     mc.intens = intens;
     mc.gscratch = gscratch;
-    mc.pending = pending;
-    mc.pending_count = &sm.pending;
-    mc.pending_cap = kPendingCap;
     mc.fallback = &sm.fallback;
     mc.M = M;
     mc.inc = inc;
@@ -352,8 +350,13 @@ __global__ void __launch_bounds__(T, 2) scan_fast_kernel(ScanBatchArgs a, FastWo
         float* pr = ranges + o;
         st_f32_if(pr, dm, pol_stream, measured);
         st_f32_if(reinterpret_cast<float*>(reinterpret_cast<char*>(pr) + i_minus_r), it, pol_stream, measured);
-      } else if (measured) {
-        mode_a_place(mc, k, r, dm, (nd.y >> 16) & 0xFFu);
+      } else {
+        uint32_t hru = 0, hb = 0, what = 0;
+        if (measured) what = mode_a_place(mc, k, r, dm, (nd.y >> 16) & 0xFFu, hru, hb);
+        const float it = __fsub_rn(__uint_as_float(((nd.y >> q_shift) & q_mask) | 0x4B000000u), 8388608.0f);
+        st_f32_if(ranges + hb, dm, pol_stream, what == 1u ? 1u : 0u);  // sole owner of its bin
+        st_f32_if(intens + hb, it, pol_stream, what == 1u ? 1u : 0u);
+        mode_a_push_heads(wlist, wcap, wcount, what == 2u, hru, hb, &sm.fallback);
       }
     };
     {
@@ -378,20 +381,8 @@ __global__ void __launch_bounds__(T, 2) scan_fast_kernel(ScanBatchArgs a, FastWo
     __syncthreads();
 
     // ---- phase 3 (Mode A): resolve bins that hold several points --------------------------
-    if (MODE_A && want_scan) {
-      const uint32_t np = min(sm.pending, kPendingCap);
-      for (uint32_t e = tid; e < np; e += T) {
-        const uint2 h = pending[e];
-        unsigned long long best = ~0ull;
-        for (uint32_t slot = h.x; slot < M; ++slot) {
-          const unsigned long long g = gscratch[slot];
-          best = min(best, g);
-          if (g & 1ull) break;
-        }
-        ranges[h.y] = __uint_as_float((uint32_t)(best >> 32));
-        intens[h.y] = quality_to_intensity((uint32_t)(best >> 8) & 0xFFu, new_proto);
-      }
-    }
+    if (MODE_A && want_scan) mode_a_resolve(mc, wlist, wcount);
+    __syncthreads();
     if (tid == 0) {
       if (sm.fallback) {
         a.fallback_list[atomicAdd(a.fallback_count, 1u)] = s;

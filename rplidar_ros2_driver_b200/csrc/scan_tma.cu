@@ -62,7 +62,6 @@ struct __align__(128) TmaSmem {
   uint32_t red[4 * kCWarps];
   uint32_t valid_count;
   uint32_t totV;
-  uint32_t pending;
   uint32_t fallback;
 };
 
@@ -168,7 +167,9 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
   const bool new_proto = a.is_new_protocol != 0;
   const bool inverted = a.inverted != 0;
   unsigned long long* gscratch = ws.group + (size_t)blockIdx.x * ws.max_nodes;
-  uint2* gpending = ws.pending + (size_t)blockIdx.x * ws.max_nodes;
+  // warp-private list of Mode A shared-bin heads (a warp sees max_nodes / kCWarps nodes)
+  const uint32_t wcap = ws.max_nodes / kCWarps;
+  uint2* wlist = ws.pending + (size_t)blockIdx.x * ws.max_nodes + (size_t)warp * wcap;
   const uint64_t pol_stream = l2_policy_evict_first();
   const uint32_t q_shift = new_proto ? 16u : 18u, q_mask = new_proto ? 0xFFu : 0x3Fu;
   uint32_t stage = 0, parity = 0;  // ring position of the next chunk to consume
@@ -230,7 +231,6 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
 #pragma unroll
       for (uint32_t j = 0; j < kKeySpace / 16 / TC; ++j) bm[j * TC + tid] = z;
       if (tid == 0) {
-        sm.pending = 0;
         sm.fallback = 0;
       }
     }
@@ -342,9 +342,6 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
     mc.ranges = ranges;
     mc.intens = intens;
     mc.gscratch = gscratch;
-    mc.pending = gpending;
-    mc.pending_count = &sm.pending;
-    mc.pending_cap = ws.max_nodes;
     mc.fallback = &sm.fallback;
     mc.M = M;
     mc.inc = inc;
@@ -352,6 +349,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
     mc.has0 = has0;
     mc.new_proto = new_proto;
 
+    uint32_t wcount = 0;
     auto place_chunk = [&](auto checked, uint32_t c) {
       mbar_wait(&sm.full[stage], parity);
       const uint2* slot = sm.ring[stage];
@@ -374,8 +372,14 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
           float* pr = ranges + o;
           st_f32_if(pr, dm, pol_stream, measured);
           st_f32_if(reinterpret_cast<float*>(reinterpret_cast<char*>(pr) + i_minus_r), it, pol_stream, measured);
-        } else if (measured) {
-          mode_a_place(mc, k, rk, dm, (nd.y >> 16) & 0xFFu);
+        } else {
+          uint32_t hru = 0, hb = 0, what = 0;
+          if (measured) what = mode_a_place(mc, k, rk, dm, (nd.y >> 16) & 0xFFu, hru, hb);
+          const float it =
+              __fsub_rn(__uint_as_float(((nd.y >> q_shift) & q_mask) | 0x4B000000u), 8388608.0f);
+          st_f32_if(ranges + hb, dm, pol_stream, what == 1u ? 1u : 0u);  // sole owner of its bin
+          st_f32_if(intens + hb, it, pol_stream, what == 1u ? 1u : 0u);
+          mode_a_push_heads(wlist, wcap, wcount, what == 2u, hru, hb, &sm.fallback);
         }
       }
       release();
@@ -386,20 +390,8 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
     consumer_sync();
 
     // ---- phase 3 (Mode A): resolve bins that hold several points --------------------------
-    if (MODE_A) {
-      const uint32_t np = min(sm.pending, ws.max_nodes);
-      for (uint32_t e = tid; e < np; e += TC) {
-        const uint2 h = gpending[e];
-        unsigned long long best = ~0ull;
-        for (uint32_t slot = h.x; slot < M; ++slot) {
-          const unsigned long long gq = gscratch[slot];
-          best = min(best, gq);
-          if (gq & 1ull) break;
-        }
-        ranges[h.y] = __uint_as_float((uint32_t)(best >> 32));
-        intens[h.y] = quality_to_intensity((uint32_t)(best >> 8) & 0xFFu, new_proto);
-      }
-    }
+    if (MODE_A) mode_a_resolve(mc, wlist, wcount);
+    consumer_sync();
     if (tid == 0) {
       if (sm.fallback) {
         a.fallback_list[atomicAdd(a.fallback_count, 1u)] = s;

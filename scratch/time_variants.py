@@ -18,7 +18,7 @@ st = torch.cuda.Stream(); torch.cuda.set_stream(st)
 ctx.synth_batch_dev(0, S, N, N, 0, nodes.data_ptr(), counts.data_ptr(), stream=st.cuda_stream)
 torch.cuda.synchronize()
 ref = {}
-for mode_a in (0,):
+for mode_a in (0, 1):
   for flags in (2, 0):
     for rep in range(2):
         ctx.profile(True)
