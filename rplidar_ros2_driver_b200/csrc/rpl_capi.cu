@@ -150,6 +150,8 @@ rpl_result ensure_staging(rpl_ctx* c, Lane& l, uint32_t scans, size_t nodes, boo
   return RPL_RESULT_OK;
 }
 
+rpl_result enqueue_args(rpl_ctx* c, Lane& l, rpl::ScanBatchArgs a, uint32_t flags, cudaStream_t stream);
+
 // queue the scan kernels for one device-resident batch on `stream`
 rpl_result enqueue_scan(rpl_ctx* c, Lane& l, const rpl_node_hq* nodes, const uint32_t* counts,
                         uint32_t n_scans, uint32_t stride, const rpl_scan_params* p,
@@ -173,6 +175,8 @@ rpl_result enqueue_scan(rpl_ctx* c, Lane& l, const rpl_node_hq* nodes, const uin
     return RPL_RESULT_INVALID_DATA;
   }
   rpl::ScanBatchArgs a{};
+  a.xyzi = nullptr;
+  a.trig = nullptr;
   a.nodes = reinterpret_cast<const uint2*>(nodes);
   a.nodes_out = reinterpret_cast<uint2*>(nodes_out);
   a.counts = counts;
@@ -190,8 +194,12 @@ rpl_result enqueue_scan(rpl_ctx* c, Lane& l, const rpl_node_hq* nodes, const uin
   a.mode_a = p->scan_processing;
   a.inverted = p->inverted;
   a.apply_ascend = p->apply_ascend;
+  return enqueue_args(c, l, a, p->flags, stream);
+}
 
-  bool force_general = (p->flags & RPL_FLAG_FORCE_GENERAL) != 0;
+rpl_result enqueue_args(rpl_ctx* c, Lane& l, rpl::ScanBatchArgs a, uint32_t flags, cudaStream_t stream) {
+  const uint32_t n_scans = a.n_scans, stride = a.stride;
+  bool force_general = (flags & RPL_FLAG_FORCE_GENERAL) != 0;
   if (a.nodes_out && !a.apply_ascend) {
     // no geometric correction requested: the buffer passes through unchanged
     // (reference lidar_driver_wrapper.cpp:330-337); a plain device copy, not kernel work
@@ -201,13 +209,15 @@ rpl_result enqueue_scan(rpl_ctx* c, Lane& l, const rpl_node_hq* nodes, const uin
     a.nodes_out = nullptr;
   }
   // status-only calls (no LaserScan, no ascended buffer) take the general kernel
-  if (!a.ranges && !a.nodes_out) force_general = true;
+  if (!a.ranges && !a.nodes_out && !a.xyzi) force_general = true;
+  // the PointCloud2 payload exists in the TMA kernel and the general kernel only
+  if (a.xyzi && ((reinterpret_cast<uintptr_t>(a.nodes) & 15u) != 0 || (stride & 1u) != 0)) force_general = true;
   if (!force_general) {
     RPL_CUDA(c, cudaMemsetAsync(l.fallback_count, 0, sizeof(uint32_t), stream), RPL_RESULT_OPERATION_FAIL);
     // the TMA-ring kernel needs every scan base 16-byte aligned
     const bool emit = a.nodes_out != nullptr;
-    const bool use_tma = !emit && (p->flags & RPL_FLAG_NO_TMA) == 0 &&
-                         (reinterpret_cast<uintptr_t>(a.nodes) & 15u) == 0 && (stride & 1u) == 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(a.nodes) & 15u) == 0 && (stride & 1u) == 0;
+    const bool use_tma = !emit && aligned && ((flags & RPL_FLAG_NO_TMA) == 0 || a.xyzi != nullptr);
     const int grid = (int)std::min<uint32_t>(n_scans, (uint32_t)(use_tma ? c->tma_grid : c->fast_grid));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->profile) {
@@ -562,22 +572,27 @@ rpl_result rpl_cloud_batch_dev(rpl_ctx* c, const rpl_node_hq* nodes, const uint3
   }
   RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
-  rpl::CloudBatchArgs a{};
+  rpl::ScanBatchArgs a{};
   a.nodes = reinterpret_cast<const uint2*>(nodes);
   a.counts = counts;
   a.n_scans = n_scans;
   a.stride = stride;
+  a.beam_counts = point_counts;  // points kept per scan
+  a.fallback_list = c->lane[0].fallback_list;
+  a.fallback_count = c->lane[0].fallback_count;
+  a.is_new_protocol = params->is_new_protocol;
   a.xyzi = reinterpret_cast<float4*>(xyzi);
-  a.point_counts = point_counts;
+  a.trig = c->lane[0].cws.trig;
   a.range_min = params->range_min;
   a.range_max = params->range_max;
   a.intensity_min = params->intensity_min;
-  a.voxel_size = params->voxel_size;
-  a.sor_k = params->sor_k;
-  a.sor_alpha = params->sor_alpha;
-  a.is_new_protocol = params->is_new_protocol;
+  // steps 1-3 inside the scan kernels, steps 4-5 as in-place post passes
+  rpl_result r = enqueue_args(c, c->lane[0], a, 0u, st);
+  if (r != RPL_RESULT_OK) return r;
   int launched = 0;
-  RPL_CUDA(c, rpl::launch_cloud(a, c->lane[0].cws, c->num_sms, st, &launched), RPL_RESULT_OPERATION_FAIL);
+  RPL_CUDA(c, rpl::launch_cloud_post(a.xyzi, point_counts, n_scans, stride, params->sor_k, params->sor_alpha,
+                                     params->voxel_size, c->lane[0].cws, st, &launched),
+           RPL_RESULT_OPERATION_FAIL);
   c->launches += launched;
   return RPL_RESULT_OK;
 }

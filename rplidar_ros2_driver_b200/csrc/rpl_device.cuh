@@ -183,6 +183,17 @@ __device__ __forceinline__ void st_hint_v2(uint2* p, uint2 v, uint64_t pol) {
   asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol));
 }
 
+__device__ __forceinline__ void st_f32x4_if(float4* p, float4 v, uint64_t pol, uint32_t pred) {
+  asm volatile(
+      "{ .reg .pred q; setp.ne.u32 q, %6, 0;\n\t"
+      "@q st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5; }" ::"l"(p),
+      "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol), "r"(pred));
+}
+// PointCloud2 window test (oracle/cloud_oracle.cpp step 1); NaN-free inputs
+__device__ __forceinline__ bool cloud_keep(float dm, float inten, float rmin, float rmax, float imin) {
+  return !(dm < rmin) && !(dm > rmax) && !(inten < imin);
+}
+
 // streaming global accesses: inputs are read at most twice, outputs written once
 __device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
   uint4 r;

@@ -24,6 +24,12 @@ struct ScanBatchArgs {
   uint8_t mode_a;
   uint8_t inverted;
   uint8_t apply_ascend;
+  // PointCloud2 payload (extensions): when `xyzi` is set the kernels keep a node iff it is
+  // measured AND range_min <= dist_m <= range_max AND intensity >= intensity_min, and write
+  // (x, y, 0, intensity) at its rank among the kept nodes; beam_counts then holds the point count
+  float4* xyzi;          // [n_scans][stride]
+  const float2* trig;    // [65536] (cos, sin) of angle_rad(key)
+  float range_min, range_max, intensity_min;
 };
 
 // per-CTA global workspace of the general kernel, sized for max_nodes

@@ -101,7 +101,15 @@ __global__ void __launch_bounds__(GT, 1)
   const bool mode_a = a.mode_a != 0;
   const bool inverted = a.inverted != 0;
   const bool ascend = a.apply_ascend != 0;
-  const bool want_scan = a.ranges != nullptr;
+  const bool cloud = a.xyzi != nullptr;  // PointCloud2 payload: window filter + polar->xyz
+  const bool want_scan = a.ranges != nullptr || cloud;
+  auto kept = [&](uint2 nd) {
+    const uint32_t d = node_dist(nd);
+    if (d == 0) return false;
+    if (!cloud) return true;
+    return cloud_keep(dist_to_m(d), quality_to_intensity(node_quality(nd), new_proto), a.range_min, a.range_max,
+                      a.intensity_min);
+  };
 
   const size_t wo = (size_t)blockIdx.x * ws.max_nodes;
   uint16_t* keyf = ws.keyf + wo;
@@ -130,10 +138,9 @@ __global__ void __launch_bounds__(GT, 1)
     // ---- measured count, first measured node ---------------------------------------------
     uint32_t cnt = 0, first = 0xFFFFFFFFu;
     for (uint32_t i = tid; i < n; i += GT) {
-      if (node_dist(base[i]) != 0) {
-        ++cnt;
-        first = min(first, i);
-      }
+      const uint2 nd = base[i];
+      if (kept(nd)) ++cnt;
+      if (node_dist(nd) != 0) first = min(first, i);
     }
     cnt = warp_sum(cnt);
     first = warp_min(first);
@@ -151,7 +158,7 @@ __global__ void __launch_bounds__(GT, 1)
       sm.valid_count = c;
       sm.first_valid = f;
       // head tune (reference sl_lidar_driver.cpp:133-147)
-      sm.front_key = (c != 0 && ascend) ? ascend_head_key(node_key(base[f]), f, ascend_step(n)) : 0u;
+      sm.front_key = (f != 0xFFFFFFFFu && ascend) ? ascend_head_key(node_key(base[f]), f, ascend_step(n)) : 0u;
     }
     __syncthreads();
     const uint32_t M = sm.valid_count;
@@ -206,15 +213,27 @@ __global__ void __launch_bounds__(GT, 1)
       const uint32_t len = (n + GT - 1) / GT;
       const uint32_t lo = min(n, tid * len), hi = min(n, lo + len);
       uint32_t c = 0;
-      for (uint32_t r = lo; r < hi; ++r) c += node_dist(base[idx1[r]]) != 0;
+      for (uint32_t r = lo; r < hi; ++r) c += kept(base[idx1[r]]) ? 1u : 0u;
       uint32_t v = block_exclusive_scan(sm, c, nullptr);
       for (uint32_t r = lo; r < hi; ++r) {
         const uint32_t i = idx1[r];
-        if (node_dist(base[i]) != 0) vidx[v++] = i;
+        if (kept(base[i])) vidx[v++] = i;
       }
     }
     __syncthreads();
 
+    if (cloud) {  // oracle/cloud_oracle.cpp steps 1-3
+      float4* out = a.xyzi + (size_t)s * a.stride;
+      for (uint32_t v = tid; v < M; v += GT) {
+        const uint2 nd = base[vidx[v]];
+        const float dm = dist_to_m(node_dist(nd));
+        const float2 cs = a.trig[node_key(nd)];
+        out[v] = make_float4(__fmul_rn(dm, cs.x), __fmul_rn(dm, cs.y), 0.0f,
+                             quality_to_intensity(node_quality(nd), new_proto));
+      }
+      __syncthreads();
+      continue;
+    }
     float* ranges = a.ranges + (size_t)s * a.stride;
     float* intens = a.intensities + (size_t)s * a.stride;
     if (!mode_a) {  // Mode B (reference rplidar_node.cpp:661-677)

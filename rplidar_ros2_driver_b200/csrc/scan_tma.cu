@@ -115,7 +115,8 @@ __device__ __forceinline__ bool scan_is_streamed(uint32_t n, uint32_t stride, ui
   return n != 0 && n <= stride && n <= max_nodes && n <= kMaxFastNodes;
 }
 
-template <bool MODE_A>
+// MODE: 0 = LaserScan Mode B, 1 = LaserScan Mode A, 2 = PointCloud2 (window + polar->xyz)
+template <int MODE>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchArgs a, FastWorkspace ws) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TmaSmem& sm = *reinterpret_cast<TmaSmem*>(smem_raw);
@@ -172,6 +173,13 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
   uint2* wlist = ws.pending + (size_t)blockIdx.x * ws.max_nodes + (size_t)warp * wcap;
   const uint64_t pol_stream = l2_policy_evict_first();
   const uint32_t q_shift = new_proto ? 16u : 18u, q_mask = new_proto ? 0xFFu : 0x3Fu;
+  constexpr bool MODE_A = (MODE == 1);
+  constexpr bool CLOUD = (MODE == 2);
+  const float w_rmin = a.range_min, w_rmax = a.range_max, w_imin = a.intensity_min;
+  // intensity straight from word y without the conversion pipe (exact for values < 2^23)
+  auto intensity_of = [&](uint32_t y) {
+    return __fsub_rn(__uint_as_float(((y >> q_shift) & q_mask) | 0x4B000000u), 8388608.0f);
+  };
   uint32_t stage = 0, parity = 0;  // ring position of the next chunk to consume
   using Checked = std::integral_constant<bool, true>;
   using Unchecked = std::integral_constant<bool, false>;
@@ -247,7 +255,9 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
       for (int r = 0; r < kRounds; ++r) v[r] = slot[r * TC + tid];
 #pragma unroll
       for (int r = 0; r < kRounds; ++r) {
-        bool valid = __funnelshift_r(v[r].x, v[r].y, 16) != 0;
+        const uint32_t dist = __funnelshift_r(v[r].x, v[r].y, 16);
+        bool valid = dist != 0;
+        if (CLOUD) valid = valid && cloud_keep(dist_to_m(dist), intensity_of(v[r].y), w_rmin, w_rmax, w_imin);
         if (decltype(checked)::value && c * CH + r * TC + tid >= n) valid = false;
         if (valid) bmap[swz_x(v[r].x)] = 1;
         cnt += valid ? 1u : 0u;
@@ -328,8 +338,9 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
     }
 
     // ---- phase 2 (place): rank and place --------------------------------------------------
-    float* ranges = a.ranges + (size_t)s * a.stride;
-    float* intens = a.intensities + (size_t)s * a.stride;
+    float* ranges = CLOUD ? nullptr : a.ranges + (size_t)s * a.stride;
+    float* intens = CLOUD ? nullptr : a.intensities + (size_t)s * a.stride;
+    float4* cloud = CLOUD ? a.xyzi + (size_t)s * a.stride : nullptr;
     const float inc = angle_increment(M, MODE_A);
     const bool has0 = (sm.rankV[0].x & 1u) != 0;
     // Mode B output slot = ob + os * rank in wrapping u32 arithmetic (reference
@@ -365,18 +376,22 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
         if (decltype(checked)::value && c * CH + r * TC + tid >= n) measured = 0;
         const uint32_t rk = rank_of(sm.rankV, k);
         const float dm = dist_to_m(dist);
-        if (!MODE_A) {  // Mode B: reference rplidar_node.cpp:661-677
+        if (CLOUD) {  // polar -> xyz at the rank among kept points (oracle/cloud_oracle.cpp 1-3)
+          const float it = intensity_of(nd.y);
+          if (!cloud_keep(dm, it, w_rmin, w_rmax, w_imin)) measured = 0;
+          const float2 cs = __ldg(a.trig + k);
+          st_f32x4_if(cloud + rk, make_float4(__fmul_rn(dm, cs.x), __fmul_rn(dm, cs.y), 0.0f, it), pol_stream,
+                      measured);
+        } else if (!MODE_A) {  // Mode B: reference rplidar_node.cpp:661-677
           const uint32_t o = ob + os * rk;
-          const float it =
-              __fsub_rn(__uint_as_float(((nd.y >> q_shift) & q_mask) | 0x4B000000u), 8388608.0f);
+          const float it = intensity_of(nd.y);
           float* pr = ranges + o;
           st_f32_if(pr, dm, pol_stream, measured);
           st_f32_if(reinterpret_cast<float*>(reinterpret_cast<char*>(pr) + i_minus_r), it, pol_stream, measured);
         } else {
           uint32_t hru = 0, hb = 0, what = 0;
           if (measured) what = mode_a_place(mc, k, rk, dm, (nd.y >> 16) & 0xFFu, hru, hb);
-          const float it =
-              __fsub_rn(__uint_as_float(((nd.y >> q_shift) & q_mask) | 0x4B000000u), 8388608.0f);
+          const float it = intensity_of(nd.y);
           st_f32_if(ranges + hb, dm, pol_stream, what == 1u ? 1u : 0u);  // sole owner of its bin
           st_f32_if(intens + hb, it, pol_stream, what == 1u ? 1u : 0u);
           mode_a_push_heads(wlist, wcap, wcount, what == 2u, hru, hb, &sm.fallback);
@@ -409,22 +424,24 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
 }  // namespace
 
 cudaError_t launch_scan_tma(const ScanBatchArgs& a, const FastWorkspace& ws, int grid, cudaStream_t stream) {
-  if (a.mode_a) scan_tma_kernel<true><<<grid, kBlock, sizeof(TmaSmem), stream>>>(a, ws);
-  else scan_tma_kernel<false><<<grid, kBlock, sizeof(TmaSmem), stream>>>(a, ws);
+  if (a.xyzi) scan_tma_kernel<2><<<grid, kBlock, sizeof(TmaSmem), stream>>>(a, ws);
+  else if (a.mode_a) scan_tma_kernel<1><<<grid, kBlock, sizeof(TmaSmem), stream>>>(a, ws);
+  else scan_tma_kernel<0><<<grid, kBlock, sizeof(TmaSmem), stream>>>(a, ws);
   return cudaGetLastError();
 }
 
 cudaError_t scan_tma_configure() {
-  cudaError_t e = cudaFuncSetAttribute(scan_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(TmaSmem));
+  const int sh = (int)sizeof(TmaSmem);
+  cudaError_t e = cudaFuncSetAttribute(scan_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sh);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(scan_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)sizeof(TmaSmem));
+  e = cudaFuncSetAttribute(scan_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sh);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(scan_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sh);
 }
 
 int scan_tma_max_ctas_per_sm() {
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, scan_tma_kernel<false>, kBlock, sizeof(TmaSmem));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, scan_tma_kernel<0>, kBlock, sizeof(TmaSmem));
   return nb;
 }
 

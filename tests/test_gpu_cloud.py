@@ -1,0 +1,133 @@
+"""GPU tests of the PointCloud2 path (north-star extensions, PARITY UNPINNED: the reference has
+no such code; oracle/cloud_oracle.cpp is the self-authored definition).  Every step of the
+definition is order independent, so the CUDA result is compared bit for bit."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def R():
+    import rplidar_ros2_driver_b200 as R
+
+    return R
+
+
+@pytest.fixture(scope="module")
+def ctx(R):
+    c = R.Context(0, 40000, 64)
+    yield c
+    c.close()
+
+
+def room_scans(oracle, n_scans, n, seed, ties=False):
+    """A square room seen from an off-centre sensor, + noise, 5% unmeasured, rotated start."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((n_scans, n), oracle.NODE_DTYPE)
+    for s in range(n_scans):
+        keys = np.sort(rng.choice(65536, size=n, replace=ties))
+        th = keys * (2 * np.pi / 65536)
+        ox, oy = rng.uniform(-1, 1, 2)
+        half = 3.0
+        with np.errstate(divide="ignore"):
+            tx = np.where(np.cos(th) > 0, (half - ox) / np.cos(th), (-half - ox) / np.cos(th))
+            ty = np.where(np.sin(th) > 0, (half - oy) / np.sin(th), (-half - oy) / np.sin(th))
+        r = np.minimum(np.abs(tx), np.abs(ty)) + rng.normal(0, 0.004, n)
+        r[rng.random(n) < 0.01] += rng.uniform(0.3, 1.5)  # outliers
+        dist = np.clip(r * 4000.0, 1, 2**31).astype(np.uint32)
+        dist[rng.random(n) < 0.05] = 0
+        nodes = oracle.make_nodes(keys, dist, rng.integers(0, 256, n), 2)
+        out[s] = np.roll(nodes, -int(rng.integers(0, n)))
+    return out
+
+
+def check_cloud(R, O, ctx, nodes, counts, **kw):
+    counts = np.asarray(counts, np.uint32)
+    xyzi, pc = ctx.cloud_batch(nodes.view(R.NODE_DTYPE), counts, R.cloud_params(**kw))
+    for s in range(nodes.shape[0]):
+        exp = O.cloud(nodes[s, : counts[s]], O.cloud_params(**kw))
+        assert pc[s] == exp.shape[0], (s, kw, pc[s], exp.shape[0])
+        assert (xyzi[s, : pc[s]].view(np.uint32) == exp.view(np.uint32)).all(), (s, kw)
+    return xyzi, pc
+
+
+@pytest.mark.parametrize("n", [1, 2, 33, 360, 3200, 32768])
+def test_polar_to_xyz_window_bit_exact(R, oracle, ctx, n):
+    nodes = oracle.synth_batch(700 + n, 4, n, 1)
+    counts = np.full(4, n, np.uint32)
+    check_cloud(R, oracle, ctx, nodes, counts, range_min=0.0, range_max=1e9)
+    check_cloud(R, oracle, ctx, nodes, counts, range_min=0.15, range_max=25.0, intensity_min=20.0, is_new_protocol=0)
+    check_cloud(R, oracle, ctx, nodes, counts, range_min=5.0, range_max=12.0, intensity_min=100.0, is_new_protocol=1)
+
+
+def test_cloud_with_duplicate_keys_uses_stable_order(R, oracle, ctx):
+    nodes = oracle.synth_batch(31, 3, 2048, 2)
+    check_cloud(R, oracle, ctx, nodes, np.full(3, 2048, np.uint32), range_min=0.15, range_max=40.0)
+
+
+@pytest.mark.parametrize("n", [5, 30, 34, 3200])
+def test_statistical_outlier_removal(R, oracle, ctx, n):
+    nodes = room_scans(oracle, 6, n, 11 + n)
+    counts = np.full(6, n, np.uint32)
+    _, pc0 = check_cloud(R, oracle, ctx, nodes, counts, range_min=0.15, range_max=40.0)
+    _, pc = check_cloud(R, oracle, ctx, nodes, counts, range_min=0.15, range_max=40.0, sor_k=8, sor_alpha=1.0)
+    if n >= 3200:
+        assert (pc < pc0).all() and (pc > 0.8 * pc0).all()  # outliers go, walls stay
+    check_cloud(R, oracle, ctx, nodes, counts, range_min=0.15, range_max=40.0, sor_k=3, sor_alpha=0.0)
+    check_cloud(R, oracle, ctx, nodes, counts, range_min=0.15, range_max=40.0, sor_k=32, sor_alpha=2.5)
+
+
+@pytest.mark.parametrize("voxel", [0.05, 0.5])
+def test_voxel_grid(R, oracle, ctx, voxel):
+    nodes = room_scans(oracle, 6, 3200, 5)
+    counts = np.full(6, 3200, np.uint32)
+    _, pc = check_cloud(R, oracle, ctx, nodes, counts, range_min=0.15, range_max=40.0, voxel_size=voxel)
+    assert (pc > 0).all() and (pc < 3200).all()
+    check_cloud(R, oracle, ctx, nodes, counts, range_min=0.15, range_max=40.0, voxel_size=voxel, sor_k=8, sor_alpha=1.0)
+
+
+def test_full_chain_on_shuffled_scans(R, oracle, ctx):
+    """BASELINE.json configs[3]: angle order forced by the kernel (variant 3 = shuffled), range
+    and intensity window, SOR k=8 alpha=1, 5 cm voxels."""
+    nodes = oracle.synth_batch(2, 4, 8192, 3)
+    check_cloud(R, oracle, ctx, nodes, np.full(4, 8192, np.uint32), range_min=0.15, range_max=40.0,
+                intensity_min=10.0, sor_k=8, sor_alpha=1.0, voxel_size=0.05)
+
+
+def test_ragged_and_empty_scans(R, oracle, ctx):
+    stride = 400
+    counts = np.array([0, 1, 399, 400, 7], np.uint32)
+    nodes = np.zeros((5, stride), oracle.NODE_DTYPE)
+    src = room_scans(oracle, 5, stride, 77)
+    for s, n in enumerate(counts):
+        nodes[s, :n] = src[s, :n]
+    nodes[3]["dist_mm_q2"] = 0  # nothing measured
+    check_cloud(R, oracle, ctx, nodes, counts, range_min=0.15, range_max=40.0, sor_k=8, sor_alpha=1.0, voxel_size=0.05)
+
+
+def test_fuse_packs_per_scan_clouds(R, oracle, ctx):
+    import torch
+
+    n_scans, n = 16, 3200
+    host = room_scans(oracle, n_scans, n, 3)
+    dev = torch.device("cuda")
+    nodes = torch.from_numpy(host.view(np.uint8).reshape(n_scans, n, 8)).to(dev)
+    counts = torch.full((n_scans,), n, dtype=torch.int32, device=dev)
+    xyzi = torch.zeros((n_scans, n, 4), dtype=torch.float32, device=dev)
+    pc = torch.zeros(n_scans, dtype=torch.int32, device=dev)
+    fused = torch.zeros((n_scans * n, 4), dtype=torch.float32, device=dev)
+    offs = torch.zeros(n_scans, dtype=torch.int32, device=dev)
+    total = torch.zeros(1, dtype=torch.int32, device=dev)
+    prm = R.cloud_params(range_min=0.15, range_max=40.0, voxel_size=0.05)
+    ctx.cloud_batch_dev(nodes.data_ptr(), counts.data_ptr(), n_scans, n, prm, xyzi.data_ptr(), pc.data_ptr())
+    ctx.cloud_fuse_dev(xyzi.data_ptr(), pc.data_ptr(), n_scans, n, fused.data_ptr(), offs.data_ptr(), total.data_ptr())
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    pcs = pc.cpu().numpy()
+    assert int(total.item()) == int(pcs.sum())
+    assert (offs.cpu().numpy() == np.concatenate([[0], np.cumsum(pcs)[:-1]])).all()
+    exp = np.concatenate([oracle.cloud(host[s], oracle.cloud_params(range_min=0.15, range_max=40.0, voxel_size=0.05))
+                          for s in range(n_scans)])
+    got = fused[: int(total.item())].cpu().numpy()
+    assert (got.view(np.uint32) == exp.view(np.uint32)).all()
