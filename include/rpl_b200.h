@@ -173,7 +173,8 @@ rpl_result rpl_cloud_fuse_dev(rpl_ctx* ctx, const float* xyzi, const uint32_t* p
 
 /* ---- synthetic scan streams ------------------------------------------ */
 /* variant 0: tie-free rotated revolution, 5% unmeasured, quality 188; 1: same, quality
- * U[0,255]; 2: iid U[0,65535] keys (ties); 3: tie-free keys in pseudo-random order.
+ * U[0,255]; 2: iid U[0,65535] keys (ties); 3: tie-free keys in pseudo-random order; 4: a
+ * "room" (16 constant-range arcs of 2..10 m + 2 cm noise; non-trivial 5 cm voxels).
  * Also writes counts[s] = n when counts != NULL. */
 rpl_result rpl_synth_batch_dev(rpl_ctx* ctx, uint64_t first_scan_id, uint32_t n_scans, uint32_t n,
                                uint32_t stride, int variant, rpl_node_hq* nodes, uint32_t* counts,

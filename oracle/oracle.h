@@ -89,7 +89,8 @@ void orc_dummy_scan(uint32_t call_index, orc_node_hq* out360);
 
 /* Deterministic synthetic scans of SURVEY.md 8(d) (splitmix64, seed 0x5EED0000+scan_id).
  * variant: 0 = C2 tie-free rotated (5% invalid, quality 188), 1 = same with U[0,255]
- * quality, 2 = tie variant (iid U[0,65535] keys), 3 = C4 (tie-free keys, iid shuffled). */
+ * quality, 2 = tie variant (iid U[0,65535] keys), 3 = C4 (tie-free keys, iid shuffled),
+ * 4 = C3 "room" (variant 0 keys, 16 constant-range arcs of 2..10 m + 2 cm noise). */
 void orc_synth_scan(uint64_t scan_id, uint32_t n, int variant, orc_node_hq* out);
 void orc_synth_batch(uint64_t first_scan_id, uint32_t n_scans, uint32_t n, uint32_t stride,
                      int variant, orc_node_hq* out, int threads);

@@ -271,7 +271,14 @@ void orc_synth_scan(uint64_t scan_id, uint32_t n, int variant, orc_node_hq* out)
     const bool invalid = (draw(seed, i, 1) % 100) < 5;
     orc_node_hq nd;
     nd.angle_z_q14 = static_cast<uint16_t>(key);
-    nd.dist_mm_q2 = invalid ? 0u : 600u + static_cast<uint32_t>(draw(seed, i, 2) % 159401ull);
+    uint32_t dist = 600u + static_cast<uint32_t>(draw(seed, i, 2) % 159401ull);
+    if (variant == 4) {
+      // a "room": 16 angular segments of constant range (2..10 m) + 2 cm of noise
+      const uint32_t seg = static_cast<uint32_t>((static_cast<uint64_t>(i) * 16) / n);
+      dist = 8000u + static_cast<uint32_t>(draw(seed, seg, 4) % 32001ull) +
+             static_cast<uint32_t>(draw(seed, i, 2) % 161ull) - 80u;
+    }
+    nd.dist_mm_q2 = invalid ? 0u : dist;
     uint8_t q = (variant == 1) ? static_cast<uint8_t>(draw(seed, i, 3) & 0xFF) : 188;
     nd.quality = invalid ? 0 : q;
     nd.flag = (p == 0) ? 1 : 2;

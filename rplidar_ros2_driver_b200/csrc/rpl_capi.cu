@@ -550,7 +550,7 @@ rpl_result rpl_scan(rpl_ctx* c, rpl_node_hq* nodes, size_t count, const rpl_scan
 rpl_result rpl_synth_batch_dev(rpl_ctx* c, uint64_t first_scan_id, uint32_t n_scans, uint32_t n,
                                uint32_t stride, int variant, rpl_node_hq* nodes, uint32_t* counts,
                                void* stream) {
-  if (!c || !nodes || n > stride || variant < 0 || variant > 3) return RPL_RESULT_INVALID_DATA;
+  if (!c || !nodes || n > stride || variant < 0 || variant > 4) return RPL_RESULT_INVALID_DATA;
   RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
   RPL_CUDA(c, rpl::launch_synth(first_scan_id, n_scans, n, stride, variant,

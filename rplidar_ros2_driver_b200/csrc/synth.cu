@@ -55,7 +55,12 @@ __global__ void synth_kernel(uint64_t first_scan_id, uint32_t n_scans, uint32_t 
       key = b0 + (span > 1 ? (uint32_t)(draw(seed, i, 0) % span) : 0u);
     }
     const bool invalid = (draw(seed, i, 1) % 100) < 5;
-    const uint32_t dist = invalid ? 0u : 600u + (uint32_t)(draw(seed, i, 2) % 159401ull);
+    uint32_t dist = 600u + (uint32_t)(draw(seed, i, 2) % 159401ull);
+    if (variant == 4) {  // a "room": 16 angular segments of constant range (2..10 m) + 2 cm noise
+      const uint32_t seg = (uint32_t)(((uint64_t)i * 16) / n);
+      dist = 8000u + (uint32_t)(draw(seed, seg, 4) % 32001ull) + (uint32_t)(draw(seed, i, 2) % 161ull) - 80u;
+    }
+    if (invalid) dist = 0u;
     uint32_t q = (variant == 1) ? (uint32_t)(draw(seed, i, 3) & 0xFF) : 188u;
     if (invalid) q = 0;
     const uint32_t flag = (p == 0) ? 1u : 2u;

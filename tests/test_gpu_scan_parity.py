@@ -197,7 +197,7 @@ def test_invalid_arguments_fail_loudly(R, ctx):
 
 
 # ---- synthetic generator and full-size properties ---------------------------------------------
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_device_synth_equals_oracle_synth(R, oracle, ctx, variant):
     import torch
 
