@@ -302,16 +302,26 @@ cudaError_t cloud_configure() { return cudaSuccess; }
 cudaError_t cloud_workspace_alloc(CloudWorkspace& ws, int num_sms, uint32_t max_nodes) {
   // trig table: (float)cos((double)angle_rad), (float)sin(...) with angle_rad exactly as
   // publish_scan computes it (reference rplidar_node.cpp:586-587)
-  std::vector<float2> h(65536);
+  std::vector<float2> h(65536), ang(65536);
+  const double two_pi = 2.0 * 3.14159265358979323846;
   for (uint32_t k = 0; k < 65536; ++k) {
     const float deg = static_cast<float>(k) * 90.0f / 16384.0f;
     const float rad = static_cast<float>(static_cast<double>(deg) * (3.14159265358979323846 / 180.0));
     h[k].x = static_cast<float>(std::cos(static_cast<double>(rad)));
     h[k].y = static_cast<float>(std::sin(static_cast<double>(rad)));
+    // Mode A angles (reference rplidar_node.cpp:641-649): plain and inverted
+    float inv = static_cast<float>(two_pi - static_cast<double>(rad));
+    if (static_cast<double>(inv) >= two_pi) inv = static_cast<float>(static_cast<double>(inv) - two_pi);
+    ang[k].x = rad;
+    ang[k].y = inv;
   }
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ws.trig), h.size() * sizeof(float2));
   if (e != cudaSuccess) return e;
   e = cudaMemcpy(ws.trig, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return e;
+  e = cudaMalloc(reinterpret_cast<void**>(&ws.angle), ang.size() * sizeof(float2));
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpy(ws.angle, ang.data(), ang.size() * sizeof(float2), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return e;
   ws.max_nodes = max_nodes;
   ws.ctas = num_sms * 2;
@@ -323,6 +333,7 @@ cudaError_t cloud_workspace_alloc(CloudWorkspace& ws, int num_sms, uint32_t max_
 
 void cloud_workspace_free(CloudWorkspace& ws) {
   cudaFree(ws.trig);
+  cudaFree(ws.angle);
   cudaFree(ws.scratch);
   ws = CloudWorkspace{};
 }

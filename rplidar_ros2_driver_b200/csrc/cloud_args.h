@@ -7,6 +7,7 @@ namespace rpl {
 
 struct CloudWorkspace {
   float2* trig = nullptr;        // [65536] (cos, sin) of angle_rad(key), rounded from double
+  float2* angle = nullptr;       // [65536] (angle_rad, inverted angle) exactly as publish_scan forms them
   void* scratch = nullptr;       // per-CTA staging, see cloud.cu
   size_t scratch_per_cta = 0;
   uint32_t max_nodes = 0;

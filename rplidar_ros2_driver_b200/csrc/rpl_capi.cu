@@ -177,6 +177,7 @@ rpl_result enqueue_scan(rpl_ctx* c, Lane& l, const rpl_node_hq* nodes, const uin
   rpl::ScanBatchArgs a{};
   a.xyzi = nullptr;
   a.trig = nullptr;
+  a.angle = l.cws.angle;
   a.nodes = reinterpret_cast<const uint2*>(nodes);
   a.nodes_out = reinterpret_cast<uint2*>(nodes_out);
   a.counts = counts;
@@ -583,6 +584,7 @@ rpl_result rpl_cloud_batch_dev(rpl_ctx* c, const rpl_node_hq* nodes, const uint3
   a.is_new_protocol = params->is_new_protocol;
   a.xyzi = reinterpret_cast<float4*>(xyzi);
   a.trig = c->lane[0].cws.trig;
+  a.angle = c->lane[0].cws.angle;
   a.range_min = params->range_min;
   a.range_max = params->range_max;
   a.intensity_min = params->intensity_min;

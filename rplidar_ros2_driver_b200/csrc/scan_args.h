@@ -29,6 +29,7 @@ struct ScanBatchArgs {
   // (x, y, 0, intensity) at its rank among the kept nodes; beam_counts then holds the point count
   float4* xyzi;          // [n_scans][stride]
   const float2* trig;    // [65536] (cos, sin) of angle_rad(key)
+  const float2* angle;   // [65536] (angle_rad, inverted angle): Mode A bins without FP64 on device
   float range_min, range_max, intensity_min;
 };
 

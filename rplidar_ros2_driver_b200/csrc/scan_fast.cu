@@ -33,7 +33,7 @@ constexpr int kUnroll = 8;
 constexpr uint32_t kDummySlot = kKeySpace;      // where unmeasured nodes "mark"
 
 struct __align__(16) FastSmem {
-  uint8_t bytemap[kKeySpace];      // presence map (swizzled); reused as the pending-head list
+  uint8_t bytemap[kKeySpace];      // presence map (swizzled); presence map (swizzled)
   uint8_t dummy[16];
   uint2 rankV[kWords];             // {bits, exclusive prefix} over measured keys
   uint2 rankA[kWords];             // same over all nodes' final keys (ascended buffer)
@@ -312,27 +312,10 @@ __global__ void __launch_bounds__(T, 2) scan_fast_kernel(ScanBatchArgs a, FastWo
     uint2* nodes_out = EMIT ? a.nodes_out + (size_t)s * a.stride : nullptr;
     const float inc = angle_increment(M, MODE_A);
     const bool has0 = (sm.rankV[0].x & 1u) != 0;
-    // warp-private lists of Mode A shared-bin heads live in the (now dead) presence map
-    constexpr uint32_t wcap = kKeySpace / 8 / kWarps;
-    uint2* wlist = reinterpret_cast<uint2*>(sm.bytemap) + warp * wcap;
-    uint32_t wcount = 0;
     // Mode B output slot = ob + os * rank in wrapping u32 arithmetic (reference
     // rplidar_node.cpp:673); intensities[] sits at a fixed byte distance from ranges[]
     const uint32_t ob = inverted ? M - 1u : 0u, os = inverted ? 0xFFFFFFFFu : 1u;
     const ptrdiff_t i_minus_r = reinterpret_cast<char*>(intens) - reinterpret_cast<char*>(ranges);
-
-    ModeACtx mc;
-    mc.rankV = sm.rankV;
-    mc.ranges = ranges;
-    mc.intens = intens;
-    mc.gscratch = gscratch;
-    mc.fallback = &sm.fallback;
-    mc.M = M;
-    mc.inc = inc;
-    mc.inverted = inverted;
-    mc.has0 = has0;
-    mc.new_proto = new_proto;
-
     auto place = [&](uint2 nd, uint32_t i, bool live) {
       const uint32_t k = nd.x & 0xFFFFu;
       const uint32_t dist = __funnelshift_r(nd.x, nd.y, 16);
@@ -350,13 +333,8 @@ __global__ void __launch_bounds__(T, 2) scan_fast_kernel(ScanBatchArgs a, FastWo
         float* pr = ranges + o;
         st_f32_if(pr, dm, pol_stream, measured);
         st_f32_if(reinterpret_cast<float*>(reinterpret_cast<char*>(pr) + i_minus_r), it, pol_stream, measured);
-      } else {
-        uint32_t hru = 0, hb = 0, what = 0;
-        if (measured) what = mode_a_place(mc, k, r, dm, (nd.y >> 16) & 0xFFu, hru, hb);
-        const float it = __fsub_rn(__uint_as_float(((nd.y >> q_shift) & q_mask) | 0x4B000000u), 8388608.0f);
-        st_f32_if(ranges + hb, dm, pol_stream, what == 1u ? 1u : 0u);  // sole owner of its bin
-        st_f32_if(intens + hb, it, pol_stream, what == 1u ? 1u : 0u);
-        mode_a_push_heads(wlist, wcap, wcount, what == 2u, hru, hb, &sm.fallback);
+      } else if (measured) {  // Mode A: packed entry at the u-rank, resolved by mode_a_emit
+        gscratch[mode_a_urank(k, r, M, inverted, has0)] = mode_a_entry(dm, k, (nd.y >> 16) & 0xFFu);
       }
     };
     {
@@ -381,7 +359,20 @@ __global__ void __launch_bounds__(T, 2) scan_fast_kernel(ScanBatchArgs a, FastWo
     __syncthreads();
 
     // ---- phase 3 (Mode A): resolve bins that hold several points --------------------------
-    if (MODE_A && want_scan) mode_a_resolve(mc, wlist, wcount);
+    if (MODE_A && want_scan) {
+      ModeAOut mo;
+      mo.ranges = ranges;
+      mo.intens = intens;
+      mo.angle = a.angle;
+      mo.M = M;
+      mo.inc = inc;
+      mo.inverted = inverted;
+      mo.new_proto = new_proto;
+      mo.policy = pol_stream;
+      // the presence map is dead by now: each warp stages entries in its own 3.4 KB of it
+      static_assert(kEmitStageBytes * kWarps <= kKeySpace, "stage buffers must fit the byte map");
+      mode_a_emit(mo, gscratch, warp, kWarps, sm.bytemap + warp * kEmitStageBytes);
+    }
     __syncthreads();
     if (tid == 0) {
       if (sm.fallback) {

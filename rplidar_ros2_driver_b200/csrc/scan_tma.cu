@@ -92,6 +92,21 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// producer-side wait: the ring is usually full, so let the hardware park the thread (suspend
+// time hint, ns) instead of spinning through issue slots the consumer warps need
+__device__ __forceinline__ void mbar_wait_relaxed(void* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(20000u)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(void* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -145,7 +160,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
         const uint32_t nch = (n + CH - 1) / CH;
         for (int pass = 0; pass < 2; ++pass) {
           for (uint32_t c = 0; c < nch; ++c) {
-            mbar_wait(&sm.empty[stage], parity);
+            mbar_wait_relaxed(&sm.empty[stage], parity);
             // an odd tail is rounded up to a whole 16 bytes; the extra node lies inside the
             // scan's stride (even stride, n odd => n + 1 <= stride) and is masked by consumers
             const uint32_t cn = min(CH, n - c * CH);
@@ -167,10 +182,6 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
   // =========================== consumer warps ==========================================
   const bool new_proto = a.is_new_protocol != 0;
   const bool inverted = a.inverted != 0;
-  unsigned long long* gscratch = ws.group + (size_t)blockIdx.x * ws.max_nodes;
-  // warp-private list of Mode A shared-bin heads (a warp sees max_nodes / kCWarps nodes)
-  const uint32_t wcap = ws.max_nodes / kCWarps;
-  uint2* wlist = ws.pending + (size_t)blockIdx.x * ws.max_nodes + (size_t)warp * wcap;
   const uint64_t pol_stream = l2_policy_evict_first();
   const uint32_t q_shift = new_proto ? 16u : 18u, q_mask = new_proto ? 0xFFu : 0x3Fu;
   constexpr bool MODE_A = (MODE == 1);
@@ -329,8 +340,9 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
       consumer_sync();
       continue;
     }
-    // duplicate keys (fewer distinct keys than measured nodes) -> general kernel (stable rule)
-    if (sm.totV != M) {
+    // duplicate keys (fewer distinct keys than measured nodes) -> general kernel (stable rule);
+    // so do Mode A scans too large for the shared-memory index map
+    if (sm.totV != M || (MODE_A && M > kModeASmemMaxPoints)) {
       if (tid == 0) a.fallback_list[atomicAdd(a.fallback_count, 1u)] = s;
       drain(nch);
       consumer_sync();
@@ -341,6 +353,8 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
     float* ranges = CLOUD ? nullptr : a.ranges + (size_t)s * a.stride;
     float* intens = CLOUD ? nullptr : a.intensities + (size_t)s * a.stride;
     float4* cloud = CLOUD ? a.xyzi + (size_t)s * a.stride : nullptr;
+    uint16_t* sidx = reinterpret_cast<uint16_t*>(sm.bytemap);  // Mode A: u-rank -> node index (map is dead)
+    const uint2* base = a.nodes + (size_t)s * a.stride;
     const float inc = angle_increment(M, MODE_A);
     const bool has0 = (sm.rankV[0].x & 1u) != 0;
     // Mode B output slot = ob + os * rank in wrapping u32 arithmetic (reference
@@ -348,19 +362,6 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
     const uint32_t ob = inverted ? M - 1u : 0u, os = inverted ? 0xFFFFFFFFu : 1u;
     const ptrdiff_t i_minus_r = reinterpret_cast<char*>(intens) - reinterpret_cast<char*>(ranges);
 
-    ModeACtx mc;
-    mc.rankV = sm.rankV;
-    mc.ranges = ranges;
-    mc.intens = intens;
-    mc.gscratch = gscratch;
-    mc.fallback = &sm.fallback;
-    mc.M = M;
-    mc.inc = inc;
-    mc.inverted = inverted;
-    mc.has0 = has0;
-    mc.new_proto = new_proto;
-
-    uint32_t wcount = 0;
     auto place_chunk = [&](auto checked, uint32_t c) {
       mbar_wait(&sm.full[stage], parity);
       const uint2* slot = sm.ring[stage];
@@ -388,13 +389,8 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
           float* pr = ranges + o;
           st_f32_if(pr, dm, pol_stream, measured);
           st_f32_if(reinterpret_cast<float*>(reinterpret_cast<char*>(pr) + i_minus_r), it, pol_stream, measured);
-        } else {
-          uint32_t hru = 0, hb = 0, what = 0;
-          if (measured) what = mode_a_place(mc, k, rk, dm, (nd.y >> 16) & 0xFFu, hru, hb);
-          const float it = intensity_of(nd.y);
-          st_f32_if(ranges + hb, dm, pol_stream, what == 1u ? 1u : 0u);  // sole owner of its bin
-          st_f32_if(intens + hb, it, pol_stream, what == 1u ? 1u : 0u);
-          mode_a_push_heads(wlist, wcap, wcount, what == 2u, hru, hb, &sm.fallback);
+        } else if (measured) {  // Mode A: remember which node sits at this u-rank (mode_a_emit_smem)
+          sidx[mode_a_urank(k, rk, M, inverted, has0)] = (uint16_t)(c * CH + r * TC + tid);
         }
       }
       release();
@@ -405,7 +401,23 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
     consumer_sync();
 
     // ---- phase 3 (Mode A): resolve bins that hold several points --------------------------
-    if (MODE_A) mode_a_resolve(mc, wlist, wcount);
+    if (MODE_A) {
+      ModeAOut mo;
+      mo.ranges = ranges;
+      mo.intens = intens;
+      mo.angle = a.angle;
+      mo.M = M;
+      mo.inc = inc;
+      mo.inverted = inverted;
+      mo.new_proto = new_proto;
+      mo.policy = pol_stream;
+      // the rank table is dead by now: each warp stages a batch of bins in its own slice of it
+      static_assert(kEmit2Stage * 2 * kCWarps <= sizeof(sm.rankV), "bin staging must fit the rank table");
+#ifndef RPL_DBG_NO_EMIT
+      mode_a_emit_smem(mo, sidx, base, warp, kCWarps,
+                       reinterpret_cast<uint16_t*>(sm.rankV) + warp * ((kEmit2Stage + 7u) & ~7u));
+#endif
+    }
     consumer_sync();
     if (tid == 0) {
       if (sm.fallback) {
