@@ -345,6 +345,35 @@ def run_b200(args, rank, local_rank, world):
             "achieved_gbs": 24 * pts_step / (f3 * 1e-3) / 1e9, "frac": 24 * pts_step / (f3 * 1e-3) / 1e9 / peak}
         del nodes_out
 
+    # ---- single-scan latency through the reference-shaped call rpl_scan (host buffers) ------------
+    if not args.no_extra and rank == 0:
+        import ctypes as C
+
+        L = R.lib()
+        lat = {}
+        lctx = R.Context(local_rank, 8192, 1)
+        prm1 = R.scan_params(0, mode_a, 0, 1)
+        for nn in (360, 3200, 8192):
+            one = np.zeros(nn, dtype=R.NODE_DTYPE)
+            one[:] = nodes[0, :nn].cpu().numpy().view(R.NODE_DTYPE).reshape(-1)
+            r1, i1 = np.zeros(nn, np.float32), np.zeros(nn, np.float32)
+            b1, a1, s1 = C.c_uint32(0), C.c_float(0), C.c_uint32(0)
+
+            def call():
+                L.rpl_scan(lctx._h, C.c_void_p(one.ctypes.data), nn, C.byref(prm1), C.c_void_p(r1.ctypes.data),
+                           C.c_void_p(i1.ctypes.data), C.byref(b1), C.byref(a1), C.byref(s1))
+
+            for _ in range(20):
+                call()
+            t0 = time.perf_counter()
+            for _ in range(300):
+                call()
+            lat[str(nn)] = (time.perf_counter() - t0) / 300 * 1e6
+        lctx.close()
+        extra["single_scan_latency_us"] = lat
+        extra["single_scan_latency_note"] = ("rpl_scan through the C-ABI (ascend + LaserScan, pageable host buffers): one "
+                                             "lidar revolution at a time, the reference's actual operating point")
+
     # ---- e2e: host buffers through rpl_scan_batch ------------------------------------------------
     e2e = None
     h_nodes = None
@@ -409,6 +438,13 @@ def run_b200(args, rank, local_rank, world):
         v_all, secs = cpu_leg(O, host, hc, mode_a, cores, 2)
         sub = min(S, 128)
         v_one, _ = cpu_leg(O, host[:sub].copy(), hc[:sub], mode_a, 1, 1)
+        per_scan = {}
+        for nn in (360, 3200, 8192):
+            sm_nodes = O.synth_batch(0, 64, nn, args.variant)
+            rr = O.pipeline_batch(sm_nodes, np.full(64, nn, np.uint32), O.scan_params(0, mode_a, 0, 1, 40.0, 0.1),
+                                  stable=False, threads=1)
+            per_scan[str(nn)] = rr["seconds"] / 64 * 1e6
+        extra["single_scan_latency_cpu_1thread_us"] = per_scan
         cpu = {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": (f"the bench batch itself, 2 passes x {S} scans x {N} nodes = {2 * S * N / 1e6:.0f} Mpoints "
                           f"({secs:.1f} s wall, {cores} worker threads, one scan per task); oracle port of "

@@ -65,6 +65,12 @@ struct rpl_ctx {
   // the pipeline asynchronous even when the caller's small arrays are pageable
   uint32_t* h_counts = nullptr;
   uint32_t* h_small = nullptr;  // [4][max_scans]: beams, angle_increment bits, status, path
+  // single-scan fast lane (rpl_scan / rpl_ascend_scan / rpl_laserscan): one pinned host block
+  // and one device block laid out [nodes in][small][nodes out][ranges][intensities] so that a
+  // scan costs one H2D copy, one or two kernel launches and one D2H copy
+  unsigned char* h_one = nullptr;
+  unsigned char* d_one = nullptr;
+  size_t one_stride = 0;  // max_nodes rounded up to even
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_fast, prof_general;
 };
@@ -323,6 +329,13 @@ rpl_result rpl_ctx_create(int device, uint32_t max_nodes, uint32_t max_scans, rp
       !cuda_ok(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_small), (size_t)max_scans * 16, cudaHostAllocDefault),
                "cudaHostAlloc"))
     return fail(RPL_RESULT_INSUFFICIENT_MEMORY);
+  {
+    c->one_stride = ((size_t)max_nodes + 1) & ~(size_t)1;
+    const size_t bytes = c->one_stride * (8 + 8 + 4 + 4) + 64;
+    if (!cuda_ok(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_one), bytes, cudaHostAllocDefault), "cudaHostAlloc") ||
+        !cuda_ok(c, cudaMalloc(reinterpret_cast<void**>(&c->d_one), bytes), "cudaMalloc"))
+      return fail(RPL_RESULT_INSUFFICIENT_MEMORY);
+  }
   *out = c;
   return RPL_RESULT_OK;
 }
@@ -334,6 +347,8 @@ void rpl_ctx_destroy(rpl_ctx* c) {
     if (c->lane[i].stream) cudaStreamSynchronize(c->lane[i].stream);
     free_lane(c->lane[i]);
   }
+  if (c->h_one) cudaFreeHost(c->h_one);
+  cudaFree(c->d_one);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->h_small) cudaFreeHost(c->h_small);
   delete c;
@@ -509,26 +524,141 @@ rpl_result rpl_laserscan_batch(rpl_ctx* c, const rpl_node_hq* nodes, const uint3
 }
 
 // ---- single scan (the reference-shaped calls) ----------------------------------------------
+namespace {
+
+struct OneSmall {  // the 64-byte control block between the input and the outputs
+  uint32_t count;
+  uint32_t fallback_count;
+  uint32_t fallback_list;
+  uint32_t beams;
+  float inc;
+  uint32_t status;
+  uint32_t path;
+  uint32_t pad[9];
+};
+static_assert(sizeof(OneSmall) == 64, "control block");
+
+// One lidar revolution: the operating point of the reference (one scan thread, ~10 Hz).  What
+// matters here is latency, so the scan travels in one pinned block each way and the general
+// kernel is launched only when the fast kernel reports a duplicate-key scan.
+rpl_result scan_single(rpl_ctx* c, const rpl_node_hq* nodes_in, size_t count, const rpl_scan_params* p,
+                       rpl_node_hq* nodes_out, float* ranges, float* intensities, uint32_t* beam_count,
+                       float* angle_increment, rpl_result* ascend_status) {
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  Lane& l = c->lane[0];
+  const size_t S = c->one_stride, n = count;
+  const size_t off_small = S * 8, off_nout = off_small + 64, off_r = off_nout + S * 8, off_i = off_r + S * 4;
+  const size_t total = off_i + S * 4;
+  std::memcpy(c->h_one, nodes_in, n * 8);
+  OneSmall* hs = reinterpret_cast<OneSmall*>(c->h_one + off_small);
+  std::memset(hs, 0, sizeof(OneSmall));
+  hs->count = (uint32_t)n;
+  // H2D: live nodes + control block (two copies only when the scan is much shorter than max_nodes)
+  if (n * 8 + 4096 >= off_small) {
+    RPL_CUDA(c, cudaMemcpyAsync(c->d_one, c->h_one, off_small + 64, cudaMemcpyHostToDevice, l.stream),
+             RPL_RESULT_OPERATION_FAIL);
+  } else {
+    RPL_CUDA(c, cudaMemcpyAsync(c->d_one, c->h_one, n * 8, cudaMemcpyHostToDevice, l.stream), RPL_RESULT_OPERATION_FAIL);
+    RPL_CUDA(c, cudaMemcpyAsync(c->d_one + off_small, hs, 64, cudaMemcpyHostToDevice, l.stream),
+             RPL_RESULT_OPERATION_FAIL);
+  }
+  OneSmall* ds = reinterpret_cast<OneSmall*>(c->d_one + off_small);
+  const bool want_nodes = nodes_out != nullptr && p->apply_ascend;
+  const bool want_scan = ranges != nullptr;
+  rpl::ScanBatchArgs a{};
+  a.nodes = reinterpret_cast<const uint2*>(c->d_one);
+  a.nodes_out = want_nodes ? reinterpret_cast<uint2*>(c->d_one + off_nout) : nullptr;
+  a.counts = &ds->count;
+  a.n_scans = 1;
+  a.stride = (uint32_t)S;
+  a.ranges = want_scan ? reinterpret_cast<float*>(c->d_one + off_r) : nullptr;
+  a.intensities = want_scan ? reinterpret_cast<float*>(c->d_one + off_i) : nullptr;
+  a.beam_counts = &ds->beams;
+  a.angle_inc = &ds->inc;
+  a.status = &ds->status;
+  a.path = &ds->path;
+  a.fallback_list = &ds->fallback_list;
+  a.fallback_count = &ds->fallback_count;
+  a.is_new_protocol = p->is_new_protocol;
+  a.mode_a = p->scan_processing;
+  a.inverted = p->inverted;
+  a.apply_ascend = p->apply_ascend;
+  a.angle = l.cws.angle;
+  const bool force_general = (p->flags & RPL_FLAG_FORCE_GENERAL) != 0 || (!want_nodes && !want_scan);
+  // D2H extent: control block + whatever was produced, trimmed to the live part
+  auto copy_back = [&]() -> rpl_result {
+    size_t end = off_nout;
+    if (want_nodes) end = off_nout + n * 8;
+    if (want_scan) end = off_i + n * 4;
+    (void)total;
+    if (want_scan && (end - off_small) > 3 * (64 + n * 16) + 8192) {
+      // short scan in a large context: three small copies beat one copy across the gaps
+      RPL_CUDA(c, cudaMemcpyAsync(hs, ds, 64 + (want_nodes ? n * 8 : 0), cudaMemcpyDeviceToHost, l.stream),
+               RPL_RESULT_OPERATION_FAIL);
+      RPL_CUDA(c, cudaMemcpyAsync(c->h_one + off_r, c->d_one + off_r, n * 4, cudaMemcpyDeviceToHost, l.stream),
+               RPL_RESULT_OPERATION_FAIL);
+      RPL_CUDA(c, cudaMemcpyAsync(c->h_one + off_i, c->d_one + off_i, n * 4, cudaMemcpyDeviceToHost, l.stream),
+               RPL_RESULT_OPERATION_FAIL);
+    } else {
+      RPL_CUDA(c, cudaMemcpyAsync(hs, ds, end - off_small, cudaMemcpyDeviceToHost, l.stream),
+               RPL_RESULT_OPERATION_FAIL);
+    }
+    RPL_CUDA(c, cudaStreamSynchronize(l.stream), RPL_RESULT_OPERATION_FAIL);
+    return RPL_RESULT_OK;
+  };
+  if (!force_general) {
+    const bool use_tma = !want_nodes && (p->flags & RPL_FLAG_NO_TMA) == 0;  // d_one and S keep bases 16-byte aligned
+    if (use_tma)
+      RPL_CUDA(c, rpl::launch_scan_tma(a, l.fws, 1, l.stream), RPL_RESULT_OPERATION_FAIL);
+    else
+      RPL_CUDA(c, rpl::launch_scan_fast(a, l.fws, 1, l.stream), RPL_RESULT_OPERATION_FAIL);
+    c->launches++;
+    rpl_result r = copy_back();
+    if (r != RPL_RESULT_OK) return r;
+  }
+  if (force_general || hs->fallback_count != 0) {
+    RPL_CUDA(c, rpl::launch_scan_general(a, l.gws, 1, true, l.stream), RPL_RESULT_OPERATION_FAIL);
+    c->launches++;
+    rpl_result r = copy_back();
+    if (r != RPL_RESULT_OK) return r;
+  }
+  const uint32_t m = hs->beams;
+  if (beam_count) *beam_count = m;
+  if (angle_increment) *angle_increment = hs->inc;
+  if (ascend_status) *ascend_status = hs->status;
+  if (hs->status == RPL_RESULT_INVALID_DATA) return RPL_RESULT_INVALID_DATA;
+  if (want_nodes) std::memcpy(nodes_out, c->h_one + off_nout, n * 8);
+  if (want_scan && m) {
+    std::memcpy(ranges, c->h_one + off_r, (size_t)m * 4);
+    std::memcpy(intensities, c->h_one + off_i, (size_t)m * 4);
+  }
+  return RPL_RESULT_OK;
+}
+
+}  // namespace
+
 rpl_result rpl_ascend_scan(rpl_ctx* c, rpl_node_hq* nodes, size_t count) {
   if (!c) return RPL_RESULT_INVALID_DATA;
   if (count == 0) return RPL_RESULT_OPERATION_FAIL;  // reference: i == count -> FAIL
   if (!nodes || count > c->max_nodes) return RPL_RESULT_INVALID_DATA;
-  uint32_t cnt = (uint32_t)count, status = RPL_RESULT_OPERATION_FAIL;
-  rpl_result r = rpl_ascend_scan_batch(c, nodes, &cnt, 1, cnt, &status);
+  rpl_scan_params p{};
+  p.apply_ascend = 1;
+  rpl_result status = RPL_RESULT_OPERATION_FAIL;
+  rpl_result r = scan_single(c, nodes, count, &p, nodes, nullptr, nullptr, nullptr, nullptr, &status);
   return r != RPL_RESULT_OK ? r : status;
 }
 
 rpl_result rpl_laserscan(rpl_ctx* c, const rpl_node_hq* nodes, size_t count,
                          const rpl_scan_params* params, float* ranges, float* intensities,
                          uint32_t* beam_count, float* angle_increment) {
-  if (!c || !beam_count) return RPL_RESULT_INVALID_DATA;
+  if (!c || !beam_count || !params) return RPL_RESULT_INVALID_DATA;
   *beam_count = 0;
   if (angle_increment) *angle_increment = 0.0f;
   if (count == 0) return RPL_RESULT_OK;  // publish_scan: nodes.empty() -> return
-  if (!nodes || count > c->max_nodes) return RPL_RESULT_INVALID_DATA;
-  uint32_t cnt = (uint32_t)count;
-  return rpl_laserscan_batch(c, nodes, &cnt, 1, cnt, params, ranges, intensities, beam_count,
-                             angle_increment);
+  if (!nodes || !ranges || !intensities || count > c->max_nodes) return RPL_RESULT_INVALID_DATA;
+  rpl_scan_params p = *params;
+  p.apply_ascend = 0;  // the LaserScan never depends on the ascended buffer
+  return scan_single(c, nodes, count, &p, nullptr, ranges, intensities, beam_count, angle_increment, nullptr);
 }
 
 rpl_result rpl_scan(rpl_ctx* c, rpl_node_hq* nodes, size_t count, const rpl_scan_params* params,
@@ -539,12 +669,9 @@ rpl_result rpl_scan(rpl_ctx* c, rpl_node_hq* nodes, size_t count, const rpl_scan
   if (angle_increment) *angle_increment = 0.0f;
   if (ascend_status) *ascend_status = params->apply_ascend ? RPL_RESULT_OPERATION_FAIL : RPL_RESULT_OK;
   if (count == 0) return RPL_RESULT_OK;
-  if (!nodes || count > c->max_nodes) return RPL_RESULT_INVALID_DATA;
-  uint32_t cnt = (uint32_t)count, status = 0;
-  rpl_result r = rpl_scan_batch(c, nodes, &cnt, 1, cnt, params, params->apply_ascend ? nodes : nullptr,
-                                ranges, intensities, beam_count, angle_increment, &status, nullptr);
-  if (ascend_status) *ascend_status = status;
-  return r;
+  if (!nodes || !ranges || !intensities || count > c->max_nodes) return RPL_RESULT_INVALID_DATA;
+  return scan_single(c, nodes, count, params, params->apply_ascend ? nodes : nullptr, ranges, intensities,
+                     beam_count, angle_increment, ascend_status);
 }
 
 // ---- synthetic streams ------------------------------------------------------------------------
