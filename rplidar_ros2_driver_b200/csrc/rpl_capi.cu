@@ -98,7 +98,6 @@ void free_lane(Lane& l) {
   cudaFree(l.fallback_list);
   cudaFree(l.fallback_count);
   cudaFree(l.fws.group);
-  cudaFree(l.fws.pending);
   cudaFree(l.gws.keyf);
   cudaFree(l.gws.idx0);
   cudaFree(l.gws.idx1);
@@ -313,7 +312,6 @@ rpl_result rpl_ctx_create(int device, uint32_t max_nodes, uint32_t max_scans, rp
     if (!cuda_ok(c, dev_alloc(&l.fallback_list, max_scans), "cudaMalloc") ||
         !cuda_ok(c, dev_alloc(&l.fallback_count, 1), "cudaMalloc") ||
         !cuda_ok(c, dev_alloc(&l.fws.group, fast_nodes), "cudaMalloc") ||
-        !cuda_ok(c, dev_alloc(&l.fws.pending, fast_nodes), "cudaMalloc") ||
         !cuda_ok(c, dev_alloc(&l.gws.keyf, gen_nodes), "cudaMalloc") ||
         !cuda_ok(c, dev_alloc(&l.gws.idx0, gen_nodes), "cudaMalloc") ||
         !cuda_ok(c, dev_alloc(&l.gws.idx1, gen_nodes), "cudaMalloc") ||

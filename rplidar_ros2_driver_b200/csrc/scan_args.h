@@ -45,8 +45,7 @@ struct GeneralWorkspace {
 
 // per-CTA global scratch of the fast kernel (Mode A collision groups)
 struct FastWorkspace {
-  unsigned long long* group;  // [ctas][max_nodes]
-  uint2* pending;             // [ctas][max_nodes] heads of shared bins (TMA kernel)
+  unsigned long long* group;  // [ctas][max_nodes] Mode A entries in bin-growth order (scan_fast.cu)
   uint32_t max_nodes;
 };
 
