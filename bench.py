@@ -195,10 +195,20 @@ def run_reference(args, rank):
 
     O.build(ref=False)
     cores = os.cpu_count() or 1
-    sample_scans = min(args.scans, 256)
+    mode_a = 1 if args.mode == "a" else 0
+    # size the per-step sample: as much of the bench batch as fits ~90 s for the whole run, and never
+    # so small that it sits in the CPUs' caches (the GPU arm streams a fresh 1 GB batch from host
+    # memory every step; a 64 MB sample replayed from L3 would not be the same workload)
+    probe = O.synth_batch(0, min(args.scans, 256), args.nodes, args.variant)
+    pc = np.full(probe.shape[0], args.nodes, np.uint32)
+    cpu_leg(O, probe, pc, mode_a, cores, 1)
+    _, t_probe = cpu_leg(O, probe, pc, mode_a, cores, 1)
+    per_scan = t_probe / probe.shape[0]
+    budget_s = 90.0
+    fit = int(budget_s / max(1, args.steps + max(args.warmup, 1)) / max(per_scan, 1e-9))
+    sample_scans = int(min(args.scans, max(min(args.scans, 1024), fit)))
     nodes = O.synth_batch(0, sample_scans, args.nodes, args.variant)
     counts = np.full(sample_scans, args.nodes, np.uint32)
-    mode_a = 1 if args.mode == "a" else 0
     for _ in range(max(args.warmup, 1)):
         cpu_leg(O, nodes, counts, mode_a, cores, 1)
     t_total, pts = 0.0, 0
