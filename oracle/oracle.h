@@ -95,6 +95,22 @@ void orc_synth_scan(uint64_t scan_id, uint32_t n, int variant, orc_node_hq* out)
 void orc_synth_batch(uint64_t first_scan_id, uint32_t n_scans, uint32_t n, uint32_t stride,
                      int variant, orc_node_hq* out, int threads);
 
+/* ---- part 1b: dense-capsule decode (decode_oracle.cpp) ------ */
+#define ORC_DENSE_CAPSULE_BYTES 84 /* reference sl_lidar_cmd.h:228-234 */
+#define ORC_CAPSULE_OK 1u                /* sync nibbles and checksum fine */
+#define ORC_CAPSULE_SYNC 2u              /* start_angle_sync_q6 bit 15: first capsule of a revolution */
+#define ORC_CAPSULE_EMIT 4u              /* this capsule released the previous capsule's 40 nodes */
+#define ORC_CAPSULE_DISCARD 8u           /* angular jump above the 100 Hz bound: nothing released */
+#define ORC_CAPSULE_CHECKSUM_ERR 16u     /* ERR_EVENT_ON_EXP_CHECKSUM_ERR */
+#define ORC_CAPSULE_ENCODER_RESET_ERR 32u /* ERR_EVENT_ON_EXP_ENCODER_RESET (with SYNC) */
+#define ORC_CAPSULE_BAD_FRAME 64u        /* wrong sync nibbles: outside the framed contract */
+/* Decodes n_capsules framed capsules of one stream.  *sync_state: in/out, the reference's
+ * function-static lastNodeSyncBit.  nodes_out must hold 40 * n_capsules nodes.  Returns the
+ * number of nodes written; capsule_node_offset[j] = nodes written before capsule j. */
+uint32_t orc_dense_decode(const uint8_t* capsules, uint32_t n_capsules, uint32_t sample_duration_us,
+                          uint32_t* sync_state, orc_node_hq* nodes_out, uint32_t* capsule_status,
+                          uint32_t* capsule_node_offset);
+
 /* ---- part 2: extensions (parity unpinned) --------------------------------------- */
 
 typedef struct orc_cloud_params {

@@ -103,6 +103,8 @@ def lib() -> C.CDLL:
         L.orc_synth_batch.restype = None
         L.orc_cloud_scan.argtypes = [vp, sz, C.POINTER(CloudParams), vp]
         L.orc_cloud_scan.restype = u32
+        L.orc_dense_decode.argtypes = [vp, u32, u32, C.POINTER(u32), vp, vp, vp]
+        L.orc_dense_decode.restype = u32
         _lib = L
     return _lib
 
@@ -120,6 +122,9 @@ def ref() -> C.CDLL:
         L.ref_dummy_grab.argtypes = [C.c_void_p, C.c_size_t]
         L.ref_dummy_grab.restype = C.c_int
         L.ref_sizeof_node.restype = C.c_size_t
+        L.ref_dense_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_void_p, C.c_size_t,
+                                       C.POINTER(C.c_uint32), C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)]
+        L.ref_dense_decode.restype = C.c_int
         _ref = L
     return _ref
 
@@ -221,3 +226,52 @@ def cloud(nodes: np.ndarray, params: CloudParams) -> np.ndarray:
     out = np.zeros((max(nodes.shape[0], 1), 4), dtype=np.float32)
     m = lib().orc_cloud_scan(_ptr(nodes), nodes.shape[0], C.byref(params), _ptr(out))
     return out[:m].copy()
+
+
+# ---- dense-capsule decode ----------------------------------------------
+CAPSULE_BYTES = 84
+CAPSULE_OK, CAPSULE_SYNC, CAPSULE_EMIT, CAPSULE_DISCARD = 1, 2, 4, 8
+CAPSULE_CHECKSUM_ERR, CAPSULE_ENCODER_RESET_ERR, CAPSULE_BAD_FRAME = 16, 32, 64
+
+
+def make_dense_capsules(start_angle_q6, sync, dist) -> np.ndarray:
+    """Builds framed dense capsules: start_angle_q6 [n] (15 bit), sync [n] bool, dist [n, 40] u16.
+    Returns uint8 [n, 84] with correct sync nibbles and checksums."""
+    start_angle_q6 = np.asarray(start_angle_q6, dtype=np.uint32)
+    n = start_angle_q6.shape[0]
+    caps = np.zeros((n, CAPSULE_BYTES), np.uint8)
+    word = (start_angle_q6 & 0x7FFF) | (np.asarray(sync, dtype=np.uint32) << 15)
+    caps[:, 2] = word & 0xFF
+    caps[:, 3] = word >> 8
+    d = np.asarray(dist, dtype=np.uint16).reshape(n, 40)
+    caps[:, 4::2] = d & 0xFF
+    caps[:, 5::2] = d >> 8
+    chk = np.bitwise_xor.reduce(caps[:, 2:], axis=1)
+    caps[:, 0] = 0xA0 | (chk & 0xF)
+    caps[:, 1] = 0x50 | (chk >> 4)
+    return caps
+
+
+def dense_decode(capsules: np.ndarray, sample_duration_us: int = 31, sync_state: int = 0):
+    """Returns (nodes, capsule_status, capsule_node_offset, sync_state_out)."""
+    capsules = np.ascontiguousarray(capsules, dtype=np.uint8).reshape(-1, CAPSULE_BYTES)
+    n = capsules.shape[0]
+    nodes = np.zeros(max(40 * n, 1), NODE_DTYPE)
+    status = np.zeros(max(n, 1), np.uint32)
+    offs = np.zeros(max(n, 1), np.uint32)
+    st = C.c_uint32(sync_state)
+    m = lib().orc_dense_decode(_ptr(capsules), n, sample_duration_us, C.byref(st), _ptr(nodes), _ptr(status), _ptr(offs))
+    return nodes[:m].copy(), status[:n].copy(), offs[:n].copy(), st.value
+
+
+def ref_dense_decode(stream_bytes: np.ndarray, sample_duration_us: int = 31, chunk: int = 84):
+    """The SDK's own unpacker on a raw byte stream.  Returns (nodes, events[n,3])."""
+    b = np.ascontiguousarray(stream_bytes, dtype=np.uint8).reshape(-1)
+    cap_nodes = 40 * (b.shape[0] // CAPSULE_BYTES + 2)
+    nodes = np.zeros(cap_nodes, NODE_DTYPE)
+    events = np.zeros((b.shape[0] // CAPSULE_BYTES * 2 + 16, 3), np.uint32)
+    nn, ne = C.c_uint32(0), C.c_uint32(0)
+    rc = ref().ref_dense_decode(_ptr(b), b.shape[0], chunk, sample_duration_us, _ptr(nodes), cap_nodes, C.byref(nn),
+                                _ptr(events), events.shape[0], C.byref(ne))
+    assert rc == 0, rc
+    return nodes[: nn.value].copy(), events[: ne.value].copy()

@@ -21,6 +21,9 @@
 #include "lidar_driver_wrapper.hpp"
 #include "sl_lidar.h"
 #include "sl_lidar_driver.h"
+// the SDK's own sample-data unpacker (reference src/sdk/src/dataunpacker/dataunpacker.h)
+#include "dataunpacker/dataunnpacker_commondef.h"
+#include "dataunpacker/dataunpacker.h"
 
 namespace {
 sl::ILidarDriver* sdk_driver() {
@@ -47,6 +50,63 @@ int ref_dummy_grab(void* out_nodes, size_t capacity_nodes) {
   if (v.size() > capacity_nodes) return -1;
   std::memcpy(out_nodes, v.data(), v.size() * sizeof(v[0]));
   return static_cast<int>(v.size());
+}
+
+// Feeds `n_bytes` of a dense-capsule answer stream (answer type 0x85, 84-byte capsules) to the
+// SDK's LIDARSampleDataUnpacker exactly as SlamtecLidarDriver::onProtocolMessageDecoded does
+// (reference src/sdk/src/sl_lidar_driver.cpp:1655-1662), `chunk` bytes per onSampleData call,
+// and records what the listener sees: decoded HQ nodes (handler_capsules.cpp:736-791), scan
+// reset requests and decoding errors, each event tagged with the number of nodes decoded
+// before it.  events: [n_events][3] = {kind (1 = scan reset, 2 = error), node_count, error code}.
+// NOTE the reference keeps `lastNodeSyncBit` in a function-static: it survives across calls.
+int ref_dense_decode(const uint8_t* bytes, size_t n_bytes, size_t chunk, uint32_t sample_duration_us,
+                     void* nodes_out, size_t cap_nodes, uint32_t* n_nodes, uint32_t* events, size_t cap_events,
+                     uint32_t* n_events) {
+  using namespace sl::internal;
+  struct Capture : public LIDARSampleDataListener {
+    sl_lidar_response_measurement_node_hq_t* out;
+    size_t cap, n = 0;
+    uint32_t* ev;
+    size_t ecap, ne = 0;
+    bool overflow = false;
+    void push(uint32_t kind, uint32_t code) {
+      if (ne < ecap) {
+        ev[3 * ne] = kind;
+        ev[3 * ne + 1] = static_cast<uint32_t>(n);
+        ev[3 * ne + 2] = code;
+        ++ne;
+      } else {
+        overflow = true;
+      }
+    }
+    void onHQNodeScanResetReq() override { push(1, 0); }
+    void onHQNodeDecoded(_u64, const rplidar_response_measurement_node_hq_t* node) override {
+      if (n < cap) out[n++] = *node;
+      else overflow = true;
+    }
+    void onDecodingError(int err, _u8, const void*, size_t) override { push(2, static_cast<uint32_t>(err)); }
+  } cap;
+  cap.out = static_cast<sl_lidar_response_measurement_node_hq_t*>(nodes_out);
+  cap.cap = cap_nodes;
+  cap.ev = events;
+  cap.ecap = cap_events;
+  LIDARSampleDataUnpacker* up = LIDARSampleDataUnpacker::CreateInstance(cap);
+  if (!up) return -1;
+  sl::SlamtecLidarTimingDesc timing{};
+  timing.sample_duration_uS = sample_duration_us;
+  timing.native_baudrate = 1000000;
+  timing.linkage_delay_uS = 0;
+  up->updateUnpackerContext(LIDARSampleDataUnpacker::UNPACKER_CONTEXT_TYPE_LIDAR_TIMING, &timing, sizeof(timing));
+  up->enable();
+  if (chunk == 0) chunk = n_bytes ? n_bytes : 1;
+  for (size_t off = 0; off < n_bytes; off += chunk) {
+    const size_t len = (n_bytes - off < chunk) ? (n_bytes - off) : chunk;
+    up->onSampleData(SL_LIDAR_ANS_TYPE_MEASUREMENT_DENSE_CAPSULED, bytes + off, len);
+  }
+  LIDARSampleDataUnpacker::ReleaseInstance(up);
+  *n_nodes = static_cast<uint32_t>(cap.n);
+  *n_events = static_cast<uint32_t>(cap.ne);
+  return cap.overflow ? 1 : 0;
 }
 
 size_t ref_sizeof_node(void) { return sizeof(sl_lidar_response_measurement_node_hq_t); }
