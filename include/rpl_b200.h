@@ -171,6 +171,35 @@ rpl_result rpl_cloud_fuse_dev(rpl_ctx* ctx, const float* xyzi, const uint32_t* p
                               uint32_t n_scans, uint32_t stride, float* fused, uint32_t* offsets,
                               uint32_t* total, void* stream);
 
+/* ---- dense-capsule decode (the step before the hot path) ------- */
+/* Replaces UnpackerHandler_DenseCapsuleNode (reference
+ * src/sdk/src/dataunpacker/unpacker/handler_capsules.cpp:639-791) for FRAMED capsules: answer
+ * type 0x85, 84 bytes each (src/sdk/include/sl_lidar_cmd.h:223-234), one capsule per protocol
+ * message.  capsules: [n_streams][stride_capsules][84]; nodes_out: [n_streams][stride_capsules*40]
+ * HQ nodes in the order the reference's listener receives them; node_counts[s] = nodes decoded.
+ * capsule_status (nullable): RPL_CAPSULE_* bits per capsule; capsule_node_offset (nullable):
+ * nodes decoded before each capsule (so scan-reset / error events keep their place in the node
+ * stream).  sync_state_in/out (nullable): the reference's function-static lastNodeSyncBit
+ * entering / leaving every stream (0 = fresh process).  sample_duration_us:
+ * SlamtecLidarTimingDesc::sample_duration_uS (sets the angular-jump discard threshold). */
+#define RPL_DENSE_CAPSULE_BYTES 84u
+#define RPL_CAPSULE_OK 1u                /* sync nibbles and checksum fine */
+#define RPL_CAPSULE_SYNC 2u              /* first capsule of a revolution: scan reset requested */
+#define RPL_CAPSULE_EMIT 4u              /* released the previous capsule's 40 nodes */
+#define RPL_CAPSULE_DISCARD 8u           /* angular jump above the 100 Hz bound: nothing released */
+#define RPL_CAPSULE_CHECKSUM_ERR 16u     /* ERR_EVENT_ON_EXP_CHECKSUM_ERR */
+#define RPL_CAPSULE_ENCODER_RESET_ERR 32u /* ERR_EVENT_ON_EXP_ENCODER_RESET */
+#define RPL_CAPSULE_BAD_FRAME 64u        /* wrong sync nibbles: outside the framed contract */
+rpl_result rpl_decode_dense_batch_dev(rpl_ctx* ctx, const uint8_t* capsules, const uint32_t* capsule_counts,
+                                      uint32_t n_streams, uint32_t stride_capsules, uint32_t sample_duration_us,
+                                      const uint32_t* sync_state_in, rpl_node_hq* nodes_out,
+                                      uint32_t* node_counts, uint32_t* capsule_status,
+                                      uint32_t* capsule_node_offset, uint32_t* sync_state_out, void* stream);
+/* One stream, host buffers.  nodes_out must hold 40 * n_capsules nodes. */
+rpl_result rpl_decode_dense(rpl_ctx* ctx, const uint8_t* capsules, uint32_t n_capsules,
+                            uint32_t sample_duration_us, uint32_t* sync_state, rpl_node_hq* nodes_out,
+                            uint32_t* node_count, uint32_t* capsule_status, uint32_t* capsule_node_offset);
+
 /* ---- synthetic scan streams ------------------------------------------ */
 /* variant 0: tie-free rotated revolution, 5% unmeasured, quality 188; 1: same, quality
  * U[0,255]; 2: iid U[0,65535] keys (ties); 3: tie-free keys in pseudo-random order; 4: a

@@ -23,6 +23,8 @@ RESULT_OPERATION_FAIL = 0x80008001
 RESULT_OPERATION_NOT_SUPPORT = 0x80008004
 FLAG_FORCE_GENERAL = 1
 FLAG_NO_TMA = 2
+CAPSULE_OK, CAPSULE_SYNC, CAPSULE_EMIT, CAPSULE_DISCARD = 1, 2, 4, 8
+CAPSULE_CHECKSUM_ERR, CAPSULE_ENCODER_RESET_ERR, CAPSULE_BAD_FRAME = 16, 32, 64
 PATH_FAST, PATH_GENERAL = 0, 1
 
 # reference src/sdk/include/sl_lidar_cmd.h:272-278
@@ -40,6 +42,7 @@ EXPORTS = [
     "rpl_host_alloc", "rpl_host_free", "rpl_ctx_launch_count", "rpl_ctx_profile", "rpl_ctx_profile_read", "rpl_ascend_scan", "rpl_laserscan",
     "rpl_scan", "rpl_scan_batch", "rpl_ascend_scan_batch", "rpl_laserscan_batch", "rpl_scan_batch_dev",
     "rpl_cloud_batch_dev", "rpl_cloud_batch", "rpl_cloud_fuse_dev", "rpl_synth_batch_dev",
+    "rpl_decode_dense_batch_dev", "rpl_decode_dense",
 ]
 
 
@@ -120,6 +123,8 @@ def lib() -> C.CDLL:
         "rpl_cloud_batch": ([vp, vp, vp, u32, u32, PCP, vp, vp], u32),
         "rpl_cloud_fuse_dev": ([vp, vp, vp, u32, u32, vp, vp, vp, vp], u32),
         "rpl_synth_batch_dev": ([vp, u64, u32, u32, u32, i32, vp, vp, vp], u32),
+        "rpl_decode_dense_batch_dev": ([vp, vp, vp, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp], u32),
+        "rpl_decode_dense": ([vp, vp, u32, u32, C.POINTER(u32), vp, C.POINTER(u32), vp, vp], u32),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)  # AttributeError here = the library does not export the ABI
@@ -278,6 +283,27 @@ class Context:
         self._check(self._L.rpl_cloud_batch(self._h, _p(nodes), _p(counts), n_scans, stride, C.byref(params),
                                             _p(xyzi), _p(pc)))
         return xyzi, pc
+
+    # ---- dense-capsule decode (the step before the hot path) -------------------------------------
+    def decode_dense(self, capsules: np.ndarray, sample_duration_us: int = 31, sync_state: int = 0):
+        """One stream of framed capsules [n, 84] -> (nodes, capsule_status, capsule_node_offset, sync_state_out)."""
+        capsules = np.ascontiguousarray(capsules, dtype=np.uint8).reshape(-1, 84)
+        n = capsules.shape[0]
+        nodes = np.zeros(max(40 * n, 1), NODE_DTYPE)
+        status = np.zeros(max(n, 1), np.uint32)
+        offs = np.zeros(max(n, 1), np.uint32)
+        st, cnt = C.c_uint32(sync_state), C.c_uint32(0)
+        self._check(self._L.rpl_decode_dense(self._h, _p(capsules), n, sample_duration_us, C.byref(st), _p(nodes),
+                                             C.byref(cnt), _p(status), _p(offs)))
+        return nodes[: cnt.value].copy(), status[:n].copy(), offs[:n].copy(), st.value
+
+    def decode_dense_batch_dev(self, capsules, capsule_counts, n_streams, stride_capsules, sample_duration_us,
+                               nodes_out, node_counts, sync_state_in=None, capsule_status=None,
+                               capsule_node_offset=None, sync_state_out=None, stream=None):
+        self._check(self._L.rpl_decode_dense_batch_dev(
+            self._h, _p(capsules), _p(capsule_counts), n_streams, stride_capsules, sample_duration_us,
+            _p(sync_state_in), _p(nodes_out), _p(node_counts), _p(capsule_status), _p(capsule_node_offset),
+            _p(sync_state_out), _p(stream)))
 
     def cloud_fuse_dev(self, xyzi, point_counts, n_scans, stride, fused, offsets, total, stream=None):
         self._check(self._L.rpl_cloud_fuse_dev(self._h, _p(xyzi), _p(point_counts), n_scans, stride, _p(fused),

@@ -1,0 +1,258 @@
+// decode.cu -- dense-capsule decode on the GPU (the step immediately
+// before the hot path).
+//
+// Replaces, for framed S2/S3 DenseBoost capsules (answer type 0x85, 84 bytes, reference
+// src/sdk/include/sl_lidar_cmd.h:223-234):
+//   UnpackerHandler_DenseCapsuleNode::onData                       handler_capsules.cpp:639-734
+//   UnpackerHandler_DenseCapsuleNode::_onScanNodeDenseCapsuleData   handler_capsules.cpp:736-791
+// (reference src/sdk/src/dataunpacker/unpacker/).  One capsule carries a start angle and 40 raw
+// distances; its 40 HQ nodes can only be produced when the NEXT capsule arrives (angles are
+// interpolated between the two start angles), and only if both checksums hold, the next capsule
+// is not a scan start, and the angular step is below the 100 Hz bound.  The reference does this
+// byte by byte in a state machine; here every capsule is a thread:
+//
+//   * the stream is staged through shared memory in tiles of 256 capsules (coalesced 128-bit
+//     loads; 21-word capsule stride is conflict free),
+//   * "does capsule j release its predecessor?" depends only on capsules j-1 and j, so the output
+//     position of every node is an exclusive block scan of the release flags,
+//   * the one genuinely sequential piece of state, the reference's function-static
+//     lastNodeSyncBit (sync_i = raw_i & ~sync_{i-1}), is carried across capsules by scanning
+//     2-bit transfer functions (out(0), out(1)) under composition,
+//   * nodes are written 8 bytes per lane, 40 consecutive nodes per capsule: fully coalesced.
+//
+// Wire bytes in: 84 per capsule (2.1 B per point); nodes out: 320 per released capsule.
+#include "decode_args.h"
+#include "rpl_device.cuh"
+
+namespace rpl {
+
+namespace {
+
+constexpr int DT = 256;              // threads = capsules per tile
+constexpr int kCapWords = 21;        // 84 bytes
+constexpr uint32_t kStOk = 1, kStSync = 2, kStEmit = 4, kStDiscard = 8, kStChecksum = 16, kStEncReset = 32,
+                   kStBadFrame = 64;
+
+struct DecodeSmem {
+  uint32_t cap[(DT + 1) * kCapWords];  // slot 0 = last capsule of the previous tile
+  unsigned long long smask[DT];        // final sync bits of the 40 nodes each capsule releases
+  uint32_t start_q8[DT + 1];           // (start & 0x7FFF) << 2, slot 0 = carry
+  uint32_t okflag[DT + 1];             // checksum + frame ok, slot 0 = carry
+  uint32_t emit_off[DT];               // node offset (within the tile) of a releasing capsule, ~0 if none
+  uint32_t warp_a[DT / 32], warp_b[DT / 32];
+  uint32_t carry_nodes;                // nodes written so far in this stream
+  uint32_t carry_sync;                 // lastNodeSyncBit entering the tile
+  uint32_t tile_nodes;
+  uint32_t red_sync;                   // lastNodeSyncBit leaving the tile
+};
+
+// raw scan-start test of the 40 interpolated samples (reference :768) as a bit mask
+__device__ __forceinline__ unsigned long long raw_sync_mask(int prev_q8, int inc_q16) {
+  unsigned long long m = 0;
+  int cur = prev_q8 << 8;
+#pragma unroll 8
+  for (int pos = 0; pos < 40; ++pos) {
+    const int nxt = cur + inc_q16;
+    if ((nxt % (360 << 16)) < (inc_q16 << 1)) m |= 1ull << pos;
+    cur = nxt;
+  }
+  return m;
+}
+// sync_i = raw_i & ~sync_{i-1} (reference :769), sync_{-1} = s_in; only set raw bits matter
+__device__ __forceinline__ unsigned long long resolve_sync(unsigned long long raw, uint32_t s_in) {
+  unsigned long long s = 0, r = raw;
+  while (r) {
+    const int i = __ffsll((long long)r) - 1;
+    r &= r - 1;
+    const uint32_t prev = (i == 0) ? s_in : (uint32_t)((s >> (i - 1)) & 1ull);
+    if (!prev) s |= 1ull << i;
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(DT) decode_dense_kernel(DecodeArgs a) {
+  __shared__ DecodeSmem sm;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int thr_q8 = (360 * 100 * 40 / (int)(1000000u / a.sample_duration_us)) << 8;
+
+  for (uint32_t s = blockIdx.x; s < a.n_streams; s += gridDim.x) {
+    const uint32_t n = a.counts[s];
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.capsules + (size_t)s * a.stride_capsules * 84);
+    uint2* out = a.nodes_out + (size_t)s * a.stride_capsules * 40;
+    uint32_t* st_out = a.capsule_status ? a.capsule_status + (size_t)s * a.stride_capsules : nullptr;
+    uint32_t* off_out = a.capsule_node_offset ? a.capsule_node_offset + (size_t)s * a.stride_capsules : nullptr;
+    if (tid == 0) {
+      sm.carry_nodes = 0;
+      sm.carry_sync = a.sync_state_in ? (a.sync_state_in[s] & 1u) : 0u;
+      sm.okflag[0] = 0;  // no previous capsule
+      sm.start_q8[0] = 0;
+    }
+    __syncthreads();
+
+    for (uint32_t c0 = 0; c0 < n; c0 += DT) {
+      const uint32_t live = min((uint32_t)DT, n - c0);
+      // ---- stage the tile: live * 21 words, coalesced ------------------------------------------
+      {
+        const uint32_t words = live * kCapWords;
+        const uint32_t* g = src + (size_t)c0 * kCapWords;
+        for (uint32_t w = tid; w < words; w += DT) sm.cap[kCapWords + w] = __ldg(g + w);
+      }
+      __syncthreads();
+      // ---- per capsule: frame, checksum, start angle --------------------------------------------
+      uint32_t st = 0, ok = 0, sync = 0, start = 0;
+      if (tid < live) {
+        const uint32_t* c = &sm.cap[(tid + 1) * kCapWords];
+        const uint32_t w0 = c[0];
+        const uint32_t b0 = w0 & 0xFF, b1 = (w0 >> 8) & 0xFF;
+        start = w0 >> 16;
+        if ((b0 >> 4) != 0xA || (b1 >> 4) != 0x5) {
+          st = kStBadFrame;
+        } else {
+          uint32_t x = w0 >> 16;  // bytes 2, 3
+#pragma unroll
+          for (int w = 1; w < kCapWords; ++w) x ^= c[w];
+          x ^= x >> 16;
+          const uint32_t sum = (x ^ (x >> 8)) & 0xFF;
+          const uint32_t recv = ((b0 & 0xF) | (b1 << 4)) & 0xFF;
+          if (recv != sum) {
+            st = kStChecksum;
+          } else {
+            ok = 1;
+            st = kStOk;
+            sync = (start >> 15) & 1u;
+            if (sync) st |= kStSync;
+          }
+        }
+        sm.okflag[tid + 1] = ok;
+        sm.start_q8[tid + 1] = (start & 0x7FFFu) << 2;
+      }
+      __syncthreads();
+      // ---- does this capsule release its predecessor? ---------------------------------------------
+      uint32_t emit = 0;
+      int prev_q8 = 0, inc_q16 = 0;
+      if (tid < live && ok) {
+        const uint32_t prev_ok = sm.okflag[tid];
+        if (sync) {
+          if (prev_ok) st |= kStEncReset;
+        } else if (prev_ok) {
+          const int cur_q8 = (int)sm.start_q8[tid + 1];
+          prev_q8 = (int)sm.start_q8[tid];
+          int diff = cur_q8 - prev_q8;
+          if (prev_q8 > cur_q8) diff += (360 << 8);
+          if (diff > thr_q8) {
+            st |= kStDiscard;
+          } else {
+            emit = 1;
+            st |= kStEmit;
+            inc_q16 = (diff << 8) / 40;
+          }
+        }
+      }
+      // exclusive scan of the release flags -> node offsets
+      const uint32_t inc_scan = warp_inclusive_scan(emit);
+      if (lane == 31) sm.warp_a[warp] = inc_scan;
+      // transfer function of the sync bit through this capsule: f(s_in) = s_out
+      unsigned long long raw = 0;
+      uint32_t f = 0x2;  // identity: f(0)=0 (bit0), f(1)=1 (bit1)
+      if (emit) {
+        raw = raw_sync_mask(prev_q8, inc_q16);
+        const uint32_t o0 = (uint32_t)(resolve_sync(raw, 0) >> 39) & 1u;
+        const uint32_t o1 = (uint32_t)(resolve_sync(raw, 1) >> 39) & 1u;
+        f = o0 | (o1 << 1);
+      }
+      // inclusive scan of the functions under composition: (g o f)(x) = g(f(x))
+      uint32_t F = f;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t p = __shfl_up_sync(0xffffffffu, F, o);  // earlier capsules' function
+        if (lane >= (uint32_t)o) F = ((F >> (p & 1u)) & 1u) | (((F >> ((p >> 1) & 1u)) & 1u) << 1);
+      }
+      if (lane == 31) sm.warp_b[warp] = F;
+      __syncthreads();
+      uint32_t base_off = 0, s_state = sm.carry_sync;
+      for (uint32_t w = 0; w < warp; ++w) {
+        base_off += sm.warp_a[w];
+        s_state = (sm.warp_b[w] >> s_state) & 1u;
+      }
+      const uint32_t my_off = base_off + inc_scan - emit;  // releasing capsules before me in the tile
+      // state entering this capsule: everything before it in the warp
+      const uint32_t Fprev = __shfl_up_sync(0xffffffffu, F, 1);
+      const uint32_t s_in = (lane == 0) ? s_state : ((Fprev >> s_state) & 1u);
+      if (tid < live) {
+        sm.smask[tid] = emit ? resolve_sync(raw, s_in) : 0ull;
+        sm.emit_off[tid] = emit ? my_off : 0xFFFFFFFFu;
+        const uint32_t node_off = sm.carry_nodes + 40u * my_off;
+        if (st_out) st_out[c0 + tid] = st;
+        if (off_out) off_out[c0 + tid] = node_off;
+      }
+      if (tid == DT - 1) {
+        uint32_t tot = 0, st2 = sm.carry_sync;
+        for (uint32_t w = 0; w < DT / 32; ++w) {
+          tot += sm.warp_a[w];
+          st2 = (sm.warp_b[w] >> st2) & 1u;
+        }
+        sm.tile_nodes = 40u * tot;
+        sm.red_sync = st2;
+      }
+      __syncthreads();
+      // ---- write the nodes: one warp per releasing capsule, 8 bytes per lane ---------------------
+      const uint32_t node_base = sm.carry_nodes;
+      for (uint32_t j = warp; j < live; j += DT / 32) {
+        const uint32_t eo = sm.emit_off[j];
+        if (eo == 0xFFFFFFFFu) continue;  // warp-uniform
+        const uint32_t* pc = &sm.cap[j * kCapWords];  // the predecessor (slot j: capsule j-1 of the tile)
+        const int pq8 = (int)sm.start_q8[j];
+        int diff = (int)sm.start_q8[j + 1] - pq8;
+        if (pq8 > (int)sm.start_q8[j + 1]) diff += (360 << 8);
+        const int inc = (diff << 8) / 40;
+        const unsigned long long sm_bits = sm.smask[j];
+        uint2* o = out + node_base + 40u * eo;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int pos = half * 32 + (int)lane;
+          if (pos < 40) {
+            const uint32_t wq = pc[1 + (pos >> 1)];
+            const int dist = (int)((pos & 1) ? (wq >> 16) : (wq & 0xFFFFu));
+            const int dist_q2 = dist << 2;
+            int angle_q6 = ((pq8 << 8) + pos * inc) >> 10;
+            if (angle_q6 < 0) angle_q6 += (360 << 6);
+            if (angle_q6 >= (360 << 6)) angle_q6 -= (360 << 6);
+            const uint32_t syncb = (uint32_t)(sm_bits >> pos) & 1u;
+            const uint32_t key = (uint32_t)((angle_q6 << 8) / 90) & 0xFFFFu;
+            const uint32_t quality = dist_q2 ? (0x2Fu << 2) : 0u;
+            const uint32_t flag = syncb | ((syncb ^ 1u) << 1);
+            uint2 nd;
+            nd.x = key | ((uint32_t)dist_q2 << 16);
+            nd.y = ((uint32_t)dist_q2 >> 16) | (quality << 16) | (flag << 24);
+            o[pos] = nd;
+          }
+        }
+      }
+      __syncthreads();
+      // ---- carry into the next tile -----------------------------------------------------------------
+      if (tid < kCapWords) sm.cap[tid] = sm.cap[live * kCapWords + tid];
+      if (tid == 0) {
+        sm.okflag[0] = sm.okflag[live];
+        sm.start_q8[0] = sm.start_q8[live];
+        sm.carry_nodes += sm.tile_nodes;
+        sm.carry_sync = sm.red_sync;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      if (a.node_counts) a.node_counts[s] = sm.carry_nodes;
+      if (a.sync_state_out) a.sync_state_out[s] = sm.carry_sync;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_decode_dense(const DecodeArgs& a, int grid, cudaStream_t stream) {
+  if (a.n_streams == 0) return cudaSuccess;
+  decode_dense_kernel<<<grid, DT, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace rpl

@@ -1,0 +1,24 @@
+// decode_args.h -- argument block of the dense-capsule decode kernel (decode.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rpl {
+
+struct DecodeArgs {
+  const uint8_t* capsules;        // [n_streams][stride_capsules][84], stream bases 4-byte aligned
+  const uint32_t* counts;         // [n_streams] capsules per stream
+  uint32_t n_streams;
+  uint32_t stride_capsules;
+  uint32_t sample_duration_us;    // SlamtecLidarTimingDesc::sample_duration_uS (jump threshold)
+  const uint32_t* sync_state_in;  // [n_streams] lastNodeSyncBit entering each stream (nullable: 0)
+  uint2* nodes_out;               // [n_streams][stride_capsules * 40]
+  uint32_t* node_counts;          // [n_streams]
+  uint32_t* capsule_status;       // [n_streams][stride_capsules] nullable
+  uint32_t* capsule_node_offset;  // [n_streams][stride_capsules] nullable
+  uint32_t* sync_state_out;       // [n_streams] nullable
+};
+
+cudaError_t launch_decode_dense(const DecodeArgs& a, int grid, cudaStream_t stream);
+
+}  // namespace rpl

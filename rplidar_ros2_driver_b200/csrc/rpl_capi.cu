@@ -15,6 +15,7 @@
 
 #include "../../include/rpl_b200.h"
 #include "cloud_args.h"
+#include "decode_args.h"
 #include "scan_args.h"
 
 namespace rpl {
@@ -670,6 +671,82 @@ rpl_result rpl_scan(rpl_ctx* c, rpl_node_hq* nodes, size_t count, const rpl_scan
   if (!nodes || !ranges || !intensities || count > c->max_nodes) return RPL_RESULT_INVALID_DATA;
   return scan_single(c, nodes, count, params, params->apply_ascend ? nodes : nullptr, ranges, intensities,
                      beam_count, angle_increment, ascend_status);
+}
+
+// ---- dense-capsule decode ---------------------------------------------
+rpl_result rpl_decode_dense_batch_dev(rpl_ctx* c, const uint8_t* capsules, const uint32_t* capsule_counts,
+                                      uint32_t n_streams, uint32_t stride_capsules, uint32_t sample_duration_us,
+                                      const uint32_t* sync_state_in, rpl_node_hq* nodes_out,
+                                      uint32_t* node_counts, uint32_t* capsule_status,
+                                      uint32_t* capsule_node_offset, uint32_t* sync_state_out, void* stream) {
+  if (!c || !capsules || !capsule_counts || !nodes_out) return RPL_RESULT_INVALID_DATA;
+  if (sample_duration_us == 0 || sample_duration_us > 1000000u) {
+    c->err = "sample_duration_us must be in [1, 1000000]";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if ((reinterpret_cast<uintptr_t>(capsules) & 3u) != 0) {
+    c->err = "capsule buffer must be 4-byte aligned";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if (n_streams == 0) return RPL_RESULT_OK;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
+  rpl::DecodeArgs a{};
+  a.capsules = capsules;
+  a.counts = capsule_counts;
+  a.n_streams = n_streams;
+  a.stride_capsules = stride_capsules;
+  a.sample_duration_us = sample_duration_us;
+  a.sync_state_in = sync_state_in;
+  a.nodes_out = reinterpret_cast<uint2*>(nodes_out);
+  a.node_counts = node_counts;
+  a.capsule_status = capsule_status;
+  a.capsule_node_offset = capsule_node_offset;
+  a.sync_state_out = sync_state_out;
+  const int grid = (int)std::min<uint32_t>(n_streams, (uint32_t)c->num_sms * 4u);
+  RPL_CUDA(c, rpl::launch_decode_dense(a, grid, st), RPL_RESULT_OPERATION_FAIL);
+  c->launches++;
+  return RPL_RESULT_OK;
+}
+
+rpl_result rpl_decode_dense(rpl_ctx* c, const uint8_t* capsules, uint32_t n_capsules, uint32_t sample_duration_us,
+                            uint32_t* sync_state, rpl_node_hq* nodes_out, uint32_t* node_count,
+                            uint32_t* capsule_status, uint32_t* capsule_node_offset) {
+  if (!c || !node_count || (n_capsules && (!capsules || !nodes_out))) return RPL_RESULT_INVALID_DATA;
+  *node_count = 0;
+  if (n_capsules == 0) return RPL_RESULT_OK;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  cudaStream_t st = c->lane[0].stream;
+  const size_t cb = (size_t)n_capsules * 84, nb = (size_t)n_capsules * 40 * 8, sb = (size_t)n_capsules * 4;
+  unsigned char* d = nullptr;  // [capsules | pad][nodes][status][offsets][count, n_nodes, sync in, sync out]
+  const size_t o_nodes = (cb + 15) & ~(size_t)15, o_st = o_nodes + nb, o_off = o_st + sb, o_small = o_off + sb;
+  RPL_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&d), o_small + 16), RPL_RESULT_INSUFFICIENT_MEMORY);
+  uint32_t small[4] = {n_capsules, 0u, sync_state ? (*sync_state & 1u) : 0u, 0u};
+  rpl_result r = RPL_RESULT_OK;
+  auto bail = [&](rpl_result code) {
+    cudaFree(d);
+    return code;
+  };
+  if (!cuda_ok(c, cudaMemcpyAsync(d, capsules, cb, cudaMemcpyHostToDevice, st), "H2D") ||
+      !cuda_ok(c, cudaMemcpyAsync(d + o_small, small, 16, cudaMemcpyHostToDevice, st), "H2D"))
+    return bail(RPL_RESULT_OPERATION_FAIL);
+  uint32_t* ds = reinterpret_cast<uint32_t*>(d + o_small);
+  r = rpl_decode_dense_batch_dev(c, d, ds, 1, n_capsules, sample_duration_us, ds + 2,
+                                 reinterpret_cast<rpl_node_hq*>(d + o_nodes), ds + 1,
+                                 reinterpret_cast<uint32_t*>(d + o_st), reinterpret_cast<uint32_t*>(d + o_off), ds + 3, st);
+  if (r != RPL_RESULT_OK) return bail(r);
+  if (!cuda_ok(c, cudaMemcpyAsync(small, ds, 16, cudaMemcpyDeviceToHost, st), "D2H") ||
+      !cuda_ok(c, cudaStreamSynchronize(st), "sync"))
+    return bail(RPL_RESULT_OPERATION_FAIL);
+  *node_count = small[1];
+  if (sync_state) *sync_state = small[3];
+  if (!cuda_ok(c, cudaMemcpy(nodes_out, d + o_nodes, (size_t)small[1] * 8, cudaMemcpyDeviceToHost), "D2H"))
+    return bail(RPL_RESULT_OPERATION_FAIL);
+  if (capsule_status && !cuda_ok(c, cudaMemcpy(capsule_status, d + o_st, sb, cudaMemcpyDeviceToHost), "D2H"))
+    return bail(RPL_RESULT_OPERATION_FAIL);
+  if (capsule_node_offset && !cuda_ok(c, cudaMemcpy(capsule_node_offset, d + o_off, sb, cudaMemcpyDeviceToHost), "D2H"))
+    return bail(RPL_RESULT_OPERATION_FAIL);
+  return bail(RPL_RESULT_OK);
 }
 
 // ---- synthetic streams ------------------------------------------------------------------------
