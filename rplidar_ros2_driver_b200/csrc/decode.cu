@@ -33,12 +33,13 @@ constexpr int kCapWords = 21;        // 84 bytes
 constexpr uint32_t kStOk = 1, kStSync = 2, kStEmit = 4, kStDiscard = 8, kStChecksum = 16, kStEncReset = 32,
                    kStBadFrame = 64;
 
-struct DecodeSmem {
-  uint32_t cap[(DT + 1) * kCapWords];  // slot 0 = last capsule of the previous tile
+struct __align__(16) DecodeSmem {
+  uint32_t cap[2][DT * kCapWords];     // double-buffered tiles (cp.async prefetch of the next tile)
+  uint32_t carry[kCapWords];           // last capsule of the previous tile
   unsigned long long smask[DT];        // final sync bits of the 40 nodes each capsule releases
   uint32_t start_q8[DT + 1];           // (start & 0x7FFF) << 2, slot 0 = carry
   uint32_t okflag[DT + 1];             // checksum + frame ok, slot 0 = carry
-  uint32_t emit_off[DT];               // node offset (within the tile) of a releasing capsule, ~0 if none
+  uint32_t emit_list[DT];              // releasing capsules of the tile, in order (compacted)
   uint32_t warp_a[DT / 32], warp_b[DT / 32];
   uint32_t carry_nodes;                // nodes written so far in this stream
   uint32_t carry_sync;                 // lastNodeSyncBit entering the tile
@@ -47,14 +48,18 @@ struct DecodeSmem {
 };
 
 // raw scan-start test of the 40 interpolated samples (reference :768) as a bit mask
+// One real modulo, then a running remainder: inc_q16 < 360 deg (the jump threshold keeps the
+// step per sample far below a revolution), so a single conditional subtraction per step suffices.
 __device__ __forceinline__ unsigned long long raw_sync_mask(int prev_q8, int inc_q16) {
+  const int kFull = 360 << 16;
   unsigned long long m = 0;
-  int cur = prev_q8 << 8;
+  int rem = ((prev_q8 << 8) + inc_q16) % kFull;  // (cur + inc) % full for pos = 0
+  const int lim = inc_q16 << 1;
 #pragma unroll 8
   for (int pos = 0; pos < 40; ++pos) {
-    const int nxt = cur + inc_q16;
-    if ((nxt % (360 << 16)) < (inc_q16 << 1)) m |= 1ull << pos;
-    cur = nxt;
+    if (rem < lim) m |= 1ull << pos;
+    rem += inc_q16;
+    if (rem >= kFull) rem -= kFull;
   }
   return m;
 }
@@ -70,8 +75,14 @@ __device__ __forceinline__ unsigned long long resolve_sync(unsigned long long ra
   return s;
 }
 
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+               : "memory");
+}
+
 __global__ void __launch_bounds__(DT) decode_dense_kernel(DecodeArgs a) {
-  __shared__ DecodeSmem sm;
+  extern __shared__ __align__(16) unsigned char decode_smem_raw[];
+  DecodeSmem& sm = *reinterpret_cast<DecodeSmem*>(decode_smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int thr_q8 = (360 * 100 * 40 / (int)(1000000u / a.sample_duration_us)) << 8;
 
@@ -89,19 +100,33 @@ __global__ void __launch_bounds__(DT) decode_dense_kernel(DecodeArgs a) {
     }
     __syncthreads();
 
-    for (uint32_t c0 = 0; c0 < n; c0 += DT) {
+    // stage a tile into buffer `b` (asynchronously when the source is 16-byte aligned)
+    auto stage = [&](uint32_t c0, uint32_t b) {
       const uint32_t live = min((uint32_t)DT, n - c0);
-      // ---- stage the tile: live * 21 words, coalesced ------------------------------------------
-      {
-        const uint32_t words = live * kCapWords;
-        const uint32_t* g = src + (size_t)c0 * kCapWords;
-        for (uint32_t w = tid; w < words; w += DT) sm.cap[kCapWords + w] = __ldg(g + w);
+      const uint32_t words = live * kCapWords;
+      const uint32_t* g = src + (size_t)c0 * kCapWords;
+      uint32_t done = 0;
+      if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
+        const uint32_t quads = words >> 2;
+        for (uint32_t q = tid; q < quads; q += DT) cp_async16(&sm.cap[b][4 * q], g + 4 * q);
+        done = quads << 2;
       }
+      for (uint32_t w = done + tid; w < words; w += DT) sm.cap[b][w] = __ldg(g + w);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (n > 0) stage(0, 0);
+    uint32_t buf = 0;
+    for (uint32_t c0 = 0; c0 < n; c0 += DT, buf ^= 1u) {
+      const uint32_t live = min((uint32_t)DT, n - c0);
+      // ---- wait for this tile, start fetching the next one ------------------------------------------
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();
+      if (c0 + DT < n) stage(c0 + DT, buf ^ 1u);
+      const uint32_t* tile = sm.cap[buf];
       // ---- per capsule: frame, checksum, start angle --------------------------------------------
       uint32_t st = 0, ok = 0, sync = 0, start = 0;
       if (tid < live) {
-        const uint32_t* c = &sm.cap[(tid + 1) * kCapWords];
+        const uint32_t* c = &tile[tid * kCapWords];
         const uint32_t w0 = c[0];
         const uint32_t b0 = w0 & 0xFF, b1 = (w0 >> 8) & 0xFF;
         start = w0 >> 16;
@@ -180,7 +205,7 @@ __global__ void __launch_bounds__(DT) decode_dense_kernel(DecodeArgs a) {
       const uint32_t s_in = (lane == 0) ? s_state : ((Fprev >> s_state) & 1u);
       if (tid < live) {
         sm.smask[tid] = emit ? resolve_sync(raw, s_in) : 0ull;
-        sm.emit_off[tid] = emit ? my_off : 0xFFFFFFFFu;
+        if (emit) sm.emit_list[my_off] = tid;
         const uint32_t node_off = sm.carry_nodes + 40u * my_off;
         if (st_out) st_out[c0 + tid] = st;
         if (off_out) off_out[c0 + tid] = node_off;
@@ -195,42 +220,38 @@ __global__ void __launch_bounds__(DT) decode_dense_kernel(DecodeArgs a) {
         sm.red_sync = st2;
       }
       __syncthreads();
-      // ---- write the nodes: one warp per releasing capsule, 8 bytes per lane ---------------------
-      const uint32_t node_base = sm.carry_nodes;
-      for (uint32_t j = warp; j < live; j += DT / 32) {
-        const uint32_t eo = sm.emit_off[j];
-        if (eo == 0xFFFFFFFFu) continue;  // warp-uniform
-        const uint32_t* pc = &sm.cap[j * kCapWords];  // the predecessor (slot j: capsule j-1 of the tile)
-        const int pq8 = (int)sm.start_q8[j];
-        int diff = (int)sm.start_q8[j + 1] - pq8;
-        if (pq8 > (int)sm.start_q8[j + 1]) diff += (360 << 8);
-        const int inc = (diff << 8) / 40;
-        const unsigned long long sm_bits = sm.smask[j];
-        uint2* o = out + node_base + 40u * eo;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int pos = half * 32 + (int)lane;
-          if (pos < 40) {
-            const uint32_t wq = pc[1 + (pos >> 1)];
-            const int dist = (int)((pos & 1) ? (wq >> 16) : (wq & 0xFFFFu));
-            const int dist_q2 = dist << 2;
-            int angle_q6 = ((pq8 << 8) + pos * inc) >> 10;
-            if (angle_q6 < 0) angle_q6 += (360 << 6);
-            if (angle_q6 >= (360 << 6)) angle_q6 -= (360 << 6);
-            const uint32_t syncb = (uint32_t)(sm_bits >> pos) & 1u;
-            const uint32_t key = (uint32_t)((angle_q6 << 8) / 90) & 0xFFFFu;
-            const uint32_t quality = dist_q2 ? (0x2Fu << 2) : 0u;
-            const uint32_t flag = syncb | ((syncb ^ 1u) << 1);
-            uint2 nd;
-            nd.x = key | ((uint32_t)dist_q2 << 16);
-            nd.y = ((uint32_t)dist_q2 >> 16) | (quality << 16) | (flag << 24);
-            o[pos] = nd;
-          }
+      // ---- write the nodes: the tile's 40 * E nodes are one contiguous run of the output; thread q
+      // handles node q (capsule emit_list[q / 40], sample q % 40): every lane busy, 8 bytes per lane
+      {
+        const uint32_t n_nodes = sm.tile_nodes;
+        uint2* o = out + sm.carry_nodes;
+        for (uint32_t q = tid; q < n_nodes; q += DT) {
+          const uint32_t e = q / 40u, pos = q - e * 40u;
+          const uint32_t j = sm.emit_list[e];
+          const uint32_t* pc = (j == 0) ? sm.carry : &tile[(j - 1) * kCapWords];  // the predecessor capsule
+          const int pq8 = (int)sm.start_q8[j];
+          int diff = (int)sm.start_q8[j + 1] - pq8;
+          if (pq8 > (int)sm.start_q8[j + 1]) diff += (360 << 8);
+          const int inc = (diff << 8) / 40;
+          const uint32_t wq = pc[1 + (pos >> 1)];
+          const int dist = (int)((pos & 1u) ? (wq >> 16) : (wq & 0xFFFFu));
+          const int dist_q2 = dist << 2;
+          int angle_q6 = ((pq8 << 8) + (int)pos * inc) >> 10;
+          if (angle_q6 < 0) angle_q6 += (360 << 6);
+          if (angle_q6 >= (360 << 6)) angle_q6 -= (360 << 6);
+          const uint32_t syncb = (uint32_t)(sm.smask[j] >> pos) & 1u;
+          const uint32_t key = (uint32_t)((angle_q6 << 8) / 90) & 0xFFFFu;
+          const uint32_t quality = dist_q2 ? (0x2Fu << 2) : 0u;
+          const uint32_t flag = syncb | ((syncb ^ 1u) << 1);
+          uint2 nd;
+          nd.x = key | ((uint32_t)dist_q2 << 16);
+          nd.y = ((uint32_t)dist_q2 >> 16) | (quality << 16) | (flag << 24);
+          o[q] = nd;
         }
       }
       __syncthreads();
       // ---- carry into the next tile -----------------------------------------------------------------
-      if (tid < kCapWords) sm.cap[tid] = sm.cap[live * kCapWords + tid];
+      if (tid < kCapWords) sm.carry[tid] = tile[(live - 1) * kCapWords + tid];
       if (tid == 0) {
         sm.okflag[0] = sm.okflag[live];
         sm.start_q8[0] = sm.start_q8[live];
@@ -251,8 +272,13 @@ __global__ void __launch_bounds__(DT) decode_dense_kernel(DecodeArgs a) {
 
 cudaError_t launch_decode_dense(const DecodeArgs& a, int grid, cudaStream_t stream) {
   if (a.n_streams == 0) return cudaSuccess;
-  decode_dense_kernel<<<grid, DT, 0, stream>>>(a);
+  decode_dense_kernel<<<grid, DT, sizeof(DecodeSmem), stream>>>(a);
   return cudaGetLastError();
+}
+
+cudaError_t decode_configure() {
+  return cudaFuncSetAttribute(decode_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)sizeof(DecodeSmem));
 }
 
 }  // namespace rpl

@@ -20,5 +20,6 @@ struct DecodeArgs {
 };
 
 cudaError_t launch_decode_dense(const DecodeArgs& a, int grid, cudaStream_t stream);
+cudaError_t decode_configure();  // opt-in dynamic shared memory, once per device
 
 }  // namespace rpl

@@ -294,7 +294,8 @@ rpl_result rpl_ctx_create(int device, uint32_t max_nodes, uint32_t max_scans, rp
   if (!cuda_ok(c, rpl::scan_fast_configure(), "scan_fast_configure") ||
       !cuda_ok(c, rpl::scan_tma_configure(), "scan_tma_configure") ||
       !cuda_ok(c, rpl::scan_general_configure(), "scan_general_configure") ||
-      !cuda_ok(c, rpl::cloud_configure(), "cloud_configure"))
+      !cuda_ok(c, rpl::cloud_configure(), "cloud_configure") ||
+      !cuda_ok(c, rpl::decode_configure(), "decode_configure"))
     return fail(RPL_RESULT_OPERATION_FAIL);
   const int occ = std::max(1, rpl::scan_fast_max_ctas_per_sm());
   c->fast_grid = c->num_sms * occ;
