@@ -92,3 +92,43 @@ extern "C" uint32_t orc_dense_decode(const uint8_t* capsules, uint32_t n_capsule
   *sync_state = static_cast<uint32_t>(last_sync);
   return n_out;
 }
+
+// ---- scan assembly ---------------------------------------------------------
+// Restatement of ScanDataHolder::pushScanNodeData + rewindCurrentScanData (reference
+// src/sdk/src/sl_lidar_driver.cpp:272-315) as a pure function of the node stream and the positions
+// of the scan-reset requests: a node with flag bit 0 opens a scan (publishing the one in progress,
+// if it holds anything), other nodes are appended only to an open scan, a reset empties the scan in
+// progress, and a scan that reaches `max_nodes` keeps overwriting its last entry.
+// PARITY PINNED: tests/test_decode_oracle_vs_ref.py runs the reference's real ScanDataHolder
+// (oracle/ref_shim_holder.cpp compiles sl_lidar_driver.cpp in place) on the same streams.
+extern "C" uint32_t orc_assemble_scans(const orc_node_hq* nodes, uint32_t n, const uint32_t* resets,
+                                       uint32_t n_resets, uint32_t max_nodes, orc_node_hq* scans_out,
+                                       uint32_t scan_stride, uint32_t* scan_len, uint32_t max_scans) {
+  uint32_t n_scans = 0, cur = 0, ri = 0;  // cur: nodes in the scan in progress
+  orc_node_hq* slot = scans_out;           // the scan in progress is built in place
+  for (uint32_t i = 0; i <= n; ++i) {
+    while (ri < n_resets && resets[ri] == i) {  // rewindCurrentScanData :310-313
+      cur = 0;
+      ++ri;
+    }
+    if (i == n) break;
+    const orc_node_hq& nd = nodes[i];
+    if (nd.flag & 1u) {  // :279-293
+      if (cur) {
+        if (n_scans < max_scans) scan_len[n_scans] = cur;
+        ++n_scans;
+        slot = (n_scans < max_scans) ? scans_out + static_cast<size_t>(n_scans) * scan_stride : nullptr;
+        cur = 0;
+      }
+    } else if (cur == 0) {
+      continue;  // :295-299 no partial scans
+    }
+    if (cur >= max_nodes) {  // :302-308
+      if (slot) slot[cur - 1] = nd;
+    } else {
+      if (slot && cur < scan_stride) slot[cur] = nd;
+      ++cur;
+    }
+  }
+  return n_scans;
+}

@@ -111,6 +111,14 @@ uint32_t orc_dense_decode(const uint8_t* capsules, uint32_t n_capsules, uint32_t
                           uint32_t* sync_state, orc_node_hq* nodes_out, uint32_t* capsule_status,
                           uint32_t* capsule_node_offset);
 
+/* Scan assembly: cuts a decoded node stream into scans exactly as
+ * ScanDataHolder does.  resets: sorted node positions before which a scan reset was requested.
+ * Published scan k goes to scans_out + k * scan_stride (scan_len[k] nodes); at most max_scans are
+ * stored.  Returns the number of published scans. */
+uint32_t orc_assemble_scans(const orc_node_hq* nodes, uint32_t n, const uint32_t* resets, uint32_t n_resets,
+                            uint32_t max_nodes, orc_node_hq* scans_out, uint32_t scan_stride,
+                            uint32_t* scan_len, uint32_t max_scans);
+
 /* ---- part 2: extensions (parity unpinned) --------------------------------------- */
 
 typedef struct orc_cloud_params {

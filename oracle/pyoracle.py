@@ -19,6 +19,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle_scan.so")
 REF_SO = os.path.join(HERE, "_ref", "libref_rplidar.so")
+REF_HOLDER_SO = os.path.join(HERE, "_ref", "libref_holder.so")
 
 NODE_DTYPE = np.dtype(
     {
@@ -105,6 +106,8 @@ def lib() -> C.CDLL:
         L.orc_cloud_scan.restype = u32
         L.orc_dense_decode.argtypes = [vp, u32, u32, C.POINTER(u32), vp, vp, vp]
         L.orc_dense_decode.restype = u32
+        L.orc_assemble_scans.argtypes = [vp, u32, vp, u32, u32, vp, u32, vp, u32]
+        L.orc_assemble_scans.restype = u32
         _lib = L
     return _lib
 
@@ -275,3 +278,46 @@ def ref_dense_decode(stream_bytes: np.ndarray, sample_duration_us: int = 31, chu
                                 _ptr(events), events.shape[0], C.byref(ne))
     assert rc == 0, rc
     return nodes[: nn.value].copy(), events[: ne.value].copy()
+
+
+# ---- scan assembly -------------------------------------------------------
+def resets_from_capsules(status: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+    """Node positions of the scan-reset requests: one per scan-start capsule."""
+    return np.ascontiguousarray(offsets[(status & CAPSULE_SYNC) != 0], dtype=np.uint32)
+
+
+def assemble_scans(nodes: np.ndarray, resets=None, max_nodes: int = 8192, max_scans: int = 64, scan_stride=None):
+    """Returns (scans [n_scans_stored, stride], lengths, n_published)."""
+    nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
+    resets = np.zeros(0, np.uint32) if resets is None else np.ascontiguousarray(resets, dtype=np.uint32)
+    stride = max_nodes if scan_stride is None else scan_stride
+    out = np.zeros((max_scans, stride), NODE_DTYPE)
+    lens = np.zeros(max_scans, np.uint32)
+    k = lib().orc_assemble_scans(_ptr(nodes), nodes.shape[0], _ptr(resets), resets.shape[0], max_nodes, _ptr(out),
+                                 stride, _ptr(lens), max_scans)
+    return out, lens, k
+
+
+_holder = None
+
+
+def have_ref_holder() -> bool:
+    return os.path.exists(REF_HOLDER_SO)
+
+
+def ref_assemble_scans(nodes: np.ndarray, resets=None, max_nodes: int = 8192, max_scans: int = 64, scan_stride=None):
+    """The reference's own ScanDataHolder on the same stream."""
+    global _holder
+    if _holder is None:
+        _holder = C.CDLL(REF_HOLDER_SO)
+        _holder.ref_assemble_scans.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
+                                               C.c_size_t, C.c_void_p, C.c_size_t]
+        _holder.ref_assemble_scans.restype = C.c_int
+    nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
+    resets = np.zeros(0, np.uint32) if resets is None else np.ascontiguousarray(resets, dtype=np.uint32)
+    stride = max_nodes if scan_stride is None else scan_stride
+    out = np.zeros((max_scans, stride), NODE_DTYPE)
+    lens = np.zeros(max_scans, np.uint32)
+    k = _holder.ref_assemble_scans(_ptr(nodes), nodes.shape[0], _ptr(resets), resets.shape[0], max_nodes, _ptr(out),
+                                   stride, _ptr(lens), max_scans)
+    return out, lens, k
