@@ -200,6 +200,23 @@ rpl_result rpl_decode_dense(rpl_ctx* ctx, const uint8_t* capsules, uint32_t n_ca
                             uint32_t sample_duration_us, uint32_t* sync_state, rpl_node_hq* nodes_out,
                             uint32_t* node_count, uint32_t* capsule_status, uint32_t* capsule_node_offset);
 
+/* ---- scan assembly (node stream -> scans, on the device) -------- */
+/* Replaces ScanDataHolder::pushScanNodeData / rewindCurrentScanData (reference
+ * src/sdk/src/sl_lidar_driver.cpp:272-315).  nodes: [n_streams][stride_nodes] decoded streams
+ * (rpl_decode_dense_batch_dev output).  capsule_status / capsule_node_offset / capsule_counts
+ * (nullable together): the decoder's per-capsule report, from which the scan-reset requests are
+ * taken (one before every RPL_CAPSULE_SYNC capsule).  max_nodes: holder capacity (8192 in the SDK);
+ * scan_stride >= max_nodes.  scans_out: [n_streams][max_scans][scan_stride]; scan_len:
+ * [n_streams][max_scans]; scans_per_stream[s] = scans published (only the first max_scans stored).
+ * The output is laid out as the input of rpl_scan_batch_dev (n_scans = n_streams * max_scans with
+ * scan_len as counts; unused slots must be zeroed by the caller or have length 0). */
+rpl_result rpl_assemble_scans_dev(rpl_ctx* ctx, const rpl_node_hq* nodes, const uint32_t* node_counts,
+                                  uint32_t n_streams, uint32_t stride_nodes, const uint32_t* capsule_status,
+                                  const uint32_t* capsule_node_offset, const uint32_t* capsule_counts,
+                                  uint32_t stride_capsules, uint32_t max_nodes, uint32_t max_scans,
+                                  uint32_t scan_stride, rpl_node_hq* scans_out, uint32_t* scan_len,
+                                  uint32_t* scans_per_stream, void* stream);
+
 /* ---- synthetic scan streams ------------------------------------------ */
 /* variant 0: tie-free rotated revolution, 5% unmeasured, quality 188; 1: same, quality
  * U[0,255]; 2: iid U[0,65535] keys (ties); 3: tie-free keys in pseudo-random order; 4: a

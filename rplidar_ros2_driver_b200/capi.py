@@ -42,7 +42,7 @@ EXPORTS = [
     "rpl_host_alloc", "rpl_host_free", "rpl_ctx_launch_count", "rpl_ctx_profile", "rpl_ctx_profile_read", "rpl_ascend_scan", "rpl_laserscan",
     "rpl_scan", "rpl_scan_batch", "rpl_ascend_scan_batch", "rpl_laserscan_batch", "rpl_scan_batch_dev",
     "rpl_cloud_batch_dev", "rpl_cloud_batch", "rpl_cloud_fuse_dev", "rpl_synth_batch_dev",
-    "rpl_decode_dense_batch_dev", "rpl_decode_dense",
+    "rpl_decode_dense_batch_dev", "rpl_decode_dense", "rpl_assemble_scans_dev",
 ]
 
 
@@ -125,6 +125,7 @@ def lib() -> C.CDLL:
         "rpl_synth_batch_dev": ([vp, u64, u32, u32, u32, i32, vp, vp, vp], u32),
         "rpl_decode_dense_batch_dev": ([vp, vp, vp, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp], u32),
         "rpl_decode_dense": ([vp, vp, u32, u32, C.POINTER(u32), vp, C.POINTER(u32), vp, vp], u32),
+        "rpl_assemble_scans_dev": ([vp, vp, vp, u32, u32, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp], u32),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)  # AttributeError here = the library does not export the ABI
@@ -304,6 +305,14 @@ class Context:
             self._h, _p(capsules), _p(capsule_counts), n_streams, stride_capsules, sample_duration_us,
             _p(sync_state_in), _p(nodes_out), _p(node_counts), _p(capsule_status), _p(capsule_node_offset),
             _p(sync_state_out), _p(stream)))
+
+    def assemble_scans_dev(self, nodes, node_counts, n_streams, stride_nodes, max_nodes, max_scans, scan_stride,
+                           scans_out, scan_len, scans_per_stream, capsule_status=None, capsule_node_offset=None,
+                           capsule_counts=None, stride_capsules=0, stream=None):
+        self._check(self._L.rpl_assemble_scans_dev(
+            self._h, _p(nodes), _p(node_counts), n_streams, stride_nodes, _p(capsule_status), _p(capsule_node_offset),
+            _p(capsule_counts), stride_capsules, max_nodes, max_scans, scan_stride, _p(scans_out), _p(scan_len),
+            _p(scans_per_stream), _p(stream)))
 
     def cloud_fuse_dev(self, xyzi, point_counts, n_scans, stride, fused, offsets, total, stream=None):
         self._check(self._L.rpl_cloud_fuse_dev(self._h, _p(xyzi), _p(point_counts), n_scans, stride, _p(fused),

@@ -72,6 +72,10 @@ struct rpl_ctx {
   unsigned char* h_one = nullptr;
   unsigned char* d_one = nullptr;
   size_t one_stride = 0;  // max_nodes rounded up to even
+  // scratch of rpl_assemble_scans_dev (grown on demand)
+  uint32_t* d_reset_prefix = nullptr;
+  uint2* d_desc = nullptr;
+  size_t reset_prefix_cap = 0, desc_cap = 0;
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_fast, prof_general;
 };
@@ -347,6 +351,8 @@ void rpl_ctx_destroy(rpl_ctx* c) {
     if (c->lane[i].stream) cudaStreamSynchronize(c->lane[i].stream);
     free_lane(c->lane[i]);
   }
+  cudaFree(c->d_reset_prefix);
+  cudaFree(c->d_desc);
   if (c->h_one) cudaFreeHost(c->h_one);
   cudaFree(c->d_one);
   if (c->h_counts) cudaFreeHost(c->h_counts);
@@ -748,6 +754,63 @@ rpl_result rpl_decode_dense(rpl_ctx* c, const uint8_t* capsules, uint32_t n_caps
   if (capsule_node_offset && !cuda_ok(c, cudaMemcpy(capsule_node_offset, d + o_off, sb, cudaMemcpyDeviceToHost), "D2H"))
     return bail(RPL_RESULT_OPERATION_FAIL);
   return bail(RPL_RESULT_OK);
+}
+
+// ---- scan assembly ------------------------------------------------------
+rpl_result rpl_assemble_scans_dev(rpl_ctx* c, const rpl_node_hq* nodes, const uint32_t* node_counts,
+                                  uint32_t n_streams, uint32_t stride_nodes, const uint32_t* capsule_status,
+                                  const uint32_t* capsule_node_offset, const uint32_t* capsule_counts,
+                                  uint32_t stride_capsules, uint32_t max_nodes, uint32_t max_scans,
+                                  uint32_t scan_stride, rpl_node_hq* scans_out, uint32_t* scan_len,
+                                  uint32_t* scans_per_stream, void* stream) {
+  if (!c || !nodes || !node_counts || !scans_out || !scan_len || !scans_per_stream) return RPL_RESULT_INVALID_DATA;
+  const bool any = capsule_status || capsule_node_offset || capsule_counts;
+  if (any && !(capsule_status && capsule_node_offset && capsule_counts)) {
+    c->err = "capsule_status, capsule_node_offset and capsule_counts go together";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if (max_nodes == 0 || max_scans == 0 || scan_stride < max_nodes) {
+    c->err = "need max_nodes > 0, max_scans > 0, scan_stride >= max_nodes";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if (n_streams == 0) return RPL_RESULT_OK;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  const size_t need_rp = (size_t)n_streams * std::max<uint32_t>(stride_capsules, 1u);
+  const size_t need_desc = (size_t)n_streams * max_scans;
+  if (need_rp > c->reset_prefix_cap) {
+    cudaFree(c->d_reset_prefix);
+    c->d_reset_prefix = nullptr;
+    RPL_CUDA(c, dev_alloc(&c->d_reset_prefix, need_rp), RPL_RESULT_INSUFFICIENT_MEMORY);
+    c->reset_prefix_cap = need_rp;
+  }
+  if (need_desc > c->desc_cap) {
+    cudaFree(c->d_desc);
+    c->d_desc = nullptr;
+    RPL_CUDA(c, dev_alloc(&c->d_desc, need_desc), RPL_RESULT_INSUFFICIENT_MEMORY);
+    c->desc_cap = need_desc;
+  }
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
+  rpl::AssembleArgs a{};
+  a.nodes = reinterpret_cast<const uint2*>(nodes);
+  a.node_counts = node_counts;
+  a.n_streams = n_streams;
+  a.stride_nodes = stride_nodes;
+  a.capsule_status = capsule_status;
+  a.capsule_node_offset = capsule_node_offset;
+  a.capsule_counts = capsule_counts;
+  a.stride_capsules = std::max<uint32_t>(stride_capsules, 1u);
+  a.max_nodes = max_nodes;
+  a.max_scans = max_scans;
+  a.scan_stride = scan_stride;
+  a.scans_out = reinterpret_cast<uint2*>(scans_out);
+  a.scan_len = scan_len;
+  a.scans_per_stream = scans_per_stream;
+  a.reset_prefix = c->d_reset_prefix;
+  a.desc = c->d_desc;
+  const int grid = (int)std::min<uint32_t>(n_streams, (uint32_t)c->num_sms * 4u);
+  RPL_CUDA(c, rpl::launch_assemble(a, grid, st), RPL_RESULT_OPERATION_FAIL);
+  c->launches++;
+  return RPL_RESULT_OK;
 }
 
 // ---- synthetic streams ------------------------------------------------------------------------

@@ -1,0 +1,174 @@
+"""GPU tests of scan assembly against the restatement orc_assemble_scans,
+which tests/test_decode_oracle_vs_ref.py pins against the reference's own ScanDataHolder.
+Index/byte work: bit-exact."""
+import numpy as np
+import pytest
+
+from test_decode_oracle_vs_ref import make_stream
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def R():
+    import rplidar_ros2_driver_b200 as R
+
+    return R
+
+
+@pytest.fixture(scope="module")
+def ctx(R):
+    c = R.Context(0, 40000, 64)
+    yield c
+    c.close()
+
+
+def random_stream(oracle, rng, n, p_sync, n_resets):
+    nodes = np.zeros(n, oracle.NODE_DTYPE)
+    nodes["angle_z_q14"] = rng.integers(0, 65536, n)
+    nodes["dist_mm_q2"] = rng.integers(0, 1 << 20, n)
+    nodes["quality"] = rng.integers(0, 256, n)
+    sync = rng.random(n) < p_sync
+    nodes["flag"] = np.where(sync, 1, 2)
+    resets = np.sort(rng.integers(0, n + 1, n_resets)).astype(np.uint32) if n else np.zeros(0, np.uint32)
+    return nodes, resets
+
+
+def run_gpu(ctx, oracle, streams, max_nodes, max_scans, with_resets=True):
+    """streams: list of (nodes, resets).  The resets travel as a fake decoder report: one SYNC
+    capsule per reset at that node offset, interleaved with plain capsules."""
+    import torch
+
+    dev = torch.device("cuda")
+    S = len(streams)
+    stride = max(max(len(n) for n, _ in streams), 1)
+    cstride = max(max(2 * len(r) for _, r in streams), 1)
+    hn = np.zeros((S, stride), oracle.NODE_DTYPE)
+    hc = np.zeros(S, np.uint32)
+    hst = np.zeros((S, cstride), np.uint32)
+    hof = np.zeros((S, cstride), np.uint32)
+    hcc = np.zeros(S, np.uint32)
+    for s, (n, r) in enumerate(streams):
+        hn[s, : len(n)] = n
+        hc[s] = len(n)
+        # every reset capsule is followed by a plain capsule at the same offset (must not count)
+        hst[s, 0: 2 * len(r): 2] = 2 | 1
+        hst[s, 1: 2 * len(r): 2] = 1
+        hof[s, 0: 2 * len(r): 2] = r
+        hof[s, 1: 2 * len(r): 2] = r
+        hcc[s] = 2 * len(r)
+    t = lambda a: torch.from_numpy(a.view(np.uint8) if a.dtype == oracle.NODE_DTYPE else a.view(np.int32)).to(dev)
+    nodes, counts, st, of, cc = t(hn), t(hc), t(hst), t(hof), t(hcc)
+    scans = torch.zeros((S, max_scans, max_nodes, 8), dtype=torch.uint8, device=dev)
+    slen = torch.zeros((S, max_scans), dtype=torch.int32, device=dev)
+    sps = torch.zeros(S, dtype=torch.int32, device=dev)
+    kw = dict(capsule_status=st.data_ptr(), capsule_node_offset=of.data_ptr(), capsule_counts=cc.data_ptr(),
+              stride_capsules=cstride) if with_resets else {}
+    ctx.assemble_scans_dev(nodes.data_ptr(), counts.data_ptr(), S, stride, max_nodes, max_scans, max_nodes,
+                           scans.data_ptr(), slen.data_ptr(), sps.data_ptr(), **kw)
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    g = scans.cpu().numpy().view(oracle.NODE_DTYPE).reshape(S, max_scans, max_nodes)
+    return g, slen.cpu().numpy().astype(np.uint32), sps.cpu().numpy().astype(np.uint32)
+
+
+def compare(oracle, streams, got, max_nodes, max_scans, with_resets=True):
+    g, glen, gk = got
+    for s, (n, r) in enumerate(streams):
+        e, elen, ek = oracle.assemble_scans(n, r if with_resets else None, max_nodes, max_scans)
+        assert gk[s] == ek, (s, gk[s], ek)
+        for k in range(min(ek, max_scans)):
+            assert glen[s, k] == elen[k], (s, k)
+            assert (g[s, k, : elen[k]].view(np.uint64) == e[k, : elen[k]].view(np.uint64)).all(), (s, k)
+
+
+@pytest.mark.parametrize("with_resets", [True, False])
+def test_random_streams(R, oracle, ctx, with_resets):
+    rng = np.random.default_rng(17)
+    streams = [random_stream(oracle, rng, int(rng.integers(0, 3000)), float(rng.choice([0.002, 0.01, 0.05, 0.5])),
+                             int(rng.integers(0, 12))) for _ in range(96)]
+    streams += [random_stream(oracle, rng, n, 0.3, 3) for n in (0, 1, 2, 255, 256, 257, 512, 513)]
+    got = run_gpu(ctx, oracle, streams, 400, 48, with_resets)
+    compare(oracle, streams, got, 400, 48, with_resets)
+
+
+def test_capacity_overwrites_the_last_entry_and_scan_overflow(R, oracle, ctx):
+    rng = np.random.default_rng(3)
+    # scans longer than the holder (cap 50) and more scans than output slots (8)
+    streams = [random_stream(oracle, rng, 4000, 0.008, 2) for _ in range(16)]
+    got = run_gpu(ctx, oracle, streams, 50, 8)
+    compare(oracle, streams, got, 50, 8)
+    assert (got[2] > 8).any() and (got[1] == 50).any()
+
+
+def test_edge_streams(R, oracle, ctx):
+    z = lambda n: np.zeros(n, np.uint32)
+    mk = lambda flags: (np.array([(i, 4 * i + 4, 7, f) for i, f in enumerate(flags)], oracle.NODE_DTYPE))
+    streams = [
+        (mk([]), z(0)),                              # empty stream
+        (mk([2, 2, 2]), z(0)),                       # never a scan start: nothing
+        (mk([1]), z(0)),                             # one open scan: not published
+        (mk([1, 1, 1, 1]), z(0)),                    # one-node scans
+        (mk([1, 2, 2, 1, 2, 1]), np.array([0], np.uint32)),   # reset before everything: harmless
+        (mk([1, 2, 2, 1, 2, 1]), np.array([3], np.uint32)),   # reset right before a scan start: kills scan 0
+        (mk([1, 2, 2, 1, 2, 1]), np.array([1, 1, 4], np.uint32)),
+        (mk([1, 2, 2, 1, 2, 1]), np.array([6], np.uint32)),   # after the last node
+    ]
+    got = run_gpu(ctx, oracle, streams, 16, 8)
+    compare(oracle, streams, got, 16, 8)
+    assert list(got[2]) == [0, 0, 0, 3, 2, 1, 0, 2]
+
+
+def test_decode_assemble_scan_chain_stays_on_the_device(R, oracle, ctx):
+    """capsules -> rpl_decode_dense_batch_dev -> rpl_assemble_scans_dev -> rpl_scan_batch_dev with no
+    host round trip, against the CPU chain decode -> assemble -> ascend -> publish."""
+    import torch
+
+    n_streams, n_caps, max_nodes, max_scans = 32, 700, 8192, 8
+    ctx = R.Context(0, max_nodes, n_streams * max_scans)
+    host = np.stack([make_stream(oracle, n_caps, 80.0 + s, seed=900 + s, sync_every=(250 + 7 * s) if s % 3 else None)
+                     for s in range(n_streams)])
+    host[5, 300, 20] ^= 0x10  # a checksum error mid-stream
+    dev = torch.device("cuda")
+    caps = torch.from_numpy(host).to(dev)
+    ccounts = torch.full((n_streams,), n_caps, dtype=torch.int32, device=dev)
+    nodes = torch.zeros((n_streams, n_caps * 40, 8), dtype=torch.uint8, device=dev)
+    ncount = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+    status = torch.zeros((n_streams, n_caps), dtype=torch.int32, device=dev)
+    offs = torch.zeros((n_streams, n_caps), dtype=torch.int32, device=dev)
+    scans = torch.zeros((n_streams, max_scans, max_nodes, 8), dtype=torch.uint8, device=dev)
+    slen = torch.zeros((n_streams, max_scans), dtype=torch.int32, device=dev)
+    sps = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+    NS = n_streams * max_scans
+    ranges = torch.full((NS, max_nodes), float("nan"), dtype=torch.float32, device=dev)
+    intens = torch.full((NS, max_nodes), float("nan"), dtype=torch.float32, device=dev)
+    beams = torch.zeros(NS, dtype=torch.int32, device=dev)
+    inc = torch.zeros(NS, dtype=torch.float32, device=dev)
+    ctx.decode_dense_batch_dev(caps.data_ptr(), ccounts.data_ptr(), n_streams, n_caps, 31, nodes.data_ptr(),
+                               ncount.data_ptr(), capsule_status=status.data_ptr(),
+                               capsule_node_offset=offs.data_ptr())
+    ctx.assemble_scans_dev(nodes.data_ptr(), ncount.data_ptr(), n_streams, n_caps * 40, max_nodes, max_scans,
+                           max_nodes, scans.data_ptr(), slen.data_ptr(), sps.data_ptr(),
+                           capsule_status=status.data_ptr(), capsule_node_offset=offs.data_ptr(),
+                           capsule_counts=ccounts.data_ptr(), stride_capsules=n_caps)
+    params = R.scan_params(1, 0, 0, 1)
+    ctx.scan_batch_dev(scans.data_ptr(), slen.data_ptr(), NS, max_nodes, params, ranges=ranges.data_ptr(),
+                       intensities=intens.data_ptr(), beam_counts=beams.data_ptr(), angle_increment=inc.data_ptr())
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    hr = ranges.cpu().numpy().reshape(n_streams, max_scans, max_nodes)
+    hb = beams.cpu().numpy().reshape(n_streams, max_scans)
+    hs, hl = sps.cpu().numpy(), slen.cpu().numpy()
+    total = 0
+    for s in range(n_streams):
+        en, es, eo, _ = oracle.dense_decode(host[s], 31, 0)
+        e, elen, ek = oracle.assemble_scans(en, oracle.resets_from_capsules(es, eo), max_nodes, max_scans)
+        assert hs[s] == ek
+        for k in range(min(ek, max_scans)):
+            assert hl[s, k] == elen[k]
+            rc, asc = oracle.ascend(e[k, : elen[k]].copy())
+            hdr, r, _ = oracle.publish(asc, oracle.scan_params(1, 0, 0, 1, 40.0, 0.1))
+            assert hb[s, k] == hdr.beam_count
+            assert (hr[s, k, : hdr.beam_count].view(np.uint32) == r.view(np.uint32)).all()
+            total += 1
+    assert total > 2 * n_streams
