@@ -119,6 +119,25 @@ uint32_t orc_assemble_scans(const orc_node_hq* nodes, uint32_t n, const uint32_t
                             uint32_t max_nodes, orc_node_hq* scans_out, uint32_t scan_stride,
                             uint32_t* scan_len, uint32_t max_scans);
 
+/* ---- part 1c: the other measurement answer formats (capsule_oracle.cpp) ---------- */
+#define ORC_ANS_NORMAL 0x81u      /* 5-byte standard nodes (raw byte stream) */
+#define ORC_ANS_EXPRESS 0x82u     /* 84 B -> 32 nodes */
+#define ORC_ANS_HQ 0x83u          /* 781 B -> 96 nodes, CRC32 */
+#define ORC_ANS_ULTRA 0x84u       /* 132 B -> 96 nodes */
+#define ORC_ANS_DENSE 0x85u       /* 84 B -> 40 nodes (decode_oracle.cpp) */
+#define ORC_ANS_ULTRA_DENSE 0x86u /* 170 B -> 64 nodes */
+uint32_t orc_capsule_bytes(uint32_t ans_type);
+uint32_t orc_capsule_nodes(uint32_t ans_type);
+uint32_t orc_crc32_padded(const uint8_t* p, uint32_t len);
+/* Framed capsules of any capsule format.  state[2]: in/out {last node sync bit, last distance}
+ * (dense / ultra-dense only).  nodes_out must hold orc_capsule_nodes * n_capsules nodes. */
+uint32_t orc_decode_capsules(uint32_t ans_type, const uint8_t* capsules, uint32_t n_capsules,
+                             uint32_t sample_duration_us, uint32_t* state, orc_node_hq* nodes_out,
+                             uint32_t* capsule_status, uint32_t* capsule_node_offset);
+/* Standard nodes from a raw byte stream, with the reference's byte-level resynchronisation. */
+uint32_t orc_decode_normal(const uint8_t* bytes, uint32_t n_bytes, orc_node_hq* nodes_out, uint32_t* node_end,
+                           uint32_t* fsm_pos);
+
 /* ---- part 2: extensions (parity unpinned) --------------------------------------- */
 
 typedef struct orc_cloud_params {

@@ -106,6 +106,16 @@ def lib() -> C.CDLL:
         L.orc_cloud_scan.restype = u32
         L.orc_dense_decode.argtypes = [vp, u32, u32, C.POINTER(u32), vp, vp, vp]
         L.orc_dense_decode.restype = u32
+        L.orc_capsule_bytes.argtypes = [u32]
+        L.orc_capsule_bytes.restype = u32
+        L.orc_capsule_nodes.argtypes = [u32]
+        L.orc_capsule_nodes.restype = u32
+        L.orc_crc32_padded.argtypes = [vp, u32]
+        L.orc_crc32_padded.restype = u32
+        L.orc_decode_capsules.argtypes = [u32, vp, u32, u32, vp, vp, vp, vp]
+        L.orc_decode_capsules.restype = u32
+        L.orc_decode_normal.argtypes = [vp, u32, vp, vp, C.POINTER(u32)]
+        L.orc_decode_normal.restype = u32
         L.orc_assemble_scans.argtypes = [vp, u32, vp, u32, u32, vp, u32, vp, u32]
         L.orc_assemble_scans.restype = u32
         _lib = L
@@ -128,6 +138,8 @@ def ref() -> C.CDLL:
         L.ref_dense_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_void_p, C.c_size_t,
                                        C.POINTER(C.c_uint32), C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)]
         L.ref_dense_decode.restype = C.c_int
+        L.ref_unpack.argtypes = [C.c_uint32] + L.ref_dense_decode.argtypes
+        L.ref_unpack.restype = C.c_int
         _ref = L
     return _ref
 
@@ -276,6 +288,78 @@ def ref_dense_decode(stream_bytes: np.ndarray, sample_duration_us: int = 31, chu
     nn, ne = C.c_uint32(0), C.c_uint32(0)
     rc = ref().ref_dense_decode(_ptr(b), b.shape[0], chunk, sample_duration_us, _ptr(nodes), cap_nodes, C.byref(nn),
                                 _ptr(events), events.shape[0], C.byref(ne))
+    assert rc == 0, rc
+    return nodes[: nn.value].copy(), events[: ne.value].copy()
+
+
+# ---- the other measurement answer formats (capsule_oracle.cpp) ------------------------------------
+ANS_NORMAL, ANS_EXPRESS, ANS_HQ, ANS_ULTRA, ANS_DENSE, ANS_ULTRA_DENSE = 0x81, 0x82, 0x83, 0x84, 0x85, 0x86
+
+
+def capsule_bytes(ans: int) -> int:
+    return int(lib().orc_capsule_bytes(ans))
+
+
+def capsule_nodes(ans: int) -> int:
+    return int(lib().orc_capsule_nodes(ans))
+
+
+def seal_capsules(ans: int, payload: np.ndarray, start_q6=None, sync=None) -> np.ndarray:
+    """Turns [n, capsule_bytes] payload bytes into well-formed capsules: optional start angle / scan-start
+    bit, then the sync markers and the checksum (CRC32 for HQ capsules)."""
+    cb = capsule_bytes(ans)
+    caps = np.ascontiguousarray(payload, dtype=np.uint8).reshape(-1, cb).copy()
+    n = caps.shape[0]
+    if ans == ANS_HQ:
+        caps[:, 0] = 0xA5
+        for j in range(n):
+            crc = lib().orc_crc32_padded(_ptr(caps[j]), cb - 4)
+            caps[j, cb - 4:] = np.frombuffer(np.uint32(crc).tobytes(), np.uint8)
+        return caps
+    off = 8 if ans == ANS_ULTRA_DENSE else 2
+    if start_q6 is not None:
+        word = (np.asarray(start_q6, dtype=np.uint32) & 0x7FFF) | (np.asarray(sync, dtype=np.uint32) << 15)
+        caps[:, off] = word & 0xFF
+        caps[:, off + 1] = word >> 8
+    chk = np.bitwise_xor.reduce(caps[:, 2:], axis=1)
+    caps[:, 0] = 0xA0 | (chk & 0xF)
+    caps[:, 1] = 0x50 | (chk >> 4)
+    return caps
+
+
+def decode_capsules(ans: int, capsules: np.ndarray, sample_duration_us: int = 31, state=(0, 0)):
+    """Returns (nodes, capsule_status, capsule_node_offset, state_out)."""
+    cb, per = capsule_bytes(ans), capsule_nodes(ans)
+    capsules = np.ascontiguousarray(capsules, dtype=np.uint8).reshape(-1, cb)
+    n = capsules.shape[0]
+    nodes = np.zeros(max(per * n, 1), NODE_DTYPE)
+    status = np.zeros(max(n, 1), np.uint32)
+    offs = np.zeros(max(n, 1), np.uint32)
+    st = np.array(state, np.uint32)
+    m = lib().orc_decode_capsules(ans, _ptr(capsules), n, sample_duration_us, _ptr(st), _ptr(nodes), _ptr(status),
+                                  _ptr(offs))
+    return nodes[:m].copy(), status[:n].copy(), offs[:n].copy(), (int(st[0]), int(st[1]))
+
+
+def decode_normal(stream_bytes: np.ndarray):
+    """Returns (nodes, node_end_byte, fsm_pos)."""
+    b = np.ascontiguousarray(stream_bytes, dtype=np.uint8).reshape(-1)
+    nodes = np.zeros(max(b.shape[0] // 5 + 1, 1), NODE_DTYPE)
+    ends = np.zeros(nodes.shape[0], np.uint32)
+    pos = C.c_uint32(0)
+    m = lib().orc_decode_normal(_ptr(b), b.shape[0], _ptr(nodes), _ptr(ends), C.byref(pos))
+    return nodes[:m].copy(), ends[:m].copy(), pos.value
+
+
+def ref_unpack(ans: int, stream_bytes: np.ndarray, sample_duration_us: int = 31, chunk: int = 0):
+    """The SDK's own unpacker on a raw byte stream of any answer type.  Returns (nodes, events[n,3])."""
+    b = np.ascontiguousarray(stream_bytes, dtype=np.uint8).reshape(-1)
+    cap_nodes = b.shape[0] + 256
+    nodes = np.zeros(cap_nodes, NODE_DTYPE)
+    events = np.zeros((b.shape[0] // 40 + 16, 3), np.uint32)
+    nn, ne = C.c_uint32(0), C.c_uint32(0)
+    rc = ref().ref_unpack(ans, _ptr(b), b.shape[0], chunk, sample_duration_us, _ptr(nodes), cap_nodes, C.byref(nn),
+                          _ptr(events), events.shape[0], C.byref(ne))
     assert rc == 0, rc
     return nodes[: nn.value].copy(), events[: ne.value].copy()
 

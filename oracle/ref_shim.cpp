@@ -59,9 +59,10 @@ int ref_dummy_grab(void* out_nodes, size_t capacity_nodes) {
 // reset requests and decoding errors, each event tagged with the number of nodes decoded
 // before it.  events: [n_events][3] = {kind (1 = scan reset, 2 = error), node_count, error code}.
 // NOTE the reference keeps `lastNodeSyncBit` in a function-static: it survives across calls.
-int ref_dense_decode(const uint8_t* bytes, size_t n_bytes, size_t chunk, uint32_t sample_duration_us,
-                     void* nodes_out, size_t cap_nodes, uint32_t* n_nodes, uint32_t* events, size_t cap_events,
-                     uint32_t* n_events) {
+// ref_unpack: the same for any measurement answer type (0x81..0x86).
+int ref_unpack(uint32_t ans_type, const uint8_t* bytes, size_t n_bytes, size_t chunk, uint32_t sample_duration_us,
+               void* nodes_out, size_t cap_nodes, uint32_t* n_nodes, uint32_t* events, size_t cap_events,
+               uint32_t* n_events) {
   using namespace sl::internal;
   struct Capture : public LIDARSampleDataListener {
     sl_lidar_response_measurement_node_hq_t* out;
@@ -101,12 +102,19 @@ int ref_dense_decode(const uint8_t* bytes, size_t n_bytes, size_t chunk, uint32_
   if (chunk == 0) chunk = n_bytes ? n_bytes : 1;
   for (size_t off = 0; off < n_bytes; off += chunk) {
     const size_t len = (n_bytes - off < chunk) ? (n_bytes - off) : chunk;
-    up->onSampleData(SL_LIDAR_ANS_TYPE_MEASUREMENT_DENSE_CAPSULED, bytes + off, len);
+    up->onSampleData(static_cast<_u8>(ans_type), bytes + off, len);
   }
   LIDARSampleDataUnpacker::ReleaseInstance(up);
   *n_nodes = static_cast<uint32_t>(cap.n);
   *n_events = static_cast<uint32_t>(cap.ne);
   return cap.overflow ? 1 : 0;
+}
+
+int ref_dense_decode(const uint8_t* bytes, size_t n_bytes, size_t chunk, uint32_t sample_duration_us,
+                     void* nodes_out, size_t cap_nodes, uint32_t* n_nodes, uint32_t* events, size_t cap_events,
+                     uint32_t* n_events) {
+  return ref_unpack(SL_LIDAR_ANS_TYPE_MEASUREMENT_DENSE_CAPSULED, bytes, n_bytes, chunk, sample_duration_us,
+                    nodes_out, cap_nodes, n_nodes, events, cap_events, n_events);
 }
 
 size_t ref_sizeof_node(void) { return sizeof(sl_lidar_response_measurement_node_hq_t); }
