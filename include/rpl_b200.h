@@ -200,6 +200,47 @@ rpl_result rpl_decode_dense(rpl_ctx* ctx, const uint8_t* capsules, uint32_t n_ca
                             uint32_t sample_duration_us, uint32_t* sync_state, rpl_node_hq* nodes_out,
                             uint32_t* node_count, uint32_t* capsule_status, uint32_t* capsule_node_offset);
 
+/* ---- the other measurement answer formats ----------------------- */
+/* ans_type is the SDK's answer type (reference src/sdk/include/sl_lidar_cmd.h:144-151):
+ *   0x82 express capsules      84 B -> 32 nodes   UnpackerHandler_CapsuleNode           handler_capsules.cpp:109-266
+ *   0x83 HQ capsules          781 B -> 96 nodes   UnpackerHandler_HQNode                handler_hqnode.cpp:93-172
+ *   0x84 ultra capsules       132 B -> 96 nodes   UnpackerHandler_UltraCapsuleNode      handler_capsules.cpp:324-580
+ *   0x85 dense capsules        84 B -> 40 nodes   (same kernel as rpl_decode_dense_batch_dev)
+ *   0x86 ultra-dense capsules 170 B -> 64 nodes   UnpackerHandler_UltraDenseCapsuleNode handler_capsules.cpp:852-1047
+ * (reference src/sdk/src/dataunpacker/unpacker/).  Framed input as for the dense decoder:
+ * capsules [n_streams][stride_capsules][rpl_capsule_bytes(ans_type)], nodes_out
+ * [n_streams][stride_capsules * rpl_capsule_nodes(ans_type)].  state_in / state_out (nullable):
+ * [n_streams][2] = {scan-start flag of the last node, last distance} -- the decoder state the SDK
+ * keeps across capsules for the dense (word 0) and ultra-dense (both) formats; 0 on a fresh decoder.
+ * The per-capsule status words are the RPL_CAPSULE_* bits above. */
+#define RPL_ANS_MEASUREMENT 0x81u
+#define RPL_ANS_MEASUREMENT_CAPSULED 0x82u
+#define RPL_ANS_MEASUREMENT_HQ 0x83u
+#define RPL_ANS_MEASUREMENT_CAPSULED_ULTRA 0x84u
+#define RPL_ANS_MEASUREMENT_DENSE_CAPSULED 0x85u
+#define RPL_ANS_MEASUREMENT_ULTRA_DENSE_CAPSULED 0x86u
+uint32_t rpl_capsule_bytes(uint32_t ans_type); /* 0 for an unknown type */
+uint32_t rpl_capsule_nodes(uint32_t ans_type);
+rpl_result rpl_decode_capsules_batch_dev(rpl_ctx* ctx, uint32_t ans_type, const uint8_t* capsules,
+                                         const uint32_t* capsule_counts, uint32_t n_streams,
+                                         uint32_t stride_capsules, uint32_t sample_duration_us,
+                                         const uint32_t* state_in, rpl_node_hq* nodes_out, uint32_t* node_counts,
+                                         uint32_t* capsule_status, uint32_t* capsule_node_offset,
+                                         uint32_t* state_out, void* stream);
+/* One stream, host buffers.  state: in/out [2] (nullable). */
+rpl_result rpl_decode_capsules(rpl_ctx* ctx, uint32_t ans_type, const uint8_t* capsules, uint32_t n_capsules,
+                               uint32_t sample_duration_us, uint32_t* state, rpl_node_hq* nodes_out,
+                               uint32_t* node_count, uint32_t* capsule_status, uint32_t* capsule_node_offset);
+/* 0x81 standard measurement nodes (5 bytes each) from RAW byte streams, with the byte-level
+ * resynchronisation of UnpackerHandler_NormalNode::onData (handler_normalnode.cpp:88-141): exact on
+ * misframed / corrupted streams.  bytes [n_streams][stride_bytes]; nodes_out
+ * [n_streams][stride_bytes / 5]; fsm_state_out (nullable): bytes still buffered at the end. */
+rpl_result rpl_decode_normal_batch_dev(rpl_ctx* ctx, const uint8_t* bytes, const uint32_t* byte_counts,
+                                       uint32_t n_streams, uint32_t stride_bytes, rpl_node_hq* nodes_out,
+                                       uint32_t* node_counts, uint32_t* fsm_state_out, void* stream);
+rpl_result rpl_decode_normal(rpl_ctx* ctx, const uint8_t* bytes, uint32_t n_bytes, rpl_node_hq* nodes_out,
+                             uint32_t* node_count);
+
 /* ---- scan assembly (node stream -> scans, on the device) -------- */
 /* Replaces ScanDataHolder::pushScanNodeData / rewindCurrentScanData (reference
  * src/sdk/src/sl_lidar_driver.cpp:272-315).  nodes: [n_streams][stride_nodes] decoded streams

@@ -43,6 +43,8 @@ EXPORTS = [
     "rpl_scan", "rpl_scan_batch", "rpl_ascend_scan_batch", "rpl_laserscan_batch", "rpl_scan_batch_dev",
     "rpl_cloud_batch_dev", "rpl_cloud_batch", "rpl_cloud_fuse_dev", "rpl_synth_batch_dev",
     "rpl_decode_dense_batch_dev", "rpl_decode_dense", "rpl_assemble_scans_dev",
+    "rpl_capsule_bytes", "rpl_capsule_nodes", "rpl_decode_capsules_batch_dev", "rpl_decode_capsules",
+    "rpl_decode_normal_batch_dev", "rpl_decode_normal",
 ]
 
 
@@ -125,6 +127,12 @@ def lib() -> C.CDLL:
         "rpl_synth_batch_dev": ([vp, u64, u32, u32, u32, i32, vp, vp, vp], u32),
         "rpl_decode_dense_batch_dev": ([vp, vp, vp, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp], u32),
         "rpl_decode_dense": ([vp, vp, u32, u32, C.POINTER(u32), vp, C.POINTER(u32), vp, vp], u32),
+        "rpl_capsule_bytes": ([u32], u32),
+        "rpl_capsule_nodes": ([u32], u32),
+        "rpl_decode_capsules_batch_dev": ([vp, u32, vp, vp, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp], u32),
+        "rpl_decode_capsules": ([vp, u32, vp, u32, u32, vp, vp, C.POINTER(u32), vp, vp], u32),
+        "rpl_decode_normal_batch_dev": ([vp, vp, vp, u32, u32, vp, vp, vp, vp], u32),
+        "rpl_decode_normal": ([vp, vp, u32, vp, C.POINTER(u32)], u32),
         "rpl_assemble_scans_dev": ([vp, vp, vp, u32, u32, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp], u32),
     }
     for name, (args, res) in sig.items():
@@ -305,6 +313,45 @@ class Context:
             self._h, _p(capsules), _p(capsule_counts), n_streams, stride_capsules, sample_duration_us,
             _p(sync_state_in), _p(nodes_out), _p(node_counts), _p(capsule_status), _p(capsule_node_offset),
             _p(sync_state_out), _p(stream)))
+
+    # ---- the other answer formats (0x82 express, 0x83 HQ, 0x84 ultra, 0x86 ultra-dense, 0x81 standard) ----
+    def decode_capsules(self, ans_type: int, capsules: np.ndarray, sample_duration_us: int = 31, state=(0, 0)):
+        """One stream of framed capsules -> (nodes, capsule_status, capsule_node_offset, state_out)."""
+        cb, per = self._L.rpl_capsule_bytes(ans_type), self._L.rpl_capsule_nodes(ans_type)
+        if cb == 0:
+            raise ValueError(f"unknown answer type {ans_type:#x}")
+        capsules = np.ascontiguousarray(capsules, dtype=np.uint8).reshape(-1, cb)
+        n = capsules.shape[0]
+        nodes = np.zeros(max(per * n, 1), NODE_DTYPE)
+        status = np.zeros(max(n, 1), np.uint32)
+        offs = np.zeros(max(n, 1), np.uint32)
+        st = np.array(state, np.uint32)
+        cnt = C.c_uint32(0)
+        self._check(self._L.rpl_decode_capsules(self._h, ans_type, _p(capsules), n, sample_duration_us, _p(st),
+                                                _p(nodes), C.byref(cnt), _p(status), _p(offs)))
+        return nodes[: cnt.value].copy(), status[:n].copy(), offs[:n].copy(), (int(st[0]), int(st[1]))
+
+    def decode_capsules_batch_dev(self, ans_type, capsules, capsule_counts, n_streams, stride_capsules,
+                                  sample_duration_us, nodes_out, node_counts, state_in=None, capsule_status=None,
+                                  capsule_node_offset=None, state_out=None, stream=None):
+        self._check(self._L.rpl_decode_capsules_batch_dev(
+            self._h, ans_type, _p(capsules), _p(capsule_counts), n_streams, stride_capsules, sample_duration_us,
+            _p(state_in), _p(nodes_out), _p(node_counts), _p(capsule_status), _p(capsule_node_offset),
+            _p(state_out), _p(stream)))
+
+    def decode_normal(self, stream_bytes: np.ndarray):
+        """Raw byte stream of 5-byte standard nodes -> nodes (byte-level resynchronisation included)."""
+        b = np.ascontiguousarray(stream_bytes, dtype=np.uint8).reshape(-1)
+        nodes = np.zeros(max(b.shape[0] // 5, 1), NODE_DTYPE)
+        cnt = C.c_uint32(0)
+        self._check(self._L.rpl_decode_normal(self._h, _p(b), b.shape[0], _p(nodes), C.byref(cnt)))
+        return nodes[: cnt.value].copy()
+
+    def decode_normal_batch_dev(self, stream_bytes, byte_counts, n_streams, stride_bytes, nodes_out, node_counts,
+                                fsm_state_out=None, stream=None):
+        self._check(self._L.rpl_decode_normal_batch_dev(
+            self._h, _p(stream_bytes), _p(byte_counts), n_streams, stride_bytes, _p(nodes_out), _p(node_counts),
+            _p(fsm_state_out), _p(stream)))
 
     def assemble_scans_dev(self, nodes, node_counts, n_streams, stride_nodes, max_nodes, max_scans, scan_stride,
                            scans_out, scan_len, scans_per_stream, capsule_status=None, capsule_node_offset=None,

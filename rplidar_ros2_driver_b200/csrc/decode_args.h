@@ -19,6 +19,33 @@ struct DecodeArgs {
   uint32_t* sync_state_out;       // [n_streams] nullable
 };
 
+// the other capsule formats (decode_formats.cu): 0x82 express, 0x83 HQ, 0x84 ultra, 0x86 ultra-dense
+struct CapsuleDecodeArgs {
+  const uint8_t* capsules;        // [n_streams][stride_capsules][capsule bytes]
+  const uint32_t* counts;         // [n_streams]
+  uint32_t n_streams, stride_capsules, sample_duration_us;
+  const uint32_t* state_in;       // [n_streams][2] {last node sync bit, last distance} (nullable: 0)
+  uint2* nodes_out;               // [n_streams][stride_capsules * nodes per capsule]
+  uint32_t* node_counts;          // [n_streams]
+  uint32_t* capsule_status;       // nullable
+  uint32_t* capsule_node_offset;  // nullable
+  uint32_t* state_out;            // [n_streams][2] nullable
+};
+
+// 5-byte standard nodes from raw byte streams
+struct NormalDecodeArgs {
+  const uint8_t* bytes;           // [n_streams][stride_bytes]
+  const uint32_t* byte_counts;    // [n_streams]
+  uint32_t n_streams, stride_bytes;
+  uint2* nodes_out;               // [n_streams][stride_bytes / 5]
+  uint32_t* node_counts;          // [n_streams]
+  uint32_t* fsm_state_out;        // [n_streams] nullable: bytes buffered when the stream ended
+};
+
+cudaError_t launch_decode_capsules(uint32_t ans_type, const CapsuleDecodeArgs& a, int grid, cudaStream_t stream);
+cudaError_t launch_decode_normal(const NormalDecodeArgs& a, int grid, cudaStream_t stream);
+cudaError_t decode_formats_configure();
+
 struct AssembleArgs {
   const uint2* nodes;                 // [n_streams][stride_nodes] decoded node streams
   const uint32_t* node_counts;        // [n_streams]

@@ -1,0 +1,714 @@
+// decode_formats.cu -- the other measurement answer formats on the GPU.
+//
+// Replaces, for framed capsules (reference src/sdk/src/dataunpacker/unpacker/):
+//   0x82 express      UnpackerHandler_CapsuleNode            handler_capsules.cpp:109-266  (84 B -> 32 nodes)
+//   0x84 ultra        UnpackerHandler_UltraCapsuleNode       handler_capsules.cpp:324-580  (132 B -> 96 nodes)
+//   0x86 ultra-dense  UnpackerHandler_UltraDenseCapsuleNode  handler_capsules.cpp:852-1047 (170 B -> 64 nodes)
+//   0x83 HQ           UnpackerHandler_HQNode                 handler_hqnode.cpp:93-172     (781 B -> 96 nodes)
+// and, for raw byte streams,
+//   0x81 standard     UnpackerHandler_NormalNode             handler_normalnode.cpp:88-141 (5 B -> 1 node)
+// (0x85 dense capsules: decode.cu.)
+//
+// Capsule formats share one skeleton (one CTA per stream, tiles of 256 capsules staged through shared
+// memory, one thread per capsule for frame / checksum / "does this capsule release its predecessor",
+// an exclusive block scan for the node offsets, then node-parallel emission so that every lane
+// writes one 8-byte node of a contiguous run).  What differs is the per-node arithmetic and the
+// state that crosses capsules:
+//   * express / ultra: none (the scan-start flag of a node is a function of its angle only);
+//   * ultra-dense: the last node's scan-start flag (a 2-bit transfer function per capsule, scanned
+//     under composition, as in decode.cu) and `_last_dist_q2`, a smoothing recurrence over
+//     neighbouring short-range samples.  A capsule's effect on that value is a function of at most
+//     nine candidate inputs (the first sample either ignores the incoming value or averages with
+//     one of 17 neighbours -> 9 results), so every capsule thread tabulates its nine outcomes, one
+//     thread chains the tables across the tile, and the capsule threads then replay their 64
+//     samples from the now-known input.
+// The standard-node decoder is a 5-state byte machine with resynchronisation; each thread folds its
+// 20 bytes into a state->state map (5 x 3 bits), the maps are scanned under composition, and the
+// threads replay their bytes from the known entry state: exact on arbitrary (misframed) streams.
+#include "decode_args.h"
+#include "rpl_device.cuh"
+
+namespace rpl {
+
+namespace {
+
+constexpr int DT = 256;  // threads = capsules per tile
+constexpr uint32_t kStOk = 1, kStSync = 2, kStEmit = 4, kStDiscard = 8, kStChecksum = 16, kStEncReset = 32,
+                   kStBadFrame = 64;
+constexpr int kFull = 360 << 16;
+
+enum { kExpress = 0, kUltra = 1, kUltraDense = 2 };
+
+template <int F>
+struct Fmt;
+template <>
+struct Fmt<kExpress> {
+  static constexpr int CB = 84, NODES = 32, START = 2;
+  static constexpr bool THRESHOLD = false, STATE = false;
+};
+template <>
+struct Fmt<kUltra> {
+  static constexpr int CB = 132, NODES = 96, START = 2;
+  static constexpr bool THRESHOLD = false, STATE = false;
+};
+template <>
+struct Fmt<kUltraDense> {
+  static constexpr int CB = 170, NODES = 64, START = 8;
+  static constexpr bool THRESHOLD = true, STATE = true;
+};
+
+__device__ __forceinline__ uint32_t ld16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+__device__ __forceinline__ uint32_t ld32(const uint8_t* p) { return ld16(p) | (ld16(p + 2) << 16); }
+
+__device__ __forceinline__ uint2 pack_node(int angle_q6, uint32_t dist_q2, uint32_t sync, uint32_t quality) {
+  if (angle_q6 < 0) angle_q6 += (360 << 6);
+  if (angle_q6 >= (360 << 6)) angle_q6 -= (360 << 6);
+  const uint32_t key = (uint32_t)((angle_q6 << 8) / 90) & 0xFFFFu;
+  const uint32_t flag = sync | ((sync ^ 1u) << 1);
+  uint2 nd;
+  nd.x = key | (dist_q2 << 16);
+  nd.y = (dist_q2 >> 16) | ((quality & 0xFFu) << 16) | (flag << 24);
+  return nd;
+}
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+               : "memory");
+}
+
+// ---- express (handler_capsules.cpp:206-266) ---------------------------------------------------------
+__device__ __forceinline__ uint2 node_express(const uint8_t* prev, int prev_q8, int diff_q8, uint32_t pos) {
+  const int inc = diff_q8 << 3;
+  const int a = (prev_q8 << 8) + (int)pos * inc;
+  const uint8_t* cab = prev + 4 + 5 * (pos >> 1);
+  const uint32_t da = ld16(cab + 2 * (pos & 1u));
+  const uint32_t ob = cab[4];
+  const int off_q3 = (int)(((pos & 1u) ? (ob >> 4) : (ob & 0xFu)) | ((da & 3u) << 4));
+  const uint32_t dist_q2 = da & 0xFFFCu;
+  const int angle_q6 = (a - (off_q3 << 13)) >> 10;
+  const uint32_t sync = (((a + inc) % kFull) < inc) ? 1u : 0u;
+  return pack_node(angle_q6, dist_q2, sync, dist_q2 ? (0x2Fu << 2) : 0u);
+}
+
+// ---- ultra (handler_capsules.cpp:422-580) --------------------------------------------------------------
+__device__ __forceinline__ uint32_t varbitscale(uint32_t scaled, uint32_t& level) {
+  if (scaled >= 3328u) { level = 4; return (1u << 14) + ((scaled - 3328u) << 4); }
+  if (scaled >= 1792u) { level = 3; return (1u << 12) + ((scaled - 1792u) << 3); }
+  if (scaled >= 1280u) { level = 2; return (1u << 11) + ((scaled - 1280u) << 2); }
+  if (scaled >= 512u) { level = 1; return (1u << 9) + ((scaled - 512u) << 1); }
+  level = 0;
+  return scaled;
+}
+__device__ __forceinline__ uint2 node_ultra(const uint8_t* prev, const uint8_t* cur, int prev_q8, int diff_q8,
+                                            uint32_t pos) {
+  const int inc = (diff_q8 << 3) / 3;
+  const int a = (prev_q8 << 8) + (int)pos * inc;
+  const uint32_t cabin = pos / 3u, c = pos - cabin * 3u;
+  const uint32_t x3 = ld32(prev + 4 + 4 * cabin);
+  const uint32_t nx = (cabin == 31u) ? ld32(cur + 4) : ld32(prev + 8 + 4 * cabin);
+  uint32_t lvl1 = 0, lvl2 = 0;
+  const int major = (int)varbitscale(x3 & 0xFFFu, lvl1);
+  const int major2 = (int)varbitscale(nx & 0xFFFu, lvl2);
+  int base1 = major;
+  if (!major && major2) {
+    base1 = major2;
+    lvl1 = lvl2;
+  }
+  int dist_q2;
+  if (c == 0) {
+    dist_q2 = major << 2;
+  } else {
+    const int predict = (c == 1) ? ((int)(x3 << 10) >> 22) : ((int)x3 >> 22);
+    if ((uint32_t)predict == 0xFFFFFE00u || (uint32_t)predict == 0x1FFu) {
+      dist_q2 = 0;
+    } else {
+      const uint32_t lvl = (c == 1) ? lvl1 : lvl2;
+      const int base = (c == 1) ? base1 : major2;
+      dist_q2 = (int)(((uint32_t)predict << lvl) + (uint32_t)base) << 2;
+    }
+  }
+  const uint32_t sync = (((a + inc) % kFull) < inc) ? 1u : 0u;
+  int off_q16 = 8578;  // (int)(7.5 * 3.1415926535 * 65536 / 180.0)
+  if (dist_q2 >= 200) {
+    const int k2 = 98361 / dist_q2;
+    off_q16 = 9150 - (k2 << 6) - (k2 * k2 * k2) / 98304;  // 9150 = (int)(8 * 3.1415926535 * 65536 / 180)
+  }
+  // int(off * 180 / 3.14159265): double division, truncation toward zero
+  const int off_deg_q16 = __double2int_rz(__ddiv_rn((double)(off_q16 * 180), 3.14159265));
+  const int angle_q6 = (a - off_deg_q16) >> 10;
+  return pack_node(angle_q6, (uint32_t)dist_q2, sync, dist_q2 ? (0x2Fu << 2) : 0u);
+}
+
+// ---- ultra-dense (handler_capsules.cpp:951-1047) -------------------------------------------------------
+// raw sample: distance before smoothing, scale code, quality
+__device__ __forceinline__ int ud_sample(const uint8_t* cap, uint32_t pos, uint32_t& scale, uint32_t& quality) {
+  const uint8_t* cab = cap + 10 + 5 * (pos >> 1);
+  const uint32_t hi = cab[4];
+  const uint32_t qds = ld16(cab + 2 * (pos & 1u)) | (((pos & 1u) ? (hi >> 4) : (hi & 0xFu)) << 16);
+  scale = qds & 3u;
+  switch (scale) {
+    case 0: quality = (qds >> 12) & 0xFFu; return (int)(qds & 0xFFCu) * 2;
+    case 1: quality = ((qds >> 13) << 1) & 0xFFu; return (int)(qds & 0x1FFCu) * 3 + (2046 << 2);
+    case 2: quality = ((qds >> 14) << 2) & 0xFFu; return (int)(qds & 0x3FFCu) * 4 + (8187 << 2);
+    default: quality = ((qds >> 15) << 3) & 0xFFu; return (int)(qds & 0x7FFCu) * 5 + (24567 << 2);
+  }
+}
+__device__ __forceinline__ int ud_smooth(int raw, uint32_t scale, int last) {
+  if (scale == 0 && last && abs(raw - last) <= 8) return (raw + last) >> 1;
+  return raw;
+}
+// scan-start test of the 64 interpolated samples before the "not twice in a row" rule
+__device__ __forceinline__ unsigned long long raw_sync_mask64(int prev_q8, int inc_q16) {
+  unsigned long long m = 0;
+  int rem = ((prev_q8 << 8) + inc_q16) % kFull;
+  const int lim = inc_q16 << 1;
+#pragma unroll 8
+  for (int pos = 0; pos < 64; ++pos) {
+    if (rem < lim) m |= 1ull << pos;
+    rem += inc_q16;
+    if (rem >= kFull) rem -= kFull;
+  }
+  return m;
+}
+__device__ __forceinline__ unsigned long long resolve_sync64(unsigned long long raw, uint32_t s_in) {
+  unsigned long long s = 0, r = raw;
+  while (r) {
+    const int i = __ffsll((long long)r) - 1;
+    r &= r - 1;
+    const uint32_t prev = (i == 0) ? s_in : (uint32_t)((s >> (i - 1)) & 1ull);
+    if (!prev) s |= 1ull << i;
+  }
+  return s;
+}
+
+template <int F>
+struct CapsuleSmem {
+  static constexpr int CB = Fmt<F>::CB;
+  static constexpr int kTileBytes = (DT * CB + 15) & ~15;
+  uint8_t cap[2][kTileBytes];          // double-buffered tiles
+  uint8_t carry[(CB + 15) & ~15];      // last capsule of the previous tile
+  uint32_t start_q8[DT + 1];           // slot 0 = carry
+  uint32_t okflag[DT + 1];
+  uint32_t emit_list[DT];
+  uint32_t warp_a[DT / 32], warp_b[DT / 32];
+  uint32_t carry_nodes, tile_nodes;
+  // ultra-dense only
+  unsigned long long smask[Fmt<F>::STATE ? DT : 1];
+  uint32_t ud_out[Fmt<F>::STATE ? DT : 1][10];   // nine outcomes of the smoothing chain + first raw sample
+  uint32_t ud_first_scale[Fmt<F>::STATE ? DT : 1];
+  uint32_t ud_last_in[Fmt<F>::STATE ? DT : 1];
+  uint16_t ud_dist[Fmt<F>::STATE ? DT : 1][64];  // smoothed short-range distances
+  uint32_t carry_sync, red_sync, carry_last;
+};
+
+template <int F>
+__global__ void __launch_bounds__(DT) decode_capsule_kernel(CapsuleDecodeArgs a) {
+  using T = Fmt<F>;
+  constexpr int CB = T::CB, NODES = T::NODES;
+  extern __shared__ __align__(16) unsigned char capsule_smem_raw[];
+  CapsuleSmem<F>& sm = *reinterpret_cast<CapsuleSmem<F>*>(capsule_smem_raw);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int thr_q8 = 0;
+  if (T::THRESHOLD) thr_q8 = (360 * 100 * 32 / (int)(1000000u / a.sample_duration_us)) << 8;
+
+  for (uint32_t s = blockIdx.x; s < a.n_streams; s += gridDim.x) {
+    const uint32_t n = a.counts[s];
+    const uint8_t* src = a.capsules + (size_t)s * a.stride_capsules * CB;
+    uint2* out = a.nodes_out + (size_t)s * a.stride_capsules * NODES;
+    uint32_t* st_out = a.capsule_status ? a.capsule_status + (size_t)s * a.stride_capsules : nullptr;
+    uint32_t* off_out = a.capsule_node_offset ? a.capsule_node_offset + (size_t)s * a.stride_capsules : nullptr;
+    if (tid == 0) {
+      sm.carry_nodes = 0;
+      sm.okflag[0] = 0;
+      sm.start_q8[0] = 0;
+      sm.carry_sync = a.state_in ? (a.state_in[2 * s] & 1u) : 0u;
+      sm.carry_last = a.state_in ? a.state_in[2 * s + 1] : 0u;
+    }
+    __syncthreads();
+
+    auto stage = [&](uint32_t c0, uint32_t b) {
+      const uint32_t live = min((uint32_t)DT, n - c0);
+      const uint32_t bytes = live * CB;
+      const uint8_t* g = src + (size_t)c0 * CB;
+      uint32_t done = 0;
+      if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
+        const uint32_t quads = bytes >> 4;
+        for (uint32_t q = tid; q < quads; q += DT) cp_async16(&sm.cap[b][16 * q], g + 16 * q);
+        done = quads << 4;
+      }
+      for (uint32_t w = done + tid; w < bytes; w += DT) sm.cap[b][w] = __ldg(g + w);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (n > 0) stage(0, 0);
+    uint32_t buf = 0;
+    for (uint32_t c0 = 0; c0 < n; c0 += DT, buf ^= 1u) {
+      const uint32_t live = min((uint32_t)DT, n - c0);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      if (c0 + DT < n) stage(c0 + DT, buf ^ 1u);
+      const uint8_t* tile = sm.cap[buf];
+      // ---- per capsule: frame, checksum, start angle ------------------------------------------------
+      uint32_t st = 0, ok = 0, sync = 0;
+      if (tid < live) {
+        const uint8_t* c = tile + tid * CB;  // 2-byte aligned at least (CB even, tiles 16-byte aligned)
+        const uint32_t b0 = c[0], b1 = c[1];
+        const uint32_t start = ld16(c + T::START);
+        if ((b0 >> 4) != 0xA || (b1 >> 4) != 0x5) {
+          st = kStBadFrame;
+        } else {
+          uint32_t x = 0;
+          const uint16_t* h = reinterpret_cast<const uint16_t*>(c);
+#pragma unroll 8
+          for (int w = 1; w < CB / 2; ++w) x ^= h[w];
+          const uint32_t sum = (x ^ (x >> 8)) & 0xFFu;
+          const uint32_t recv = ((b0 & 0xFu) | (b1 << 4)) & 0xFFu;
+          if (recv != sum) {
+            st = kStChecksum;
+          } else {
+            ok = 1;
+            st = kStOk;
+            sync = (start >> 15) & 1u;
+            if (sync) st |= kStSync;
+          }
+        }
+        sm.okflag[tid + 1] = ok;
+        sm.start_q8[tid + 1] = (start & 0x7FFFu) << 2;
+      }
+      __syncthreads();
+      // ---- does this capsule release its predecessor? ---------------------------------------------
+      uint32_t emit = 0;
+      int prev_q8 = 0, diff = 0;
+      if (tid < live && ok) {
+        const uint32_t prev_ok = sm.okflag[tid];
+        if (sync) {
+          if (prev_ok) st |= kStEncReset;
+        } else if (prev_ok) {
+          const int cur_q8 = (int)sm.start_q8[tid + 1];
+          prev_q8 = (int)sm.start_q8[tid];
+          diff = cur_q8 - prev_q8;
+          if (prev_q8 > cur_q8) diff += (360 << 8);
+          if (T::THRESHOLD && diff > thr_q8) {
+            st |= kStDiscard;
+          } else {
+            emit = 1;
+            st |= kStEmit;
+          }
+        }
+      }
+      const uint32_t inc_scan = warp_inclusive_scan(emit);
+      if (lane == 31) sm.warp_a[warp] = inc_scan;
+      // ultra-dense: transfer function of the scan-start flag through this capsule
+      unsigned long long raw = 0;
+      uint32_t Fsync = 0x2;  // identity
+      if constexpr (T::STATE) {
+        uint32_t f = 0x2;
+        if (emit) {
+          raw = raw_sync_mask64(prev_q8, (diff << 8) / 64);
+          const uint32_t o0 = (uint32_t)(resolve_sync64(raw, 0) >> 63) & 1u;
+          const uint32_t o1 = (uint32_t)(resolve_sync64(raw, 1) >> 63) & 1u;
+          f = o0 | (o1 << 1);
+        }
+        Fsync = f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t p = __shfl_up_sync(0xffffffffu, Fsync, o);
+          if (lane >= (uint32_t)o) Fsync = ((Fsync >> (p & 1u)) & 1u) | (((Fsync >> ((p >> 1) & 1u)) & 1u) << 1);
+        }
+        if (lane == 31) sm.warp_b[warp] = Fsync;
+      }
+      __syncthreads();
+      uint32_t base_off = 0, s_state = T::STATE ? sm.carry_sync : 0u;
+      for (uint32_t w = 0; w < warp; ++w) {
+        base_off += sm.warp_a[w];
+        if (T::STATE) s_state = (sm.warp_b[w] >> s_state) & 1u;
+      }
+      const uint32_t my_off = base_off + inc_scan - emit;
+      if constexpr (T::STATE) {
+        const uint32_t Fprev = __shfl_up_sync(0xffffffffu, Fsync, 1);
+        const uint32_t s_in = (lane == 0) ? s_state : ((Fprev >> s_state) & 1u);
+        if (tid < live) sm.smask[tid] = emit ? resolve_sync64(raw, s_in) : 0ull;
+      }
+      if (tid < live) {
+        if (emit) sm.emit_list[my_off] = tid;
+        if (st_out) st_out[c0 + tid] = st;
+        if (off_out) off_out[c0 + tid] = sm.carry_nodes + (uint32_t)NODES * my_off;
+      }
+      if (tid == DT - 1) {
+        uint32_t tot = 0, st2 = T::STATE ? sm.carry_sync : 0u;
+        for (uint32_t w = 0; w < DT / 32; ++w) {
+          tot += sm.warp_a[w];
+          if (T::STATE) st2 = (sm.warp_b[w] >> st2) & 1u;
+        }
+        sm.tile_nodes = (uint32_t)NODES * tot;
+        if (T::STATE) sm.red_sync = st2;
+      }
+      if constexpr (T::STATE) {
+        // ---- smoothing chain, step 1: the nine outcomes of this capsule's 64 samples ------------------
+        if (emit) {
+          const uint8_t* pc = (tid == 0) ? sm.carry : tile + (tid - 1) * CB;
+          uint32_t sc, q;
+          const int r0 = ud_sample(pc, 0, sc, q);
+          sm.ud_first_scale[tid] = sc;
+          int cand[9];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) cand[k] = (sc == 0) ? (r0 - 4 + k) : r0;
+          bool merged = (sc != 0);
+          for (uint32_t pos = 1; pos < 64; ++pos) {
+            const int r = ud_sample(pc, pos, sc, q);
+            if (merged) {
+              cand[0] = ud_smooth(r, sc, cand[0]);
+            } else {
+              int lo = 0x7fffffff, hi = -0x7fffffff;
+#pragma unroll
+              for (int k = 0; k < 9; ++k) {
+                cand[k] = ud_smooth(r, sc, cand[k]);
+                lo = min(lo, cand[k]);
+                hi = max(hi, cand[k]);
+              }
+              merged = (lo == hi);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 9; ++k) sm.ud_out[tid][k] = (uint32_t)(merged ? cand[0] : cand[k]);
+          sm.ud_out[tid][9] = (uint32_t)r0;
+        }
+      }
+      __syncthreads();
+      if constexpr (T::STATE) {
+        // ---- step 2: one thread chains the tables across the tile's releasing capsules ---------------
+        if (tid == 0) {
+          int last = (int)sm.carry_last;
+          const uint32_t E = sm.tile_nodes / NODES;
+          for (uint32_t e = 0; e < E; ++e) {
+            const uint32_t j = sm.emit_list[e];
+            sm.ud_last_in[j] = (uint32_t)last;
+            const int r0 = (int)sm.ud_out[j][9];
+            int k = 4;
+            if (sm.ud_first_scale[j] == 0 && last && abs(r0 - last) <= 8) k = ((r0 + last) >> 1) - (r0 - 4);
+            last = (int)sm.ud_out[j][k];
+          }
+          sm.carry_last = (uint32_t)last;
+        }
+        __syncthreads();
+        // ---- step 3: replay the samples from the known input, keep the smoothed distances ------------
+        if (emit) {
+          const uint8_t* pc = (tid == 0) ? sm.carry : tile + (tid - 1) * CB;
+          int last = (int)sm.ud_last_in[tid];
+          for (uint32_t pos = 0; pos < 64; ++pos) {
+            uint32_t sc, q;
+            const int r = ud_sample(pc, pos, sc, q);
+            last = ud_smooth(r, sc, last);
+            sm.ud_dist[tid][pos] = (uint16_t)last;  // only read back for scale-0 samples (< 8192)
+          }
+        }
+        __syncthreads();
+      }
+      // ---- node-parallel emission: one contiguous run of NODES * E nodes -------------------------------
+      {
+        const uint32_t n_nodes = sm.tile_nodes;
+        uint2* o = out + sm.carry_nodes;
+        for (uint32_t q = tid; q < n_nodes; q += DT) {
+          const uint32_t e = q / (uint32_t)NODES, pos = q - e * (uint32_t)NODES;
+          const uint32_t j = sm.emit_list[e];
+          const uint8_t* pc = (j == 0) ? sm.carry : tile + (j - 1) * CB;
+          const int pq8 = (int)sm.start_q8[j];
+          int d = (int)sm.start_q8[j + 1] - pq8;
+          if (pq8 > (int)sm.start_q8[j + 1]) d += (360 << 8);
+          uint2 nd;
+          if constexpr (F == kExpress) {
+            nd = node_express(pc, pq8, d, pos);
+          } else if constexpr (F == kUltra) {
+            nd = node_ultra(pc, tile + j * CB, pq8, d, pos);
+          } else {
+            const int inc = (d << 8) / 64;
+            const int ang = (pq8 << 8) + (int)pos * inc;
+            uint32_t sc, quality;
+            int dist = ud_sample(pc, pos, sc, quality);
+            if (sc == 0) dist = (int)sm.ud_dist[j][pos];
+            const uint32_t syncb = (uint32_t)(sm.smask[j] >> pos) & 1u;
+            nd = pack_node(ang >> 10, (uint32_t)dist, syncb, quality);
+          }
+          o[q] = nd;
+        }
+      }
+      __syncthreads();
+      // ---- carry into the next tile -----------------------------------------------------------------
+      for (uint32_t b = tid; b < (uint32_t)CB; b += DT) sm.carry[b] = tile[(live - 1) * CB + b];
+      if (tid == 0) {
+        sm.okflag[0] = sm.okflag[live];
+        sm.start_q8[0] = sm.start_q8[live];
+        sm.carry_nodes += sm.tile_nodes;
+        if (T::STATE) sm.carry_sync = sm.red_sync;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      if (a.node_counts) a.node_counts[s] = sm.carry_nodes;
+      if (a.state_out) {
+        a.state_out[2 * s] = T::STATE ? sm.carry_sync : 0u;
+        a.state_out[2 * s + 1] = T::STATE ? sm.carry_last : 0u;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- HQ capsules (handler_hqnode.cpp:93-172): CRC32 + pass-through -----------------------------------
+constexpr int HT = 128;         // threads = capsules per tile
+constexpr int kHqBytes = 781;   // 1 sync + 8 timestamp + 96 * 8 nodes + 4 crc
+struct HqSmem {
+  uint8_t cap[(HT * kHqBytes + 15) & ~15];
+  uint32_t table[256];
+  uint32_t emit_list[HT];
+  uint32_t warp_a[HT / 32];
+  uint32_t carry_nodes, tile_nodes;
+};
+
+__global__ void __launch_bounds__(HT) decode_hq_kernel(CapsuleDecodeArgs a) {
+  extern __shared__ __align__(16) unsigned char capsule_smem_raw[];
+  HqSmem& sm = *reinterpret_cast<HqSmem*>(capsule_smem_raw);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (uint32_t i = tid; i < 256; i += HT) {  // reflected 0x04C11DB7 (sl_crc.cpp:52-69)
+    uint32_t c = i;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c = (c & 1u) ? (0xEDB88320u ^ (c >> 1)) : (c >> 1);
+    sm.table[i] = c;
+  }
+  for (uint32_t s = blockIdx.x; s < a.n_streams; s += gridDim.x) {
+    const uint32_t n = a.counts[s];
+    const uint8_t* src = a.capsules + (size_t)s * a.stride_capsules * kHqBytes;
+    uint2* out = a.nodes_out + (size_t)s * a.stride_capsules * 96;
+    uint32_t* st_out = a.capsule_status ? a.capsule_status + (size_t)s * a.stride_capsules : nullptr;
+    uint32_t* off_out = a.capsule_node_offset ? a.capsule_node_offset + (size_t)s * a.stride_capsules : nullptr;
+    if (tid == 0) sm.carry_nodes = 0;
+    __syncthreads();
+    for (uint32_t c0 = 0; c0 < n; c0 += HT) {
+      const uint32_t live = min((uint32_t)HT, n - c0);
+      const uint32_t bytes = live * kHqBytes;
+      const uint8_t* g = src + (size_t)c0 * kHqBytes;
+      uint32_t done = 0;
+      if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
+        const uint32_t quads = bytes >> 4;
+        for (uint32_t q = tid; q < quads; q += HT) cp_async16(&sm.cap[16 * q], g + 16 * q);
+        done = quads << 4;
+      }
+      for (uint32_t w = done + tid; w < bytes; w += HT) sm.cap[w] = __ldg(g + w);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      uint32_t st = 0, emit = 0;
+      if (tid < live) {
+        const uint8_t* c = sm.cap + tid * kHqBytes;
+        if (c[0] != 0xA5) {
+          st = kStBadFrame;
+        } else {
+          uint32_t crc = 0xFFFFFFFFu;
+          for (int i = 0; i < kHqBytes - 4; ++i) crc = (crc >> 8) ^ sm.table[(crc ^ c[i]) & 0xFFu];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) crc = (crc >> 8) ^ sm.table[crc & 0xFFu];  // zero padding to 780 bytes
+          crc ^= 0xFFFFFFFFu;
+          if (crc == ld32(c + kHqBytes - 4)) {
+            st = kStOk | kStEmit;
+            emit = 1;
+          } else {
+            st = kStChecksum;
+          }
+        }
+      }
+      const uint32_t inc_scan = warp_inclusive_scan(emit);
+      if (lane == 31) sm.warp_a[warp] = inc_scan;
+      __syncthreads();
+      uint32_t base_off = 0;
+      for (uint32_t w = 0; w < warp; ++w) base_off += sm.warp_a[w];
+      const uint32_t my_off = base_off + inc_scan - emit;
+      if (tid < live) {
+        if (emit) sm.emit_list[my_off] = tid;
+        if (st_out) st_out[c0 + tid] = st;
+        if (off_out) off_out[c0 + tid] = sm.carry_nodes + 96u * my_off;
+      }
+      if (tid == HT - 1) {
+        uint32_t tot = 0;
+        for (uint32_t w = 0; w < HT / 32; ++w) tot += sm.warp_a[w];
+        sm.tile_nodes = 96u * tot;
+      }
+      __syncthreads();
+      const uint32_t n_nodes = sm.tile_nodes;
+      uint2* o = out + sm.carry_nodes;
+      for (uint32_t q = tid; q < n_nodes; q += HT) {
+        const uint32_t e = q / 96u, pos = q - e * 96u;
+        const uint8_t* p = sm.cap + sm.emit_list[e] * kHqBytes + 9 + 8 * pos;
+        o[q] = make_uint2(ld32(p), ld32(p + 4));
+      }
+      __syncthreads();
+      if (tid == 0) sm.carry_nodes += sm.tile_nodes;
+      __syncthreads();
+    }
+    if (tid == 0) {
+      if (a.node_counts) a.node_counts[s] = sm.carry_nodes;
+      if (a.state_out) a.state_out[2 * s] = a.state_out[2 * s + 1] = 0u;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- standard nodes (handler_normalnode.cpp:88-141): 5-state byte machine ----------------------------
+constexpr int NT = 256;       // threads
+constexpr int kChunk = 20;    // bytes per thread per tile
+constexpr int kNormTile = NT * kChunk;
+struct NormalSmem {
+  uint8_t bytes[4 + kNormTile + 12];  // 4 bytes of the previous tile in front
+  uint32_t warp_f[NT / 32], warp_c[NT / 32];
+  uint16_t ends[kNormTile / 5 + 8];   // tile-relative index of each record's last byte
+  uint32_t carry_state, carry_nodes, tile_nodes, red_state;
+};
+// packed state->state map: 3 bits per entry, entry s = image of state s
+constexpr uint32_t kIdentityMap = 0 | (1 << 3) | (2 << 6) | (3 << 9) | (4 << 12);
+__device__ __forceinline__ uint32_t byte_map(uint32_t b) {
+  const uint32_t t0 = (((b >> 1) ^ b) & 1u);      // state 0: sync bit and its inverse
+  const uint32_t t1 = (b & 1u) ? 2u : 0u;         // state 1: check bit
+  return t0 | (t1 << 3) | (3u << 6) | (4u << 9);  // 2 -> 3, 3 -> 4, 4 -> 0
+}
+// (g o f)(s) = g(f(s))
+__device__ __forceinline__ uint32_t compose_map(uint32_t g, uint32_t f) {
+  uint32_t r = 0;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) r |= ((g >> (3u * ((f >> (3 * s)) & 7u))) & 7u) << (3 * s);
+  return r;
+}
+
+__global__ void __launch_bounds__(NT) decode_normal_kernel(NormalDecodeArgs a) {
+  __shared__ NormalSmem sm;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (uint32_t s = blockIdx.x; s < a.n_streams; s += gridDim.x) {
+    const uint32_t n = a.byte_counts[s];
+    const uint8_t* src = a.bytes + (size_t)s * a.stride_bytes;
+    uint2* out = a.nodes_out + (size_t)s * (a.stride_bytes / 5u);
+    if (tid == 0) {
+      sm.carry_state = 0;
+      sm.carry_nodes = 0;
+    }
+    if (tid < 4) sm.bytes[tid] = 0;
+    __syncthreads();
+    for (uint32_t t0 = 0; t0 < n; t0 += kNormTile) {
+      const uint32_t live = min((uint32_t)kNormTile, n - t0);
+      for (uint32_t i = tid; i < live; i += NT) sm.bytes[4 + i] = __ldg(src + t0 + i);
+      __syncthreads();
+      // fold this thread's bytes into one map
+      const uint32_t b0 = tid * kChunk;
+      uint32_t f = kIdentityMap;
+      for (uint32_t i = 0; i < (uint32_t)kChunk; ++i) {
+        if (b0 + i < live) f = compose_map(byte_map(sm.bytes[4 + b0 + i]), f);
+      }
+      uint32_t Fm = f;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t p = __shfl_up_sync(0xffffffffu, Fm, o);
+        if (lane >= (uint32_t)o) Fm = compose_map(Fm, p);
+      }
+      if (lane == 31) sm.warp_f[warp] = Fm;
+      __syncthreads();
+      uint32_t state = sm.carry_state;
+      for (uint32_t w = 0; w < warp; ++w) state = (sm.warp_f[w] >> (3u * state)) & 7u;
+      const uint32_t Fprev = __shfl_up_sync(0xffffffffu, Fm, 1);
+      if (lane != 0) state = (Fprev >> (3u * state)) & 7u;
+      // replay from the known entry state: which bytes complete a record?
+      uint32_t ends = 0, cnt = 0, st = state;
+      for (uint32_t i = 0; i < (uint32_t)kChunk; ++i) {
+        if (b0 + i < live) {
+          if (st == 4) {
+            ends |= 1u << i;
+            ++cnt;
+          }
+          st = (byte_map(sm.bytes[4 + b0 + i]) >> (3u * st)) & 7u;
+        }
+      }
+      const uint32_t inc_scan = warp_inclusive_scan(cnt);
+      if (lane == 31) sm.warp_c[warp] = inc_scan;
+      __syncthreads();
+      uint32_t off = inc_scan - cnt;
+      for (uint32_t w = 0; w < warp; ++w) off += sm.warp_c[w];
+      while (ends) {
+        const uint32_t i = __ffs(ends) - 1;
+        ends &= ends - 1;
+        sm.ends[off++] = (uint16_t)(b0 + i);
+      }
+      if (tid == NT - 1) {
+        uint32_t tot = 0, st2 = sm.carry_state;
+        for (uint32_t w = 0; w < NT / 32; ++w) {
+          tot += sm.warp_c[w];
+          st2 = (sm.warp_f[w] >> (3u * st2)) & 7u;
+        }
+        sm.tile_nodes = tot;
+        sm.red_state = st2;
+      }
+      __syncthreads();
+      const uint32_t n_nodes = sm.tile_nodes;
+      uint2* o = out + sm.carry_nodes;
+      for (uint32_t q = tid; q < n_nodes; q += NT) {
+        const uint8_t* r = sm.bytes + sm.ends[q];  // record = bytes[end-4 .. end], shifted by the 4-byte halo
+        const uint32_t sq = r[0];
+        const uint32_t angle_chk = ld16(r + 1), dist = ld16(r + 3);
+        const uint32_t key = (((angle_chk >> 1) << 8) / 90u) & 0xFFFFu;
+        uint2 nd;
+        nd.x = key | (dist << 16);
+        nd.y = (((sq >> 2) << 2) << 16) | ((sq & 1u) << 24);
+        o[q] = nd;
+      }
+      __syncthreads();
+      if (tid < 4) sm.bytes[tid] = sm.bytes[live + tid];  // last four bytes of this tile (live >= 4 or stream ends)
+      if (tid == 0) {
+        sm.carry_nodes += sm.tile_nodes;
+        sm.carry_state = sm.red_state;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      if (a.node_counts) a.node_counts[s] = sm.carry_nodes;
+      if (a.fsm_state_out) a.fsm_state_out[s] = sm.carry_state;
+    }
+    __syncthreads();
+  }
+}
+
+template <int F>
+cudaError_t launch_fmt(const CapsuleDecodeArgs& a, int grid, cudaStream_t stream) {
+  decode_capsule_kernel<F><<<grid, DT, sizeof(CapsuleSmem<F>), stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_decode_capsules(uint32_t ans_type, const CapsuleDecodeArgs& a, int grid, cudaStream_t stream) {
+  if (a.n_streams == 0) return cudaSuccess;
+  switch (ans_type) {
+    case 0x82: return launch_fmt<kExpress>(a, grid, stream);
+    case 0x84: return launch_fmt<kUltra>(a, grid, stream);
+    case 0x86: return launch_fmt<kUltraDense>(a, grid, stream);
+    case 0x83:
+      decode_hq_kernel<<<grid, HT, sizeof(HqSmem), stream>>>(a);
+      return cudaGetLastError();
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_decode_normal(const NormalDecodeArgs& a, int grid, cudaStream_t stream) {
+  if (a.n_streams == 0) return cudaSuccess;
+  decode_normal_kernel<<<grid, NT, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t decode_formats_configure() {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(decode_capsule_kernel<kExpress>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(CapsuleSmem<kExpress>));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(decode_capsule_kernel<kUltra>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(CapsuleSmem<kUltra>));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(decode_capsule_kernel<kUltraDense>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(CapsuleSmem<kUltraDense>));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(decode_hq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HqSmem));
+}
+
+}  // namespace rpl

@@ -76,6 +76,8 @@ struct rpl_ctx {
   uint32_t* d_reset_prefix = nullptr;
   uint2* d_desc = nullptr;
   size_t reset_prefix_cap = 0, desc_cap = 0;
+  uint32_t* d_state_tmp = nullptr;  // dense decoder reached through the [2]-word state interface
+  size_t state_tmp_cap = 0;
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_fast, prof_general;
 };
@@ -299,7 +301,8 @@ rpl_result rpl_ctx_create(int device, uint32_t max_nodes, uint32_t max_scans, rp
       !cuda_ok(c, rpl::scan_tma_configure(), "scan_tma_configure") ||
       !cuda_ok(c, rpl::scan_general_configure(), "scan_general_configure") ||
       !cuda_ok(c, rpl::cloud_configure(), "cloud_configure") ||
-      !cuda_ok(c, rpl::decode_configure(), "decode_configure"))
+      !cuda_ok(c, rpl::decode_configure(), "decode_configure") ||
+      !cuda_ok(c, rpl::decode_formats_configure(), "decode_formats_configure"))
     return fail(RPL_RESULT_OPERATION_FAIL);
   const int occ = std::max(1, rpl::scan_fast_max_ctas_per_sm());
   c->fast_grid = c->num_sms * occ;
@@ -351,6 +354,7 @@ void rpl_ctx_destroy(rpl_ctx* c) {
     if (c->lane[i].stream) cudaStreamSynchronize(c->lane[i].stream);
     free_lane(c->lane[i]);
   }
+  cudaFree(c->d_state_tmp);
   cudaFree(c->d_reset_prefix);
   cudaFree(c->d_desc);
   if (c->h_one) cudaFreeHost(c->h_one);
@@ -756,6 +760,202 @@ rpl_result rpl_decode_dense(rpl_ctx* c, const uint8_t* capsules, uint32_t n_caps
   return bail(RPL_RESULT_OK);
 }
 
+// ---- the other answer formats ----------------------------------------------
+uint32_t rpl_capsule_bytes(uint32_t ans_type) {
+  switch (ans_type) {
+    case 0x82: return 84;
+    case 0x83: return 781;
+    case 0x84: return 132;
+    case 0x85: return 84;
+    case 0x86: return 170;
+    default: return 0;
+  }
+}
+uint32_t rpl_capsule_nodes(uint32_t ans_type) {
+  switch (ans_type) {
+    case 0x82: return 32;
+    case 0x83: return 96;
+    case 0x84: return 96;
+    case 0x85: return 40;
+    case 0x86: return 64;
+    default: return 0;
+  }
+}
+
+namespace {
+// word 0 of every [2]-state pair, strided: the dense kernel keeps a single word per stream
+__global__ void gather_state_kernel(const uint32_t* in2, uint32_t* out1, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out1[i] = in2[2 * i] & 1u;
+}
+__global__ void scatter_state_kernel(const uint32_t* in1, uint32_t* out2, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    out2[2 * i] = in1[i];
+    out2[2 * i + 1] = 0u;
+  }
+}
+}  // namespace
+
+rpl_result rpl_decode_capsules_batch_dev(rpl_ctx* c, uint32_t ans_type, const uint8_t* capsules,
+                                         const uint32_t* capsule_counts, uint32_t n_streams,
+                                         uint32_t stride_capsules, uint32_t sample_duration_us,
+                                         const uint32_t* state_in, rpl_node_hq* nodes_out, uint32_t* node_counts,
+                                         uint32_t* capsule_status, uint32_t* capsule_node_offset,
+                                         uint32_t* state_out, void* stream) {
+  if (!c || !capsules || !capsule_counts || !nodes_out) return RPL_RESULT_INVALID_DATA;
+  if (rpl_capsule_bytes(ans_type) == 0) {
+    c->err = "unknown answer type (capsule formats are 0x82..0x86)";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if (sample_duration_us == 0 || sample_duration_us > 1000000u) {
+    c->err = "sample_duration_us must be in [1, 1000000]";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if (n_streams == 0) return RPL_RESULT_OK;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
+  if (ans_type == 0x85) {  // the dense kernel keeps one state word per stream
+    uint32_t* tmp = nullptr;
+    if (state_in || state_out) {
+      if (n_streams > c->state_tmp_cap) {
+        cudaFree(c->d_state_tmp);
+        c->d_state_tmp = nullptr;
+        RPL_CUDA(c, dev_alloc(&c->d_state_tmp, (size_t)2 * n_streams), RPL_RESULT_INSUFFICIENT_MEMORY);
+        c->state_tmp_cap = n_streams;
+      }
+      tmp = c->d_state_tmp;
+    }
+    const uint32_t blocks = (n_streams + 255) / 256;
+    if (state_in) gather_state_kernel<<<blocks, 256, 0, st>>>(state_in, tmp, n_streams);
+    rpl_result r = rpl_decode_dense_batch_dev(c, capsules, capsule_counts, n_streams, stride_capsules,
+                                              sample_duration_us, state_in ? tmp : nullptr, nodes_out, node_counts,
+                                              capsule_status, capsule_node_offset,
+                                              state_out ? tmp + n_streams : nullptr, st);
+    if (r != RPL_RESULT_OK) return r;
+    if (state_out) scatter_state_kernel<<<blocks, 256, 0, st>>>(tmp + n_streams, state_out, n_streams);
+    RPL_CUDA(c, cudaGetLastError(), RPL_RESULT_OPERATION_FAIL);
+    return RPL_RESULT_OK;
+  }
+  rpl::CapsuleDecodeArgs a{};
+  a.capsules = capsules;
+  a.counts = capsule_counts;
+  a.n_streams = n_streams;
+  a.stride_capsules = stride_capsules;
+  a.sample_duration_us = sample_duration_us;
+  a.state_in = state_in;
+  a.nodes_out = reinterpret_cast<uint2*>(nodes_out);
+  a.node_counts = node_counts;
+  a.capsule_status = capsule_status;
+  a.capsule_node_offset = capsule_node_offset;
+  a.state_out = state_out;
+  const int grid = (int)std::min<uint32_t>(n_streams, (uint32_t)c->num_sms * 2u);
+  RPL_CUDA(c, rpl::launch_decode_capsules(ans_type, a, grid, st), RPL_RESULT_OPERATION_FAIL);
+  c->launches++;
+  return RPL_RESULT_OK;
+}
+
+namespace {
+// one stream from host buffers through a device-side entry: shared by the capsule and byte decoders
+struct HostDecode {
+  unsigned char* d = nullptr;
+  size_t o_nodes = 0, o_st = 0, o_off = 0, o_small = 0;
+  ~HostDecode() { cudaFree(d); }
+};
+}  // namespace
+
+rpl_result rpl_decode_capsules(rpl_ctx* c, uint32_t ans_type, const uint8_t* capsules, uint32_t n_capsules,
+                               uint32_t sample_duration_us, uint32_t* state, rpl_node_hq* nodes_out,
+                               uint32_t* node_count, uint32_t* capsule_status, uint32_t* capsule_node_offset) {
+  if (!c || !node_count || (n_capsules && (!capsules || !nodes_out))) return RPL_RESULT_INVALID_DATA;
+  *node_count = 0;
+  const uint32_t cbytes = rpl_capsule_bytes(ans_type), per = rpl_capsule_nodes(ans_type);
+  if (cbytes == 0) {
+    c->err = "unknown answer type (capsule formats are 0x82..0x86)";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if (n_capsules == 0) return RPL_RESULT_OK;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  cudaStream_t st = c->lane[0].stream;
+  const size_t cb = (size_t)n_capsules * cbytes, nb = (size_t)n_capsules * per * 8, sb = (size_t)n_capsules * 4;
+  HostDecode h;  // [capsules | pad][nodes][status][offsets][count, n_nodes, state in x2, state out x2]
+  h.o_nodes = (cb + 15) & ~(size_t)15;
+  h.o_st = h.o_nodes + nb;
+  h.o_off = h.o_st + sb;
+  h.o_small = h.o_off + sb;
+  RPL_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&h.d), h.o_small + 32), RPL_RESULT_INSUFFICIENT_MEMORY);
+  uint32_t small[8] = {n_capsules, 0u, state ? state[0] : 0u, state ? state[1] : 0u, 0u, 0u, 0u, 0u};
+  RPL_CUDA(c, cudaMemcpyAsync(h.d, capsules, cb, cudaMemcpyHostToDevice, st), RPL_RESULT_OPERATION_FAIL);
+  RPL_CUDA(c, cudaMemcpyAsync(h.d + h.o_small, small, 32, cudaMemcpyHostToDevice, st), RPL_RESULT_OPERATION_FAIL);
+  uint32_t* ds = reinterpret_cast<uint32_t*>(h.d + h.o_small);
+  rpl_result r = rpl_decode_capsules_batch_dev(c, ans_type, h.d, ds, 1, n_capsules, sample_duration_us, ds + 2,
+                                               reinterpret_cast<rpl_node_hq*>(h.d + h.o_nodes), ds + 1,
+                                               reinterpret_cast<uint32_t*>(h.d + h.o_st),
+                                               reinterpret_cast<uint32_t*>(h.d + h.o_off), ds + 4, st);
+  if (r != RPL_RESULT_OK) return r;
+  RPL_CUDA(c, cudaMemcpyAsync(small, ds, 32, cudaMemcpyDeviceToHost, st), RPL_RESULT_OPERATION_FAIL);
+  RPL_CUDA(c, cudaStreamSynchronize(st), RPL_RESULT_OPERATION_FAIL);
+  *node_count = small[1];
+  if (state) {
+    state[0] = small[4];
+    state[1] = small[5];
+  }
+  RPL_CUDA(c, cudaMemcpy(nodes_out, h.d + h.o_nodes, (size_t)small[1] * 8, cudaMemcpyDeviceToHost),
+           RPL_RESULT_OPERATION_FAIL);
+  if (capsule_status)
+    RPL_CUDA(c, cudaMemcpy(capsule_status, h.d + h.o_st, sb, cudaMemcpyDeviceToHost), RPL_RESULT_OPERATION_FAIL);
+  if (capsule_node_offset)
+    RPL_CUDA(c, cudaMemcpy(capsule_node_offset, h.d + h.o_off, sb, cudaMemcpyDeviceToHost), RPL_RESULT_OPERATION_FAIL);
+  return RPL_RESULT_OK;
+}
+
+rpl_result rpl_decode_normal_batch_dev(rpl_ctx* c, const uint8_t* bytes, const uint32_t* byte_counts,
+                                       uint32_t n_streams, uint32_t stride_bytes, rpl_node_hq* nodes_out,
+                                       uint32_t* node_counts, uint32_t* fsm_state_out, void* stream) {
+  if (!c || !bytes || !byte_counts || !nodes_out) return RPL_RESULT_INVALID_DATA;
+  if (n_streams == 0) return RPL_RESULT_OK;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
+  rpl::NormalDecodeArgs a{};
+  a.bytes = bytes;
+  a.byte_counts = byte_counts;
+  a.n_streams = n_streams;
+  a.stride_bytes = stride_bytes;
+  a.nodes_out = reinterpret_cast<uint2*>(nodes_out);
+  a.node_counts = node_counts;
+  a.fsm_state_out = fsm_state_out;
+  const int grid = (int)std::min<uint32_t>(n_streams, (uint32_t)c->num_sms * 8u);
+  RPL_CUDA(c, rpl::launch_decode_normal(a, grid, st), RPL_RESULT_OPERATION_FAIL);
+  c->launches++;
+  return RPL_RESULT_OK;
+}
+
+rpl_result rpl_decode_normal(rpl_ctx* c, const uint8_t* bytes, uint32_t n_bytes, rpl_node_hq* nodes_out,
+                             uint32_t* node_count) {
+  if (!c || !node_count || (n_bytes && (!bytes || !nodes_out))) return RPL_RESULT_INVALID_DATA;
+  *node_count = 0;
+  if (n_bytes < 5) return RPL_RESULT_OK;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  cudaStream_t st = c->lane[0].stream;
+  HostDecode h;  // [bytes | pad][nodes][byte count, node count]
+  h.o_nodes = ((size_t)n_bytes + 15) & ~(size_t)15;
+  h.o_small = h.o_nodes + (size_t)(n_bytes / 5) * 8;
+  RPL_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&h.d), h.o_small + 16), RPL_RESULT_INSUFFICIENT_MEMORY);
+  uint32_t small[2] = {n_bytes, 0u};
+  RPL_CUDA(c, cudaMemcpyAsync(h.d, bytes, n_bytes, cudaMemcpyHostToDevice, st), RPL_RESULT_OPERATION_FAIL);
+  RPL_CUDA(c, cudaMemcpyAsync(h.d + h.o_small, small, 8, cudaMemcpyHostToDevice, st), RPL_RESULT_OPERATION_FAIL);
+  uint32_t* ds = reinterpret_cast<uint32_t*>(h.d + h.o_small);
+  rpl_result r = rpl_decode_normal_batch_dev(c, h.d, ds, 1, n_bytes, reinterpret_cast<rpl_node_hq*>(h.d + h.o_nodes),
+                                             ds + 1, nullptr, st);
+  if (r != RPL_RESULT_OK) return r;
+  RPL_CUDA(c, cudaMemcpyAsync(small, ds, 8, cudaMemcpyDeviceToHost, st), RPL_RESULT_OPERATION_FAIL);
+  RPL_CUDA(c, cudaStreamSynchronize(st), RPL_RESULT_OPERATION_FAIL);
+  *node_count = small[1];
+  RPL_CUDA(c, cudaMemcpy(nodes_out, h.d + h.o_nodes, (size_t)small[1] * 8, cudaMemcpyDeviceToHost),
+           RPL_RESULT_OPERATION_FAIL);
+  return RPL_RESULT_OK;
+}
+
 // ---- scan assembly ------------------------------------------------------
 rpl_result rpl_assemble_scans_dev(rpl_ctx* c, const rpl_node_hq* nodes, const uint32_t* node_counts,
                                   uint32_t n_streams, uint32_t stride_nodes, const uint32_t* capsule_status,
@@ -778,7 +978,8 @@ rpl_result rpl_assemble_scans_dev(rpl_ctx* c, const rpl_node_hq* nodes, const ui
   const size_t need_rp = (size_t)n_streams * std::max<uint32_t>(stride_capsules, 1u);
   const size_t need_desc = (size_t)n_streams * max_scans;
   if (need_rp > c->reset_prefix_cap) {
-    cudaFree(c->d_reset_prefix);
+    cudaFree(c->d_state_tmp);
+  cudaFree(c->d_reset_prefix);
     c->d_reset_prefix = nullptr;
     RPL_CUDA(c, dev_alloc(&c->d_reset_prefix, need_rp), RPL_RESULT_INSUFFICIENT_MEMORY);
     c->reset_prefix_cap = need_rp;
