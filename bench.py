@@ -55,9 +55,12 @@ def parse():
     ap.add_argument("--nodes", type=int, default=NODES_PER_SCAN, help="nodes per scan")
     ap.add_argument("--mode", default="b", choices=["a", "b"], help="LaserScan mode of the headline")
     ap.add_argument("--variant", type=int, default=0, help="synthetic variant (SURVEY 8(d))")
-    ap.add_argument("--workload", default="scan", choices=["scan", "cloud", "decode"],
+    ap.add_argument("--workload", default="scan", choices=["scan", "cloud", "decode", "chain"],
                     help="scan: LaserScan path (headline, BASELINE configs[1]); cloud: PointCloud2 path "
                          "(configs[2]/[4]: 64 S3 streams per GPU, polar->xyz + 5 cm voxels, all-gather of the fused cloud)")
+    ap.add_argument("--format", default="0x85",
+                    help="decode workload: SDK answer type (0x81 standard nodes, 0x82 express, 0x83 HQ, 0x84 ultra, "
+                         "0x85 dense, 0x86 ultra-dense)")
     ap.add_argument("--sor", type=int, default=0, help="cloud workload: SOR k (0 = off)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -655,6 +658,227 @@ def run_decode(args, rank, local_rank, world):
     ctx.close()
 
 
+def run_decode_format(args, rank, local_rank, world):
+    """SURVEY.md 8(f) rank 1, the other answer formats: 512 streams per GPU, ~12 MB of wire bytes each
+    in total; random payload bits, plausible start angles (see tests/test_capsule_oracle_vs_ref.py)."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+
+    import rplidar_ros2_driver_b200 as R
+    from oracle import pyoracle as O  # capsule builder + cpu_baseline leg only
+
+    fmt = int(args.format, 0)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    names = {0x81: "standard nodes (UnpackerHandler_NormalNode)", 0x82: "express capsules (UnpackerHandler_CapsuleNode)",
+             0x83: "HQ capsules (UnpackerHandler_HQNode)", 0x84: "ultra capsules (UnpackerHandler_UltraCapsuleNode)",
+             0x86: "ultra-dense capsules (UnpackerHandler_UltraDenseCapsuleNode)"}
+    kernels = {0x81: "decode_normal_kernel", 0x82: "decode_capsule_kernel<express>", 0x83: "decode_hq_kernel",
+               0x84: "decode_capsule_kernel<ultra>", 0x86: "decode_capsule_kernel<ultra-dense>"}
+    n_streams, distinct = 512, 16
+    rng = np.random.default_rng(1 + rank)
+    ctx = R.Context(local_rank, 8192, 1)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sp = stream.cuda_stream
+    if fmt == 0x81:
+        n_rec = 65536
+        host = []
+        for _ in range(distinct):
+            rec = np.zeros((n_rec, 5), np.uint8)
+            s1 = (np.arange(n_rec) % 360 == 0).astype(np.uint8)
+            rec[:, 0] = (rng.integers(0, 64, n_rec).astype(np.uint8) << 2) | ((1 - s1) << 1) | s1
+            w = ((((np.arange(n_rec) % 360) * 64).astype(np.uint16)) << 1) | 1
+            rec[:, 1], rec[:, 2] = w & 0xFF, w >> 8
+            rec[:, 3:] = rng.integers(0, 256, (n_rec, 2))
+            host.append(rec.reshape(-1))
+        host = np.stack(host)
+        stride = host.shape[1]
+        wire = torch.from_numpy(np.tile(host, (n_streams // distinct, 1))).to(dev)
+        counts = torch.full((n_streams,), stride, dtype=torch.int32, device=dev)
+        nodes = torch.empty((n_streams, stride // 5, 8), dtype=torch.uint8, device=dev)
+        ncount = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+        wire_bytes = n_streams * stride
+
+        def step():
+            ctx.decode_normal_batch_dev(wire.data_ptr(), counts.data_ptr(), n_streams, stride, nodes.data_ptr(),
+                                        ncount.data_ptr(), stream=sp)
+
+        cpu_one = lambda i: O.decode_normal(host[i % distinct])
+        shape = f"{n_streams} streams x {n_rec} five-byte records"
+    else:
+        cb, per = O.capsule_bytes(fmt), O.capsule_nodes(fmt)
+        n_caps = {0x82: 4096, 0x83: 512, 0x84: 2048, 0x86: 2048}[fmt]
+        host = []
+        for _ in range(distinct):
+            payload = rng.integers(0, 256, (n_caps, cb), dtype=np.uint8)
+            if fmt == 0x83:
+                host.append(O.seal_capsules(fmt, payload))
+                continue
+            step_deg = 360.0 * per / 3200.0  # 3200 points per revolution
+            ang = (rng.uniform(0, 360) + np.arange(n_caps) * step_deg + rng.normal(0, 0.03, n_caps)) % 360.0
+            q6 = np.round(ang * 64).astype(np.uint32) % (360 * 64)
+            sync = np.zeros(n_caps, bool)
+            sync[0] = True
+            host.append(O.seal_capsules(fmt, payload, q6, sync))
+        host = np.stack(host)
+        wire = torch.from_numpy(np.tile(host, (n_streams // distinct, 1, 1))).to(dev)
+        counts = torch.full((n_streams,), n_caps, dtype=torch.int32, device=dev)
+        nodes = torch.empty((n_streams, n_caps * per, 8), dtype=torch.uint8, device=dev)
+        ncount = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+        wire_bytes = n_streams * n_caps * cb
+
+        def step():
+            ctx.decode_capsules_batch_dev(fmt, wire.data_ptr(), counts.data_ptr(), n_streams, n_caps, 31,
+                                          nodes.data_ptr(), ncount.data_ptr(), stream=sp)
+
+        cpu_one = lambda i: O.decode_capsules(fmt, host[i % distinct], 31)
+        shape = f"{n_streams} streams x {n_caps} framed {cb}-byte capsules ({per} points each)"
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ctx.launch_count
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    pts = int(ncount.sum().item())
+    peak, peak_src = measured_peak()
+    alg = wire_bytes + pts * 8
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    cpu_one(0)
+    t_one = time.perf_counter() - t0
+    reps = max(cores, 32)
+    with ThreadPoolExecutor(cores) as ex:
+        t0 = time.perf_counter()
+        list(ex.map(cpu_one, range(reps)))
+        t_all = time.perf_counter() - t0
+    pts_stream = pts / n_streams
+    line = {
+        "metric": f"Mpoints/s through answer-type {fmt:#x} decode (wire bytes -> HQ nodes)",
+        "value": pts / (ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": W,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic",
+        "config": {"workload": f"{names[fmt]}: {shape}, random payload bits",
+                   "l2": f"{wire_bytes / 1e6:.0f} MB in + {pts * 8 / 1e6:.0f} MB out per step exceed the 126 MB L2"},
+        "roofline": {"bound": "hbm", "kernel": kernels[fmt], "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak,
+                     "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg, "bytes_per_point": alg / max(pts, 1)},
+        "cpu_baseline": {"value": reps * pts_stream / t_all / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{reps} streams through the oracle port (validated against the compiled SDK "
+                                   f"unpacker)", "value_1thread": pts_stream / t_one / 1e6},
+        "e2e": None, "gpu_launches": ctx.launch_count - l0,
+    }
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
+def run_chain(args, rank, local_rank, world):
+    """Wire bytes -> LaserScan on the device: dense-capsule decode -> scan assembly -> scan kernel, three
+    launches per step and no host round trip (SURVEY.md 8(f) rank 1 + 2 + the hot path)."""
+    import torch
+
+    import rplidar_ros2_driver_b200 as R
+    from oracle import pyoracle as O  # capsule builder only
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    n_streams, n_caps, distinct, max_nodes, max_scans = 512, 4096, 16, 4096, 56
+    rng = np.random.default_rng(1 + rank)
+    host = []
+    for sidx in range(distinct):
+        ang = (rng.uniform(0, 360) + np.arange(n_caps) * 4.5 + rng.normal(0, 0.03, n_caps)) % 360.0
+        q6 = np.round(ang * 64).astype(np.uint32) % (360 * 64)
+        dist = rng.integers(1, 40000, (n_caps, 40))
+        dist[rng.random((n_caps, 40)) < 0.05] = 0
+        sync = np.zeros(n_caps, bool)
+        sync[0] = True
+        host.append(O.make_dense_capsules(q6, sync, dist))
+    host = np.stack(host)
+    NS = n_streams * max_scans
+    ctx = R.Context(local_rank, max_nodes, NS)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sp = stream.cuda_stream
+    caps = torch.from_numpy(np.tile(host, (n_streams // distinct, 1, 1))).to(dev)
+    ccounts = torch.full((n_streams,), n_caps, dtype=torch.int32, device=dev)
+    nodes = torch.empty((n_streams, n_caps * 40, 8), dtype=torch.uint8, device=dev)
+    ncount = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+    status = torch.zeros((n_streams, n_caps), dtype=torch.int32, device=dev)
+    offs = torch.zeros((n_streams, n_caps), dtype=torch.int32, device=dev)
+    scans = torch.zeros((NS, max_nodes, 8), dtype=torch.uint8, device=dev)
+    slen = torch.zeros(NS, dtype=torch.int32, device=dev)
+    sps = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+    ranges = torch.empty((NS, max_nodes), dtype=torch.float32, device=dev)
+    intens = torch.empty((NS, max_nodes), dtype=torch.float32, device=dev)
+    beams = torch.zeros(NS, dtype=torch.int32, device=dev)
+    inc = torch.zeros(NS, dtype=torch.float32, device=dev)
+    params = R.scan_params(1, 0, 0, 1)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def step(timed=False):
+        if timed:
+            ev[0].record(stream)
+        ctx.decode_dense_batch_dev(caps.data_ptr(), ccounts.data_ptr(), n_streams, n_caps, 31, nodes.data_ptr(),
+                                   ncount.data_ptr(), capsule_status=status.data_ptr(),
+                                   capsule_node_offset=offs.data_ptr(), stream=sp)
+        if timed:
+            ev[1].record(stream)
+        ctx.assemble_scans_dev(nodes.data_ptr(), ncount.data_ptr(), n_streams, n_caps * 40, max_nodes, max_scans,
+                               max_nodes, scans.data_ptr(), slen.data_ptr(), sps.data_ptr(),
+                               capsule_status=status.data_ptr(), capsule_node_offset=offs.data_ptr(),
+                               capsule_counts=ccounts.data_ptr(), stride_capsules=n_caps, stream=sp)
+        if timed:
+            ev[2].record(stream)
+        ctx.scan_batch_dev(scans.data_ptr(), slen.data_ptr(), NS, max_nodes, params, ranges=ranges.data_ptr(),
+                           intensities=intens.data_ptr(), beam_counts=beams.data_ptr(),
+                           angle_increment=inc.data_ptr(), stream=sp)
+        if timed:
+            ev[3].record(stream)
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    step(True)
+    torch.cuda.synchronize()
+    parts = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ctx.launch_count
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    pts = int(slen.sum().item())      # nodes that reached a published scan
+    n_scans = int(sps.sum().item())
+    peak, peak_src = measured_peak()
+    wire = n_streams * n_caps * 84
+    alg = wire + int(ncount.sum().item()) * 8 + pts * (8 + 8 + 8 + 8)  # decode out, assemble in+out, scan in+out
+    line = {
+        "metric": "Mpoints/s wire capsules -> LaserScan (decode + scan assembly + scan kernel on the device)",
+        "value": pts / (ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": W,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",
+        "data": "synthetic",
+        "config": {"workload": f"{n_streams} streams x {n_caps} dense capsules -> {n_scans} revolutions of ~3200 nodes, "
+                               f"Mode B, angle_compensate on", "l2": "every stage streams > 126 MB"},
+        "roofline": {"bound": "hbm", "kernel": "decode_dense + assemble + scan", "achieved": alg / (ms * 1e-3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg},
+        "cpu_baseline": None, "e2e": None, "gpu_launches": ctx.launch_count - l0,
+        "extra": {"ms_decode": parts[0], "ms_assemble": parts[1], "ms_scan": parts[2], "scans_published": n_scans,
+                  "points_decoded": int(ncount.sum().item())},
+    }
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -666,9 +890,16 @@ def main():
     if args.workload == "cloud":
         run_cloud(args, rank, local_rank, world)
         return
+    if args.workload == "chain":
+        if rank == 0:
+            run_chain(args, rank, local_rank, world)
+        return
     if args.workload == "decode":
         if rank == 0:
-            run_decode(args, rank, local_rank, world)
+            if int(args.format, 0) == 0x85:
+                run_decode(args, rank, local_rank, world)
+            else:
+                run_decode_format(args, rank, local_rank, world)
         return
     run_b200(args, rank, local_rank, world)
 

@@ -101,6 +101,17 @@ def test_capacity_overwrites_the_last_entry_and_scan_overflow(R, oracle, ctx):
     assert (got[2] > 8).any() and (got[1] == 50).any()
 
 
+def test_many_scan_starts_and_many_resets_take_the_block_scan_path(R, oracle, ctx):
+    rng = np.random.default_rng(23)
+    streams = [random_stream(oracle, rng, 20000, 0.4, 5),       # > 4096 scan starts
+               random_stream(oracle, rng, 30000, 0.01, 1500),   # > 1024 resets
+               random_stream(oracle, rng, 9000, 0.45, 1100),    # exactly around both limits
+               random_stream(oracle, rng, 5000, 0.002, 2)]      # list path in the same launch
+    got = run_gpu(ctx, oracle, streams, 300, 64)
+    compare(oracle, streams, got, 300, 64)
+    assert got[2][0] > 4096
+
+
 def test_edge_streams(R, oracle, ctx):
     z = lambda n: np.zeros(n, np.uint32)
     mk = lambda flags: (np.array([(i, 4 * i + 4, 7, f) for i, f in enumerate(flags)], oracle.NODE_DTYPE))
