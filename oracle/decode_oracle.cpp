@@ -101,9 +101,13 @@ extern "C" uint32_t orc_dense_decode(const uint8_t* capsules, uint32_t n_capsule
 // progress, and a scan that reaches `max_nodes` keeps overwriting its last entry.
 // PARITY PINNED: tests/test_decode_oracle_vs_ref.py runs the reference's real ScanDataHolder
 // (oracle/ref_shim_holder.cpp compiles sl_lidar_driver.cpp in place) on the same streams.
-extern "C" uint32_t orc_assemble_scans(const orc_node_hq* nodes, uint32_t n, const uint32_t* resets,
-                                       uint32_t n_resets, uint32_t max_nodes, orc_node_hq* scans_out,
-                                       uint32_t scan_stride, uint32_t* scan_len, uint32_t max_scans) {
+// node_ts / scan_ts (nullable): a published scan carries the timestamp of the scan-start node that
+// opened it (:293, reported by waitAndLockAvailableScan :326-328).
+extern "C" uint32_t orc_assemble_scans_ts(const orc_node_hq* nodes, uint32_t n, const uint32_t* resets,
+                                          uint32_t n_resets, uint32_t max_nodes, orc_node_hq* scans_out,
+                                          uint32_t scan_stride, uint32_t* scan_len, uint32_t max_scans,
+                                          const uint64_t* node_ts, uint64_t* scan_ts) {
+  uint64_t begin_ts = 0;
   uint32_t n_scans = 0, cur = 0, ri = 0;  // cur: nodes in the scan in progress
   orc_node_hq* slot = scans_out;           // the scan in progress is built in place
   for (uint32_t i = 0; i <= n; ++i) {
@@ -115,11 +119,15 @@ extern "C" uint32_t orc_assemble_scans(const orc_node_hq* nodes, uint32_t n, con
     const orc_node_hq& nd = nodes[i];
     if (nd.flag & 1u) {  // :279-293
       if (cur) {
-        if (n_scans < max_scans) scan_len[n_scans] = cur;
+        if (n_scans < max_scans) {
+          scan_len[n_scans] = cur;
+          if (scan_ts) scan_ts[n_scans] = begin_ts;
+        }
         ++n_scans;
         slot = (n_scans < max_scans) ? scans_out + static_cast<size_t>(n_scans) * scan_stride : nullptr;
         cur = 0;
       }
+      begin_ts = node_ts ? node_ts[i] : 0;
     } else if (cur == 0) {
       continue;  // :295-299 no partial scans
     }
@@ -131,4 +139,11 @@ extern "C" uint32_t orc_assemble_scans(const orc_node_hq* nodes, uint32_t n, con
     }
   }
   return n_scans;
+}
+
+extern "C" uint32_t orc_assemble_scans(const orc_node_hq* nodes, uint32_t n, const uint32_t* resets,
+                                       uint32_t n_resets, uint32_t max_nodes, orc_node_hq* scans_out,
+                                       uint32_t scan_stride, uint32_t* scan_len, uint32_t max_scans) {
+  return orc_assemble_scans_ts(nodes, n, resets, n_resets, max_nodes, scans_out, scan_stride, scan_len, max_scans,
+                               nullptr, nullptr);
 }

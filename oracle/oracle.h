@@ -138,6 +138,19 @@ uint32_t orc_decode_capsules(uint32_t ans_type, const uint8_t* capsules, uint32_
 uint32_t orc_decode_normal(const uint8_t* bytes, uint32_t n_bytes, orc_node_hq* nodes_out, uint32_t* node_end,
                            uint32_t* fsm_pos);
 
+/* ---- part 1d: per-sample timestamps (timestamp_oracle.cpp) ---- */
+/* timing4 = {sample_duration_uS, native_baudrate, linkage_delay_uS, native_interface_type}
+ * (sl::SlamtecLidarTimingDesc, reference src/sdk/include/sl_lidar_driver.h:156-166). */
+uint64_t orc_sample_delay_us(uint32_t ans_type, const uint32_t* timing4, uint32_t sample_idx);
+void orc_node_timestamps(uint32_t ans_type, const uint32_t* timing4, const uint64_t* capsule_rx_us,
+                         const uint32_t* capsule_status, const uint32_t* capsule_node_offset, uint32_t n_capsules,
+                         uint64_t* ts_out);
+void orc_normal_timestamps(const uint32_t* timing4, const uint32_t* node_end, uint32_t n_nodes, uint32_t chunk_bytes,
+                           const uint64_t* chunk_rx_us, uint64_t* ts_out);
+uint32_t orc_assemble_scans_ts(const orc_node_hq* nodes, uint32_t n, const uint32_t* resets, uint32_t n_resets,
+                               uint32_t max_nodes, orc_node_hq* scans_out, uint32_t scan_stride, uint32_t* scan_len,
+                               uint32_t max_scans, const uint64_t* node_ts, uint64_t* scan_ts);
+
 /* ---- part 2: extensions (parity unpinned) --------------------------------------- */
 
 typedef struct orc_cloud_params {

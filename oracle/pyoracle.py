@@ -20,6 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle_scan.so")
 REF_SO = os.path.join(HERE, "_ref", "libref_rplidar.so")
 REF_HOLDER_SO = os.path.join(HERE, "_ref", "libref_holder.so")
+REF_CLOCK_SO = os.path.join(HERE, "_ref", "libref_clock.so")
 
 NODE_DTYPE = np.dtype(
     {
@@ -116,6 +117,14 @@ def lib() -> C.CDLL:
         L.orc_decode_capsules.restype = u32
         L.orc_decode_normal.argtypes = [vp, u32, vp, vp, C.POINTER(u32)]
         L.orc_decode_normal.restype = u32
+        L.orc_sample_delay_us.argtypes = [u32, vp, u32]
+        L.orc_sample_delay_us.restype = C.c_uint64
+        L.orc_node_timestamps.argtypes = [u32, vp, vp, vp, vp, u32, vp]
+        L.orc_node_timestamps.restype = None
+        L.orc_normal_timestamps.argtypes = [vp, vp, u32, u32, vp, vp]
+        L.orc_normal_timestamps.restype = None
+        L.orc_assemble_scans_ts.argtypes = [vp, u32, vp, u32, u32, vp, u32, vp, u32, vp, vp]
+        L.orc_assemble_scans_ts.restype = u32
         L.orc_assemble_scans.argtypes = [vp, u32, vp, u32, u32, vp, u32, vp, u32]
         L.orc_assemble_scans.restype = u32
         _lib = L
@@ -405,3 +414,84 @@ def ref_assemble_scans(nodes: np.ndarray, resets=None, max_nodes: int = 8192, ma
     k = _holder.ref_assemble_scans(_ptr(nodes), nodes.shape[0], _ptr(resets), resets.shape[0], max_nodes, _ptr(out),
                                    stride, _ptr(lens), max_scans)
     return out, lens, k
+
+
+# ---- per-sample timestamps ---------------------------------------------------
+def timing4(sample_duration_us=31, native_baudrate=0, linkage_delay_us=0, native_interface_type=0) -> np.ndarray:
+    return np.array([sample_duration_us, native_baudrate, linkage_delay_us, native_interface_type], np.uint32)
+
+
+def node_timestamps(ans: int, timing: np.ndarray, capsule_rx_us, status, offsets, n_nodes: int) -> np.ndarray:
+    rx = np.ascontiguousarray(capsule_rx_us, dtype=np.uint64)
+    status = np.ascontiguousarray(status, dtype=np.uint32)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+    ts = np.zeros(max(n_nodes, 1), np.uint64)
+    lib().orc_node_timestamps(ans, _ptr(timing), _ptr(rx), _ptr(status), _ptr(offsets), status.shape[0], _ptr(ts))
+    return ts[:n_nodes]
+
+
+def normal_timestamps(timing: np.ndarray, node_end, chunk_bytes: int, chunk_rx_us) -> np.ndarray:
+    node_end = np.ascontiguousarray(node_end, dtype=np.uint32)
+    rx = np.ascontiguousarray(chunk_rx_us, dtype=np.uint64)
+    ts = np.zeros(max(node_end.shape[0], 1), np.uint64)
+    lib().orc_normal_timestamps(_ptr(timing), _ptr(node_end), node_end.shape[0], chunk_bytes, _ptr(rx), _ptr(ts))
+    return ts[: node_end.shape[0]]
+
+
+def assemble_scans_ts(nodes, node_ts, resets=None, max_nodes: int = 8192, max_scans: int = 64):
+    """Returns (scans, lengths, n_published, scan_begin_ts)."""
+    nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
+    node_ts = np.ascontiguousarray(node_ts, dtype=np.uint64)
+    resets = np.zeros(0, np.uint32) if resets is None else np.ascontiguousarray(resets, dtype=np.uint32)
+    out = np.zeros((max_scans, max_nodes), NODE_DTYPE)
+    lens = np.zeros(max_scans, np.uint32)
+    sts = np.zeros(max_scans, np.uint64)
+    k = lib().orc_assemble_scans_ts(_ptr(nodes), nodes.shape[0], _ptr(resets), resets.shape[0], max_nodes, _ptr(out),
+                                    max_nodes, _ptr(lens), max_scans, _ptr(node_ts), _ptr(sts))
+    return out, lens, k, sts
+
+
+_clock = None
+
+
+def have_ref_clock() -> bool:
+    return os.path.exists(REF_CLOCK_SO)
+
+
+def ref_unpack_ts(ans: int, stream_bytes, chunk: int, rx_us, timing: np.ndarray):
+    """The SDK's own unpacker, fed `chunk` bytes at a time with its clock set to rx_us[k] before piece k.
+    Returns (nodes, timestamps)."""
+    global _clock
+    if _clock is None:
+        _clock = C.CDLL(REF_CLOCK_SO)
+        _clock.ref_unpack_ts.argtypes = [C.c_uint32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)]
+        _clock.ref_unpack_ts.restype = C.c_int
+    b = np.ascontiguousarray(stream_bytes, dtype=np.uint8).reshape(-1)
+    rx = np.ascontiguousarray(rx_us, dtype=np.uint64)
+    assert rx.shape[0] >= (b.shape[0] + chunk - 1) // chunk
+    cap_nodes = b.shape[0] + 256
+    nodes = np.zeros(cap_nodes, NODE_DTYPE)
+    ts = np.zeros(cap_nodes, np.uint64)
+    nn = C.c_uint32(0)
+    rc = _clock.ref_unpack_ts(ans, _ptr(b), b.shape[0], chunk, _ptr(rx), _ptr(timing), _ptr(nodes), _ptr(ts), cap_nodes,
+                              C.byref(nn))
+    assert rc == 0, rc
+    return nodes[: nn.value].copy(), ts[: nn.value].copy()
+
+
+def ref_assemble_scans_ts(nodes, node_ts, resets=None, max_nodes: int = 8192, max_scans: int = 64):
+    """The reference's own ScanDataHolder with timestamps: (scans, lengths, n_published, scan_begin_ts)."""
+    h = C.CDLL(REF_HOLDER_SO)
+    h.ref_assemble_scans_ts.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
+                                        C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    h.ref_assemble_scans_ts.restype = C.c_int
+    nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
+    node_ts = np.ascontiguousarray(node_ts, dtype=np.uint64)
+    resets = np.zeros(0, np.uint32) if resets is None else np.ascontiguousarray(resets, dtype=np.uint32)
+    out = np.zeros((max_scans, max_nodes), NODE_DTYPE)
+    lens = np.zeros(max_scans, np.uint32)
+    sts = np.zeros(max_scans, np.uint64)
+    k = h.ref_assemble_scans_ts(_ptr(nodes), nodes.shape[0], _ptr(resets), resets.shape[0], max_nodes, _ptr(out),
+                                max_nodes, _ptr(lens), max_scans, _ptr(node_ts), _ptr(sts))
+    return out, lens, k, sts

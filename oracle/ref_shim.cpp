@@ -25,6 +25,18 @@
 #include "dataunpacker/dataunnpacker_commondef.h"
 #include "dataunpacker/dataunpacker.h"
 
+#ifdef REF_FAKE_CLOCK
+// libref_clock.so: the SDK compiled WITHOUT its arch/linux/timer.cpp; the two clock functions that
+// file defines are supplied here and return a value the test sets, so that the timestamps the
+// unpackers attach to every node (rx time - _getSampleDelayOffsetIn*Mode) become reproducible.
+#include "arch/linux/arch_linux.h"
+static _u64 g_fake_now_us = 0;
+namespace rp { namespace arch {
+_u64 rp_getus() { return g_fake_now_us; }
+_u64 rp_getms() { return g_fake_now_us / 1000; }
+}}
+#endif
+
 namespace {
 sl::ILidarDriver* sdk_driver() {
   // createLidarDriver() needs no device: it only constructs SlamtecLidarDriver.
@@ -116,6 +128,53 @@ int ref_dense_decode(const uint8_t* bytes, size_t n_bytes, size_t chunk, uint32_
   return ref_unpack(SL_LIDAR_ANS_TYPE_MEASUREMENT_DENSE_CAPSULED, bytes, n_bytes, chunk, sample_duration_us,
                     nodes_out, cap_nodes, n_nodes, events, cap_events, n_events);
 }
+
+#ifdef REF_FAKE_CLOCK
+// Like ref_unpack, but the stream is fed one `chunk`-byte piece at a time with the fake clock set to
+// rx_us[k] before piece k, and the timestamp of every decoded node is recorded.
+// timing: {sample_duration_uS, native_baudrate, linkage_delay_uS, native_interface_type}.
+int ref_unpack_ts(uint32_t ans_type, const uint8_t* bytes, size_t n_bytes, size_t chunk, const uint64_t* rx_us,
+                  const uint32_t* timing4, void* nodes_out, uint64_t* ts_out, size_t cap_nodes, uint32_t* n_nodes) {
+  using namespace sl::internal;
+  struct Capture : public LIDARSampleDataListener {
+    sl_lidar_response_measurement_node_hq_t* out;
+    uint64_t* ts;
+    size_t cap, n = 0;
+    bool overflow = false;
+    void onHQNodeScanResetReq() override {}
+    void onHQNodeDecoded(_u64 t, const rplidar_response_measurement_node_hq_t* node) override {
+      if (n < cap) {
+        out[n] = *node;
+        ts[n++] = t;
+      } else {
+        overflow = true;
+      }
+    }
+    void onDecodingError(int, _u8, const void*, size_t) override {}
+  } cap;
+  cap.out = static_cast<sl_lidar_response_measurement_node_hq_t*>(nodes_out);
+  cap.ts = ts_out;
+  cap.cap = cap_nodes;
+  LIDARSampleDataUnpacker* up = LIDARSampleDataUnpacker::CreateInstance(cap);
+  if (!up) return -1;
+  sl::SlamtecLidarTimingDesc timing{};
+  timing.sample_duration_uS = timing4[0];
+  timing.native_baudrate = timing4[1];
+  timing.linkage_delay_uS = timing4[2];
+  timing.native_interface_type = static_cast<sl::LIDARInterfaceType>(timing4[3]);
+  up->updateUnpackerContext(LIDARSampleDataUnpacker::UNPACKER_CONTEXT_TYPE_LIDAR_TIMING, &timing, sizeof(timing));
+  up->enable();
+  size_t k = 0;
+  for (size_t off = 0; off < n_bytes; off += chunk, ++k) {
+    const size_t len = (n_bytes - off < chunk) ? (n_bytes - off) : chunk;
+    g_fake_now_us = rx_us[k];
+    up->onSampleData(static_cast<_u8>(ans_type), bytes + off, len);
+  }
+  LIDARSampleDataUnpacker::ReleaseInstance(up);
+  *n_nodes = static_cast<uint32_t>(cap.n);
+  return cap.overflow ? 1 : 0;
+}
+#endif
 
 size_t ref_sizeof_node(void) { return sizeof(sl_lidar_response_measurement_node_hq_t); }
 
