@@ -234,10 +234,13 @@ rpl_result rpl_decode_capsules(rpl_ctx* ctx, uint32_t ans_type, const uint8_t* c
 /* 0x81 standard measurement nodes (5 bytes each) from RAW byte streams, with the byte-level
  * resynchronisation of UnpackerHandler_NormalNode::onData (handler_normalnode.cpp:88-141): exact on
  * misframed / corrupted streams.  bytes [n_streams][stride_bytes]; nodes_out
- * [n_streams][stride_bytes / 5]; fsm_state_out (nullable): bytes still buffered at the end. */
+ * [n_streams][stride_bytes / 5]; fsm_state_out (nullable): bytes still buffered at the end; node_end
+ * (nullable, [n_streams][stride_bytes / 5]): index of the last byte of each decoded record (what
+ * rpl_normal_timestamps_dev needs to find the piece of the stream a record arrived in). */
 rpl_result rpl_decode_normal_batch_dev(rpl_ctx* ctx, const uint8_t* bytes, const uint32_t* byte_counts,
                                        uint32_t n_streams, uint32_t stride_bytes, rpl_node_hq* nodes_out,
-                                       uint32_t* node_counts, uint32_t* fsm_state_out, void* stream);
+                                       uint32_t* node_counts, uint32_t* fsm_state_out, uint32_t* node_end,
+                                       void* stream);
 rpl_result rpl_decode_normal(rpl_ctx* ctx, const uint8_t* bytes, uint32_t n_bytes, rpl_node_hq* nodes_out,
                              uint32_t* node_count);
 
@@ -250,13 +253,41 @@ rpl_result rpl_decode_normal(rpl_ctx* ctx, const uint8_t* bytes, uint32_t n_byte
  * scan_stride >= max_nodes.  scans_out: [n_streams][max_scans][scan_stride]; scan_len:
  * [n_streams][max_scans]; scans_per_stream[s] = scans published (only the first max_scans stored).
  * The output is laid out as the input of rpl_scan_batch_dev (n_scans = n_streams * max_scans with
- * scan_len as counts; unused slots must be zeroed by the caller or have length 0). */
+ * scan_len as counts; unused slots must be zeroed by the caller or have length 0).
+ * node_ts_us (nullable, [n_streams][stride_nodes]) / scan_begin_ts_us (nullable,
+ * [n_streams][max_scans]): every published scan reports the stamp of the scan-start node that opened
+ * it (ScanDataHolder::_scan_begin_timestamp_uS, :293,:326-328; what grabScanDataHqWithTimeStamp returns). */
 rpl_result rpl_assemble_scans_dev(rpl_ctx* ctx, const rpl_node_hq* nodes, const uint32_t* node_counts,
                                   uint32_t n_streams, uint32_t stride_nodes, const uint32_t* capsule_status,
                                   const uint32_t* capsule_node_offset, const uint32_t* capsule_counts,
                                   uint32_t stride_capsules, uint32_t max_nodes, uint32_t max_scans,
                                   uint32_t scan_stride, rpl_node_hq* scans_out, uint32_t* scan_len,
-                                  uint32_t* scans_per_stream, void* stream);
+                                  uint32_t* scans_per_stream, const uint64_t* node_ts_us,
+                                  uint64_t* scan_begin_ts_us, void* stream);
+
+/* ---- per-sample timestamps -------------------------------------- */
+/* sl::SlamtecLidarTimingDesc (reference src/sdk/include/sl_lidar_driver.h:156-166). */
+typedef struct rpl_timing {
+  uint32_t sample_duration_us;
+  uint32_t native_baudrate;        /* 0 = the per-format default the SDK assumes */
+  uint32_t linkage_delay_us;
+  uint32_t native_interface_type;  /* sl::LIDARInterfaceType: 0 UART, 1 ETHERNET, 2 USB, 5 CANBUS */
+} rpl_timing;
+/* The stamp the SDK's unpackers attach to every node: receive time of a capsule minus
+ * _getSampleDelayOffsetIn{Legacy,Express,HQ,UltraBoost,Dense,UltraDense}Mode (handler_normalnode.cpp:49-68,
+ * handler_capsules.cpp:55-76,272-293,586-607,795-816, handler_hqnode.cpp:53-72).  capsule_rx_us:
+ * [n_streams][stride_capsules] receive times; capsule_status / capsule_node_offset: the decoder's report;
+ * node_ts_us: [n_streams][stride_capsules * rpl_capsule_nodes(ans_type)], written for released nodes. */
+rpl_result rpl_node_timestamps_dev(rpl_ctx* ctx, uint32_t ans_type, const rpl_timing* timing,
+                                   const uint64_t* capsule_rx_us, const uint32_t* capsule_status,
+                                   const uint32_t* capsule_node_offset, const uint32_t* capsule_counts,
+                                   uint32_t n_streams, uint32_t stride_capsules, uint64_t* node_ts_us, void* stream);
+/* Standard nodes: the record ending at byte node_end[i] is stamped with the receive time of the
+ * chunk_bytes-sized piece of the stream that byte arrived in (chunk_rx_us [n_streams][stride_chunks]). */
+rpl_result rpl_normal_timestamps_dev(rpl_ctx* ctx, const rpl_timing* timing, const uint32_t* node_end,
+                                     const uint32_t* node_counts, uint32_t n_streams, uint32_t stride_nodes,
+                                     uint32_t chunk_bytes, const uint64_t* chunk_rx_us, uint32_t stride_chunks,
+                                     uint64_t* node_ts_us, void* stream);
 
 /* ---- synthetic scan streams ------------------------------------------ */
 /* variant 0: tie-free rotated revolution, 5% unmeasured, quality 188; 1: same, quality

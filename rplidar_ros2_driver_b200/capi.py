@@ -44,8 +44,14 @@ EXPORTS = [
     "rpl_cloud_batch_dev", "rpl_cloud_batch", "rpl_cloud_fuse_dev", "rpl_synth_batch_dev",
     "rpl_decode_dense_batch_dev", "rpl_decode_dense", "rpl_assemble_scans_dev",
     "rpl_capsule_bytes", "rpl_capsule_nodes", "rpl_decode_capsules_batch_dev", "rpl_decode_capsules",
-    "rpl_decode_normal_batch_dev", "rpl_decode_normal",
+    "rpl_decode_normal_batch_dev", "rpl_decode_normal", "rpl_node_timestamps_dev", "rpl_normal_timestamps_dev",
 ]
+
+
+class Timing(C.Structure):
+    """rpl_timing == sl::SlamtecLidarTimingDesc without the bool."""
+    _fields_ = [("sample_duration_us", C.c_uint32), ("native_baudrate", C.c_uint32),
+                ("linkage_delay_us", C.c_uint32), ("native_interface_type", C.c_uint32)]
 
 
 class ScanParams(C.Structure):
@@ -131,9 +137,11 @@ def lib() -> C.CDLL:
         "rpl_capsule_nodes": ([u32], u32),
         "rpl_decode_capsules_batch_dev": ([vp, u32, vp, vp, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp], u32),
         "rpl_decode_capsules": ([vp, u32, vp, u32, u32, vp, vp, C.POINTER(u32), vp, vp], u32),
-        "rpl_decode_normal_batch_dev": ([vp, vp, vp, u32, u32, vp, vp, vp, vp], u32),
+        "rpl_decode_normal_batch_dev": ([vp, vp, vp, u32, u32, vp, vp, vp, vp, vp], u32),
+        "rpl_node_timestamps_dev": ([vp, u32, C.POINTER(Timing), vp, vp, vp, vp, u32, u32, vp, vp], u32),
+        "rpl_normal_timestamps_dev": ([vp, C.POINTER(Timing), vp, vp, u32, u32, u32, vp, u32, vp, vp], u32),
         "rpl_decode_normal": ([vp, vp, u32, vp, C.POINTER(u32)], u32),
-        "rpl_assemble_scans_dev": ([vp, vp, vp, u32, u32, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp], u32),
+        "rpl_assemble_scans_dev": ([vp, vp, vp, u32, u32, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp, vp, vp], u32),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)  # AttributeError here = the library does not export the ABI
@@ -348,18 +356,32 @@ class Context:
         return nodes[: cnt.value].copy()
 
     def decode_normal_batch_dev(self, stream_bytes, byte_counts, n_streams, stride_bytes, nodes_out, node_counts,
-                                fsm_state_out=None, stream=None):
+                                fsm_state_out=None, node_end=None, stream=None):
         self._check(self._L.rpl_decode_normal_batch_dev(
             self._h, _p(stream_bytes), _p(byte_counts), n_streams, stride_bytes, _p(nodes_out), _p(node_counts),
-            _p(fsm_state_out), _p(stream)))
+            _p(fsm_state_out), _p(node_end), _p(stream)))
+
+    # ---- per-sample timestamps ---------------------------------------------------------------------
+    def node_timestamps_dev(self, ans_type, timing: Timing, capsule_rx_us, capsule_status, capsule_node_offset,
+                            capsule_counts, n_streams, stride_capsules, node_ts_us, stream=None):
+        self._check(self._L.rpl_node_timestamps_dev(
+            self._h, ans_type, C.byref(timing), _p(capsule_rx_us), _p(capsule_status), _p(capsule_node_offset),
+            _p(capsule_counts), n_streams, stride_capsules, _p(node_ts_us), _p(stream)))
+
+    def normal_timestamps_dev(self, timing: Timing, node_end, node_counts, n_streams, stride_nodes, chunk_bytes,
+                              chunk_rx_us, stride_chunks, node_ts_us, stream=None):
+        self._check(self._L.rpl_normal_timestamps_dev(
+            self._h, C.byref(timing), _p(node_end), _p(node_counts), n_streams, stride_nodes, chunk_bytes,
+            _p(chunk_rx_us), stride_chunks, _p(node_ts_us), _p(stream)))
 
     def assemble_scans_dev(self, nodes, node_counts, n_streams, stride_nodes, max_nodes, max_scans, scan_stride,
                            scans_out, scan_len, scans_per_stream, capsule_status=None, capsule_node_offset=None,
-                           capsule_counts=None, stride_capsules=0, stream=None):
+                           capsule_counts=None, stride_capsules=0, node_ts_us=None, scan_begin_ts_us=None,
+                           stream=None):
         self._check(self._L.rpl_assemble_scans_dev(
             self._h, _p(nodes), _p(node_counts), n_streams, stride_nodes, _p(capsule_status), _p(capsule_node_offset),
             _p(capsule_counts), stride_capsules, max_nodes, max_scans, scan_stride, _p(scans_out), _p(scan_len),
-            _p(scans_per_stream), _p(stream)))
+            _p(scans_per_stream), _p(node_ts_us), _p(scan_begin_ts_us), _p(stream)))
 
     def cloud_fuse_dev(self, xyzi, point_counts, n_scans, stride, fused, offsets, total, stream=None):
         self._check(self._L.rpl_cloud_fuse_dev(self._h, _p(xyzi), _p(point_counts), n_scans, stride, _p(fused),

@@ -231,6 +231,10 @@ __global__ void __launch_bounds__(AT) assemble_kernel(AssembleArgs a) {
       if (tid == 0) {
         if (d.y > cnt) o[cnt - 1] = src[d.y - 1];
         out_len[k] = cnt;
+        // the scan-start node's stamp (ScanDataHolder::_scan_begin_timestamp_uS, sl_lidar_driver.cpp:293)
+        if (a.scan_begin_ts_us)
+          a.scan_begin_ts_us[(size_t)s * a.max_scans + k] =
+              a.node_ts_us ? a.node_ts_us[(size_t)s * a.stride_nodes + d.x] : 0ull;
       }
     }
     __syncthreads();

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 namespace rpl {
 
 struct DecodeArgs {
@@ -40,7 +42,30 @@ struct NormalDecodeArgs {
   uint2* nodes_out;               // [n_streams][stride_bytes / 5]
   uint32_t* node_counts;          // [n_streams]
   uint32_t* fsm_state_out;        // [n_streams] nullable: bytes buffered when the stream ended
+  uint32_t* node_end;             // [n_streams][stride_bytes / 5] nullable: index of each record's last byte
 };
+
+// per-sample timestamps (timestamps.cu)
+struct TimingDesc {  // sl::SlamtecLidarTimingDesc without the bool
+  uint32_t sample_duration_us, native_baudrate, linkage_delay_us, native_interface_type;
+};
+struct TimestampArgs {
+  const unsigned long long* capsule_rx_us;  // [n_streams][stride_capsules]
+  const uint32_t* capsule_status;
+  const uint32_t* capsule_node_offset;
+  const uint32_t* capsule_counts;           // [n_streams]
+  uint32_t n_streams, stride_capsules;
+  unsigned long long* node_ts_us;           // [n_streams][stride_capsules * nodes per capsule]
+};
+struct NormalTimestampArgs {
+  const uint32_t* node_end;                 // [n_streams][stride_nodes] (decode_normal's report)
+  const uint32_t* node_counts;              // [n_streams]
+  uint32_t n_streams, stride_nodes, chunk_bytes, stride_chunks;
+  const unsigned long long* chunk_rx_us;    // [n_streams][stride_chunks]
+  unsigned long long* node_ts_us;           // [n_streams][stride_nodes]
+};
+cudaError_t launch_node_timestamps(uint32_t ans_type, const TimingDesc& t, const TimestampArgs& a, cudaStream_t stream);
+cudaError_t launch_normal_timestamps(const TimingDesc& t, const NormalTimestampArgs& a, cudaStream_t stream);
 
 cudaError_t launch_decode_capsules(uint32_t ans_type, const CapsuleDecodeArgs& a, int grid, cudaStream_t stream);
 cudaError_t launch_decode_normal(const NormalDecodeArgs& a, int grid, cudaStream_t stream);
@@ -59,6 +84,8 @@ struct AssembleArgs {
   uint2* scans_out;                   // [n_streams][max_scans][scan_stride]
   uint32_t* scan_len;                 // [n_streams][max_scans]
   uint32_t* scans_per_stream;         // [n_streams] published scans (may exceed max_scans)
+  const unsigned long long* node_ts_us;  // [n_streams][stride_nodes] nullable
+  unsigned long long* scan_begin_ts_us;  // [n_streams][max_scans] nullable
   uint32_t* reset_prefix;             // scratch [n_streams][stride_capsules]
   uint2* desc;                        // scratch [n_streams][max_scans]
 };

@@ -583,6 +583,7 @@ __global__ void __launch_bounds__(NT) decode_normal_kernel(NormalDecodeArgs a) {
     const uint32_t n = a.byte_counts[s];
     const uint8_t* src = a.bytes + (size_t)s * a.stride_bytes;
     uint2* out = a.nodes_out + (size_t)s * (a.stride_bytes / 5u);
+    uint32_t* end_out = a.node_end ? a.node_end + (size_t)s * (a.stride_bytes / 5u) : nullptr;
     if (tid == 0) {
       sm.carry_state = 0;
       sm.carry_nodes = 0;
@@ -653,6 +654,7 @@ __global__ void __launch_bounds__(NT) decode_normal_kernel(NormalDecodeArgs a) {
         nd.x = key | (dist << 16);
         nd.y = (((sq >> 2) << 2) << 16) | ((sq & 1u) << 24);
         o[q] = nd;
+        if (end_out) end_out[sm.carry_nodes + q] = t0 + sm.ends[q];
       }
       __syncthreads();
       if (tid < 4) sm.bytes[tid] = sm.bytes[live + tid];  // last four bytes of this tile (live >= 4 or stream ends)

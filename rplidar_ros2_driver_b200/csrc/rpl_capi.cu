@@ -911,7 +911,8 @@ rpl_result rpl_decode_capsules(rpl_ctx* c, uint32_t ans_type, const uint8_t* cap
 
 rpl_result rpl_decode_normal_batch_dev(rpl_ctx* c, const uint8_t* bytes, const uint32_t* byte_counts,
                                        uint32_t n_streams, uint32_t stride_bytes, rpl_node_hq* nodes_out,
-                                       uint32_t* node_counts, uint32_t* fsm_state_out, void* stream) {
+                                       uint32_t* node_counts, uint32_t* fsm_state_out, uint32_t* node_end,
+                                       void* stream) {
   if (!c || !bytes || !byte_counts || !nodes_out) return RPL_RESULT_INVALID_DATA;
   if (n_streams == 0) return RPL_RESULT_OK;
   RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
@@ -924,6 +925,7 @@ rpl_result rpl_decode_normal_batch_dev(rpl_ctx* c, const uint8_t* bytes, const u
   a.nodes_out = reinterpret_cast<uint2*>(nodes_out);
   a.node_counts = node_counts;
   a.fsm_state_out = fsm_state_out;
+  a.node_end = node_end;
   const int grid = (int)std::min<uint32_t>(n_streams, (uint32_t)c->num_sms * 8u);
   RPL_CUDA(c, rpl::launch_decode_normal(a, grid, st), RPL_RESULT_OPERATION_FAIL);
   c->launches++;
@@ -946,7 +948,7 @@ rpl_result rpl_decode_normal(rpl_ctx* c, const uint8_t* bytes, uint32_t n_bytes,
   RPL_CUDA(c, cudaMemcpyAsync(h.d + h.o_small, small, 8, cudaMemcpyHostToDevice, st), RPL_RESULT_OPERATION_FAIL);
   uint32_t* ds = reinterpret_cast<uint32_t*>(h.d + h.o_small);
   rpl_result r = rpl_decode_normal_batch_dev(c, h.d, ds, 1, n_bytes, reinterpret_cast<rpl_node_hq*>(h.d + h.o_nodes),
-                                             ds + 1, nullptr, st);
+                                             ds + 1, nullptr, nullptr, st);
   if (r != RPL_RESULT_OK) return r;
   RPL_CUDA(c, cudaMemcpyAsync(small, ds, 8, cudaMemcpyDeviceToHost, st), RPL_RESULT_OPERATION_FAIL);
   RPL_CUDA(c, cudaStreamSynchronize(st), RPL_RESULT_OPERATION_FAIL);
@@ -962,7 +964,8 @@ rpl_result rpl_assemble_scans_dev(rpl_ctx* c, const rpl_node_hq* nodes, const ui
                                   const uint32_t* capsule_node_offset, const uint32_t* capsule_counts,
                                   uint32_t stride_capsules, uint32_t max_nodes, uint32_t max_scans,
                                   uint32_t scan_stride, rpl_node_hq* scans_out, uint32_t* scan_len,
-                                  uint32_t* scans_per_stream, void* stream) {
+                                  uint32_t* scans_per_stream, const uint64_t* node_ts_us,
+                                  uint64_t* scan_begin_ts_us, void* stream) {
   if (!c || !nodes || !node_counts || !scans_out || !scan_len || !scans_per_stream) return RPL_RESULT_INVALID_DATA;
   const bool any = capsule_status || capsule_node_offset || capsule_counts;
   if (any && !(capsule_status && capsule_node_offset && capsule_counts)) {
@@ -1006,10 +1009,66 @@ rpl_result rpl_assemble_scans_dev(rpl_ctx* c, const rpl_node_hq* nodes, const ui
   a.scans_out = reinterpret_cast<uint2*>(scans_out);
   a.scan_len = scan_len;
   a.scans_per_stream = scans_per_stream;
+  a.node_ts_us = reinterpret_cast<const unsigned long long*>(node_ts_us);
+  a.scan_begin_ts_us = reinterpret_cast<unsigned long long*>(scan_begin_ts_us);
   a.reset_prefix = c->d_reset_prefix;
   a.desc = c->d_desc;
   const int grid = (int)std::min<uint32_t>(n_streams, (uint32_t)c->num_sms * 4u);
   RPL_CUDA(c, rpl::launch_assemble(a, grid, st), RPL_RESULT_OPERATION_FAIL);
+  c->launches++;
+  return RPL_RESULT_OK;
+}
+
+// ---- per-sample timestamps ----------------------------------------------
+rpl_result rpl_node_timestamps_dev(rpl_ctx* c, uint32_t ans_type, const rpl_timing* timing,
+                                   const uint64_t* capsule_rx_us, const uint32_t* capsule_status,
+                                   const uint32_t* capsule_node_offset, const uint32_t* capsule_counts,
+                                   uint32_t n_streams, uint32_t stride_capsules, uint64_t* node_ts_us, void* stream) {
+  if (!c || !timing || !capsule_rx_us || !capsule_status || !capsule_node_offset || !capsule_counts || !node_ts_us)
+    return RPL_RESULT_INVALID_DATA;
+  if (rpl_capsule_bytes(ans_type) == 0) {
+    c->err = "unknown answer type (capsule formats are 0x82..0x86)";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if (n_streams == 0) return RPL_RESULT_OK;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
+  rpl::TimingDesc t{timing->sample_duration_us, timing->native_baudrate, timing->linkage_delay_us,
+                    timing->native_interface_type};
+  rpl::TimestampArgs a{};
+  a.capsule_rx_us = reinterpret_cast<const unsigned long long*>(capsule_rx_us);
+  a.capsule_status = capsule_status;
+  a.capsule_node_offset = capsule_node_offset;
+  a.capsule_counts = capsule_counts;
+  a.n_streams = n_streams;
+  a.stride_capsules = stride_capsules;
+  a.node_ts_us = reinterpret_cast<unsigned long long*>(node_ts_us);
+  RPL_CUDA(c, rpl::launch_node_timestamps(ans_type, t, a, st), RPL_RESULT_OPERATION_FAIL);
+  c->launches++;
+  return RPL_RESULT_OK;
+}
+
+rpl_result rpl_normal_timestamps_dev(rpl_ctx* c, const rpl_timing* timing, const uint32_t* node_end,
+                                     const uint32_t* node_counts, uint32_t n_streams, uint32_t stride_nodes,
+                                     uint32_t chunk_bytes, const uint64_t* chunk_rx_us, uint32_t stride_chunks,
+                                     uint64_t* node_ts_us, void* stream) {
+  if (!c || !timing || !node_end || !node_counts || !chunk_rx_us || !node_ts_us || chunk_bytes == 0)
+    return RPL_RESULT_INVALID_DATA;
+  if (n_streams == 0) return RPL_RESULT_OK;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
+  rpl::TimingDesc t{timing->sample_duration_us, timing->native_baudrate, timing->linkage_delay_us,
+                    timing->native_interface_type};
+  rpl::NormalTimestampArgs a{};
+  a.node_end = node_end;
+  a.node_counts = node_counts;
+  a.n_streams = n_streams;
+  a.stride_nodes = stride_nodes;
+  a.chunk_bytes = chunk_bytes;
+  a.stride_chunks = stride_chunks;
+  a.chunk_rx_us = reinterpret_cast<const unsigned long long*>(chunk_rx_us);
+  a.node_ts_us = reinterpret_cast<unsigned long long*>(node_ts_us);
+  RPL_CUDA(c, rpl::launch_normal_timestamps(t, a, st), RPL_RESULT_OPERATION_FAIL);
   c->launches++;
   return RPL_RESULT_OK;
 }
