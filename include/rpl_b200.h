@@ -265,6 +265,35 @@ rpl_result rpl_assemble_scans_dev(rpl_ctx* ctx, const rpl_node_hq* nodes, const 
                                   uint32_t* scans_per_stream, const uint64_t* node_ts_us,
                                   uint64_t* scan_begin_ts_us, void* stream);
 
+/* ---- LaserScan / PointCloud2 -> wire ---------------------------- */
+/* The serialised message the RMW layer would produce from the message the reference publishes
+ * (scan_pub_->publish, reference src/rplidar_node.cpp:679): XCDR1 little endian, 4-byte
+ * encapsulation header, members in declaration order.  The host publishes the bytes as they are
+ * (rclcpp::SerializedMessage).  The reference tree holds no serialiser (it is in
+ * the RMW dependency): the format follows the OMG CDR rules; parity unpinned. */
+typedef struct rpl_laserscan_meta { /* sensor_msgs/LaserScan minus frame_id and the arrays */
+  int32_t stamp_sec;
+  uint32_t stamp_nanosec;
+  float angle_min, angle_max, angle_increment, time_increment, scan_time, range_min, range_max;
+} rpl_laserscan_meta;
+uint32_t rpl_laserscan_cdr_size(uint32_t frame_id_len, uint32_t beam_count);
+/* meta: [n_scans] on the device; angle_increment (nullable, device [n_scans]): the scan kernel's
+ * output, overrides meta[s].angle_increment; ranges / intensities [n_scans][stride] and beam_counts
+ * as rpl_scan_batch_dev wrote them.  cdr_out: [n_scans][cdr_stride] with cdr_stride % 4 == 0 and
+ * cdr_stride >= rpl_laserscan_cdr_size(strlen(frame_id), stride); cdr_sizes (nullable): bytes used. */
+rpl_result rpl_laserscan_cdr_batch_dev(rpl_ctx* ctx, const rpl_laserscan_meta* meta, const float* angle_increment,
+                                       const char* frame_id, const float* ranges, const float* intensities,
+                                       const uint32_t* beam_counts, uint32_t n_scans, uint32_t stride,
+                                       uint8_t* cdr_out, uint32_t cdr_stride, uint32_t* cdr_sizes, void* stream);
+uint32_t rpl_pointcloud2_cdr_size(uint32_t frame_id_len, uint32_t n_points);
+/* sensor_msgs/PointCloud2 with fields x, y, z, intensity (float32, point_step 16, height 1, is_dense),
+ * the layout laser_geometry produces and rpl_cloud_batch_dev writes.  stamps: device [n_clouds][2]
+ * {sec, nanosec}; xyzi [n_clouds][stride][4]; cdr_stride % 16 == 0. */
+rpl_result rpl_pointcloud2_cdr_batch_dev(rpl_ctx* ctx, const uint32_t* stamps, const char* frame_id,
+                                         const float* xyzi, const uint32_t* point_counts, uint32_t n_clouds,
+                                         uint32_t stride, uint8_t* cdr_out, uint32_t cdr_stride,
+                                         uint32_t* cdr_sizes, void* stream);
+
 /* ---- per-sample timestamps -------------------------------------- */
 /* sl::SlamtecLidarTimingDesc (reference src/sdk/include/sl_lidar_driver.h:156-166). */
 typedef struct rpl_timing {

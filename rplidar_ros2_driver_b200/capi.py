@@ -45,7 +45,20 @@ EXPORTS = [
     "rpl_decode_dense_batch_dev", "rpl_decode_dense", "rpl_assemble_scans_dev",
     "rpl_capsule_bytes", "rpl_capsule_nodes", "rpl_decode_capsules_batch_dev", "rpl_decode_capsules",
     "rpl_decode_normal_batch_dev", "rpl_decode_normal", "rpl_node_timestamps_dev", "rpl_normal_timestamps_dev",
+    "rpl_laserscan_cdr_size", "rpl_laserscan_cdr_batch_dev", "rpl_pointcloud2_cdr_size", "rpl_pointcloud2_cdr_batch_dev",
 ]
+
+
+class LaserScanMeta(C.Structure):
+    """rpl_laserscan_meta: sensor_msgs/LaserScan minus frame_id and the arrays."""
+    _fields_ = [("stamp_sec", C.c_int32), ("stamp_nanosec", C.c_uint32), ("angle_min", C.c_float),
+                ("angle_max", C.c_float), ("angle_increment", C.c_float), ("time_increment", C.c_float),
+                ("scan_time", C.c_float), ("range_min", C.c_float), ("range_max", C.c_float)]
+
+
+LASERSCAN_META_DTYPE = np.dtype([("stamp_sec", "<i4"), ("stamp_nanosec", "<u4"), ("angle_min", "<f4"),
+                                 ("angle_max", "<f4"), ("angle_increment", "<f4"), ("time_increment", "<f4"),
+                                 ("scan_time", "<f4"), ("range_min", "<f4"), ("range_max", "<f4")])
 
 
 class Timing(C.Structure):
@@ -138,6 +151,10 @@ def lib() -> C.CDLL:
         "rpl_decode_capsules_batch_dev": ([vp, u32, vp, vp, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp], u32),
         "rpl_decode_capsules": ([vp, u32, vp, u32, u32, vp, vp, C.POINTER(u32), vp, vp], u32),
         "rpl_decode_normal_batch_dev": ([vp, vp, vp, u32, u32, vp, vp, vp, vp, vp], u32),
+        "rpl_laserscan_cdr_size": ([u32, u32], u32),
+        "rpl_pointcloud2_cdr_size": ([u32, u32], u32),
+        "rpl_laserscan_cdr_batch_dev": ([vp, vp, vp, C.c_char_p, vp, vp, vp, u32, u32, vp, u32, vp, vp], u32),
+        "rpl_pointcloud2_cdr_batch_dev": ([vp, vp, C.c_char_p, vp, vp, u32, u32, vp, u32, vp, vp], u32),
         "rpl_node_timestamps_dev": ([vp, u32, C.POINTER(Timing), vp, vp, vp, vp, u32, u32, vp, vp], u32),
         "rpl_normal_timestamps_dev": ([vp, C.POINTER(Timing), vp, vp, u32, u32, u32, vp, u32, vp, vp], u32),
         "rpl_decode_normal": ([vp, vp, u32, vp, C.POINTER(u32)], u32),
@@ -360,6 +377,19 @@ class Context:
         self._check(self._L.rpl_decode_normal_batch_dev(
             self._h, _p(stream_bytes), _p(byte_counts), n_streams, stride_bytes, _p(nodes_out), _p(node_counts),
             _p(fsm_state_out), _p(node_end), _p(stream)))
+
+    # ---- messages -> CDR (the step after the hot path) -----------------------------------------------
+    def laserscan_cdr_batch_dev(self, meta, frame_id: str, ranges, intensities, beam_counts, n_scans, stride,
+                                cdr_out, cdr_stride, cdr_sizes=None, angle_increment=None, stream=None):
+        self._check(self._L.rpl_laserscan_cdr_batch_dev(
+            self._h, _p(meta), _p(angle_increment), frame_id.encode(), _p(ranges), _p(intensities), _p(beam_counts),
+            n_scans, stride, _p(cdr_out), cdr_stride, _p(cdr_sizes), _p(stream)))
+
+    def pointcloud2_cdr_batch_dev(self, stamps, frame_id: str, xyzi, point_counts, n_clouds, stride, cdr_out,
+                                  cdr_stride, cdr_sizes=None, stream=None):
+        self._check(self._L.rpl_pointcloud2_cdr_batch_dev(
+            self._h, _p(stamps), frame_id.encode(), _p(xyzi), _p(point_counts), n_clouds, stride, _p(cdr_out),
+            cdr_stride, _p(cdr_sizes), _p(stream)))
 
     # ---- per-sample timestamps ---------------------------------------------------------------------
     def node_timestamps_dev(self, ans_type, timing: Timing, capsule_rx_us, capsule_status, capsule_node_offset,

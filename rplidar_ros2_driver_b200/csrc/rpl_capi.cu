@@ -15,6 +15,7 @@
 
 #include "../../include/rpl_b200.h"
 #include "cloud_args.h"
+#include "cdr_args.h"
 #include "decode_args.h"
 #include "scan_args.h"
 
@@ -1015,6 +1016,143 @@ rpl_result rpl_assemble_scans_dev(rpl_ctx* c, const rpl_node_hq* nodes, const ui
   a.desc = c->d_desc;
   const int grid = (int)std::min<uint32_t>(n_streams, (uint32_t)c->num_sms * 4u);
   RPL_CUDA(c, rpl::launch_assemble(a, grid, st), RPL_RESULT_OPERATION_FAIL);
+  c->launches++;
+  return RPL_RESULT_OK;
+}
+
+// ---- LaserScan / PointCloud2 -> CDR -------------------------------------
+namespace {
+struct CdrWriter {  // XCDR1 little endian; alignment counts from the byte after the encapsulation header
+  uint8_t* b;
+  uint32_t n = 0;
+  explicit CdrWriter(uint8_t* buf) : b(buf) {
+    const uint8_t enc[4] = {0x00, 0x01, 0x00, 0x00};
+    std::memcpy(b, enc, 4);
+    n = 4;
+  }
+  void align(uint32_t a) {
+    while ((n - 4) % a) b[n++] = 0;
+  }
+  void u32(uint32_t v) {
+    align(4);
+    std::memcpy(b + n, &v, 4);
+    n += 4;
+  }
+  void u8(uint8_t v) { b[n++] = v; }
+  void str(const char* s, uint32_t len) {
+    u32(len + 1);
+    std::memcpy(b + n, s, len);
+    n += len;
+    b[n++] = 0;
+  }
+};
+uint32_t header_bytes(uint32_t frame_id_len) { return 4 + ((12 + frame_id_len + 1 + 3) & ~3u); }
+}  // namespace
+
+uint32_t rpl_laserscan_cdr_size(uint32_t frame_id_len, uint32_t beam_count) {
+  return header_bytes(frame_id_len) + 28 + 4 + 4 * beam_count + 4 + 4 * beam_count;
+}
+
+uint32_t rpl_pointcloud2_cdr_size(uint32_t frame_id_len, uint32_t n_points) {
+  // height, width, fields count; x/y/z (20 bytes each), intensity (28); is_bigendian + pad; point_step,
+  // row_step, data length; data; is_dense
+  return header_bytes(frame_id_len) + 12 + 3 * 20 + 28 + 4 + 12 + 16 * n_points + 1;
+}
+
+rpl_result rpl_laserscan_cdr_batch_dev(rpl_ctx* c, const rpl_laserscan_meta* meta, const float* angle_increment,
+                                       const char* frame_id, const float* ranges, const float* intensities,
+                                       const uint32_t* beam_counts, uint32_t n_scans, uint32_t stride,
+                                       uint8_t* cdr_out, uint32_t cdr_stride, uint32_t* cdr_sizes, void* stream) {
+  if (!c || !meta || !frame_id || !ranges || !intensities || !beam_counts || !cdr_out) return RPL_RESULT_INVALID_DATA;
+  const size_t L = std::strlen(frame_id);
+  if (L > 255) {
+    c->err = "frame_id longer than 255 characters";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if ((cdr_stride & 3u) || cdr_stride < rpl_laserscan_cdr_size((uint32_t)L, stride) ||
+      (reinterpret_cast<uintptr_t>(cdr_out) & 3u)) {
+    c->err = "cdr_out must be 4-byte aligned, cdr_stride a multiple of 4 and >= rpl_laserscan_cdr_size(len, stride)";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if (n_scans == 0) return RPL_RESULT_OK;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
+  rpl::CdrTemplate t{};
+  CdrWriter w(t.prefix);
+  w.u32(0);  // stamp.sec     (patched)
+  w.u32(0);  // stamp.nanosec (patched)
+  w.str(frame_id, (uint32_t)L);
+  for (int i = 0; i < 7; ++i) w.u32(0);  // angle_min .. range_max (patched)
+  w.u32(0);                              // ranges count (patched)
+  t.prefix_bytes = w.n;
+  rpl::LaserScanCdrArgs a{};
+  a.meta = reinterpret_cast<const rpl::LaserScanMeta*>(meta);
+  a.angle_increment = angle_increment;
+  a.ranges = ranges;
+  a.intensities = intensities;
+  a.beam_counts = beam_counts;
+  a.n_scans = n_scans;
+  a.stride = stride;
+  a.cdr_out = cdr_out;
+  a.cdr_stride = cdr_stride;
+  a.cdr_sizes = cdr_sizes;
+  RPL_CUDA(c, rpl::launch_laserscan_cdr(a, t, st), RPL_RESULT_OPERATION_FAIL);
+  c->launches++;
+  return RPL_RESULT_OK;
+}
+
+rpl_result rpl_pointcloud2_cdr_batch_dev(rpl_ctx* c, const uint32_t* stamps, const char* frame_id,
+                                         const float* xyzi, const uint32_t* point_counts, uint32_t n_clouds,
+                                         uint32_t stride, uint8_t* cdr_out, uint32_t cdr_stride,
+                                         uint32_t* cdr_sizes, void* stream) {
+  if (!c || !stamps || !frame_id || !xyzi || !point_counts || !cdr_out) return RPL_RESULT_INVALID_DATA;
+  const size_t L = std::strlen(frame_id);
+  if (L > 255) {
+    c->err = "frame_id longer than 255 characters";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if ((cdr_stride & 15u) || cdr_stride < rpl_pointcloud2_cdr_size((uint32_t)L, stride) ||
+      (reinterpret_cast<uintptr_t>(cdr_out) & 15u)) {
+    c->err = "cdr_out must be 16-byte aligned, cdr_stride a multiple of 16 and >= rpl_pointcloud2_cdr_size(len, stride)";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if (n_clouds == 0) return RPL_RESULT_OK;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
+  rpl::CdrTemplate t{};
+  CdrWriter w(t.prefix);
+  w.u32(0);
+  w.u32(0);
+  w.str(frame_id, (uint32_t)L);
+  w.u32(1);  // height
+  w.align(4);
+  t.patch_width = w.n;
+  w.u32(0);  // width (patched)
+  w.u32(4);  // fields
+  const char* names[4] = {"x", "y", "z", "intensity"};
+  for (uint32_t f = 0; f < 4; ++f) {
+    w.str(names[f], (uint32_t)std::strlen(names[f]));
+    w.u32(4 * f);  // offset
+    w.u8(7);       // datatype FLOAT32
+    w.u32(1);      // count
+  }
+  w.u8(0);         // is_bigendian
+  w.u32(16);       // point_step
+  w.align(4);
+  t.patch_row_step = w.n;
+  w.u32(0);        // row_step (patched)
+  w.u32(0);        // data length (patched)
+  t.prefix_bytes = w.n;
+  rpl::PointCloudCdrArgs a{};
+  a.stamps = stamps;
+  a.xyzi = xyzi;
+  a.point_counts = point_counts;
+  a.n_clouds = n_clouds;
+  a.stride = stride;
+  a.cdr_out = cdr_out;
+  a.cdr_stride = cdr_stride;
+  a.cdr_sizes = cdr_sizes;
+  RPL_CUDA(c, rpl::launch_pointcloud2_cdr(a, t, st), RPL_RESULT_OPERATION_FAIL);
   c->launches++;
   return RPL_RESULT_OK;
 }
