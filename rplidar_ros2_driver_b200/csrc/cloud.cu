@@ -25,28 +25,28 @@ namespace {
 constexpr int CT = 256;  // threads per CTA of the post-processing kernels
 constexpr int kHalfWindow = 16;
 
+// One hash-table entry.  The table is kept CLEAN between scans (every cell a scan touched is reset by
+// the thread that emits it), so no per-scan clear of the whole table is needed.
+struct __align__(32) VoxelCell {
+  unsigned long long key;  // packed (ix, iy), kVoxelEmpty when free
+  long long sx, sy;        // sums of llrintf(v * 65536)
+  unsigned long long nsi;  // count << 32 | intensity sum
+};
+// no cell has ix == INT_MIN: |x| <= range_max < 1000 m and voxel >= 1e-6 m (checked by the C-ABI)
+constexpr unsigned long long kVoxelEmpty = 0x8000000000000000ull;
+
 struct CloudScratch {  // per CTA, sized for max_nodes
   unsigned long long* q;  // [max_nodes] SOR: fixed-point mean neighbour distance (llrintf)
   uint32_t* slot;      // [max_nodes] voxel: hash slot of every point
-  unsigned long long* hkey;  // [hsize] packed cell (EMPTY = ~0)
-  long long* hsx;            // [hsize]
-  long long* hsy;
-  unsigned long long* hsi;
-  uint32_t* hn;
-  uint32_t* hfirst;
-  uint32_t* horder;
+  VoxelCell* cell;     // [hsize] one 32-byte sector per cell: key + the three integer sums
+  uint2* first_order;  // [hsize] (first member, output position)
 };
 
 __device__ __forceinline__ CloudScratch carve(void* base, size_t per_cta, uint32_t max_nodes, uint32_t hsize) {
   unsigned char* p = static_cast<unsigned char*>(base) + (size_t)blockIdx.x * per_cta;
   CloudScratch s;
-  s.hkey = reinterpret_cast<unsigned long long*>(p); p += (size_t)hsize * 8;
-  s.hsx = reinterpret_cast<long long*>(p); p += (size_t)hsize * 8;
-  s.hsy = reinterpret_cast<long long*>(p); p += (size_t)hsize * 8;
-  s.hsi = reinterpret_cast<unsigned long long*>(p); p += (size_t)hsize * 8;
-  s.hn = reinterpret_cast<uint32_t*>(p); p += (size_t)hsize * 4;
-  s.hfirst = reinterpret_cast<uint32_t*>(p); p += (size_t)hsize * 4;
-  s.horder = reinterpret_cast<uint32_t*>(p); p += (size_t)hsize * 4;
+  s.cell = reinterpret_cast<VoxelCell*>(p); p += (size_t)hsize * sizeof(VoxelCell);
+  s.first_order = reinterpret_cast<uint2*>(p); p += (size_t)hsize * 8;
   s.q = reinterpret_cast<unsigned long long*>(p); p += (size_t)max_nodes * 8;
   s.slot = reinterpret_cast<uint32_t*>(p);
   return s;
@@ -76,9 +76,13 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_u32(uint32_t v, uint32_
 }
 
 // ---- step 4: statistical outlier removal (oracle/cloud_oracle.cpp step 4) -----------------
+// K = compile-time bound of sor_k: the K smallest distances live in a sorted register array (branch-free
+// insertion), the neighbours' coordinates are staged through shared memory once per chunk of CT points.
+template <int K>
 __global__ void __launch_bounds__(CT) cloud_sor_kernel(float4* xyzi, uint32_t* point_counts, uint32_t n_scans,
                                                        uint32_t stride, uint32_t sor_k, float sor_alpha,
                                                        void* scratch, size_t per_cta, uint32_t max_nodes) {
+  __shared__ float2 s_xy[CT + 2 * kHalfWindow];
   __shared__ uint32_t s_warp[CT / 32];
   __shared__ long long s_s1[CT / 32];
   __shared__ unsigned long long s_s2[CT / 32];
@@ -92,37 +96,56 @@ __global__ void __launch_bounds__(CT) cloud_sor_kernel(float4* xyzi, uint32_t* p
     const bool all_others = (m - 1) <= 2u * kHalfWindow;
     long long s1 = 0;
     unsigned long long s2 = 0;
-    for (uint32_t i = tid; i < m; i += CT) {
-      const float4 me = pts[i];
-      float d[2 * kHalfWindow];
+    for (uint32_t c0 = 0; c0 < m; c0 += CT) {
+      // stage (x, y) of this chunk's points and their +-16 neighbours (all points when the scan is tiny)
+      __syncthreads();
+      if (all_others) {
+        for (uint32_t t = tid; t < m; t += CT) {
+          const float4 o = pts[t];
+          s_xy[t] = make_float2(o.x, o.y);
+        }
+      } else {
+        for (uint32_t t = tid; t < (uint32_t)(CT + 2 * kHalfWindow); t += CT) {
+          uint32_t j = c0 + t + m - (uint32_t)kHalfWindow;  // index c0 + t - 16, modulo m
+          j %= m;
+          const float4 o = pts[j];
+          s_xy[t] = make_float2(o.x, o.y);
+        }
+      }
+      __syncthreads();
+      const uint32_t i = c0 + tid;
+      if (i >= m) continue;
+      const float2 me = all_others ? s_xy[i] : s_xy[tid + kHalfWindow];
+      float top[K];  // ascending; +inf = empty
+#pragma unroll
+      for (int t = 0; t < K; ++t) top[t] = __int_as_float(0x7f800000);
       uint32_t nd = 0;
-      auto add = [&](uint32_t j) {
-        const float4 o = pts[j];
+      auto add = [&](float2 o) {
         const float dx = __fsub_rn(o.x, me.x), dy = __fsub_rn(o.y, me.y);
-        d[nd++] = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+        float v = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+#pragma unroll
+        for (int t = 0; t < K; ++t) {
+          const float lo = fminf(top[t], v), hi = fmaxf(top[t], v);
+          top[t] = lo;
+          v = hi;
+        }
+        ++nd;
       };
       if (all_others) {
         for (uint32_t j = 0; j < m; ++j)
-          if (j != i) add(j);
+          if (j != i) add(s_xy[j]);
       } else {
+#pragma unroll 4
         for (uint32_t o = 1; o <= (uint32_t)kHalfWindow; ++o) {
-          add(i >= o ? i - o : i + m - o);
-          add(i + o < m ? i + o : i + o - m);
+          add(s_xy[tid + kHalfWindow - o]);
+          add(s_xy[tid + kHalfWindow + o]);
         }
-      }
-      // ascending insertion sort (values are distances: no NaN), then the k smallest in order
-      for (uint32_t x = 1; x < nd; ++x) {
-        const float v = d[x];
-        uint32_t y = x;
-        while (y > 0 && d[y - 1] > v) {
-          d[y] = d[y - 1];
-          --y;
-        }
-        d[y] = v;
       }
       const uint32_t k = min(sor_k, nd);
       float sum = 0.0f;
-      for (uint32_t t = 0; t < k; ++t) sum = __fadd_rn(sum, d[t]);
+#pragma unroll
+      for (int t = 0; t < K; ++t)
+        if ((uint32_t)t < k) sum = __fadd_rn(sum, top[t]);
       const float mean = __fdiv_rn(sum, __uint2float_rn(k));
       const long long q = __float2ll_rn(__fmul_rn(mean, 65536.0f));  // llrintf
       sc.q[i] = (unsigned long long)q;
@@ -178,49 +201,83 @@ __global__ void __launch_bounds__(CT) cloud_sor_kernel(float4* xyzi, uint32_t* p
 }
 
 // ---- step 5: voxel grid (oracle/cloud_oracle.cpp step 5) -----------------------------------
+__global__ void cloud_table_init_kernel(void* scratch, size_t per_cta, uint32_t max_nodes) {
+  const uint32_t hsize = hash_size_for(max_nodes);
+  const CloudScratch sc = carve(scratch, per_cta, max_nodes, hsize);
+  for (uint32_t j = threadIdx.x; j < hsize; j += blockDim.x) {
+    sc.cell[j] = VoxelCell{kVoxelEmpty, 0, 0, 0};
+    sc.first_order[j] = make_uint2(0xFFFFFFFFu, 0u);
+  }
+}
+
 __global__ void __launch_bounds__(CT) cloud_voxel_kernel(float4* xyzi, uint32_t* point_counts, uint32_t n_scans,
                                                          uint32_t stride, float voxel, void* scratch, size_t per_cta,
                                                          uint32_t max_nodes) {
   __shared__ uint32_t s_warp[CT / 32];
-  const uint32_t hsize = hash_size_for(max_nodes);
-  const CloudScratch sc = carve(scratch, per_cta, max_nodes, hsize);
-  const uint32_t tid = threadIdx.x;
-  const unsigned long long kEmpty = ~0ull;
+  // the whole table (>= 2 * max_nodes slots) is clean on entry; a scan uses a prefix sized to its own
+  // point count so that the slots all resident CTAs touch stay inside the L2
+  const CloudScratch sc = carve(scratch, per_cta, max_nodes, hash_size_for(max_nodes));
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
   for (uint32_t s = blockIdx.x; s < n_scans; s += gridDim.x) {
     float4* pts = xyzi + (size_t)s * stride;
     const uint32_t m = point_counts[s];
     if (m == 0 || m > max_nodes) continue;
-    uint32_t hs = 64;  // table for this scan: >= 2 m slots
-    while (hs < 2u * m) hs <<= 1;
-    for (uint32_t j = tid; j < hs; j += CT) {
-      sc.hkey[j] = kEmpty;
-      sc.hsx[j] = 0;
-      sc.hsy[j] = 0;
-      sc.hsi[j] = 0;
-      sc.hn[j] = 0;
-      sc.hfirst[j] = 0xFFFFFFFFu;
-    }
-    __syncthreads();
-    // insert: exact integer sums, first member by atomicMin
-    for (uint32_t i = tid; i < m; i += CT) {
-      const float4 p = pts[i];
+    uint32_t hs = 64;
+    while (hs < m + (m >> 2)) hs <<= 1;  // load factor <= 0.8 even if every point had its own cell
+    // insert: exact integer sums, first member by atomicMin.  Points arrive in angular order, so the
+    // members of a cell are mostly neighbours: every warp first folds runs of equal cells among its 32
+    // consecutive points (segmented suffix sums with shuffles) and only the head of a run touches the
+    // table -- all sums are integers, so the grouping cannot change the result.
+    for (uint32_t c0 = 0; c0 < m; c0 += CT) {
+      const uint32_t i = c0 + tid;
+      const bool valid = i < m;
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) {  // read once: keep the table, not the points, in the L2
+        const uint4 r = ld_hint_v4(pts + i, l2_policy_evict_first());
+        p = make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
+      }
       const int ix = __float2int_rd(__fdiv_rn(p.x, voxel));  // floorf(x / voxel)
       const int iy = __float2int_rd(__fdiv_rn(p.y, voxel));
-      const unsigned long long key = ((unsigned long long)(uint32_t)ix << 32) | (uint32_t)iy;
-      uint32_t h = (uint32_t)(mix64(key) & (hs - 1));
-      for (;;) {
-        const unsigned long long prev = atomicCAS(&sc.hkey[h], kEmpty, key);
-        if (prev == kEmpty || prev == key) break;
-        h = (h + 1) & (hs - 1);
+      // lanes past the end get the key no cell can have
+      const unsigned long long key = valid ? (((unsigned long long)(uint32_t)ix << 32) | (uint32_t)iy) : kVoxelEmpty;
+      const unsigned long long key_prev = __shfl_up_sync(0xffffffffu, key, 1);
+      const bool head = lane == 0 || key != key_prev;
+      int hl = head ? (int)lane : 0;  // lane of this point's run head
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, hl, o);
+        if ((int)lane >= o) hl = max(hl, t);
       }
-      sc.slot[i] = h;
-      atomicAdd(reinterpret_cast<unsigned long long*>(&sc.hsx[h]),
-                (unsigned long long)__float2ll_rn(__fmul_rn(p.x, 65536.0f)));
-      atomicAdd(reinterpret_cast<unsigned long long*>(&sc.hsy[h]),
-                (unsigned long long)__float2ll_rn(__fmul_rn(p.y, 65536.0f)));
-      atomicAdd(&sc.hsi[h], (unsigned long long)(long long)__float2ll_rn(p.w));
-      atomicAdd(&sc.hn[h], 1u);
-      atomicMin(&sc.hfirst[h], i);
+      long long sx = __float2ll_rn(__fmul_rn(p.x, 65536.0f));
+      long long sy = __float2ll_rn(__fmul_rn(p.y, 65536.0f));
+      unsigned long long nsi = (1ull << 32) + (unsigned long long)__float2ll_rn(p.w);  // count | intensity sum
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int hl_o = __shfl_down_sync(0xffffffffu, hl, o);
+        const long long sx_o = __shfl_down_sync(0xffffffffu, sx, o);
+        const long long sy_o = __shfl_down_sync(0xffffffffu, sy, o);
+        const unsigned long long nsi_o = __shfl_down_sync(0xffffffffu, nsi, o);
+        if ((int)lane + o < 32 && hl_o == hl) {
+          sx += sx_o;
+          sy += sy_o;
+          nsi += nsi_o;
+        }
+      }
+      uint32_t h = 0;
+      if (head && valid) {
+        h = (uint32_t)(mix64(key) & (hs - 1));
+        for (;;) {
+          const unsigned long long prev = atomicCAS(&sc.cell[h].key, kVoxelEmpty, key);
+          if (prev == kVoxelEmpty || prev == key) break;
+          h = (h + 1) & (hs - 1);
+        }
+        atomicAdd(reinterpret_cast<unsigned long long*>(&sc.cell[h].sx), (unsigned long long)sx);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&sc.cell[h].sy), (unsigned long long)sy);
+        atomicAdd(&sc.cell[h].nsi, nsi);
+        atomicMin(&sc.first_order[h].x, i);
+      }
+      h = __shfl_sync(0xffffffffu, h, hl);
+      if (valid) sc.slot[i] = h;
     }
     __syncthreads();
     // cells in order of their first member: exclusive scan over "i is a first member"
@@ -230,26 +287,31 @@ __global__ void __launch_bounds__(CT) cloud_voxel_kernel(float4* xyzi, uint32_t*
       uint32_t rep = 0, h = 0;
       if (i < m) {
         h = sc.slot[i];
-        rep = (sc.hfirst[h] == i) ? 1u : 0u;
+        rep = (sc.first_order[h].x == i) ? 1u : 0u;
       }
       uint32_t tot = 0;
       const uint32_t pos = block_exclusive_scan_u32(rep, s_warp, &tot);
-      if (rep) sc.horder[h] = done + pos;
+      if (rep) sc.first_order[h].y = done + pos;
       done += tot;
     }
     __syncthreads();
-    // emit centroids (all reads of the point array happened before the first barrier above)
+    // emit centroids (all reads of the point array happened before the first barrier above) and hand
+    // the cell back clean
     for (uint32_t i = tid; i < m; i += CT) {
       const uint32_t h = sc.slot[i];
-      if (sc.hfirst[h] != i) continue;
-      const double cnt = (double)sc.hn[h];
+      const uint2 fo = sc.first_order[h];
+      if (fo.x != i) continue;
+      const VoxelCell c = sc.cell[h];
+      const double cnt = (double)(uint32_t)(c.nsi >> 32);
       const double den = __dmul_rn(65536.0, cnt);
       float4 o;
-      o.x = __double2float_rn(__ddiv_rn((double)sc.hsx[h], den));
-      o.y = __double2float_rn(__ddiv_rn((double)sc.hsy[h], den));
+      o.x = __double2float_rn(__ddiv_rn((double)c.sx, den));
+      o.y = __double2float_rn(__ddiv_rn((double)c.sy, den));
       o.z = 0.0f;
-      o.w = __double2float_rn(__ddiv_rn((double)(long long)sc.hsi[h], cnt));
-      pts[sc.horder[h]] = o;
+      o.w = __double2float_rn(__ddiv_rn((double)(long long)(c.nsi & 0xFFFFFFFFull), cnt));
+      pts[fo.y] = o;
+      sc.cell[h] = VoxelCell{kVoxelEmpty, 0, 0, 0};
+      sc.first_order[h] = make_uint2(0xFFFFFFFFu, 0u);
     }
     if (tid == 0) point_counts[s] = done;
     __syncthreads();
@@ -324,11 +386,19 @@ cudaError_t cloud_workspace_alloc(CloudWorkspace& ws, int num_sms, uint32_t max_
   e = cudaMemcpy(ws.angle, ang.data(), ang.size() * sizeof(float2), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return e;
   ws.max_nodes = max_nodes;
-  ws.ctas = num_sms * 2;
   const uint32_t hsize = hash_size_for(max_nodes);
-  ws.scratch_per_cta = (size_t)hsize * (8 * 4 + 4 * 3) + (size_t)max_nodes * 12 + 64;
+  ws.scratch_per_cta = (size_t)hsize * (sizeof(VoxelCell) + 8) + (size_t)max_nodes * 12 + 64;
   ws.scratch_per_cta = (ws.scratch_per_cta + 255) & ~(size_t)255;
-  return cudaMalloc(&ws.scratch, ws.scratch_per_cta * ws.ctas);
+  // the post kernels wait on L2 atomics and block scans: 4 CTAs of 256 threads per SM hide that latency;
+  // fewer when the per-CTA tables are large (at most 1 GiB of scratch per lane, at least 2 CTAs per SM)
+  const size_t budget_ctas = ((size_t)1 << 30) / ws.scratch_per_cta;
+  ws.ctas = (int)std::min<size_t>((size_t)num_sms * 4, std::max<size_t>((size_t)num_sms * 2, budget_ctas));
+  e = cudaMalloc(&ws.scratch, ws.scratch_per_cta * ws.ctas);
+  if (e != cudaSuccess) return e;
+  cloud_table_init_kernel<<<ws.ctas, 256>>>(ws.scratch, ws.scratch_per_cta, max_nodes);  // tables start clean
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return cudaDeviceSynchronize();
 }
 
 void cloud_workspace_free(CloudWorkspace& ws) {
@@ -343,8 +413,12 @@ cudaError_t launch_cloud_post(float4* xyzi, uint32_t* point_counts, uint32_t n_s
                               cudaStream_t stream, int* launched) {
   const int grid = (int)min((uint32_t)ws.ctas, n_scans);
   if (sor_k > 0) {
-    cloud_sor_kernel<<<grid, CT, 0, stream>>>(xyzi, point_counts, n_scans, stride, sor_k, sor_alpha, ws.scratch,
-                                              ws.scratch_per_cta, ws.max_nodes);
+    auto k = cloud_sor_kernel<32>;
+    if (sor_k <= 4) k = cloud_sor_kernel<4>;
+    else if (sor_k <= 8) k = cloud_sor_kernel<8>;
+    else if (sor_k <= 16) k = cloud_sor_kernel<16>;
+    k<<<grid, CT, 0, stream>>>(xyzi, point_counts, n_scans, stride, sor_k, sor_alpha, ws.scratch, ws.scratch_per_cta,
+                               ws.max_nodes);
     if (launched) ++*launched;
   }
   if (voxel > 0.0f) {

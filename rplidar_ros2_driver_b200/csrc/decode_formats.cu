@@ -91,6 +91,8 @@ __device__ __forceinline__ uint2 node_express(const uint8_t* prev, int prev_q8, 
 }
 
 // ---- ultra (handler_capsules.cpp:422-580) --------------------------------------------------------------
+__device__ int g_ultra_offset[493];  // read through L1 (divergent index: not constant memory)
+
 __device__ __forceinline__ uint32_t varbitscale(uint32_t scaled, uint32_t& level) {
   if (scaled >= 3328u) { level = 4; return (1u << 14) + ((scaled - 3328u) << 4); }
   if (scaled >= 1792u) { level = 3; return (1u << 12) + ((scaled - 1792u) << 3); }
@@ -128,13 +130,10 @@ __device__ __forceinline__ uint2 node_ultra(const uint8_t* prev, const uint8_t* 
     }
   }
   const uint32_t sync = (((a + inc) % kFull) < inc) ? 1u : 0u;
-  int off_q16 = 8578;  // (int)(7.5 * 3.1415926535 * 65536 / 180.0)
-  if (dist_q2 >= 200) {
-    const int k2 = 98361 / dist_q2;
-    off_q16 = 9150 - (k2 << 6) - (k2 * k2 * k2) / 98304;  // 9150 = (int)(8 * 3.1415926535 * 65536 / 180)
-  }
-  // int(off * 180 / 3.14159265): double division, truncation toward zero
-  const int off_deg_q16 = __double2int_rz(__ddiv_rn((double)(off_q16 * 180), 3.14159265));
+  // the angle correction int(off_q16 * 180 / 3.14159265) depends on the distance only through
+  // k2 = 98361 / dist_q2 in [0, 491] (dist_q2 >= 200): a 493-entry table built on the host with the
+  // reference's own double arithmetic (entry 492 = the short-range default)
+  const int off_deg_q16 = __ldg(&g_ultra_offset[dist_q2 >= 200 ? 98361 / dist_q2 : 492]);
   const int angle_q6 = (a - off_deg_q16) >> 10;
   return pack_node(angle_q6, (uint32_t)dist_q2, sync, dist_q2 ? (0x2Fu << 2) : 0u);
 }
@@ -594,6 +593,35 @@ __global__ void __launch_bounds__(NT) decode_normal_kernel(NormalDecodeArgs a) {
       const uint32_t live = min((uint32_t)kNormTile, n - t0);
       for (uint32_t i = tid; i < live; i += NT) sm.bytes[4 + i] = __ldg(src + t0 + i);
       __syncthreads();
+      // ---- fast path: the tile is entered between records and holds only whole, well-formed records.
+      // Then the byte machine accepts every record where it lies (state 0 -> 1 -> 2 -> 3 -> 4 -> 0), so
+      // record q is bytes [5q, 5q+5) and the nodes can be written without the scans below.
+      {
+        const uint32_t n_rec = live / 5u;
+        int ok = (sm.carry_state == 0 && n_rec * 5u == live) ? 1 : 0;
+        for (uint32_t q = tid; q < n_rec; q += NT) {
+          const uint32_t c0 = sm.bytes[4 + 5 * q], c1 = sm.bytes[5 + 5 * q];
+          ok &= (int)(((c0 >> 1) ^ c0) & c1 & 1u);
+        }
+        if (__syncthreads_and(ok)) {
+          uint2* o = out + sm.carry_nodes;
+          for (uint32_t q = tid; q < n_rec; q += NT) {
+            const uint8_t* r = sm.bytes + 4 + 5 * q;
+            const uint32_t sq = r[0];
+            const uint32_t angle_chk = ld16(r + 1), dist = ld16(r + 3);
+            uint2 nd;
+            nd.x = ((((angle_chk >> 1) << 8) / 90u) & 0xFFFFu) | (dist << 16);
+            nd.y = (((sq >> 2) << 2) << 16) | ((sq & 1u) << 24);
+            o[q] = nd;
+            if (end_out) end_out[sm.carry_nodes + q] = t0 + 5 * q + 4;
+          }
+          __syncthreads();
+          if (tid < 4) sm.bytes[tid] = sm.bytes[live + tid];
+          if (tid == 0) sm.carry_nodes += n_rec;
+          __syncthreads();
+          continue;
+        }
+      }
       // fold this thread's bytes into one map
       const uint32_t b0 = tid * kChunk;
       uint32_t f = kIdentityMap;
@@ -701,6 +729,17 @@ cudaError_t launch_decode_normal(const NormalDecodeArgs& a, int grid, cudaStream
 
 cudaError_t decode_formats_configure() {
   cudaError_t e;
+  {  // handler_capsules.cpp:546-556, evaluated exactly as written there (double arithmetic, truncation)
+    int table[493];
+    for (int k2 = 0; k2 < 492; ++k2) {
+      const int off_q16 = (int)(8 * 3.1415926535 * (1 << 16) / 180) - (k2 << 6) - (k2 * k2 * k2) / 98304;
+      table[k2] = int(off_q16 * 180 / 3.14159265);
+    }
+    const int off_default = (int)(7.5 * 3.1415926535 * (1 << 16) / 180.0);
+    table[492] = int(off_default * 180 / 3.14159265);
+    e = cudaMemcpyToSymbol(g_ultra_offset, table, sizeof(table));
+    if (e != cudaSuccess) return e;
+  }
   e = cudaFuncSetAttribute(decode_capsule_kernel<kExpress>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)sizeof(CapsuleSmem<kExpress>));
   if (e != cudaSuccess) return e;

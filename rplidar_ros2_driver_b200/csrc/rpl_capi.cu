@@ -1235,6 +1235,10 @@ rpl_result rpl_cloud_batch_dev(rpl_ctx* c, const rpl_node_hq* nodes, const uint3
     c->err = "n_scans exceeds max_scans or sor_k > 32";
     return RPL_RESULT_INVALID_DATA;
   }
+  if (params->voxel_size != 0.0f && !(params->voxel_size >= 1e-6f && params->range_max < 1000.0f)) {
+    c->err = "voxel grid: voxel_size must be >= 1e-6 m and range_max < 1000 m (cell indices must fit 31 bits)";
+    return RPL_RESULT_INVALID_DATA;
+  }
   RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
   rpl::ScanBatchArgs a{};

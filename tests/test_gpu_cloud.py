@@ -78,6 +78,17 @@ def test_statistical_outlier_removal(R, oracle, ctx, n):
     check_cloud(R, oracle, ctx, nodes, counts, range_min=0.15, range_max=40.0, sor_k=32, sor_alpha=2.5)
 
 
+def test_voxel_cells_around_the_origin(R, oracle, ctx):
+    """Voxels larger than range_min: points fall into the cells (-1,-1), (-1,0), (0,-1), (0,0) around the
+    sensor (cell (-1,-1) has the all-ones key: it must not be mistaken for an empty table slot)."""
+    nodes = oracle.synth_batch(50, 6, 3200, variant=0)
+    nodes["dist_mm_q2"] = (nodes["dist_mm_q2"] % 3000) + 40  # 1 cm .. 76 cm
+    counts = np.full(6, 3200, np.uint32)
+    for voxel in (1.0, 0.4):
+        _, pc = check_cloud(R, oracle, ctx, nodes, counts, range_min=0.0, range_max=40.0, voxel_size=voxel)
+        assert (pc <= 16).all() and (pc >= 4).all()
+
+
 @pytest.mark.parametrize("voxel", [0.05, 0.5])
 def test_voxel_grid(R, oracle, ctx, voxel):
     nodes = room_scans(oracle, 6, 3200, 5)
