@@ -35,7 +35,7 @@ for mode_a in (0, 1):
         print("   TMA == v1 outputs:", ok)
     print("   mode", "A" if mode_a else "B", "flags", flags, "kernel ms %%.4f  -> %%.0f GB/s  general-path scans %%d" %% (fm / fn, 16 * S * N / (fm / fn * 1e-3) / 1e9, int((path != 0).sum())))
 ''' % root
-for lib in sorted(glob.glob(os.path.join(root, "scratch/libs/*.so"))) + [""]:
+for lib in sorted(glob.glob(os.path.join(root, "tools/libs/*.so"))) + [""]:
     env = dict(os.environ)
     if lib: env["RPL_B200_LIB"] = lib
     print(lib or "default build", flush=True)
