@@ -61,6 +61,9 @@ def parse():
     ap.add_argument("--format", default="0x85",
                     help="decode workload: SDK answer type (0x81 standard nodes, 0x82 express, 0x83 HQ, 0x84 ultra, "
                          "0x85 dense, 0x86 ultra-dense)")
+    ap.add_argument("--push-gather", action="store_true",
+                    help="cloud workload: fuse + all-gather in one kernel over NVLink peer memory "
+                         "(rpl_cloud_fuse_push_dev) instead of rpl_cloud_fuse_dev + NCCL all_gather")
     ap.add_argument("--sor", type=int, default=0, help="cloud workload: SOR k (0 = off)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -476,6 +479,8 @@ def run_b200(args, rank, local_rank, world):
             "extra": extra,
         }
         print(json.dumps(line), flush=True)
+    if args.push_gather:
+        gather.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -488,7 +493,7 @@ def run_cloud(args, rank, local_rank, world):
     import torch.distributed as dist
 
     import rplidar_ros2_driver_b200 as R
-    from rplidar_ros2_driver_b200.multi_gpu import FusedCloudGather, shard_streams
+    from rplidar_ros2_driver_b200.multi_gpu import FusedCloudGather, PeerCloudGather, shard_streams
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -515,12 +520,20 @@ def run_cloud(args, rank, local_rank, world):
     kept = int(pc.sum().item())
     cap = int(kept * 1.1) + 1024
     fused = torch.zeros((cap, 4), dtype=torch.float32, device=dev)
-    gather = FusedCloudGather(cap, dev)
+    if world > 1:  # one slot size for every rank
+        cap_t = torch.tensor([cap], device=dev)
+        dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)
+        cap = int(cap_t.item())
+        fused = torch.zeros((cap, 4), dtype=torch.float32, device=dev)
+    gather = PeerCloudGather(ctx, cap, dev) if args.push_gather else FusedCloudGather(cap, dev)
 
     def step():
         ctx.cloud_batch_dev(nodes.data_ptr(), counts.data_ptr(), S, N, prm, xyzi.data_ptr(), pc.data_ptr(), stream=sp)
-        ctx.cloud_fuse_dev(xyzi.data_ptr(), pc.data_ptr(), S, N, fused.data_ptr(), offs.data_ptr(), total.data_ptr(), stream=sp)
-        gather(fused, total)
+        if args.push_gather:
+            gather.push(xyzi.data_ptr(), pc.data_ptr(), S, N, offs.data_ptr(), total.data_ptr(), stream=sp)
+        else:
+            ctx.cloud_fuse_dev(xyzi.data_ptr(), pc.data_ptr(), S, N, fused.data_ptr(), offs.data_ptr(), total.data_ptr(), stream=sp)
+            gather(fused, total)
 
     W = max(args.warmup, 3)
     for _ in range(W):
@@ -561,7 +574,8 @@ def run_cloud(args, rank, local_rank, world):
             "config": {"workload": (f"PointCloud2 path: {64} S3 streams per GPU x {scans_per_stream} scans x {N} nodes "
                                     f"(synthetic variant 4 'room'), window [0.15, 40] m, polar->xyz, 5 cm voxel grid"
                                     f"{', SOR k=%d' % args.sor if args.sor else ''}, fused per-GPU cloud, one all-gather"),
-                       "streams_total": streams_total, "parallelism": f"{world} ranks x 64 streams, 1 all_gather_into_tensor/step",
+                       "streams_total": streams_total, "parallelism": (f"{world} ranks x 64 streams, fuse + all-gather in one kernel over NVLink peer memory"
+                                       if args.push_gather else f"{world} ranks x 64 streams, 1 all_gather_into_tensor/step"),
                        "l2": f"inputs {pts_step * 8 / 1e6:.0f} MB + outputs {pts_step * 16 / 1e6:.0f} MB per step exceed the 126 MB L2"},
             "roofline": {"bound": "hbm", "kernel": "scan_tma_kernel<cloud>", "achieved": alg / (fast_ms * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": alg / (fast_ms * 1e-3) / 1e9 / peak, "traffic": None,
@@ -572,6 +586,8 @@ def run_cloud(args, rank, local_rank, world):
                       "allgather_payload_bytes": gather.payload_bytes(), "post_kernels": "voxel" + ("+sor" if args.sor else "")},
         }
         print(json.dumps(line), flush=True)
+    if args.push_gather:
+        gather.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

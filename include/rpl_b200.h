@@ -171,6 +171,29 @@ rpl_result rpl_cloud_fuse_dev(rpl_ctx* ctx, const float* xyzi, const uint32_t* p
                               uint32_t n_scans, uint32_t stride, float* fused, uint32_t* offsets,
                               uint32_t* total, void* stream);
 
+/* ---- fuse + all-gather through peer memory (one process per GPU, NVLink P2P) ---- */
+/* rpl_cloud_fuse_dev + one NCCL all-gather writes the dense cloud locally and lets the collective read
+ * it again.  rpl_cloud_fuse_push_dev does both in ONE kernel: every point is stored straight into slot
+ * `rank` of every rank's gather buffer.  The buffers are allocated with rpl_peer_alloc (cudaMalloc +
+ * cudaIpcGetMemHandle), the 64-byte handles are exchanged by the host (torch.distributed in this repo) and
+ * opened with rpl_peer_open (cudaIpcOpenMemHandle: NVLink peer mapping).  Gather buffer layout:
+ * [256-byte header: uint32 point count of every rank][world][slot_points][16 B]; size
+ * rpl_peer_gather_bytes(world, slot_points).  peer_bases: HOST array [world] of device pointers, entry
+ * `rank` = this rank's own buffer.  Completion: the stores are visible on the peers once this rank's
+ * kernel has finished; a consumer needs one barrier over all ranks after the call (any tiny collective on
+ * the same stream) and must not let the next push overwrite a buffer that is still being read
+ * (rplidar_ros2_driver_b200/multi_gpu.py::PeerCloudGather alternates two buffers). */
+#define RPL_IPC_HANDLE_BYTES 64u
+#define RPL_MAX_PEERS 16u
+size_t rpl_peer_gather_bytes(uint32_t world, uint32_t slot_points);
+rpl_result rpl_peer_alloc(rpl_ctx* ctx, size_t bytes, void** dev_ptr, uint8_t* handle_out /* [64] */);
+rpl_result rpl_peer_open(rpl_ctx* ctx, const uint8_t* handle /* [64] */, void** peer_ptr);
+rpl_result rpl_peer_close(rpl_ctx* ctx, void* peer_ptr);
+rpl_result rpl_peer_free(rpl_ctx* ctx, void* dev_ptr);
+rpl_result rpl_cloud_fuse_push_dev(rpl_ctx* ctx, const float* xyzi, const uint32_t* point_counts, uint32_t n_scans,
+                                   uint32_t stride, void* const* peer_bases, uint32_t world, uint32_t rank,
+                                   uint32_t slot_points, uint32_t* offsets, uint32_t* total, void* stream);
+
 /* ---- dense-capsule decode (the step before the hot path) ------- */
 /* Replaces UnpackerHandler_DenseCapsuleNode (reference
  * src/sdk/src/dataunpacker/unpacker/handler_capsules.cpp:639-791) for FRAMED capsules: answer

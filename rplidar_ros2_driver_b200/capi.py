@@ -45,6 +45,8 @@ EXPORTS = [
     "rpl_decode_dense_batch_dev", "rpl_decode_dense", "rpl_assemble_scans_dev",
     "rpl_capsule_bytes", "rpl_capsule_nodes", "rpl_decode_capsules_batch_dev", "rpl_decode_capsules",
     "rpl_decode_normal_batch_dev", "rpl_decode_normal", "rpl_node_timestamps_dev", "rpl_normal_timestamps_dev",
+    "rpl_peer_gather_bytes", "rpl_peer_alloc", "rpl_peer_open", "rpl_peer_close", "rpl_peer_free",
+    "rpl_cloud_fuse_push_dev",
     "rpl_laserscan_cdr_size", "rpl_laserscan_cdr_batch_dev", "rpl_pointcloud2_cdr_size", "rpl_pointcloud2_cdr_batch_dev",
 ]
 
@@ -151,6 +153,12 @@ def lib() -> C.CDLL:
         "rpl_decode_capsules_batch_dev": ([vp, u32, vp, vp, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp], u32),
         "rpl_decode_capsules": ([vp, u32, vp, u32, u32, vp, vp, C.POINTER(u32), vp, vp], u32),
         "rpl_decode_normal_batch_dev": ([vp, vp, vp, u32, u32, vp, vp, vp, vp, vp], u32),
+        "rpl_peer_gather_bytes": ([u32, u32], C.c_size_t),
+        "rpl_peer_alloc": ([vp, C.c_size_t, C.POINTER(vp), vp], u32),
+        "rpl_peer_open": ([vp, vp, C.POINTER(vp)], u32),
+        "rpl_peer_close": ([vp, vp], u32),
+        "rpl_peer_free": ([vp, vp], u32),
+        "rpl_cloud_fuse_push_dev": ([vp, vp, vp, u32, u32, vp, u32, u32, u32, vp, vp, vp], u32),
         "rpl_laserscan_cdr_size": ([u32, u32], u32),
         "rpl_pointcloud2_cdr_size": ([u32, u32], u32),
         "rpl_laserscan_cdr_batch_dev": ([vp, vp, vp, C.c_char_p, vp, vp, vp, u32, u32, vp, u32, vp, vp], u32),
@@ -377,6 +385,33 @@ class Context:
         self._check(self._L.rpl_decode_normal_batch_dev(
             self._h, _p(stream_bytes), _p(byte_counts), n_streams, stride_bytes, _p(nodes_out), _p(node_counts),
             _p(fsm_state_out), _p(node_end), _p(stream)))
+
+    # ---- peer memory: fuse + all-gather in one kernel ---------------------------------------------------
+    def peer_alloc(self, nbytes: int):
+        """cudaMalloc + IPC handle: returns (device pointer, 64-byte handle)."""
+        ptr = C.c_void_p()
+        handle = np.zeros(64, np.uint8)
+        self._check(self._L.rpl_peer_alloc(self._h, nbytes, C.byref(ptr), _p(handle)))
+        return int(ptr.value), handle.tobytes()
+
+    def peer_open(self, handle: bytes) -> int:
+        h = np.frombuffer(handle, np.uint8).copy()
+        ptr = C.c_void_p()
+        self._check(self._L.rpl_peer_open(self._h, _p(h), C.byref(ptr)))
+        return int(ptr.value)
+
+    def peer_close(self, ptr: int):
+        self._check(self._L.rpl_peer_close(self._h, C.c_void_p(ptr)))
+
+    def peer_free(self, ptr: int):
+        self._check(self._L.rpl_peer_free(self._h, C.c_void_p(ptr)))
+
+    def cloud_fuse_push_dev(self, xyzi, point_counts, n_scans, stride, peer_bases, rank, slot_points, offsets, total,
+                            stream=None):
+        bases = (C.c_void_p * len(peer_bases))(*[C.c_void_p(int(b)) for b in peer_bases])
+        self._check(self._L.rpl_cloud_fuse_push_dev(self._h, _p(xyzi), _p(point_counts), n_scans, stride, bases,
+                                                    len(peer_bases), rank, slot_points, _p(offsets), _p(total),
+                                                    _p(stream)))
 
     # ---- messages -> CDR (the step after the hot path) -----------------------------------------------
     def laserscan_cdr_batch_dev(self, meta, frame_id: str, ranges, intensities, beam_counts, n_scans, stride,

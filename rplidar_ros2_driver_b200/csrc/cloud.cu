@@ -357,7 +357,43 @@ __global__ void cloud_pack_kernel(const float4* xyzi, const uint32_t* counts, co
   }
 }
 
+// fuse + all-gather in one kernel: every point of this rank's fused cloud is stored straight into slot
+// `rank` of EVERY rank's gather buffer (the peers' buffers are mapped through CUDA IPC, the stores travel
+// over NVLink), so the dense per-GPU cloud is never written locally and read again by a collective.
+// Gather buffer layout: [256-byte header: point count of every rank][world][slot_points][16 B].
+__global__ void cloud_push_kernel(const float4* xyzi, const uint32_t* counts, const uint32_t* offsets,
+                                  const uint32_t* total, uint32_t n_scans, uint32_t stride, PeerBases peers,
+                                  uint32_t world, uint32_t rank, uint32_t slot_points) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < world)
+    reinterpret_cast<uint32_t*>(peers.base[threadIdx.x])[rank] = *total;  // > slot_points tells the reader it overflowed
+  const size_t slot0 = (size_t)rank * slot_points;
+  for (uint32_t s = blockIdx.y; s < n_scans; s += gridDim.y) {
+    const uint32_t m = counts[s], off = offsets[s];
+    const float4* src = xyzi + (size_t)s * stride;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+      if (off + i >= slot_points) break;
+      const float4 v = src[i];
+      for (uint32_t p = 0; p < world; ++p)
+        reinterpret_cast<float4*>(peers.base[p] + kPeerHeaderBytes)[slot0 + off + i] = v;
+    }
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_cloud_fuse_push(const float4* xyzi, const uint32_t* point_counts, uint32_t n_scans,
+                                   uint32_t stride, const PeerBases& peers, uint32_t world, uint32_t rank,
+                                   uint32_t slot_points, uint32_t* offsets, uint32_t* total, cudaStream_t stream,
+                                   int* launched) {
+  if (n_scans == 0) return cudaSuccess;
+  cloud_offsets_kernel<<<1, 1024, 0, stream>>>(point_counts, n_scans, offsets, total);
+  const uint32_t gy = min(n_scans, 65535u);
+  const uint32_t gx = max(1u, min(32u, (stride + 255u) / 256u));
+  cloud_push_kernel<<<dim3(gx, gy), 256, 0, stream>>>(xyzi, point_counts, offsets, total, n_scans, stride, peers,
+                                                      world, rank, slot_points);
+  if (launched) *launched += 2;
+  return cudaGetLastError();
+}
 
 cudaError_t cloud_configure() { return cudaSuccess; }
 

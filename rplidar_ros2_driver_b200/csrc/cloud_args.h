@@ -21,6 +21,16 @@ void cloud_workspace_free(CloudWorkspace& ws);
 cudaError_t launch_cloud_post(float4* xyzi, uint32_t* point_counts, uint32_t n_scans, uint32_t stride,
                               uint32_t sor_k, float sor_alpha, float voxel, const CloudWorkspace& ws,
                               cudaStream_t stream, int* launched);
+// fuse + all-gather through peer memory (NVLink P2P, CUDA IPC)
+constexpr uint32_t kMaxPeers = 16;
+constexpr uint32_t kPeerHeaderBytes = 256;
+struct PeerBases {
+  unsigned char* base[kMaxPeers];
+};
+cudaError_t launch_cloud_fuse_push(const float4* xyzi, const uint32_t* point_counts, uint32_t n_scans,
+                                   uint32_t stride, const PeerBases& peers, uint32_t world, uint32_t rank,
+                                   uint32_t slot_points, uint32_t* offsets, uint32_t* total, cudaStream_t stream,
+                                   int* launched);
 cudaError_t launch_cloud_fuse(const float4* xyzi, const uint32_t* point_counts, uint32_t n_scans,
                               uint32_t stride, float4* fused, uint32_t* offsets, uint32_t* total,
                               cudaStream_t stream, int* launched);

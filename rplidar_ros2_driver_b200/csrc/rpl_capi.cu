@@ -1307,4 +1307,74 @@ rpl_result rpl_cloud_fuse_dev(rpl_ctx* c, const float* xyzi, const uint32_t* poi
   return RPL_RESULT_OK;
 }
 
+// ---- peer memory: fuse + all-gather in one kernel ---------------------------------
+size_t rpl_peer_gather_bytes(uint32_t world, uint32_t slot_points) {
+  return (size_t)rpl::kPeerHeaderBytes + (size_t)world * slot_points * 16;
+}
+
+rpl_result rpl_peer_alloc(rpl_ctx* c, size_t bytes, void** dev_ptr, uint8_t* handle_out) {
+  if (!c || !dev_ptr || !handle_out || bytes == 0) return RPL_RESULT_INVALID_DATA;
+  static_assert(sizeof(cudaIpcMemHandle_t) == RPL_IPC_HANDLE_BYTES, "IPC handle size");
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  void* p = nullptr;
+  RPL_CUDA(c, cudaMalloc(&p, bytes), RPL_RESULT_INSUFFICIENT_MEMORY);
+  cudaIpcMemHandle_t h;
+  if (!cuda_ok(c, cudaMemset(p, 0, bytes), "cudaMemset") || !cuda_ok(c, cudaIpcGetMemHandle(&h, p), "cudaIpcGetMemHandle")) {
+    cudaFree(p);
+    return RPL_RESULT_OPERATION_FAIL;
+  }
+  std::memcpy(handle_out, &h, sizeof(h));
+  *dev_ptr = p;
+  return RPL_RESULT_OK;
+}
+
+rpl_result rpl_peer_open(rpl_ctx* c, const uint8_t* handle, void** peer_ptr) {
+  if (!c || !handle || !peer_ptr) return RPL_RESULT_INVALID_DATA;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  RPL_CUDA(c, cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess), RPL_RESULT_OPERATION_FAIL);
+  return RPL_RESULT_OK;
+}
+
+rpl_result rpl_peer_close(rpl_ctx* c, void* peer_ptr) {
+  if (!c || !peer_ptr) return RPL_RESULT_INVALID_DATA;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  RPL_CUDA(c, cudaIpcCloseMemHandle(peer_ptr), RPL_RESULT_OPERATION_FAIL);
+  return RPL_RESULT_OK;
+}
+
+rpl_result rpl_peer_free(rpl_ctx* c, void* dev_ptr) {
+  if (!c || !dev_ptr) return RPL_RESULT_INVALID_DATA;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  RPL_CUDA(c, cudaFree(dev_ptr), RPL_RESULT_OPERATION_FAIL);
+  return RPL_RESULT_OK;
+}
+
+rpl_result rpl_cloud_fuse_push_dev(rpl_ctx* c, const float* xyzi, const uint32_t* point_counts, uint32_t n_scans,
+                                   uint32_t stride, void* const* peer_bases, uint32_t world, uint32_t rank,
+                                   uint32_t slot_points, uint32_t* offsets, uint32_t* total, void* stream) {
+  if (!c || !xyzi || !point_counts || !peer_bases || !offsets || !total) return RPL_RESULT_INVALID_DATA;
+  if (world == 0 || world > rpl::kMaxPeers || rank >= world) {
+    c->err = "world must be in [1, 16] and rank < world";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  rpl::PeerBases peers{};
+  for (uint32_t p = 0; p < world; ++p) {
+    if (!peer_bases[p] || (reinterpret_cast<uintptr_t>(peer_bases[p]) & 15u)) {
+      c->err = "peer buffers must be non-null and 16-byte aligned";
+      return RPL_RESULT_INVALID_DATA;
+    }
+    peers.base[p] = static_cast<unsigned char*>(peer_bases[p]);
+  }
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
+  int launched = 0;
+  RPL_CUDA(c, rpl::launch_cloud_fuse_push(reinterpret_cast<const float4*>(xyzi), point_counts, n_scans, stride, peers,
+                                          world, rank, slot_points, offsets, total, st, &launched),
+           RPL_RESULT_OPERATION_FAIL);
+  c->launches += launched;
+  return RPL_RESULT_OK;
+}
+
 }  // extern "C"
