@@ -236,6 +236,13 @@ rpl_result rpl_decode_dense(rpl_ctx* ctx, const uint8_t* capsules, uint32_t n_ca
  * [n_streams][2] = {scan-start flag of the last node, last distance} -- the decoder state the SDK
  * keeps across capsules for the dense (word 0) and ultra-dense (both) formats; 0 on a fresh decoder.
  * The per-capsule status words are the RPL_CAPSULE_* bits above. */
+/* sl::SlamtecLidarTimingDesc (reference src/sdk/include/sl_lidar_driver.h:156-166). */
+typedef struct rpl_timing {
+  uint32_t sample_duration_us;
+  uint32_t native_baudrate;        /* 0 = the per-format default the SDK assumes */
+  uint32_t linkage_delay_us;
+  uint32_t native_interface_type;  /* sl::LIDARInterfaceType: 0 UART, 1 ETHERNET, 2 USB, 5 CANBUS */
+} rpl_timing;
 #define RPL_ANS_MEASUREMENT 0x81u
 #define RPL_ANS_MEASUREMENT_CAPSULED 0x82u
 #define RPL_ANS_MEASUREMENT_HQ 0x83u
@@ -250,10 +257,13 @@ rpl_result rpl_decode_capsules_batch_dev(rpl_ctx* ctx, uint32_t ans_type, const 
                                          const uint32_t* state_in, rpl_node_hq* nodes_out, uint32_t* node_counts,
                                          uint32_t* capsule_status, uint32_t* capsule_node_offset,
                                          uint32_t* state_out, void* stream);
-/* One stream, host buffers.  state: in/out [2] (nullable). */
+/* One stream, host buffers.  state: in/out [2] (nullable).  timing / capsule_rx_us / node_ts_us (nullable
+ * together): also return the per-node stamps of rpl_node_timestamps_dev (below) for the receive times
+ * capsule_rx_us[n_capsules]; sample_duration_us is then taken from timing. */
 rpl_result rpl_decode_capsules(rpl_ctx* ctx, uint32_t ans_type, const uint8_t* capsules, uint32_t n_capsules,
                                uint32_t sample_duration_us, uint32_t* state, rpl_node_hq* nodes_out,
-                               uint32_t* node_count, uint32_t* capsule_status, uint32_t* capsule_node_offset);
+                               uint32_t* node_count, uint32_t* capsule_status, uint32_t* capsule_node_offset,
+                               const rpl_timing* timing, const uint64_t* capsule_rx_us, uint64_t* node_ts_us);
 /* 0x81 standard measurement nodes (5 bytes each) from RAW byte streams, with the byte-level
  * resynchronisation of UnpackerHandler_NormalNode::onData (handler_normalnode.cpp:88-141): exact on
  * misframed / corrupted streams.  bytes [n_streams][stride_bytes]; nodes_out
@@ -318,13 +328,7 @@ rpl_result rpl_pointcloud2_cdr_batch_dev(rpl_ctx* ctx, const uint32_t* stamps, c
                                          uint32_t* cdr_sizes, void* stream);
 
 /* ---- per-sample timestamps -------------------------------------- */
-/* sl::SlamtecLidarTimingDesc (reference src/sdk/include/sl_lidar_driver.h:156-166). */
-typedef struct rpl_timing {
-  uint32_t sample_duration_us;
-  uint32_t native_baudrate;        /* 0 = the per-format default the SDK assumes */
-  uint32_t linkage_delay_us;
-  uint32_t native_interface_type;  /* sl::LIDARInterfaceType: 0 UART, 1 ETHERNET, 2 USB, 5 CANBUS */
-} rpl_timing;
+/* (rpl_timing is declared with the decoders above.) */
 /* The stamp the SDK's unpackers attach to every node: receive time of a capsule minus
  * _getSampleDelayOffsetIn{Legacy,Express,HQ,UltraBoost,Dense,UltraDense}Mode (handler_normalnode.cpp:49-68,
  * handler_capsules.cpp:55-76,272-293,586-607,795-816, handler_hqnode.cpp:53-72).  capsule_rx_us:

@@ -151,7 +151,7 @@ def lib() -> C.CDLL:
         "rpl_capsule_bytes": ([u32], u32),
         "rpl_capsule_nodes": ([u32], u32),
         "rpl_decode_capsules_batch_dev": ([vp, u32, vp, vp, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp], u32),
-        "rpl_decode_capsules": ([vp, u32, vp, u32, u32, vp, vp, C.POINTER(u32), vp, vp], u32),
+        "rpl_decode_capsules": ([vp, u32, vp, u32, u32, vp, vp, C.POINTER(u32), vp, vp, vp, vp, vp], u32),
         "rpl_decode_normal_batch_dev": ([vp, vp, vp, u32, u32, vp, vp, vp, vp, vp], u32),
         "rpl_peer_gather_bytes": ([u32, u32], C.c_size_t),
         "rpl_peer_alloc": ([vp, C.c_size_t, C.POINTER(vp), vp], u32),
@@ -348,8 +348,10 @@ class Context:
             _p(sync_state_out), _p(stream)))
 
     # ---- the other answer formats (0x82 express, 0x83 HQ, 0x84 ultra, 0x86 ultra-dense, 0x81 standard) ----
-    def decode_capsules(self, ans_type: int, capsules: np.ndarray, sample_duration_us: int = 31, state=(0, 0)):
-        """One stream of framed capsules -> (nodes, capsule_status, capsule_node_offset, state_out)."""
+    def decode_capsules(self, ans_type: int, capsules: np.ndarray, sample_duration_us: int = 31, state=(0, 0),
+                        timing: "Timing | None" = None, capsule_rx_us=None):
+        """One stream of framed capsules -> (nodes, capsule_status, capsule_node_offset, state_out); with
+        timing + capsule_rx_us also the per-node timestamps as a fifth element."""
         cb, per = self._L.rpl_capsule_bytes(ans_type), self._L.rpl_capsule_nodes(ans_type)
         if cb == 0:
             raise ValueError(f"unknown answer type {ans_type:#x}")
@@ -360,9 +362,15 @@ class Context:
         offs = np.zeros(max(n, 1), np.uint32)
         st = np.array(state, np.uint32)
         cnt = C.c_uint32(0)
+        rx = ts = None
+        if timing is not None:
+            rx = np.ascontiguousarray(capsule_rx_us, dtype=np.uint64)
+            ts = np.zeros(max(per * n, 1), np.uint64)
         self._check(self._L.rpl_decode_capsules(self._h, ans_type, _p(capsules), n, sample_duration_us, _p(st),
-                                                _p(nodes), C.byref(cnt), _p(status), _p(offs)))
-        return nodes[: cnt.value].copy(), status[:n].copy(), offs[:n].copy(), (int(st[0]), int(st[1]))
+                                                _p(nodes), C.byref(cnt), _p(status), _p(offs),
+                                                C.byref(timing) if timing is not None else None, _p(rx), _p(ts)))
+        out = (nodes[: cnt.value].copy(), status[:n].copy(), offs[:n].copy(), (int(st[0]), int(st[1])))
+        return out + (ts[: cnt.value].copy(),) if timing is not None else out
 
     def decode_capsules_batch_dev(self, ans_type, capsules, capsule_counts, n_streams, stride_capsules,
                                   sample_duration_us, nodes_out, node_counts, state_in=None, capsule_status=None,

@@ -867,8 +867,15 @@ struct HostDecode {
 
 rpl_result rpl_decode_capsules(rpl_ctx* c, uint32_t ans_type, const uint8_t* capsules, uint32_t n_capsules,
                                uint32_t sample_duration_us, uint32_t* state, rpl_node_hq* nodes_out,
-                               uint32_t* node_count, uint32_t* capsule_status, uint32_t* capsule_node_offset) {
+                               uint32_t* node_count, uint32_t* capsule_status, uint32_t* capsule_node_offset,
+                               const rpl_timing* timing, const uint64_t* capsule_rx_us, uint64_t* node_ts_us) {
   if (!c || !node_count || (n_capsules && (!capsules || !nodes_out))) return RPL_RESULT_INVALID_DATA;
+  const bool want_ts = timing || capsule_rx_us || node_ts_us;
+  if (want_ts && !(timing && capsule_rx_us && node_ts_us)) {
+    c->err = "timing, capsule_rx_us and node_ts_us go together";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if (want_ts) sample_duration_us = timing->sample_duration_us;
   *node_count = 0;
   const uint32_t cbytes = rpl_capsule_bytes(ans_type), per = rpl_capsule_nodes(ans_type);
   if (cbytes == 0) {
@@ -879,12 +886,14 @@ rpl_result rpl_decode_capsules(rpl_ctx* c, uint32_t ans_type, const uint8_t* cap
   RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
   cudaStream_t st = c->lane[0].stream;
   const size_t cb = (size_t)n_capsules * cbytes, nb = (size_t)n_capsules * per * 8, sb = (size_t)n_capsules * 4;
-  HostDecode h;  // [capsules | pad][nodes][status][offsets][count, n_nodes, state in x2, state out x2]
+  HostDecode h;  // [capsules | pad][nodes][status][offsets][count, n_nodes, state in x2, state out x2][rx][ts]
   h.o_nodes = (cb + 15) & ~(size_t)15;
   h.o_st = h.o_nodes + nb;
   h.o_off = h.o_st + sb;
   h.o_small = h.o_off + sb;
-  RPL_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&h.d), h.o_small + 32), RPL_RESULT_INSUFFICIENT_MEMORY);
+  const size_t o_rx = (h.o_small + 32 + 7) & ~(size_t)7, o_ts = o_rx + (size_t)n_capsules * 8;
+  const size_t total_bytes = want_ts ? o_ts + (size_t)n_capsules * per * 8 : h.o_small + 32;
+  RPL_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&h.d), total_bytes), RPL_RESULT_INSUFFICIENT_MEMORY);
   uint32_t small[8] = {n_capsules, 0u, state ? state[0] : 0u, state ? state[1] : 0u, 0u, 0u, 0u, 0u};
   RPL_CUDA(c, cudaMemcpyAsync(h.d, capsules, cb, cudaMemcpyHostToDevice, st), RPL_RESULT_OPERATION_FAIL);
   RPL_CUDA(c, cudaMemcpyAsync(h.d + h.o_small, small, 32, cudaMemcpyHostToDevice, st), RPL_RESULT_OPERATION_FAIL);
@@ -894,6 +903,14 @@ rpl_result rpl_decode_capsules(rpl_ctx* c, uint32_t ans_type, const uint8_t* cap
                                                reinterpret_cast<uint32_t*>(h.d + h.o_st),
                                                reinterpret_cast<uint32_t*>(h.d + h.o_off), ds + 4, st);
   if (r != RPL_RESULT_OK) return r;
+  if (want_ts) {
+    RPL_CUDA(c, cudaMemcpyAsync(h.d + o_rx, capsule_rx_us, (size_t)n_capsules * 8, cudaMemcpyHostToDevice, st),
+             RPL_RESULT_OPERATION_FAIL);
+    r = rpl_node_timestamps_dev(c, ans_type, timing, reinterpret_cast<const uint64_t*>(h.d + o_rx),
+                                reinterpret_cast<uint32_t*>(h.d + h.o_st), reinterpret_cast<uint32_t*>(h.d + h.o_off), ds,
+                                1, n_capsules, reinterpret_cast<uint64_t*>(h.d + o_ts), st);
+    if (r != RPL_RESULT_OK) return r;
+  }
   RPL_CUDA(c, cudaMemcpyAsync(small, ds, 32, cudaMemcpyDeviceToHost, st), RPL_RESULT_OPERATION_FAIL);
   RPL_CUDA(c, cudaStreamSynchronize(st), RPL_RESULT_OPERATION_FAIL);
   *node_count = small[1];
@@ -901,6 +918,9 @@ rpl_result rpl_decode_capsules(rpl_ctx* c, uint32_t ans_type, const uint8_t* cap
     state[0] = small[4];
     state[1] = small[5];
   }
+  if (want_ts)
+    RPL_CUDA(c, cudaMemcpy(node_ts_us, h.d + o_ts, (size_t)small[1] * 8, cudaMemcpyDeviceToHost),
+             RPL_RESULT_OPERATION_FAIL);
   RPL_CUDA(c, cudaMemcpy(nodes_out, h.d + h.o_nodes, (size_t)small[1] * 8, cudaMemcpyDeviceToHost),
            RPL_RESULT_OPERATION_FAIL);
   if (capsule_status)

@@ -63,3 +63,43 @@ def test_host_mirror_gpu(exe, files):
     r = subprocess.run([exe, "gpu", files["raw"], files["asc"], files["ranges"], files["intens"]],
                        capture_output=True, text=True, env=_env(), timeout=300)
     assert r.returncode == 0 and "OK gpu" in r.stdout, r.stdout + r.stderr
+
+
+# ---- the sample-data unpacker seam (SURVEY.md 8(f) rank 1 + 4) ------------------------------------------
+@pytest.fixture(scope="module")
+def unpacker_exe(tmp_path_factory):
+    import rplidar_ros2_driver_b200 as R
+
+    if not os.path.exists(R.capi.LIB_PATH):
+        R.build()
+    out = str(tmp_path_factory.mktemp("cpp") / "unpacker_mirror_test")
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-I", os.path.join(PKG, "host"),
+           os.path.join(ROOT, "tests", "cpp", "unpacker_mirror_test.cpp"), "-L", PKG, "-lrplidar_b200",
+           f"-Wl,-rpath,{PKG}", "-Wl,--allow-shlib-undefined", "-lpthread", "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return out
+
+
+def test_unpacker_mirror_cpu(unpacker_exe):
+    r = subprocess.run([unpacker_exe, "cpu"], capture_output=True, text=True, env=_env(), timeout=120)
+    assert r.returncode == 0 and "OK cpu" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ans", [0x82, 0x83, 0x84, 0x85, 0x86])
+@pytest.mark.parametrize("batch", [1, 7, 256])
+def test_unpacker_mirror_replays_the_sdk_callbacks(unpacker_exe, golden_dir, tmp_path, ans, batch):
+    """Same callbacks, same order, same timestamps as the SDK's LIDARSampleDataUnpacker made on the captured
+    streams (tests/golden/wire_golden.npz), whatever the batch size."""
+    g = np.load(f"{golden_dir}/wire_golden.npz")
+    t = f"{ans:02x}"
+    paths = {}
+    for k in ("wire", "rx", "nodes", "ts", "events"):
+        paths[k] = str(tmp_path / f"{k}.bin")
+        np.ascontiguousarray(g[f"{k}_{t}"]).tofile(paths[k])
+    paths["timing"] = str(tmp_path / "timing.bin")
+    g["timing"].astype(np.uint32).tofile(paths["timing"])
+    r = subprocess.run([unpacker_exe, "gpu", hex(ans), str(batch), paths["wire"], paths["rx"], paths["nodes"], paths["ts"],
+                        paths["events"], paths["timing"]], capture_output=True, text=True, env=_env(), timeout=300)
+    assert r.returncode == 0 and "OK gpu" in r.stdout, r.stdout + r.stderr
