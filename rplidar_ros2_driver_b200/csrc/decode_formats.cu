@@ -43,17 +43,18 @@ template <int F>
 struct Fmt;
 template <>
 struct Fmt<kExpress> {
-  static constexpr int CB = 84, NODES = 32, START = 2;
+  static constexpr int CB = 84, NODES = 32, START = 2, BUFFERS = 2;
   static constexpr bool THRESHOLD = false, STATE = false;
 };
 template <>
 struct Fmt<kUltra> {
-  static constexpr int CB = 132, NODES = 96, START = 2;
+  static constexpr int CB = 132, NODES = 96, START = 2, BUFFERS = 2;
   static constexpr bool THRESHOLD = false, STATE = false;
 };
 template <>
 struct Fmt<kUltraDense> {
-  static constexpr int CB = 170, NODES = 64, START = 8;
+  // one tile buffer: with the smoothing tables a second one would leave a single CTA (8 warps) per SM
+  static constexpr int CB = 170, NODES = 64, START = 8, BUFFERS = 1;
   static constexpr bool THRESHOLD = true, STATE = true;
 };
 
@@ -184,7 +185,7 @@ template <int F>
 struct CapsuleSmem {
   static constexpr int CB = Fmt<F>::CB;
   static constexpr int kTileBytes = (DT * CB + 15) & ~15;
-  uint8_t cap[2][kTileBytes];          // double-buffered tiles
+  uint8_t cap[Fmt<F>::BUFFERS][kTileBytes];  // tiles (double-buffered: cp.async prefetch of the next one)
   uint8_t carry[(CB + 15) & ~15];      // last capsule of the previous tile
   uint32_t start_q8[DT + 1];           // slot 0 = carry
   uint32_t okflag[DT + 1];
@@ -194,10 +195,10 @@ struct CapsuleSmem {
   // ultra-dense only
   unsigned long long smask[Fmt<F>::STATE ? DT : 1];
   uint32_t ud_out[Fmt<F>::STATE ? DT : 1][10];   // nine outcomes of the smoothing chain + first raw sample
-  uint32_t ud_first_scale[Fmt<F>::STATE ? DT : 1];
+  uint32_t ud_first_scale[Fmt<F>::STATE ? DT : 1];  // bit 31: the capsule's outcome does not depend on its input
   uint32_t ud_last_in[Fmt<F>::STATE ? DT : 1];
   uint16_t ud_dist[Fmt<F>::STATE ? DT : 1][64];  // smoothed short-range distances
-  uint32_t carry_sync, red_sync, carry_last;
+  uint32_t carry_sync, red_sync, carry_last, red_last;
 };
 
 template <int F>
@@ -238,13 +239,14 @@ __global__ void __launch_bounds__(DT) decode_capsule_kernel(CapsuleDecodeArgs a)
       for (uint32_t w = done + tid; w < bytes; w += DT) sm.cap[b][w] = __ldg(g + w);
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    if (n > 0) stage(0, 0);
+    if (T::BUFFERS == 2 && n > 0) stage(0, 0);
     uint32_t buf = 0;
-    for (uint32_t c0 = 0; c0 < n; c0 += DT, buf ^= 1u) {
+    for (uint32_t c0 = 0; c0 < n; c0 += DT, buf ^= (uint32_t)(T::BUFFERS - 1)) {
       const uint32_t live = min((uint32_t)DT, n - c0);
+      if (T::BUFFERS == 1) stage(c0, 0);  // the previous tile was released by the barrier that ends its iteration
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();
-      if (c0 + DT < n) stage(c0 + DT, buf ^ 1u);
+      if (T::BUFFERS == 2 && c0 + DT < n) stage(c0 + DT, buf ^ 1u);
       const uint8_t* tile = sm.cap[buf];
       // ---- per capsule: frame, checksum, start angle ------------------------------------------------
       uint32_t st = 0, ok = 0, sync = 0;
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(DT) decode_capsule_kernel(CapsuleDecodeArgs a)
           const uint8_t* pc = (tid == 0) ? sm.carry : tile + (tid - 1) * CB;
           uint32_t sc, q;
           const int r0 = ud_sample(pc, 0, sc, q);
-          sm.ud_first_scale[tid] = sc;
+          const uint32_t sc_first = sc;
           int cand[9];
 #pragma unroll
           for (int k = 0; k < 9; ++k) cand[k] = (sc == 0) ? (r0 - 4 + k) : r0;
@@ -370,23 +372,34 @@ __global__ void __launch_bounds__(DT) decode_capsule_kernel(CapsuleDecodeArgs a)
 #pragma unroll
           for (int k = 0; k < 9; ++k) sm.ud_out[tid][k] = (uint32_t)(merged ? cand[0] : cand[k]);
           sm.ud_out[tid][9] = (uint32_t)r0;
+          sm.ud_first_scale[tid] = sc_first | (merged ? 0x80000000u : 0u);
         }
       }
       __syncthreads();
       if constexpr (T::STATE) {
-        // ---- step 2: one thread chains the tables across the tile's releasing capsules ---------------
-        if (tid == 0) {
-          int last = (int)sm.carry_last;
+        // ---- step 2: the value entering every releasing capsule.  A capsule whose nine outcomes agree
+        // (any far sample inside it) is a constant: each thread walks back to the nearest such capsule (or
+        // to the tile's input) and applies the tables from there -- usually one or two steps.
+        {
           const uint32_t E = sm.tile_nodes / NODES;
-          for (uint32_t e = 0; e < E; ++e) {
-            const uint32_t j = sm.emit_list[e];
-            sm.ud_last_in[j] = (uint32_t)last;
+          auto apply = [&](uint32_t j, int last) -> int {
+            const uint32_t fs = sm.ud_first_scale[j];
             const int r0 = (int)sm.ud_out[j][9];
             int k = 4;
-            if (sm.ud_first_scale[j] == 0 && last && abs(r0 - last) <= 8) k = ((r0 + last) >> 1) - (r0 - 4);
-            last = (int)sm.ud_out[j][k];
+            if ((fs & 3u) == 0 && last && abs(r0 - last) <= 8) k = ((r0 + last) >> 1) - (r0 - 4);
+            return (int)sm.ud_out[j][k];
+          };
+          if (tid < E) {
+            int e0 = (int)tid - 1;  // last capsule before this one whose outcome is known without its input
+            while (e0 >= 0 && !(sm.ud_first_scale[sm.emit_list[e0]] & 0x80000000u)) --e0;
+            int last = (e0 >= 0) ? (int)sm.ud_out[sm.emit_list[e0]][0] : (int)sm.carry_last;
+            for (int e = e0 + 1; e < (int)tid; ++e) last = apply(sm.emit_list[e], last);
+            const uint32_t j = sm.emit_list[tid];
+            sm.ud_last_in[j] = (uint32_t)last;
+            if (tid == E - 1) sm.red_last = (uint32_t)apply(j, last);
           }
-          sm.carry_last = (uint32_t)last;
+          __syncthreads();
+          if (tid == 0 && E > 0) sm.carry_last = sm.red_last;
         }
         __syncthreads();
         // ---- step 3: replay the samples from the known input, keep the smoothed distances ------------
