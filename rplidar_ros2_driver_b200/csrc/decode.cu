@@ -38,6 +38,7 @@ struct __align__(16) DecodeSmem {
   uint32_t carry[kCapWords];           // last capsule of the previous tile
   unsigned long long smask[DT];        // final sync bits of the 40 nodes each capsule releases
   uint32_t start_q8[DT + 1];           // (start & 0x7FFF) << 2, slot 0 = carry
+  int inc_q16[DT];                     // angular step per sample of the capsule each capsule releases
   uint32_t okflag[DT + 1];             // checksum + frame ok, slot 0 = carry
   uint32_t emit_list[DT];              // releasing capsules of the tile, in order (compacted)
   uint32_t warp_a[DT / 32], warp_b[DT / 32];
@@ -55,6 +56,9 @@ __device__ __forceinline__ unsigned long long raw_sync_mask(int prev_q8, int inc
   unsigned long long m = 0;
   int rem = ((prev_q8 << 8) + inc_q16) % kFull;  // (cur + inc) % full for pos = 0
   const int lim = inc_q16 << 1;
+  // no wrap inside the capsule and already past the two steps after the last one: nothing to mark
+  // (79 of 80 capsules of a revolution)
+  if (rem >= lim && rem + 39 * inc_q16 < kFull) return 0ull;
 #pragma unroll 8
   for (int pos = 0; pos < 40; ++pos) {
     if (rem < lim) m |= 1ull << pos;
@@ -170,6 +174,7 @@ __global__ void __launch_bounds__(DT) decode_dense_kernel(DecodeArgs a) {
             emit = 1;
             st |= kStEmit;
             inc_q16 = (diff << 8) / 40;
+            sm.inc_q16[tid] = inc_q16;
           }
         }
       }
@@ -230,9 +235,7 @@ __global__ void __launch_bounds__(DT) decode_dense_kernel(DecodeArgs a) {
           const uint32_t j = sm.emit_list[e];
           const uint32_t* pc = (j == 0) ? sm.carry : &tile[(j - 1) * kCapWords];  // the predecessor capsule
           const int pq8 = (int)sm.start_q8[j];
-          int diff = (int)sm.start_q8[j + 1] - pq8;
-          if (pq8 > (int)sm.start_q8[j + 1]) diff += (360 << 8);
-          const int inc = (diff << 8) / 40;
+          const int inc = sm.inc_q16[j];
           const uint32_t wq = pc[1 + (pos >> 1)];
           const int dist = (int)((pos & 1u) ? (wq >> 16) : (wq & 0xFFFFu));
           const int dist_q2 = dist << 2;

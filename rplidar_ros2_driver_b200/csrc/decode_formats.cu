@@ -162,6 +162,7 @@ __device__ __forceinline__ unsigned long long raw_sync_mask64(int prev_q8, int i
   unsigned long long m = 0;
   int rem = ((prev_q8 << 8) + inc_q16) % kFull;
   const int lim = inc_q16 << 1;
+  if (rem >= lim && rem + 63 * inc_q16 < kFull) return 0ull;  // no wrap inside this capsule: nothing to mark
 #pragma unroll 8
   for (int pos = 0; pos < 64; ++pos) {
     if (rem < lim) m |= 1ull << pos;
