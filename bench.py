@@ -900,6 +900,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # rank 0's stdout carries exactly one JSON line: NCCL prints its banner ("NCCL version ...") and its
+    # diagnostics to stdout whenever NCCL_DEBUG is set (WARN included) -- send them to stderr instead
+    if os.environ.get("NCCL_DEBUG"):
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         run_reference(args, rank)
         return
