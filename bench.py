@@ -902,7 +902,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     # rank 0's stdout carries exactly one JSON line: NCCL prints its banner ("NCCL version ...") and its
     # diagnostics to stdout whenever NCCL_DEBUG is set (WARN included) -- send them to stderr instead
+    # (NCCL honours NCCL_DEBUG_FILE only above the VERSION level, and prints the banner at WARN as well)
     if os.environ.get("NCCL_DEBUG"):
+        if os.environ["NCCL_DEBUG"].upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         run_reference(args, rank)
