@@ -26,6 +26,21 @@
  *                              outlier removal, voxel grid); defined by oracle/cloud_oracle.cpp
  *   rpl_synth_batch_dev      synthetic scan streams of SURVEY.md 8(d) generated in HBM
  *
+ * and, either side of that path:
+ *
+ *   rpl_decode_*             the SDK's sample-data unpackers, all six measurement answer types
+ *                              src/sdk/src/dataunpacker/unpacker/handler_{capsules,normalnode,hqnode}.cpp
+ *   rpl_node_timestamps_dev  the timestamp the unpackers attach to every node (_getSampleDelayOffsetIn*Mode)
+ *   rpl_assemble_scans_dev   ScanDataHolder::pushScanNodeData / rewindCurrentScanData
+ *                              src/sdk/src/sl_lidar_driver.cpp:272-315
+ *   rpl_*_cdr_batch_dev      the serialised form of the message scan_pub_->publish hands to the RMW layer
+ *                              src/rplidar_node.cpp:679
+ *   rpl_cloud_fuse_push_dev  (with rpl_peer_*) the fused cloud's all-gather across GPUs, in the pack kernel
+ *
+ * Buffer contract of the *_dev entry points: every count array entry must be <= its stride (counts are
+ * read on the device and not clamped), device pointers must belong to the context's device, and work is
+ * ordered on the stream passed in (NULL = the context's own stream).
+ *
  * Tie rule.  The reference sorts with std::sort (unstable); on equal angle_z_q14 its order
  * is whatever libstdc++'s introsort produces.  This library defines the order: equal keys
  * keep buffer order (stable).  On tie-free scans results are bit-identical to the reference.
