@@ -97,6 +97,9 @@ bool cuda_ok(rpl_ctx* c, cudaError_t e, const char* what) {
     if (!cuda_ok((c), (call), #call)) return (code); \
   } while (0)
 
+// device buffers of 8-byte records (nodes, 64-bit stamps) are accessed with 8-byte loads and stores
+inline bool misaligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) != 0; }
+
 template <class P>
 cudaError_t dev_alloc(P** p, size_t count) {
   return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(P));
@@ -185,6 +188,10 @@ rpl_result enqueue_scan(rpl_ctx* c, Lane& l, const rpl_node_hq* nodes, const uin
   }
   if (nodes_out && static_cast<const void*>(nodes_out) == static_cast<const void*>(nodes)) {
     c->err = "nodes_out must not alias nodes on the device path";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if (misaligned8(nodes) || misaligned8(nodes_out)) {
+    c->err = "node buffers must be 8-byte aligned";
     return RPL_RESULT_INVALID_DATA;
   }
   rpl::ScanBatchArgs a{};
@@ -696,8 +703,8 @@ rpl_result rpl_decode_dense_batch_dev(rpl_ctx* c, const uint8_t* capsules, const
     c->err = "sample_duration_us must be in [1, 1000000]";
     return RPL_RESULT_INVALID_DATA;
   }
-  if ((reinterpret_cast<uintptr_t>(capsules) & 3u) != 0) {
-    c->err = "capsule buffer must be 4-byte aligned";
+  if ((reinterpret_cast<uintptr_t>(capsules) & 3u) != 0 || misaligned8(nodes_out)) {
+    c->err = "capsule buffer must be 4-byte aligned, nodes_out 8-byte aligned";
     return RPL_RESULT_INVALID_DATA;
   }
   if (n_streams == 0) return RPL_RESULT_OK;
@@ -807,6 +814,10 @@ rpl_result rpl_decode_capsules_batch_dev(rpl_ctx* c, uint32_t ans_type, const ui
   if (!c || !capsules || !capsule_counts || !nodes_out) return RPL_RESULT_INVALID_DATA;
   if (rpl_capsule_bytes(ans_type) == 0) {
     c->err = "unknown answer type (capsule formats are 0x82..0x86)";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if (misaligned8(nodes_out)) {
+    c->err = "nodes_out must be 8-byte aligned";
     return RPL_RESULT_INVALID_DATA;
   }
   if (sample_duration_us == 0 || sample_duration_us > 1000000u) {
@@ -935,6 +946,10 @@ rpl_result rpl_decode_normal_batch_dev(rpl_ctx* c, const uint8_t* bytes, const u
                                        uint32_t* node_counts, uint32_t* fsm_state_out, uint32_t* node_end,
                                        void* stream) {
   if (!c || !bytes || !byte_counts || !nodes_out) return RPL_RESULT_INVALID_DATA;
+  if (misaligned8(nodes_out)) {
+    c->err = "nodes_out must be 8-byte aligned";
+    return RPL_RESULT_INVALID_DATA;
+  }
   if (n_streams == 0) return RPL_RESULT_OK;
   RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
@@ -995,6 +1010,10 @@ rpl_result rpl_assemble_scans_dev(rpl_ctx* c, const rpl_node_hq* nodes, const ui
   }
   if (max_nodes == 0 || max_scans == 0 || scan_stride < max_nodes) {
     c->err = "need max_nodes > 0, max_scans > 0, scan_stride >= max_nodes";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if (misaligned8(nodes) || misaligned8(scans_out) || misaligned8(node_ts_us) || misaligned8(scan_begin_ts_us)) {
+    c->err = "node and timestamp buffers must be 8-byte aligned";
     return RPL_RESULT_INVALID_DATA;
   }
   if (n_streams == 0) return RPL_RESULT_OK;
@@ -1184,6 +1203,10 @@ rpl_result rpl_node_timestamps_dev(rpl_ctx* c, uint32_t ans_type, const rpl_timi
                                    uint32_t n_streams, uint32_t stride_capsules, uint64_t* node_ts_us, void* stream) {
   if (!c || !timing || !capsule_rx_us || !capsule_status || !capsule_node_offset || !capsule_counts || !node_ts_us)
     return RPL_RESULT_INVALID_DATA;
+  if (misaligned8(capsule_rx_us) || misaligned8(node_ts_us)) {
+    c->err = "timestamp buffers must be 8-byte aligned";
+    return RPL_RESULT_INVALID_DATA;
+  }
   if (rpl_capsule_bytes(ans_type) == 0) {
     c->err = "unknown answer type (capsule formats are 0x82..0x86)";
     return RPL_RESULT_INVALID_DATA;
@@ -1212,6 +1235,10 @@ rpl_result rpl_normal_timestamps_dev(rpl_ctx* c, const rpl_timing* timing, const
                                      uint64_t* node_ts_us, void* stream) {
   if (!c || !timing || !node_end || !node_counts || !chunk_rx_us || !node_ts_us || chunk_bytes == 0)
     return RPL_RESULT_INVALID_DATA;
+  if (misaligned8(chunk_rx_us) || misaligned8(node_ts_us)) {
+    c->err = "timestamp buffers must be 8-byte aligned";
+    return RPL_RESULT_INVALID_DATA;
+  }
   if (n_streams == 0) return RPL_RESULT_OK;
   RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
