@@ -593,13 +593,53 @@ def run_cloud(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+# ---- synthetic wire input for the decode / chain workloads (the oracle is only their CPU baseline) ----------
+WIRE_CAPSULE = {0x82: (84, 32), 0x83: (781, 96), 0x84: (132, 96), 0x85: (84, 40), 0x86: (170, 64)}  # bytes, nodes
+
+
+def wire_seal_capsules(fmt: int, payload: np.ndarray, start_q6=None, sync=None) -> np.ndarray:
+    """Well-formed capsules from [n, capsule bytes] payload bytes: start angle / scan-start bit, sync markers and
+    checksum (XOR of bytes 2.., split over the low nibbles of bytes 0 and 1; CRC-32 with the SDK's zero padding
+    for 0x83)."""
+    import zlib
+
+    cb = WIRE_CAPSULE[fmt][0]
+    caps = np.ascontiguousarray(payload, dtype=np.uint8).reshape(-1, cb).copy()
+    if fmt == 0x83:
+        caps[:, 0] = 0xA5
+        pad = b"\0" * (4 - ((cb - 4) & 3))
+        for j in range(caps.shape[0]):
+            crc = zlib.crc32(caps[j, : cb - 4].tobytes() + pad) & 0xFFFFFFFF
+            caps[j, cb - 4:] = np.frombuffer(np.uint32(crc).tobytes(), np.uint8)
+        return caps
+    off = 8 if fmt == 0x86 else 2
+    if start_q6 is not None:
+        word = (np.asarray(start_q6, dtype=np.uint32) & 0x7FFF) | (np.asarray(sync, dtype=np.uint32) << 15)
+        caps[:, off] = word & 0xFF
+        caps[:, off + 1] = word >> 8
+    chk = np.bitwise_xor.reduce(caps[:, 2:], axis=1)
+    caps[:, 0] = 0xA0 | (chk & 0xF)
+    caps[:, 1] = 0x50 | (chk >> 4)
+    return caps
+
+
+def wire_dense_capsules(start_q6, sync, dist) -> np.ndarray:
+    """Dense (0x85) capsules: start_q6 [n], sync [n] bool, dist [n, 40] u16."""
+    n = len(start_q6)
+    payload = np.zeros((n, 84), np.uint8)
+    d = np.asarray(dist, dtype=np.uint16).reshape(n, 40)
+    payload[:, 4::2] = d & 0xFF
+    payload[:, 5::2] = d >> 8
+    return wire_seal_capsules(0x85, payload, start_q6, sync)
+
+
 def run_decode(args, rank, local_rank, world):
     """dense-capsule decode, 512 streams x 4096 framed capsules per GPU."""
     import torch
     from concurrent.futures import ThreadPoolExecutor
 
     import rplidar_ros2_driver_b200 as R
-    from oracle import pyoracle as O  # capsule builder + cpu_baseline leg only
+    from oracle import pyoracle as O  # cpu_baseline leg only
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -613,7 +653,7 @@ def run_decode(args, rank, local_rank, world):
         dist[rng.random((n_caps, 40)) < 0.05] = 0
         sync = np.zeros(n_caps, bool)
         sync[::80] = True
-        host.append(O.make_dense_capsules(q6, sync, dist))
+        host.append(wire_dense_capsules(q6, sync, dist))
     host = np.stack(host)
     ctx = R.Context(local_rank, 8192, 1)
     stream = torch.cuda.Stream(device=dev)
@@ -681,7 +721,7 @@ def run_decode_format(args, rank, local_rank, world):
     from concurrent.futures import ThreadPoolExecutor
 
     import rplidar_ros2_driver_b200 as R
-    from oracle import pyoracle as O  # capsule builder + cpu_baseline leg only
+    from oracle import pyoracle as O  # cpu_baseline leg only
 
     fmt = int(args.format, 0)
     torch.cuda.set_device(local_rank)
@@ -723,20 +763,20 @@ def run_decode_format(args, rank, local_rank, world):
         cpu_one = lambda i: O.decode_normal(host[i % distinct])
         shape = f"{n_streams} streams x {n_rec} five-byte records"
     else:
-        cb, per = O.capsule_bytes(fmt), O.capsule_nodes(fmt)
+        cb, per = WIRE_CAPSULE[fmt]
         n_caps = {0x82: 4096, 0x83: 512, 0x84: 2048, 0x86: 2048}[fmt]
         host = []
         for _ in range(distinct):
             payload = rng.integers(0, 256, (n_caps, cb), dtype=np.uint8)
             if fmt == 0x83:
-                host.append(O.seal_capsules(fmt, payload))
+                host.append(wire_seal_capsules(fmt, payload))
                 continue
             step_deg = 360.0 * per / 3200.0  # 3200 points per revolution
             ang = (rng.uniform(0, 360) + np.arange(n_caps) * step_deg + rng.normal(0, 0.03, n_caps)) % 360.0
             q6 = np.round(ang * 64).astype(np.uint32) % (360 * 64)
             sync = np.zeros(n_caps, bool)
             sync[0] = True
-            host.append(O.seal_capsules(fmt, payload, q6, sync))
+            host.append(wire_seal_capsules(fmt, payload, q6, sync))
         host = np.stack(host)
         wire = torch.from_numpy(np.tile(host, (n_streams // distinct, 1, 1))).to(dev)
         counts = torch.full((n_streams,), n_caps, dtype=torch.int32, device=dev)
@@ -800,8 +840,6 @@ def run_chain(args, rank, local_rank, world):
     import torch
 
     import rplidar_ros2_driver_b200 as R
-    from oracle import pyoracle as O  # capsule builder only
-
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     n_streams, n_caps, distinct, max_nodes, max_scans = 512, 4096, 16, 4096, 56
@@ -814,7 +852,7 @@ def run_chain(args, rank, local_rank, world):
         dist[rng.random((n_caps, 40)) < 0.05] = 0
         sync = np.zeros(n_caps, bool)
         sync[0] = True
-        host.append(O.make_dense_capsules(q6, sync, dist))
+        host.append(wire_dense_capsules(q6, sync, dist))
     host = np.stack(host)
     NS = n_streams * max_scans
     ctx = R.Context(local_rank, max_nodes, NS)
