@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "lidar_driver_wrapper.hpp"
+#include "publish_cloud_b200.hpp"
 #include "publish_scan_b200.hpp"
 
 namespace {
@@ -25,6 +26,21 @@ struct FakeLaserScan {  // same members as sensor_msgs::msg::LaserScan
   Header header;
   float angle_min, angle_max, angle_increment, time_increment, scan_time, range_min, range_max;
   std::vector<float> ranges, intensities;
+};
+struct FakePointField {  // same members as sensor_msgs::msg::PointField
+  std::string name;
+  uint32_t offset = 0;
+  uint8_t datatype = 0;
+  uint32_t count = 0;
+};
+struct FakePointCloud2 {  // same members as sensor_msgs::msg::PointCloud2
+  Header header;
+  uint32_t height = 0, width = 0;
+  std::vector<FakePointField> fields;
+  bool is_bigendian = true;
+  uint32_t point_step = 0, row_step = 0;
+  std::vector<uint8_t> data;
+  bool is_dense = false;
 };
 int fail(const char* what) { std::printf("FAIL: %s\n", what); return 1; }
 }  // namespace
@@ -46,6 +62,18 @@ int main(int argc, char** argv) {
       return fail("dummy scan differs from the captured reference");
   }
   if (drv->get_hw_max_distance() != 40.0f) return fail("hw max distance");
+  {  // PointCloud2 message from the cloud path's [n][x, y, z, intensity] points (pure host code)
+    const float pts[8] = {1.0f, 2.0f, 0.0f, 47.0f, -3.0f, 4.5f, 0.0f, 12.0f};
+    FakePointCloud2 pc;
+    rplidar_b200::fill_pointcloud2_msg(pc, pts, 2, 7, std::string("laser_frame"));
+    if (pc.header.stamp != 7 || pc.header.frame_id != "laser_frame" || pc.height != 1 || pc.width != 2 ||
+        pc.fields.size() != 4 || pc.fields[3].name != "intensity" || pc.fields[3].offset != 12 ||
+        pc.fields[1].datatype != 7 || pc.fields[2].count != 1 || pc.is_bigendian || pc.point_step != 16 ||
+        pc.row_step != 32 || pc.data.size() != 32 || std::memcmp(pc.data.data(), pts, 32) != 0 || !pc.is_dense)
+      return fail("PointCloud2 layout");
+    rplidar_b200::fill_pointcloud2_msg(pc, nullptr, 0, 8, std::string());
+    if (pc.width != 0 || !pc.data.empty() || pc.row_step != 0) return fail("empty PointCloud2");
+  }
   if (mode == "cpu") {
     bool threw = false;
     try {
