@@ -1,0 +1,170 @@
+"""Plain-Python models of the parallel formulations the kernels use, checked against the (pinned) serial
+restatements in oracle/.  They document WHY the kernels may reorder the reference's serial loops:
+
+  * scan assembly (csrc/assemble.cu): a scan [s, e) between two scan-start nodes is published iff no reset
+    position r has s < r <= e; lengths clamp at the holder capacity with the scan's last node in the last slot;
+  * standard-node decoder (csrc/decode_formats.cu): the 5-state byte machine as composition of per-byte
+    state->state maps (associative, so chunks can be folded independently and scanned);
+  * ultra-dense smoothing (csrc/decode_formats.cu): a capsule's effect on `_last_dist_q2` is a table of at most
+    nine outcomes selected by its first sample, and a capsule whose nine outcomes agree cuts the chain.
+
+CPU only, small sizes (pure-Python loops)."""
+import numpy as np
+import pytest
+
+
+# ---- scan assembly ---------------------------------------------------------------------------------------
+def assemble_model(flags, resets, cap):
+    """Descriptors (start, stored length, last-node index) of the published scans, the way the kernel finds them."""
+    starts = np.flatnonzero(flags & 1)
+    resets = np.sort(np.asarray(resets, dtype=np.int64))
+    upto = lambda x: int(np.searchsorted(resets, x, side="right"))  # number of reset positions <= x
+    out = []
+    for s, e in zip(starts[:-1], starts[1:]):
+        if upto(e) == upto(s):
+            n = int(e - s)
+            out.append((int(s), min(n, cap), int(e - 1)))
+    return out
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_scan_assembly_descriptor_rule(oracle, seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 1500))
+    nodes = np.zeros(n, oracle.NODE_DTYPE)
+    nodes["angle_z_q14"] = rng.integers(0, 65536, n)
+    nodes["dist_mm_q2"] = np.arange(n) + 1  # identifies the node
+    nodes["flag"] = np.where(rng.random(n) < rng.choice([0.01, 0.1, 0.5]), 1, 2)
+    resets = np.sort(rng.integers(0, n + 1, int(rng.integers(0, 10)))).astype(np.uint32)
+    cap = int(rng.choice([4, 37, 8192]))
+    scans, lens, k = oracle.assemble_scans(nodes, resets, cap, 2048)
+    model = assemble_model(nodes["flag"], resets, cap)
+    assert k == len(model)
+    for i, (s, ln, last) in enumerate(model):
+        assert lens[i] == ln
+        assert (scans[i, : ln - 1]["dist_mm_q2"] == nodes[s: s + ln - 1]["dist_mm_q2"]).all()
+        assert scans[i, ln - 1]["dist_mm_q2"] == nodes[last]["dist_mm_q2"]  # capacity rule: last node in the last slot
+
+
+# ---- standard nodes: byte machine as map composition ---------------------------------------------------------
+def byte_map(b):
+    t0 = 1 if ((b >> 1) ^ b) & 1 else 0
+    t1 = 2 if b & 1 else 0
+    return (t0, t1, 3, 4, 0)
+
+
+def compose(g, f):  # (g o f)(s) = g(f(s))
+    return tuple(g[f[s]] for s in range(5))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_byte_machine_by_map_composition(oracle, seed):
+    rng = np.random.default_rng(seed)
+    n = 700
+    rec = np.zeros((n, 5), np.uint8)
+    rec[:, 0] = (rng.integers(0, 64, n).astype(np.uint8) << 2) | 2
+    w = (rng.integers(0, 360 * 64, n).astype(np.uint16) << 1) | 1
+    rec[:, 1], rec[:, 2] = w & 0xFF, w >> 8
+    rec[:, 3:] = rng.integers(0, 256, (n, 2))
+    b = rec.reshape(-1).copy()
+    b[rng.choice(len(b), 80, replace=False)] = rng.integers(0, 256, 80)
+    b = np.delete(b, rng.choice(len(b), 9, replace=False))
+    _, ends, _ = oracle.decode_normal(b)
+    # fold chunks of 20 bytes independently, scan the maps, replay each chunk from its entry state
+    chunk = 20
+    maps = []
+    for c0 in range(0, len(b), chunk):
+        f = (0, 1, 2, 3, 4)
+        for x in b[c0: c0 + chunk]:
+            f = compose(byte_map(int(x)), f)
+        maps.append(f)
+    state, got = 0, []
+    for ci, c0 in enumerate(range(0, len(b), chunk)):
+        st = state
+        for i, x in enumerate(b[c0: c0 + chunk]):
+            if st == 4:
+                got.append(c0 + i)
+            st = byte_map(int(x))[st]
+        assert st == maps[ci][state]  # the folded map predicts the chunk's exit state
+        state = st
+    assert got == ends.tolist()
+    # associativity: folding maps pairwise in any grouping gives the same total map
+    total = (0, 1, 2, 3, 4)
+    for f in maps:
+        total = compose(f, total)
+    pair = [compose(maps[i + 1], maps[i]) if i + 1 < len(maps) else maps[i] for i in range(0, len(maps), 2)]
+    total2 = (0, 1, 2, 3, 4)
+    for f in pair:
+        total2 = compose(f, total2)
+    assert total == total2
+
+
+# ---- ultra-dense smoothing chain ---------------------------------------------------------------------------------
+def ud_samples(cap):
+    """(raw distance, scale) of the 64 samples of one 170-byte ultra-dense capsule."""
+    out = []
+    for pos in range(64):
+        cab = cap[10 + 5 * (pos >> 1): 15 + 5 * (pos >> 1)].astype(np.int64)
+        lo = int(cab[2] | (cab[3] << 8)) if pos & 1 else int(cab[0] | (cab[1] << 8))
+        hi = int(cab[4] >> 4) if pos & 1 else int(cab[4] & 0xF)
+        qds = lo | (hi << 16)
+        sc = qds & 3
+        d = [(qds & 0xFFC) * 2, (qds & 0x1FFC) * 3 + (2046 << 2), (qds & 0x3FFC) * 4 + (8187 << 2),
+             (qds & 0x7FFC) * 5 + (24567 << 2)][sc]
+        out.append((d, sc))
+    return out
+
+
+def smooth(raw, sc, last):
+    return (raw + last) >> 1 if (sc == 0 and last and abs(raw - last) <= 8) else raw
+
+
+def chain(samples, last):
+    for raw, sc in samples:
+        last = smooth(raw, sc, last)
+    return last
+
+
+def capsule_table(samples):
+    """(first raw, first scale, nine outcomes, constant?) -- what every capsule thread tabulates."""
+    r0, sc0 = samples[0]
+    outs = [chain(samples[1:], (r0 - 4 + k) if sc0 == 0 else r0) for k in range(9)]
+    return r0, sc0, outs, len(set(outs)) == 1
+
+
+def apply_table(tab, last):
+    r0, sc0, outs, _ = tab
+    k = 4
+    if sc0 == 0 and last and abs(r0 - last) <= 8:
+        k = ((r0 + last) >> 1) - (r0 - 4)
+    return outs[k]
+
+
+@pytest.mark.parametrize("near", [False, True])
+def test_ultra_dense_chain_tables(oracle, near):
+    from test_capsule_oracle_vs_ref import make_capsules
+
+    caps = make_capsules(oracle, 0x86, 60, 50.0, seed=3 if near else 4, near=near)
+    tabs = [capsule_table(ud_samples(c)) for c in caps]
+    rng = np.random.default_rng(0)
+    # 1. a table reproduces the serial chain for any incoming value
+    for tab, c in zip(tabs, caps):
+        s = ud_samples(c)
+        for last in [0, 1, s[0][0], s[0][0] + 8, s[0][0] - 8, s[0][0] + 9, 100000] + rng.integers(0, 9000, 20).tolist():
+            if last < 0:
+                continue
+            assert apply_table(tab, int(last)) == chain(s, int(last))
+    # 2. the value entering capsule e: walk back to the nearest constant capsule, apply the tables from there
+    serial, last = [], 777
+    for c in caps:
+        serial.append(last)
+        last = chain(ud_samples(c), last)
+    for e in range(len(caps)):
+        e0 = e - 1
+        while e0 >= 0 and not tabs[e0][3]:
+            e0 -= 1
+        v = tabs[e0][2][0] if e0 >= 0 else 777
+        for j in range(e0 + 1, e):
+            v = apply_table(tabs[j], v)
+        assert v == serial[e]
+    assert any(t[3] for t in tabs) or near
