@@ -168,3 +168,58 @@ def test_ultra_dense_chain_tables(oracle, near):
             v = apply_table(tabs[j], v)
         assert v == serial[e]
     assert any(t[3] for t in tabs) or near
+
+
+# ---- dense / ultra-dense scan-start flags ---------------------------------------------------------------------
+K_FULL = 360 << 16
+
+
+def raw_sync_bits(prev_q8, inc, n):
+    """The reference's per-sample test ((cur + inc) % 360deg) < 2 * inc, before the 'not twice in a row' rule."""
+    cur, bits = prev_q8 << 8, []
+    for _ in range(n):
+        bits.append(1 if ((cur + inc) % K_FULL) < (inc << 1) else 0)
+        cur += inc
+    return bits
+
+
+def resolve(bits, s_in):
+    out, last = [], s_in
+    for b in bits:
+        s = b & (1 - last)  # sync = (raw ^ last) & raw
+        out.append(s)
+        last = s
+    return out
+
+
+@pytest.mark.parametrize("n", [40, 64])
+def test_no_wrap_shortcut_and_transfer_functions(n):
+    """(1) If the first remainder is already >= 2*inc and the capsule cannot wrap, no sample is a scan start
+    (the shortcut the decoders take for most capsules).  (2) The flag leaving a capsule is a function of the
+    flag entering it; composing those 2-entry functions over capsules equals the serial recurrence."""
+    rng = np.random.default_rng(n)
+    hits = 0
+    for _ in range(4000):
+        prev_q8 = int(rng.integers(0, 360 << 8))
+        diff_q8 = int(rng.integers(1, 40 << 8)) if rng.random() < 0.8 else int(rng.integers(1, 360 << 8))
+        inc = (diff_q8 << 8) // n
+        rem = ((prev_q8 << 8) + inc) % K_FULL
+        bits = raw_sync_bits(prev_q8, inc, n)
+        if rem >= (inc << 1) and rem + (n - 1) * inc < K_FULL:
+            hits += 1
+            assert not any(bits)
+    assert hits > 1000
+    # transfer functions
+    caps = [raw_sync_bits(int(rng.integers(0, 360 << 8)), int(rng.integers(1, 300000)), n) for _ in range(200)]
+    # make some capsules end right after a wrap so that the state matters
+    f = [(resolve(b, 0)[-1], resolve(b, 1)[-1]) for b in caps]
+    for s0 in (0, 1):
+        serial, s = [], s0
+        for b in caps:
+            serial.append(s)
+            s = resolve(b, s)[-1]
+        composed, acc = [], (0, 1)  # identity
+        for fj in f:
+            composed.append(acc[s0])
+            acc = (fj[acc[0]], fj[acc[1]])
+        assert composed == serial
