@@ -223,3 +223,30 @@ def test_no_wrap_shortcut_and_transfer_functions(n):
             composed.append(acc[s0])
             acc = (fj[acc[0]], fj[acc[1]])
         assert composed == serial
+
+
+# ---- the hot path: sort = rank lookup over a presence bitmap ---------------------------------------------------
+@pytest.mark.parametrize("n", [1, 7, 360, 3200, 32768])
+def test_rank_lookup_equals_the_sort_for_tie_free_scans(oracle, n):
+    """rank(key) = prefix[key >> 5] + popcount(bits[key >> 5] & below(key)) over the 65536-bit presence map is
+    the position std::sort gives the node, and `popcount(map) != measured count` detects duplicate keys."""
+    nodes = oracle.synth_batch(90 + n, 1, n, variant=3)[0]  # shuffled, tie-free
+    key = nodes["angle_z_q14"].astype(np.int64)
+    valid = nodes["dist_mm_q2"] != 0
+    bits = np.zeros(65536, np.uint8)
+    bits[key[valid]] = 1
+    assert bits.sum() == valid.sum()  # tie-free
+    words = np.packbits(bits.reshape(2048, 32), axis=1, bitorder="little").view("<u4").reshape(2048)
+    pop = np.array([bin(int(w)).count("1") for w in words])
+    prefix = np.concatenate([[0], np.cumsum(pop)[:-1]])
+    below = lambda k: (1 << (k & 31)) - 1
+    rank = np.array([prefix[k >> 5] + bin(int(words[k >> 5]) & below(int(k))).count("1") for k in key[valid]])
+    order = np.argsort(key[valid], kind="stable")
+    assert (rank[order] == np.arange(valid.sum())).all()
+    # a duplicate key makes the popcount fall short of the measured count
+    if valid.sum() >= 2:
+        k2 = key[valid].copy()
+        k2[1] = k2[0]
+        b2 = np.zeros(65536, np.uint8)
+        b2[k2] = 1
+        assert b2.sum() == valid.sum() - 1
