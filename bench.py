@@ -180,16 +180,30 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU loop (oracle port) on the host cores
+# reference arm: the reference's CPU loop on the host cores
 # ------------------------------------------------------------------------------------------------
+def cpu_kind(O):
+    """("reference", text) when the reference's own code is available as oracle/_ref/libref_node.so (built in the
+    authoring container from /root/reference: the SDK's ascendScanData + the node's real publish_scan, the latter
+    compiled against ROS API stubs), else ("port", text): the line-by-line restatement in oracle/scan_oracle.cpp."""
+    if O.have_ref_node():
+        return "reference", ("the reference's own code: grab_scan_data's ascend glue + sl::ascendScanData + "
+                             "RPlidarNode::publish_scan compiled from the reference sources (oracle/_ref/libref_node.so)")
+    return "port", "oracle port of ascendScanData+publish_scan (validated against the compiled reference)"
+
+
 def cpu_leg(O, nodes_host, counts, mode_a, threads, reps):
     """ascendScanData + publish_scan per scan (one scan per worker).  Returns (Mpoints/s, seconds)."""
     prm = O.scan_params(0, mode_a, 0, 1, 40.0, 0.1)
     total_pts = int(counts.sum())
     secs = 0.0
+    use_ref = O.have_ref_node()
     for _ in range(reps):
-        buf = nodes_host.copy()  # ascend works in place: start every rep from the raw buffers
-        res = O.pipeline_batch(buf, counts, prm, stable=False, threads=threads)
+        if use_ref:  # copies every scan into its own buffer first, as the SDK delivers it
+            res = O.ref_pipeline_batch(nodes_host, counts, prm, threads=threads, outputs=False)
+        else:
+            buf = nodes_host.copy()  # ascend works in place: start every rep from the raw buffers
+            res = O.pipeline_batch(buf, counts, prm, stable=False, threads=threads)
         secs += res["seconds"]
     return total_pts * reps / secs / 1e6, secs
 
@@ -224,15 +238,15 @@ def run_reference(args, rank):
         pts += int(counts.sum())
     value = pts / t_total / 1e6
     one, _ = cpu_leg(O, nodes[:32].copy(), counts[:32], mode_a, 1, 1)
+    kind, what = cpu_kind(O)
     sample = (f"{sample_scans} scans x {args.nodes} nodes per step ({sample_scans * args.nodes / 1e6:.1f} Mpoints), "
-              f"oracle port of ascendScanData+publish_scan (validated against the compiled reference), "
-              f"one scan per worker thread, {cores} threads")
+              f"{what}, one scan per worker thread, {cores} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "scans_per_step": sample_scans, "nodes_per_scan": args.nodes},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                          "value_1thread": one},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -457,14 +471,18 @@ def run_b200(args, rank, local_rank, world):
         per_scan = {}
         for nn in (360, 3200, 8192):
             sm_nodes = O.synth_batch(0, 64, nn, args.variant)
-            rr = O.pipeline_batch(sm_nodes, np.full(64, nn, np.uint32), O.scan_params(0, mode_a, 0, 1, 40.0, 0.1),
-                                  stable=False, threads=1)
+            if O.have_ref_node():
+                rr = O.ref_pipeline_batch(sm_nodes, np.full(64, nn, np.uint32), O.scan_params(0, mode_a, 0, 1, 40.0, 0.1),
+                                          threads=1, outputs=False)
+            else:
+                rr = O.pipeline_batch(sm_nodes, np.full(64, nn, np.uint32), O.scan_params(0, mode_a, 0, 1, 40.0, 0.1),
+                                      stable=False, threads=1)
             per_scan[str(nn)] = rr["seconds"] / 64 * 1e6
         extra["single_scan_latency_cpu_1thread_us"] = per_scan
-        cpu = {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
+        kind, what = cpu_kind(O)
+        cpu = {"value": v_all, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": (f"the bench batch itself, 2 passes x {S} scans x {N} nodes = {2 * S * N / 1e6:.0f} Mpoints "
-                          f"({secs:.1f} s wall, {cores} worker threads, one scan per task); oracle port of "
-                          f"ascendScanData+publish_scan, validated against the compiled reference"),
+                          f"({secs:.1f} s wall, {cores} worker threads, one scan per task); {what}"),
                "value_1thread": v_one, "sample_1thread": f"{sub} scans x {N} nodes"}
 
     if rank == 0:

@@ -21,6 +21,7 @@ ORACLE_SO = os.path.join(HERE, "liboracle_scan.so")
 REF_SO = os.path.join(HERE, "_ref", "libref_rplidar.so")
 REF_HOLDER_SO = os.path.join(HERE, "_ref", "libref_holder.so")
 REF_CLOCK_SO = os.path.join(HERE, "_ref", "libref_clock.so")
+REF_NODE_SO = os.path.join(HERE, "_ref", "libref_node.so")
 
 NODE_DTYPE = np.dtype(
     {
@@ -495,3 +496,59 @@ def ref_assemble_scans_ts(nodes, node_ts, resets=None, max_nodes: int = 8192, ma
     k = h.ref_assemble_scans_ts(_ptr(nodes), nodes.shape[0], _ptr(resets), resets.shape[0], max_nodes, _ptr(out),
                                 max_nodes, _ptr(lens), max_scans, _ptr(node_ts), _ptr(sts))
     return out, lens, k, sts
+
+
+# ---- the reference's real RPlidarNode::publish_scan (compiled against the ROS API stubs) ----------------------
+_node = None
+
+
+def have_ref_node() -> bool:
+    return os.path.exists(REF_NODE_SO)
+
+
+def _node_lib():
+    global _node
+    if _node is None:
+        _node = C.CDLL(REF_NODE_SO)
+        _node.ref_publish_scan.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_float, C.c_double,
+                                           C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_uint32)]
+        _node.ref_publish_scan.restype = C.c_int
+        _node.ref_pipeline_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_float, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        _node.ref_pipeline_batch.restype = C.c_double
+    return _node
+
+
+def ref_pipeline_batch(nodes: np.ndarray, counts: np.ndarray, params: ScanParams, threads=1, outputs=True):
+    """The reference's own per-scan path over a batch (grab_scan_data's ascend glue + RPlidarNode::publish_scan,
+    compiled from the reference sources): dict like pipeline_batch; with outputs=False only the wall time."""
+    assert nodes.dtype == NODE_DTYPE and nodes.ndim == 2 and nodes.flags.c_contiguous
+    n_scans, stride = nodes.shape
+    counts = np.ascontiguousarray(counts, dtype=np.uint32)
+    ranges = inten = beams = None
+    if outputs:
+        ranges = np.zeros((n_scans, stride), np.float32)
+        inten = np.zeros((n_scans, stride), np.float32)
+        beams = np.zeros(n_scans, np.uint32)
+    secs = _node_lib().ref_pipeline_batch(_ptr(nodes), _ptr(counts), n_scans, stride, int(params.is_new_protocol),
+                                          int(params.scan_processing), int(params.inverted), int(params.apply_ascend),
+                                          float(params.range_max), float(params.scan_duration),
+                                          _ptr(ranges) if outputs else None, _ptr(inten) if outputs else None,
+                                          _ptr(beams) if outputs else None, int(threads))
+    return dict(seconds=secs, ranges=ranges, intensities=inten, beam_counts=beams)
+
+
+def ref_publish(nodes: np.ndarray, params: ScanParams):
+    """RPlidarNode::publish_scan itself (reference src/rplidar_node.cpp:556-680) on one scan.
+    Returns (published, header7, ranges, intensities)."""
+    nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
+    n = nodes.shape[0]
+    ranges = np.full(max(n, 1), np.nan, np.float32)
+    inten = np.full(max(n, 1), np.nan, np.float32)
+    hdr = np.zeros(7, np.float32)
+    beams = C.c_uint32(0)
+    rc = _node_lib().ref_publish_scan(_ptr(nodes), n, int(params.is_new_protocol), int(params.scan_processing),
+                                int(params.inverted), float(params.range_max), float(params.scan_duration),
+                                _ptr(ranges), _ptr(inten), ranges.shape[0], _ptr(hdr), C.byref(beams))
+    assert rc >= 0, rc
+    return rc == 1, hdr, ranges[: beams.value].copy(), inten[: beams.value].copy()

@@ -11,9 +11,12 @@
 //       reference src/lidar_driver_wrapper.cpp:441-471
 //
 // PARITY PINNED: tests/test_oracle_vs_ref.py checks orc_ascend_scan against the
-// reference's own compiled ascendScanData (oracle/_ref) node-for-node, and
-// tests/test_oracle_golden.py checks everything against tests/golden/ fixtures captured
-// from the compiled reference.
+// reference's own compiled ascendScanData (oracle/_ref/libref_rplidar.so) node-for-node and
+// orc_publish_scan against the reference's REAL RPlidarNode::publish_scan, bit for bit
+// (oracle/_ref/libref_node.so: src/rplidar_node.cpp compiled in place against the ROS API stubs
+// in oracle/ros_stubs/, since rclcpp is not installed here); tests/test_oracle_golden.py checks
+// everything against tests/golden/ fixtures, which the same test file confirms to be what the
+// compiled reference produces.
 //
 // Build: g++ -std=c++17 -O2 -ffp-contract=off (x86-64 baseline: mul and add are rounded
 // separately, as in the reference build).

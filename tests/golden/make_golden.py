@@ -19,9 +19,9 @@ Fixtures:
     the reference's ascendScanData outputs
   laserscan_golden.npz
     for every variant x {is_new_protocol} x {Mode A, Mode B} x {inverted}:
-    ranges / intensities / header scalars produced by the oracle restatement of
-    publish_scan (rclcpp is absent, so the node itself cannot run here) applied to the
-    reference-ascended buffer and to the raw buffer.
+    ranges / intensities / header scalars of the reference's REAL RPlidarNode::publish_scan
+    (src/rplidar_node.cpp compiled in place against the ROS API stubs in oracle/ros_stubs/ ->
+    oracle/_ref/libref_node.so) applied to the reference-ascended buffer and to the raw buffer.
 """
 from __future__ import annotations
 
@@ -82,7 +82,7 @@ def edge_cases():
 
 def main():
     O.build(ref=True)
-    assert O.have_ref(), "oracle/_ref missing: run in the authoring container"
+    assert O.have_ref() and O.have_ref_node(), "oracle/_ref missing: run in the authoring container"
     assert O.ref().ref_sizeof_node() == 8
 
     raw = np.stack([O.ref_dummy_grab() for _ in range(16)])
@@ -114,14 +114,13 @@ def main():
                 for mode_a in (0, 1):
                     for inv in (0, 1):
                         prm = O.scan_params(newp, mode_a, inv, use_asc, 12.0, 0.1)
-                        hdr, r, it = O.publish(nodes, prm)
+                        published, h7, r, it = O.ref_publish(nodes, prm)  # the node's own publish_scan
+                        assert published
                         g[f"cfg_{idx}"] = np.array([vi, use_asc, newp, mode_a, inv], dtype=np.int32)
                         g[f"ranges_{idx}"] = r
                         g[f"intens_{idx}"] = it
-                        g[f"hdr_{idx}"] = np.array(
-                            [hdr.angle_min, hdr.angle_max, hdr.angle_increment, hdr.time_increment,
-                             hdr.scan_time, hdr.range_min, hdr.range_max], dtype=np.float32)
-                        g[f"beams_{idx}"] = np.uint32(hdr.beam_count)
+                        g[f"hdr_{idx}"] = h7.astype(np.float32)
+                        g[f"beams_{idx}"] = np.uint32(len(r))
                         idx += 1
     g["n"] = np.int32(idx)
     np.savez_compressed(os.path.join(OUT, "laserscan_golden.npz"), **g)
