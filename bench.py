@@ -198,6 +198,9 @@ def cpu_leg(O, nodes_host, counts, mode_a, threads, reps):
     total_pts = int(counts.sum())
     secs = 0.0
     use_ref = O.have_ref_node()
+    if use_ref:  # untimed: every worker allocates (and first touches) its buffers once
+        warm = min(nodes_host.shape[0], 2 * threads)
+        O.ref_pipeline_batch(nodes_host[:warm], counts[:warm], prm, threads=threads, outputs=False)
     for _ in range(reps):
         if use_ref:  # copies every scan into its own buffer first, as the SDK delivers it
             res = O.ref_pipeline_batch(nodes_host, counts, prm, threads=threads, outputs=False)

@@ -32,8 +32,9 @@ struct Worker {
   RPlidarNode node;
   std::unique_ptr<LidarDriverInterface> real{new RealLidarDriver()};
   std::unique_ptr<LidarDriverInterface> dummy{new DummyLidarDriver()};
-  sl::ILidarDriver* sdk = *sl::createLidarDriver();
   std::vector<sl_lidar_response_measurement_node_hq_t> raw, nodes;
+  // the SDK driver object the wrapper itself holds and calls ascendScanData on (lidar_driver_wrapper.cpp:78,329)
+  sl::ILidarDriver* sdk() { return static_cast<RealLidarDriver*>(real.get())->drv_; }
   void configure(int is_new_protocol, int scan_processing, int inverted, float max_range) {
     static_cast<RealLidarDriver*>(real.get())->profile_.protocol =
         is_new_protocol ? ProtocolType::NEW_TYPE : ProtocolType::OLD_TYPE;
@@ -68,11 +69,9 @@ double ref_pipeline_batch(const void* nodes_v, const uint32_t* counts, uint32_t 
   // on the heap lets the reference's loop scale across the host's cores as separate node processes would.
   mallopt(M_MMAP_THRESHOLD, 1 << 30);
   mallopt(M_TRIM_THRESHOLD, 1 << 30);
-  std::vector<std::unique_ptr<Worker>> workers;
-  for (int t = 0; t < threads; ++t) {
-    workers.emplace_back(new Worker());
-    workers.back()->configure(is_new_protocol, scan_processing, inverted, max_range);
-  }
+  static std::vector<std::unique_ptr<Worker>> workers;  // built once, reused by later calls
+  while (static_cast<int>(workers.size()) < threads) workers.emplace_back(new Worker());
+  for (int t = 0; t < threads; ++t) workers[t]->configure(is_new_protocol, scan_processing, inverted, max_range);
   std::atomic<uint32_t> next{0};
   const auto t0 = std::chrono::steady_clock::now();
   std::vector<std::thread> pool;
@@ -95,7 +94,7 @@ double ref_pipeline_batch(const void* nodes_v, const uint32_t* counts, uint32_t 
         const uint32_t n = counts[s];
         if (beams) beams[s] = 0;
         w.raw.assign(all + static_cast<size_t>(s) * stride, all + static_cast<size_t>(s) * stride + n);
-        if (apply_ascend) w.sdk->ascendScanData(w.raw.data(), n);
+        if (apply_ascend) w.sdk()->ascendScanData(w.raw.data(), n);
         w.nodes.assign(w.raw.begin(), w.raw.begin() + n);
         w.node.publish_scan(w.nodes, rclcpp::Time(0), scan_duration);
       }
