@@ -61,13 +61,11 @@ def parse():
     ap.add_argument("--format", default="0x85",
                     help="decode workload: SDK answer type (0x81 standard nodes, 0x82 express, 0x83 HQ, 0x84 ultra, "
                          "0x85 dense, 0x86 ultra-dense)")
-    ap.add_argument("--push-gather", action="store_true",
-                    help="cloud workload: fuse + all-gather in one kernel over NVLink peer memory "
-                         "(rpl_cloud_fuse_push_dev) instead of rpl_cloud_fuse_dev + NCCL all_gather")
     ap.add_argument("--sor", type=int, default=0, help="cloud workload: SOR k (0 = off)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-cloud", action="store_true", help="skip the PointCloud2 + exchange leg (extra.cloud)")
     return ap.parse_args()
 
 
@@ -75,6 +73,94 @@ def workload_name(args):
     return (f"S2 DenseBoost {args.nodes} nodes/scan x {args.scans} scans per GPU, synthetic variant "
             f"{args.variant} (tie-free rotated revolution, 5% unmeasured), LaserScan Mode "
             f"{'A' if args.mode == 'a' else 'B'}, angle_compensate on")
+
+
+def effective_cores():
+    """(usable host threads, how it was derived): CPU affinity of this process capped by the cgroup CPU quota --
+    os.cpu_count() reports the machine, not the lease."""
+    aff = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota, src = None, None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:  # cgroup v2
+            q, per = f.read().split()[:2]
+        if q != "max":
+            quota, src = int(q) / int(per), "cgroup v2 cpu.max"
+    except Exception:
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:
+                q = int(f.read())
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                per = int(f.read())
+            if q > 0:
+                quota, src = q / per, "cgroup v1 cfs quota"
+        except Exception:
+            pass
+    n = aff
+    how = f"sched_getaffinity={aff}, os.cpu_count()={os.cpu_count()}"
+    if quota is not None:
+        n = max(1, min(aff, int(quota + 0.999)))
+        how += f", {src}={quota:.2f} CPUs"
+    else:
+        how += ", no cgroup CPU quota"
+    return n, how
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def numa_pin(dev_index):
+    """Bind this process (and so the pinned host buffers it allocates from now on: first touch, local policy) to the
+    CPUs of the NUMA node the GPU hangs off.  Returns a dict for the report; never raises.  Without it the ranks of
+    one socket's GPUs stream their pinned buffers across the inter-socket link (SCALE_r01: e2e efficiency 0.54)."""
+    info = {"pinned": False}
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(dev_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read())
+        info.update({"pci": bdf, "numa_node": node})
+        if node < 0:
+            info["note"] = "platform reports no NUMA node for this GPU"
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        before = os.sched_getaffinity(0)
+        want = cpus & before
+        if not want:
+            info["note"] = "no allowed CPU on the GPU's NUMA node"
+            return info
+        os.sched_setaffinity(0, want)
+        info.update({"pinned": True, "cpus": len(want), "cpus_before": len(before)})
+        info["_before"] = before
+    except Exception as e:  # pragma: no cover - depends on the host
+        info["note"] = f"not pinned: {e!r}"
+    return info
+
+
+def numa_unpin(info):
+    before = info.pop("_before", None)
+    if before:
+        try:
+            os.sched_setaffinity(0, before)
+        except Exception:
+            pass
+
+
+def bench_config(args, world):
+    """The `config` object -- the same keys and values in both arms (repo and --impl reference; the reference arm's
+    bounded per-step sample is described in its cpu_baseline.sample, not here)."""
+    return {"workload": workload_name(args), "scans_per_gpu": args.scans, "nodes_per_scan": args.nodes,
+            "parallelism": f"{world} x independent stream shards (no data-path collective on the LaserScan path)",
+            "l2": "inputs 1.07 GB + outputs 1.07 GB per step exceed the 126 MB L2; no flush needed"}
 
 
 def measured_peak():
@@ -156,6 +242,21 @@ class ClockSampler:
     def window(self, t0, t1, name):
         self.windows.append((t0, t1, name))
 
+    def summary_for(self, t0, t1):
+        """Clocks over one window only (the per-leg `clocks` objects)."""
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML unavailable"}
+        w = [x for x in self.samples if t0 <= x[0] <= t1]
+        if not w:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0,
+                    "note": "window shorter than the 2 ms sampling period"}
+        mask = 0
+        for x in w:
+            mask |= x[2]
+        return {"sm_mhz": statistics.median([x[1] for x in w]), "sm_max_mhz": self.max_mhz,
+                "reasons": [v for k, v in self.REASONS.items() if mask & k], "samples": len(w),
+                "power_w_max": max(x[3] for x in w)}
+
     def summary(self):
         if not self.ok:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML unavailable"}
@@ -182,6 +283,19 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU loop on the host cores
 # ------------------------------------------------------------------------------------------------
+def start_sampler(dev, local_rank):
+    import torch
+
+    uuid = None
+    try:
+        uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        pass
+    sp = ClockSampler(uuid, local_rank)
+    sp.start()
+    return sp
+
+
 def cpu_kind(O):
     """("reference", text) when the reference's own code is available as oracle/_ref/libref_node.so (built in the
     authoring container from /root/reference: the SDK's ascendScanData + the node's real publish_scan, the latter
@@ -217,7 +331,7 @@ def run_reference(args, rank):
     from oracle import pyoracle as O
 
     O.build(ref=False)
-    cores = os.cpu_count() or 1
+    cores, cores_how = effective_cores()
     mode_a = 1 if args.mode == "a" else 0
     # size the per-step sample: as much of the bench batch as fits ~90 s for the whole run, and never
     # so small that it sits in the CPUs' caches (the GPU arm streams a fresh 1 GB batch from host
@@ -248,9 +362,9 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "scans_per_step": sample_scans, "nodes_per_scan": args.nodes},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
-                         "value_1thread": one},
+        "config": bench_config(args, max(args.gpus, 1)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "cores_how": cores_how, "kind": kind,
+                         "sample": sample, "value_1thread": one},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -270,6 +384,7 @@ def run_b200(args, rank, local_rank, world):
         raise SystemExit("bench.py needs a CUDA device: the CUDA library is the only implementation of this path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = numa_pin(local_rank)  # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -351,10 +466,11 @@ def run_b200(args, rank, local_rank, world):
     peak, peak_src = measured_peak()
     alg_bytes = BYTES_PER_NODE_LASERSCAN * pts_step
     achieved = alg_bytes / (fast_ms * 1e-3) / 1e9
+    # DRAM bytes per launch from the committed ncu capture of THIS shape and mode (null when none exists)
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(f"scan_tma_kernel.mode_{args.mode}")
+            traffic = json.load(f).get(f"scan.mode_{args.mode}.{S}x{N}")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "scan_tma_kernel<Mode %s> (TMA-ring fast kernel, scan_tma.cu)" % args.mode.upper(),
@@ -454,8 +570,19 @@ def run_b200(args, rank, local_rank, world):
                "steps": ke, "ms_per_step": dt / ke * 1e3, "api": "rpl_scan_batch (pinned host buffers)",
                "matches_device_path": same, "beam_count_scan0": int(res["beam_counts"][0]),
                "link_h2d_gbs": pc[0], "link_d2h_gbs": pc[1]}
+    # ---- BASELINE configs[2]/[4]: PointCloud2 path + the one exchange, at this world size --------
+    if not args.no_cloud:
+        try:
+            extra["cloud"] = cloud_leg(args, ctx_factory=lambda mn, ms: R.Context(local_rank, mn, ms), rank=rank,
+                                       world=world, dev=dev, stream=stream, sampler=sampler,
+                                       steps=max(5, min(args.steps, 20)), barrier=barrier, max_over_ranks=max_over_ranks)
+        except Exception as e:  # the headline line must still be printed
+            import traceback
+
+            extra["cloud"] = {"error": repr(e), "trace": traceback.format_exc()[-1500:]}
     sampler.stop()
     clocks = sampler.summary()
+    numa_unpin(numa)  # the CPU baseline may use every core the lease has
 
     # ---- cpu baseline: rank 0, N=1 only -----------------------------------------------------------
     cpu = None
@@ -463,7 +590,7 @@ def run_b200(args, rank, local_rank, world):
         from oracle import pyoracle as O
 
         O.build(ref=False)
-        cores = os.cpu_count() or 1
+        cores, cores_how = effective_cores()
         if h_nodes is None:
             h_nodes = nodes.cpu().numpy().view(R.NODE_DTYPE).reshape(S, N)
         hc = np.full(S, N, np.uint32)
@@ -483,7 +610,7 @@ def run_b200(args, rank, local_rank, world):
             per_scan[str(nn)] = rr["seconds"] / 64 * 1e6
         extra["single_scan_latency_cpu_1thread_us"] = per_scan
         kind, what = cpu_kind(O)
-        cpu = {"value": v_all, "unit": UNIT, "cores": cores, "kind": kind,
+        cpu = {"value": v_all, "unit": UNIT, "cores": cores, "cores_how": cores_how, "kind": kind,
                "sample": (f"the bench batch itself, 2 passes x {S} scans x {N} nodes = {2 * S * N / 1e6:.0f} Mpoints "
                           f"({secs:.1f} s wall, {cores} worker threads, one scan per task); {what}"),
                "value_1thread": v_one, "sample_1thread": f"{sub} scans x {N} nodes"}
@@ -493,39 +620,36 @@ def run_b200(args, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "scans_per_gpu": S, "nodes_per_scan": N,
-                       "parallelism": f"{world} x independent stream shards (no data-path collective on the LaserScan path)",
-                       "l2": "inputs 1.07 GB + outputs 1.07 GB per step exceed the 126 MB L2; no flush needed"},
+            "config": bench_config(args, world),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "extra": extra,
         }
+        line["extra"]["numa"] = {k: v for k, v in numa.items() if not k.startswith("_")}
         print(json.dumps(line), flush=True)
-    if args.push_gather:
-        gather.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_cloud(args, rank, local_rank, world):
-    """PointCloud2 workload: 64 S3 streams per GPU (3200 nodes/scan, 256 scans each) ->
-    window + polar->xyz + 5 cm voxel grid per scan -> fused per-GPU cloud -> ONE all-gather."""
+CLOUD_STREAMS_PER_GPU, CLOUD_SCANS_PER_STREAM, CLOUD_NODES = 64, 256, 3200
+
+
+def cloud_leg(args, ctx_factory, rank, world, dev, stream, sampler, steps, barrier, max_over_ranks, sor=0):
+    """BASELINE configs[2] (N=1) / configs[4] (N>1): 64 synthetic S3 streams per GPU (256 revolutions x 3200 nodes
+    each) -> window + polar->xyz + 5 cm voxel grid (+ SOR) per revolution -> fused per-GPU cloud -> ONE all-gather
+    of the fused cloud, with both exchanges (NCCL all-gather, fused pack+push over NVLink peer memory).  Before
+    anything is timed the two exchanges must deliver identical bytes on every rank at this world size."""
     import torch
     import torch.distributed as dist
 
     import rplidar_ros2_driver_b200 as R
     from rplidar_ros2_driver_b200.multi_gpu import FusedCloudGather, PeerCloudGather, shard_streams
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    streams_total, scans_per_stream, N = 64 * world, 256, 3200
+    N = CLOUD_NODES
+    streams_total = CLOUD_STREAMS_PER_GPU * world
     mine = shard_streams(streams_total, world, rank)
-    S = len(mine) * scans_per_stream
-    ctx = R.Context(local_rank, N, S)
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
+    S = len(mine) * CLOUD_SCANS_PER_STREAM
+    ctx = ctx_factory(N, S)
     sp = stream.cuda_stream
     nodes = torch.empty((S, N, 8), dtype=torch.uint8, device=dev)
     counts = torch.empty(S, dtype=torch.int32, device=dev)
@@ -533,83 +657,210 @@ def run_cloud(args, rank, local_rank, world):
     pc = torch.empty(S, dtype=torch.int32, device=dev)
     offs = torch.empty(S, dtype=torch.int32, device=dev)
     total = torch.zeros(1, dtype=torch.int32, device=dev)
-    ctx.synth_batch_dev(mine.start * scans_per_stream, S, N, N, 4, nodes.data_ptr(), counts.data_ptr(), stream=sp)
-    prm = R.cloud_params(range_min=0.15, range_max=40.0, voxel_size=0.05, sor_k=args.sor, sor_alpha=1.0)
-    # capacity of the per-rank slot: measured once (voxelised cloud), padded
-    ctx.cloud_batch_dev(nodes.data_ptr(), counts.data_ptr(), S, N, prm, xyzi.data_ptr(), pc.data_ptr(), stream=sp)
+    ctx.synth_batch_dev(mine.start * CLOUD_SCANS_PER_STREAM, S, N, N, 4, nodes.data_ptr(), counts.data_ptr(), stream=sp)
+    prm = R.cloud_params(range_min=0.15, range_max=40.0, voxel_size=0.05, sor_k=sor, sor_alpha=1.0)
+
+    def compute():
+        ctx.cloud_batch_dev(nodes.data_ptr(), counts.data_ptr(), S, N, prm, xyzi.data_ptr(), pc.data_ptr(), stream=sp)
+
+    compute()
     torch.cuda.synchronize()
     kept = int(pc.sum().item())
-    cap = int(kept * 1.1) + 1024
-    fused = torch.zeros((cap, 4), dtype=torch.float32, device=dev)
+    cap = kept + 1024  # the synthetic batch is the same every step: the slot holds exactly this rank's cloud
     if world > 1:  # one slot size for every rank
         cap_t = torch.tensor([cap], device=dev)
         dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)
         cap = int(cap_t.item())
-        fused = torch.zeros((cap, 4), dtype=torch.float32, device=dev)
-    gather = PeerCloudGather(ctx, cap, dev) if args.push_gather else FusedCloudGather(cap, dev)
+    fused = torch.zeros((cap, 4), dtype=torch.float32, device=dev)
+    g_nccl = FusedCloudGather(cap, dev)
+    g_push = PeerCloudGather(ctx, cap, dev)
 
-    def step():
-        ctx.cloud_batch_dev(nodes.data_ptr(), counts.data_ptr(), S, N, prm, xyzi.data_ptr(), pc.data_ptr(), stream=sp)
-        if args.push_gather:
-            gather.push(xyzi.data_ptr(), pc.data_ptr(), S, N, offs.data_ptr(), total.data_ptr(), stream=sp)
-        else:
-            ctx.cloud_fuse_dev(xyzi.data_ptr(), pc.data_ptr(), S, N, fused.data_ptr(), offs.data_ptr(), total.data_ptr(), stream=sp)
-            gather(fused, total)
+    def exch_nccl():
+        ctx.cloud_fuse_dev(xyzi.data_ptr(), pc.data_ptr(), S, N, fused.data_ptr(), offs.data_ptr(), total.data_ptr(), stream=sp)
+        g_nccl(fused, total)
 
-    W = max(args.warmup, 3)
-    for _ in range(W):
-        step()
+    last_half = [0]
+
+    def exch_push():
+        last_half[0] = g_push.push(xyzi.data_ptr(), pc.data_ptr(), S, N, offs.data_ptr(), total.data_ptr(), stream=sp)
+
+    # ---- on-box parity of the two exchanges at THIS world size (driver-visible evidence) --------------
+    compute()
+    exch_nccl()
+    exch_push()
     torch.cuda.synchronize()
-    ctx.profile_read()
-    ctx.profile(True)
+    c_n = g_nccl.counts.clone()
+    c_p = g_push.counts(last_half[0]).clone()
+    a = g_nccl.compact()
+    gp = g_push.gathered(last_half[0])
+    b = torch.cat([gp[r, : int(c_p[r])] for r in range(world)], dim=0)
+    own_lo = int(c_n[:rank].sum().item())
+    ok = bool((c_n == c_p).all().item()) and a.shape == b.shape and bool(torch.equal(a.view(torch.int32), b.view(torch.int32)))
+    ok = ok and int(c_n[rank]) == int(total.item()) and bool(
+        torch.equal(a[own_lo: own_lo + int(total.item())].view(torch.int32), fused[: int(total.item())].view(torch.int32)))
+    ok_t = torch.tensor([1 if ok else 0], device=dev)
+    sums = torch.tensor([float(a.double().sum().item())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+        smin, smax = sums.clone(), sums.clone()
+        dist.all_reduce(smin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(smax, op=dist.ReduceOp.MAX)
+        ok_t *= int(float(smin.item()) == float(smax.item()))  # every rank holds the same gathered cloud
+    if int(ok_t.item()) != 1:
+        raise RuntimeError("fused push and NCCL all-gather disagree (or ranks hold different clouds)")
+    points_all = int(c_n.sum().item())
+
+    def timed(fn, K, W=3):
+        for _ in range(W):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(K):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / K, (t0, t1)
+
     l0 = ctx.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    prof = ctx.profile_read()
+    ms_compute, w_c = timed(compute, steps)
+    res = {}
+    win = [w_c]
+    for name, ex in (("nccl", exch_nccl), ("push", exch_push)):
+        ms_ex, w1 = timed(ex, steps)
+
+        def full(ex=ex):
+            compute()
+            ex()
+
+        ms_step, w2 = timed(full, steps)
+        win += [w1, w2]
+        recv_real = (points_all - int(c_n[rank])) * 16
+        recv_moved = (world - 1) * cap * 16 if name == "nccl" else recv_real
+        res[name] = {"ms_per_step": ms_step, "exchange_ms": ms_ex,
+                     "mpoints_s": world * S * N / (ms_step * 1e-3) / 1e6,
+                     "payload_bytes_received_per_rank": recv_moved, "real_bytes_received_per_rank": recv_real,
+                     "exchange_gbs_in_per_rank": (recv_moved / (ms_ex * 1e-3) / 1e9) if world > 1 else None}
     launches = ctx.launch_count - l0
+    t_lo, t_hi = min(w[0] for w in win), max(w[1] for w in win)
+    sampler.window(t_lo, t_hi, "cloud leg")
     pts_step = S * N
-    rho_voxel = kept / pts_step
     peak, peak_src = measured_peak()
-    fast_ms = prof[0] / max(prof[1], 1)
-    window_kept = 0.95  # synthetic variant 4: 5% unmeasured, window keeps the rest
-    alg = (8 + 16 * window_kept) * pts_step
+    rho = kept / pts_step
+    alg = (8 + 16 * rho) * pts_step
+    best = min(res, key=lambda k: res[k]["ms_per_step"])
+    out = {
+        "workload": (f"PointCloud2 path: {CLOUD_STREAMS_PER_GPU} S3 streams per GPU x {CLOUD_SCANS_PER_STREAM} scans x {N} nodes "
+                     f"(synthetic variant 4 'room'), window [0.15, 40] m, polar->xyz, 5 cm voxel grid"
+                     f"{', SOR k=%d' % sor if sor else ''}, fused per-GPU cloud, one all-gather per step"),
+        "n_gpus": world, "streams_total": streams_total, "steps": steps,
+        "impl": best, "ms_per_step": res[best]["ms_per_step"], "mpoints_s": res[best]["mpoints_s"],
+        "exchange_ms": res[best]["exchange_ms"], "payload_bytes": res[best]["payload_bytes_received_per_rank"],
+        "compute_ms": ms_compute, "compute_mpoints_s_per_gpu": pts_step / (ms_compute * 1e-3) / 1e6,
+        "rho_after_voxel": rho, "points_out_per_gpu": kept, "points_gathered": points_all,
+        "exchanges_bit_identical": True, "by_exchange": res,
+        "roofline": {"bound": "hbm", "kernels": "scan kernel<cloud> + voxel (+ SOR) post passes",
+                     "algorithmic_bytes_per_step": alg, "bytes_per_point": f"8 B read + 16 B x rho ({rho:.3f}) written",
+                     "achieved": alg / (ms_compute * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg / (ms_compute * 1e-3) / 1e9 / peak, "peak_source": peak_src},
+        "nvlink": ({"limiting_collective": "all-gather of the fused cloud (every rank receives every other rank's points)",
+                    "gbs_in_per_rank": res[best]["exchange_gbs_in_per_rank"], "peak_gbs_per_direction": 900.0}
+                   if world > 1 else None),
+        "gpu_launches": launches, "clocks": sampler.summary_for(t_lo, t_hi),
+    }
+    g_push.close()
+    ctx.close()
+    return out
+
+
+def cloud_cpu_baseline(sor):
+    """The cloud definition (oracle/cloud_oracle.cpp, a self-authored port: the reference has no PointCloud2 code)
+    on the host cores: a bounded sample of the same synthetic streams, one revolution per task."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import pyoracle as O
+
+    O.build(ref=False)
+    cores, cores_how = effective_cores()
+    n_scans = max(256, 8 * cores)
+    nodes = O.synth_batch(0, n_scans, CLOUD_NODES, 4)
+    prm = O.cloud_params(range_min=0.15, range_max=40.0, voxel_size=0.05, sor_k=sor, sor_alpha=1.0)
+    t0 = time.perf_counter()
+    for i in range(16):
+        O.cloud(nodes[i], prm)
+    one = 16 * CLOUD_NODES / (time.perf_counter() - t0) / 1e6
+    with ThreadPoolExecutor(cores) as ex:
+        list(ex.map(lambda i: O.cloud(nodes[i], prm), range(min(n_scans, 2 * cores))))  # warm
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 8.0:
+            list(ex.map(lambda i: O.cloud(nodes[i], prm), range(n_scans)))
+            reps += 1
+        dt = time.perf_counter() - t0
+    return {"value": reps * n_scans * CLOUD_NODES / dt / 1e6, "unit": UNIT, "cores": cores, "cores_how": cores_how,
+            "kind": "port", "value_1thread": one,
+            "sample": f"{reps} x {n_scans} revolutions x {CLOUD_NODES} nodes through oracle/cloud_oracle.cpp "
+                      f"(window, sort, polar->xyz, voxel{', SOR' if sor else ''}), one revolution per task, {cores} threads"}
+
+
+def run_cloud(args, rank, local_rank, world):
+    """`--workload cloud [--sor k]`: the PointCloud2 leg on its own JSON line (the default run carries the same
+    object under extra.cloud)."""
+    import torch
+    import torch.distributed as dist
+
+    import rplidar_ros2_driver_b200 as R
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    numa = numa_pin(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    uuid = None
+    try:
+        uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        pass
+    sampler = ClockSampler(uuid, local_rank)
+    sampler.start()
+    c = cloud_leg(args, lambda mn, ms: R.Context(local_rank, mn, ms), rank, world, dev, stream, sampler, args.steps,
+                  barrier, max_over_ranks, sor=args.sor)
+    sampler.stop()
+    numa_unpin(numa)
+    cpu = cloud_cpu_baseline(args.sor) if (rank == 0 and world == 1 and not args.no_cpu) else None
     if rank == 0:
         line = {
-            "metric": METRIC, "value": world * pts_step * args.steps / (ms * 1e-3) / 1e6, "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": (f"PointCloud2 path: {64} S3 streams per GPU x {scans_per_stream} scans x {N} nodes "
-                                    f"(synthetic variant 4 'room'), window [0.15, 40] m, polar->xyz, 5 cm voxel grid"
-                                    f"{', SOR k=%d' % args.sor if args.sor else ''}, fused per-GPU cloud, one all-gather"),
-                       "streams_total": streams_total, "parallelism": (f"{world} ranks x 64 streams, fuse + all-gather in one kernel over NVLink peer memory"
-                                       if args.push_gather else f"{world} ranks x 64 streams, 1 all_gather_into_tensor/step"),
-                       "l2": f"inputs {pts_step * 8 / 1e6:.0f} MB + outputs {pts_step * 16 / 1e6:.0f} MB per step exceed the 126 MB L2"},
-            "roofline": {"bound": "hbm", "kernel": "scan_tma_kernel<cloud>", "achieved": alg / (fast_ms * 1e-3) / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": alg / (fast_ms * 1e-3) / 1e9 / peak, "traffic": None,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": fast_ms,
-                         "bytes_per_node": "8 B read + 16 B x 0.95 kept (window) written by the scan kernel"},
-            "cpu_baseline": None, "e2e": None, "gpu_launches": launches,
-            "extra": {"rho_after_voxel": rho_voxel, "points_out_per_gpu": kept,
-                      "allgather_payload_bytes": gather.payload_bytes(), "post_kernels": "voxel" + ("+sor" if args.sor else "")},
+            "metric": METRIC, "value": c["mpoints_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": 3, "ms_per_step": c["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": c["workload"], "streams_total": c["streams_total"],
+                       "parallelism": f"{world} ranks x {CLOUD_STREAMS_PER_GPU} streams, one all-gather of the fused cloud per step ({c['impl']})",
+                       "l2": "inputs 419 MB + outputs per step exceed the 126 MB L2"},
+            "roofline": dict(c["roofline"], traffic=None), "cpu_baseline": cpu, "e2e": None,
+            "gpu_launches": c["gpu_launches"], "clocks": c["clocks"],
+            "extra": {k: v for k, v in c.items() if k not in ("roofline", "clocks", "workload")},
         }
+        line["extra"]["numa"] = {k: v for k, v in numa.items() if not k.startswith("_")}
         print(json.dumps(line), flush=True)
-    if args.push_gather:
-        gather.close()
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -695,17 +946,22 @@ def run_decode(args, rank, local_rank, world):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = ctx.launch_count
+    sampler = start_sampler(dev, local_rank)
+    tw0 = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
         step()
     e1.record(stream)
     torch.cuda.synchronize()
+    tw1 = time.perf_counter()
+    sampler.stop()
+    clocks = sampler.summary_for(tw0, tw1)
     ms = e0.elapsed_time(e1) / args.steps
     pts = int(ncount.sum().item())
     peak, peak_src = measured_peak()
     alg = n_streams * n_caps * 84 + pts * 8
     # CPU: the oracle's decode loop, one stream per task
-    cores = os.cpu_count() or 1
+    cores, _cores_how = effective_cores()
     t0 = time.perf_counter()
     O.dense_decode(host[0], 31, 0)
     t_one = time.perf_counter() - t0
@@ -729,7 +985,7 @@ def run_decode(args, rank, local_rank, world):
                          "sample": f"{reps} streams x {n_caps} capsules through the oracle port of "
                                    f"UnpackerHandler_DenseCapsuleNode (validated against the compiled SDK unpacker)",
                          "value_1thread": pts_stream / t_one / 1e6},
-        "e2e": None, "gpu_launches": ctx.launch_count - l0,
+        "e2e": None, "gpu_launches": ctx.launch_count - l0, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
     ctx.close()
@@ -817,16 +1073,21 @@ def run_decode_format(args, rank, local_rank, world):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = ctx.launch_count
+    sampler = start_sampler(dev, local_rank)
+    tw0 = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
         step()
     e1.record(stream)
     torch.cuda.synchronize()
+    tw1 = time.perf_counter()
+    sampler.stop()
+    clocks = sampler.summary_for(tw0, tw1)
     ms = e0.elapsed_time(e1) / args.steps
     pts = int(ncount.sum().item())
     peak, peak_src = measured_peak()
     alg = wire_bytes + pts * 8
-    cores = os.cpu_count() or 1
+    cores, _cores_how = effective_cores()
     t0 = time.perf_counter()
     cpu_one(0)
     t_one = time.perf_counter() - t0
@@ -849,7 +1110,7 @@ def run_decode_format(args, rank, local_rank, world):
         "cpu_baseline": {"value": reps * pts_stream / t_all / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{reps} streams through the oracle port (validated against the compiled SDK "
                                    f"unpacker)", "value_1thread": pts_stream / t_one / 1e6},
-        "e2e": None, "gpu_launches": ctx.launch_count - l0,
+        "e2e": None, "gpu_launches": ctx.launch_count - l0, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
     ctx.close()
@@ -925,11 +1186,16 @@ def run_chain(args, rank, local_rank, world):
     parts = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = ctx.launch_count
+    sampler = start_sampler(dev, local_rank)
+    tw0 = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
         step()
     e1.record(stream)
     torch.cuda.synchronize()
+    tw1 = time.perf_counter()
+    sampler.stop()
+    clocks = sampler.summary_for(tw0, tw1)
     ms = e0.elapsed_time(e1) / args.steps
     pts = int(slen.sum().item())      # nodes that reached a published scan
     n_scans = int(sps.sum().item())
@@ -946,7 +1212,7 @@ def run_chain(args, rank, local_rank, world):
         "roofline": {"bound": "hbm", "kernel": "decode_dense + assemble + scan", "achieved": alg / (ms * 1e-3) / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg},
-        "cpu_baseline": None, "e2e": None, "gpu_launches": ctx.launch_count - l0,
+        "cpu_baseline": None, "e2e": None, "gpu_launches": ctx.launch_count - l0, "clocks": clocks,
         "extra": {"ms_decode": parts[0], "ms_assemble": parts[1], "ms_scan": parts[2], "scans_published": n_scans,
                   "points_decoded": int(ncount.sum().item())},
     }

@@ -217,8 +217,12 @@ __global__ void __launch_bounds__(AT) assemble_kernel(AssembleArgs a) {
       const uint32_t cnt = min(d.y, a.max_nodes);
       uint2* o = out + (size_t)k * a.scan_stride;
       const uint2* src = nodes + d.x;
+      // a scan that hit the cap kept overwriting its last entry: its last slot takes the scan's last node.
+      // The copy leaves that slot alone (one writer per output element, no ordering between threads needed).
+      const bool capped = d.y > cnt;
+      const uint32_t ncopy = capped ? cnt - 1 : cnt;
       uint32_t q = tid;
-      for (; q + 3 * AT < cnt; q += 4 * AT) {  // four independent loads in flight per thread
+      for (; q + 3 * AT < ncopy; q += 4 * AT) {  // four independent loads in flight per thread
         const uint2 v0 = ld_hint_v2(src + q, l2_policy_evict_first()), v1 = ld_hint_v2(src + q + AT, l2_policy_evict_first());
         const uint2 v2 = ld_hint_v2(src + q + 2 * AT, l2_policy_evict_first()), v3 = ld_hint_v2(src + q + 3 * AT, l2_policy_evict_first());
         o[q] = v0;
@@ -226,10 +230,9 @@ __global__ void __launch_bounds__(AT) assemble_kernel(AssembleArgs a) {
         o[q + 2 * AT] = v2;
         o[q + 3 * AT] = v3;
       }
-      for (; q < cnt; q += AT) o[q] = src[q];
-      // a scan that hit the cap kept overwriting its last entry: it ends with the scan's last node
+      for (; q < ncopy; q += AT) o[q] = src[q];
       if (tid == 0) {
-        if (d.y > cnt) o[cnt - 1] = src[d.y - 1];
+        if (capped) o[cnt - 1] = src[d.y - 1];
         out_len[k] = cnt;
         // the scan-start node's stamp (ScanDataHolder::_scan_begin_timestamp_uS, sl_lidar_driver.cpp:293)
         if (a.scan_begin_ts_us)

@@ -430,7 +430,12 @@ rpl_result rpl_scan_batch_dev(rpl_ctx* c, const rpl_node_hq* nodes, const uint32
                               uint32_t* path, void* stream) {
   if (!c) return RPL_RESULT_INVALID_DATA;
   RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
-  if (stride > c->max_nodes && false) return RPL_RESULT_INVALID_DATA;
+  if (n_scans != 0 && stride == 0) {
+    c->err = "stride == 0";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  // counts[] live on the device: a scan with counts[s] > stride or > the context's max_nodes is reported
+  // through status[s] = RPL_RESULT_INVALID_DATA by the kernels (nothing else is written for it)
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
   return enqueue_scan(c, c->lane[0], nodes, counts, n_scans, stride, params, nodes_out, ranges,
                       intensities, beam_counts, angle_increment, status, path, st);
@@ -475,10 +480,8 @@ rpl_result rpl_scan_batch(rpl_ctx* c, const rpl_node_hq* nodes, const uint32_t* 
   uint32_t* hs_inc = c->h_small + c->max_scans;
   uint32_t* hs_status = c->h_small + 2 * (size_t)c->max_scans;
   uint32_t* hs_path = c->h_small + 3 * (size_t)c->max_scans;
-  uint32_t ci = 0;
-  for (uint32_t s0 = 0; s0 < n_scans; s0 += chunk, ++ci) {
-    Lane& l = c->lane[ci % kLanes];
-    const uint32_t ns = std::min(chunk, n_scans - s0);
+  // one chunk through one lane; any failure leaves the loop with copies possibly still in flight
+  auto run_chunk = [&](Lane& l, uint32_t s0, uint32_t ns) -> rpl_result {
     const size_t off = (size_t)s0 * stride, cnt = (size_t)ns * stride;
     // the lane's previous chunk (2 chunks ago) must have left its staging buffers
     RPL_CUDA(c, cudaStreamSynchronize(l.stream), RPL_RESULT_OPERATION_FAIL);
@@ -486,6 +489,12 @@ rpl_result rpl_scan_batch(rpl_ctx* c, const rpl_node_hq* nodes, const uint32_t* 
              RPL_RESULT_OPERATION_FAIL);
     RPL_CUDA(c, cudaMemcpyAsync(l.d_counts, c->h_counts + s0, ns * sizeof(uint32_t), h2d, l.stream),
              RPL_RESULT_OPERATION_FAIL);
+    // The kernels write only the first counts[s] nodes of a scan they ascend (nothing for an empty or
+    // unmeasured scan: the reference leaves those buffers untouched).  The whole [ns][stride] region goes
+    // back to the caller, so it starts out as the caller's own bytes, not as leftovers of an earlier chunk.
+    if (nodes_out && params->apply_ascend)
+      RPL_CUDA(c, cudaMemcpyAsync(l.d_nodes_out, l.d_nodes, cnt * sizeof(rpl_node_hq), cudaMemcpyDeviceToDevice, l.stream),
+               RPL_RESULT_OPERATION_FAIL);
     rpl_result r = enqueue_scan(c, l, reinterpret_cast<rpl_node_hq*>(l.d_nodes), l.d_counts, ns, stride,
                                 params, nodes_out ? reinterpret_cast<rpl_node_hq*>(l.d_nodes_out) : nullptr,
                                 want_scan ? l.d_ranges : nullptr, want_scan ? l.d_intens : nullptr,
@@ -512,6 +521,18 @@ rpl_result rpl_scan_batch(rpl_ctx* c, const rpl_node_hq* nodes, const uint32_t* 
     if (path)
       RPL_CUDA(c, cudaMemcpyAsync(hs_path + s0, l.d_path, ns * sizeof(uint32_t), d2h, l.stream),
                RPL_RESULT_OPERATION_FAIL);
+    return RPL_RESULT_OK;
+  };
+  uint32_t ci = 0;
+  for (uint32_t s0 = 0; s0 < n_scans; s0 += chunk, ++ci) {
+    const rpl_result r = run_chunk(c->lane[ci % kLanes], s0, std::min(chunk, n_scans - s0));
+    if (r != RPL_RESULT_OK) {
+      // nothing may still be writing into the caller's buffers when the error is reported
+      const std::string why = c->err;
+      for (int i = 0; i < kLanes; ++i) cudaStreamSynchronize(c->lane[i].stream);
+      c->err = why;
+      return r;
+    }
   }
   const rpl_result rs = rpl_ctx_synchronize(c);
   if (rs != RPL_RESULT_OK) return rs;
@@ -1021,8 +1042,7 @@ rpl_result rpl_assemble_scans_dev(rpl_ctx* c, const rpl_node_hq* nodes, const ui
   const size_t need_rp = (size_t)n_streams * std::max<uint32_t>(stride_capsules, 1u);
   const size_t need_desc = (size_t)n_streams * max_scans;
   if (need_rp > c->reset_prefix_cap) {
-    cudaFree(c->d_state_tmp);
-  cudaFree(c->d_reset_prefix);
+    cudaFree(c->d_reset_prefix);
     c->d_reset_prefix = nullptr;
     RPL_CUDA(c, dev_alloc(&c->d_reset_prefix, need_rp), RPL_RESULT_INSUFFICIENT_MEMORY);
     c->reset_prefix_cap = need_rp;
