@@ -90,6 +90,8 @@ typedef struct rpl_scan_params {
 #define RPL_FLAG_FORCE_GENERAL 1u /* route every scan through the general (radix-sort) kernel */
 #define RPL_FLAG_NO_TMA 2u        /* use the register-streamed fast kernel (scan_fast.cu) even when the
                                      TMA-ring kernel (scan_tma.cu) applies; for A/B measurements */
+#define RPL_FLAG_NO_SMALL 4u      /* do not use the shared-memory-resident kernels (scan_small.cu) for
+                                     revolutions of at most 4096 nodes; for A/B measurements */
 
 /* per-scan path report (optional output) */
 #define RPL_PATH_FAST 0u    /* tie-free scan: bitmap-rank kernel */
@@ -103,8 +105,11 @@ typedef struct rpl_cloud_params {
   uint32_t sor_k;      /* 0 disables statistical outlier removal; <= 32 */
   float sor_alpha;
   uint8_t is_new_protocol;
-  uint8_t pad[3];
+  uint8_t flags;       /* RPL_CLOUD_* */
+  uint8_t pad[2];
 } rpl_cloud_params;
+#define RPL_CLOUD_NO_FUSED 1u /* run SOR / voxel grid as separate passes even where the shared-memory kernel
+                                 could fuse them (A/B measurements, second implementation for the tests) */
 
 typedef struct rpl_ctx rpl_ctx;
 
@@ -208,6 +213,41 @@ rpl_result rpl_peer_free(rpl_ctx* ctx, void* dev_ptr);
 rpl_result rpl_cloud_fuse_push_dev(rpl_ctx* ctx, const float* xyzi, const uint32_t* point_counts, uint32_t n_scans,
                                    uint32_t stride, void* const* peer_bases, uint32_t world, uint32_t rank,
                                    uint32_t slot_points, uint32_t* offsets, uint32_t* total, void* stream);
+
+/* ---- the exchange as a host-side C++ object (one process per GPU, ONE all-gather of the fused
+ * cloud per step over NVLink, overlapped with the next batch's kernels) ------------------------------------
+ * The reference has no analogue (it publishes one scan: src/rplidar_node.cpp:679); parity = every rank ends up
+ * with the concatenation, in rank order, of what the ranks produce on their own.  NCCL is loaded at run time
+ * (dlopen libnccl.so.2); the embedding process only carries the 128-byte unique id from rank 0 to the others.
+ * rpl_exchange_create is collective (every rank, same id / world / slot_points); it creates the communicator
+ * (ncclCommInitRank), a high-priority exchange stream, two gather buffers of `world` slots
+ * [16-byte header: uint32 point count][slot_points x 16 B] and -- unless RPL_EXCHANGE_NO_PEER_MAP -- maps every
+ * peer's buffers (CUDA IPC handles all-gathered through the communicator).
+ * rpl_exchange_allgather packs the per-scan clouds of rpl_cloud_batch_dev (xyzi [n_scans][stride][4],
+ * point_counts) into this rank's slot on `stream` and starts the transfer on the exchange stream:
+ *   RPL_EXCHANGE_NCCL  one in-place ncclAllGather of the slot;
+ *   RPL_EXCHANGE_COPY  world-1 peer-to-peer copies of the slot by the copy engines (no SM), then a 4-byte
+ *                      all-reduce as the barrier.
+ * `stream` is NOT made to wait for the transfer: the caller's next batch overlaps it.  *buffer_index (0/1) names
+ * the buffer this step fills; a consumer calls rpl_exchange_wait(index, its stream) before reading the slots
+ * (rpl_exchange_slot) and rpl_exchange_release(index, its stream) after its last read -- the exchange that reuses
+ * the buffer two steps later waits for that.  A slot whose count exceeds slot_points overflowed (points dropped). */
+#define RPL_EXCHANGE_ID_BYTES 128u
+#define RPL_EXCHANGE_NCCL 0u
+#define RPL_EXCHANGE_COPY 1u
+#define RPL_EXCHANGE_NO_PEER_MAP 1u /* create flag: NCCL mode only, no CUDA IPC mappings */
+typedef struct rpl_exchange rpl_exchange;
+rpl_result rpl_exchange_unique_id(uint8_t* id_out /* [128], call on rank 0 */);
+rpl_result rpl_exchange_create(rpl_ctx* ctx, const uint8_t* id /* [128]; may be NULL when world == 1 */, uint32_t world,
+                               uint32_t rank, uint32_t slot_points, uint32_t flags, rpl_exchange** out);
+void rpl_exchange_destroy(rpl_exchange* ex); /* collective when world > 1 */
+rpl_result rpl_exchange_allgather(rpl_exchange* ex, const float* xyzi, const uint32_t* point_counts, uint32_t n_scans,
+                                  uint32_t stride, uint32_t mode, void* stream, uint32_t* buffer_index);
+rpl_result rpl_exchange_wait(rpl_exchange* ex, uint32_t buffer_index, void* stream);
+rpl_result rpl_exchange_release(rpl_exchange* ex, uint32_t buffer_index, void* stream);
+rpl_result rpl_exchange_slot(rpl_exchange* ex, uint32_t buffer_index, uint32_t rank, const float** points,
+                             const uint32_t** count);
+rpl_result rpl_exchange_synchronize(rpl_exchange* ex);
 
 /* ---- dense-capsule decode (the step before the hot path) ------- */
 /* Replaces UnpackerHandler_DenseCapsuleNode (reference

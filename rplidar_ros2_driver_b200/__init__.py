@@ -8,6 +8,6 @@ frozenreboot/rplidar_ros2_driver behind a C-ABI (include/rpl_b200.h).
 There is no CPU implementation here: the oracle lives under /oracle and is test-only.
 """
 from .capi import (  # noqa: F401
-    NODE_DTYPE, Context, RplError, Timing, build, cloud_params, host_alloc, lib, scan_params,
-    FLAG_FORCE_GENERAL, FLAG_NO_TMA, PATH_FAST, PATH_GENERAL, RESULT_OK, RESULT_OPERATION_FAIL, RESULT_INVALID_DATA,
+    NODE_DTYPE, Context, Exchange, RplError, exchange_unique_id, EXCHANGE_NCCL, EXCHANGE_COPY, Timing, build, cloud_params, host_alloc, lib, scan_params,
+    FLAG_FORCE_GENERAL, FLAG_NO_TMA, FLAG_NO_SMALL, CLOUD_NO_FUSED, PATH_FAST, PATH_GENERAL, RESULT_OK, RESULT_OPERATION_FAIL, RESULT_INVALID_DATA,
 )

@@ -32,5 +32,5 @@ for p in "${pids[@]:-}"; do
   if [[ -n "$p" ]]; then wait "$p" || rc=1; fi
 done
 if [[ $rc -ne 0 ]]; then echo "compile failed" >&2; exit 1; fi
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -cudart shared -o "$OUT" "${objs[@]}"
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -cudart shared -o "$OUT" "${objs[@]}" -ldl
 echo "built $OUT"

@@ -23,6 +23,8 @@ RESULT_OPERATION_FAIL = 0x80008001
 RESULT_OPERATION_NOT_SUPPORT = 0x80008004
 FLAG_FORCE_GENERAL = 1
 FLAG_NO_TMA = 2
+FLAG_NO_SMALL = 4
+CLOUD_NO_FUSED = 1
 CAPSULE_OK, CAPSULE_SYNC, CAPSULE_EMIT, CAPSULE_DISCARD = 1, 2, 4, 8
 CAPSULE_CHECKSUM_ERR, CAPSULE_ENCODER_RESET_ERR, CAPSULE_BAD_FRAME = 16, 32, 64
 PATH_FAST, PATH_GENERAL = 0, 1
@@ -47,6 +49,8 @@ EXPORTS = [
     "rpl_decode_normal_batch_dev", "rpl_decode_normal", "rpl_node_timestamps_dev", "rpl_normal_timestamps_dev",
     "rpl_peer_gather_bytes", "rpl_peer_alloc", "rpl_peer_open", "rpl_peer_close", "rpl_peer_free",
     "rpl_cloud_fuse_push_dev",
+    "rpl_exchange_unique_id", "rpl_exchange_create", "rpl_exchange_destroy", "rpl_exchange_allgather",
+    "rpl_exchange_wait", "rpl_exchange_release", "rpl_exchange_slot", "rpl_exchange_synchronize",
     "rpl_laserscan_cdr_size", "rpl_laserscan_cdr_batch_dev", "rpl_pointcloud2_cdr_size", "rpl_pointcloud2_cdr_batch_dev",
 ]
 
@@ -88,7 +92,8 @@ class CloudParams(C.Structure):
         ("sor_k", C.c_uint32),
         ("sor_alpha", C.c_float),
         ("is_new_protocol", C.c_uint8),
-        ("pad", C.c_uint8 * 3),
+        ("flags", C.c_uint8),
+        ("pad", C.c_uint8 * 2),
     ]
 
 
@@ -159,6 +164,14 @@ def lib() -> C.CDLL:
         "rpl_peer_close": ([vp, vp], u32),
         "rpl_peer_free": ([vp, vp], u32),
         "rpl_cloud_fuse_push_dev": ([vp, vp, vp, u32, u32, vp, u32, u32, u32, vp, vp, vp], u32),
+        "rpl_exchange_unique_id": ([vp], u32),
+        "rpl_exchange_create": ([vp, vp, u32, u32, u32, u32, C.POINTER(vp)], u32),
+        "rpl_exchange_destroy": ([vp], None),
+        "rpl_exchange_allgather": ([vp, vp, vp, u32, u32, u32, vp, C.POINTER(u32)], u32),
+        "rpl_exchange_wait": ([vp, u32, vp], u32),
+        "rpl_exchange_release": ([vp, u32, vp], u32),
+        "rpl_exchange_slot": ([vp, u32, u32, C.POINTER(vp), C.POINTER(vp)], u32),
+        "rpl_exchange_synchronize": ([vp], u32),
         "rpl_laserscan_cdr_size": ([u32, u32], u32),
         "rpl_pointcloud2_cdr_size": ([u32, u32], u32),
         "rpl_laserscan_cdr_batch_dev": ([vp, vp, vp, C.c_char_p, vp, vp, vp, u32, u32, vp, u32, vp, vp], u32),
@@ -181,9 +194,9 @@ def scan_params(is_new_protocol=0, scan_processing=1, inverted=0, apply_ascend=1
 
 
 def cloud_params(range_min=0.15, range_max=40.0, intensity_min=0.0, voxel_size=0.0, sor_k=0,
-                 sor_alpha=1.0, is_new_protocol=0) -> CloudParams:
+                 sor_alpha=1.0, is_new_protocol=0, flags=0) -> CloudParams:
     return CloudParams(float(range_min), float(range_max), float(intensity_min), float(voxel_size),
-                       int(sor_k), float(sor_alpha), int(is_new_protocol), (C.c_uint8 * 3)(0, 0, 0))
+                       int(sor_k), float(sor_alpha), int(is_new_protocol), int(flags), (C.c_uint8 * 2)(0, 0))
 
 
 def _p(a):
@@ -459,6 +472,55 @@ class Context:
     def cloud_fuse_dev(self, xyzi, point_counts, n_scans, stride, fused, offsets, total, stream=None):
         self._check(self._L.rpl_cloud_fuse_dev(self._h, _p(xyzi), _p(point_counts), n_scans, stride, _p(fused),
                                                _p(offsets), _p(total), _p(stream)))
+
+
+EXCHANGE_NCCL, EXCHANGE_COPY = 0, 1
+
+
+def exchange_unique_id() -> bytes:
+    """rank 0: a fresh NCCL unique id (128 bytes) for rpl_exchange_create on every rank."""
+    buf = np.zeros(128, np.uint8)
+    rc = lib().rpl_exchange_unique_id(_p(buf))
+    if rc != RESULT_OK:
+        raise RplError(rc, "rpl_exchange_unique_id failed (is libnccl.so.2 loadable?)")
+    return buf.tobytes()
+
+
+class Exchange:
+    """rpl_exchange wrapper: the C++ all-gather of the fused cloud (include/rpl_b200.h)."""
+
+    def __init__(self, ctx: "Context", unique_id, world: int, rank: int, slot_points: int, flags: int = 0):
+        self._L, self._ctx = ctx._L, ctx
+        idbuf = np.frombuffer(unique_id, np.uint8).copy() if unique_id is not None else None
+        h = C.c_void_p()
+        ctx._check(self._L.rpl_exchange_create(ctx._h, _p(idbuf), world, rank, slot_points, flags, C.byref(h)))
+        self._h, self.world, self.rank, self.slot_points = h, world, rank, slot_points
+
+    def allgather(self, xyzi, point_counts, n_scans, stride, mode=EXCHANGE_NCCL, stream=None) -> int:
+        idx = C.c_uint32(0)
+        self._ctx._check(self._L.rpl_exchange_allgather(self._h, _p(xyzi), _p(point_counts), n_scans, stride, mode,
+                                                        _p(stream), C.byref(idx)))
+        return idx.value
+
+    def wait(self, index: int, stream=None):
+        self._ctx._check(self._L.rpl_exchange_wait(self._h, index, _p(stream)))
+
+    def release(self, index: int, stream=None):
+        self._ctx._check(self._L.rpl_exchange_release(self._h, index, _p(stream)))
+
+    def slot(self, index: int, rank: int):
+        """(device address of the points, device address of the uint32 count) of one rank's slot."""
+        pts, cnt = C.c_void_p(), C.c_void_p()
+        self._ctx._check(self._L.rpl_exchange_slot(self._h, index, rank, C.byref(pts), C.byref(cnt)))
+        return int(pts.value), int(cnt.value)
+
+    def synchronize(self):
+        self._ctx._check(self._L.rpl_exchange_synchronize(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.rpl_exchange_destroy(self._h)
+            self._h = None
 
 
 def host_alloc(nbytes: int) -> np.ndarray:

@@ -81,7 +81,8 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_u32(uint32_t v, uint32_
 template <int K>
 __global__ void __launch_bounds__(CT) cloud_sor_kernel(float4* xyzi, uint32_t* point_counts, uint32_t n_scans,
                                                        uint32_t stride, uint32_t sor_k, float sor_alpha,
-                                                       void* scratch, size_t per_cta, uint32_t max_nodes) {
+                                                       void* scratch, size_t per_cta, uint32_t max_nodes,
+                                                       const uint32_t* list, const uint32_t* list_count) {
   __shared__ float2 s_xy[CT + 2 * kHalfWindow];
   __shared__ uint32_t s_warp[CT / 32];
   __shared__ long long s_s1[CT / 32];
@@ -89,7 +90,10 @@ __global__ void __launch_bounds__(CT) cloud_sor_kernel(float4* xyzi, uint32_t* p
   __shared__ double s_thr;
   const CloudScratch sc = carve(scratch, per_cta, max_nodes, hash_size_for(max_nodes));
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (uint32_t s = blockIdx.x; s < n_scans; s += gridDim.x) {
+  // `list` (nullable): only these scans (the duplicate-key scans the shared-memory kernel handed on)
+  const uint32_t n_work = list ? min(*list_count, n_scans) : n_scans;
+  for (uint32_t sj = blockIdx.x; sj < n_work; sj += gridDim.x) {
+    const uint32_t s = list ? list[sj] : sj;
     float4* pts = xyzi + (size_t)s * stride;
     const uint32_t m = point_counts[s];
     if (m < 2 || m > max_nodes) continue;  // fewer than 2 points keep everything
@@ -212,13 +216,16 @@ __global__ void cloud_table_init_kernel(void* scratch, size_t per_cta, uint32_t 
 
 __global__ void __launch_bounds__(CT) cloud_voxel_kernel(float4* xyzi, uint32_t* point_counts, uint32_t n_scans,
                                                          uint32_t stride, float voxel, void* scratch, size_t per_cta,
-                                                         uint32_t max_nodes) {
+                                                         uint32_t max_nodes, const uint32_t* list,
+                                                         const uint32_t* list_count) {
   __shared__ uint32_t s_warp[CT / 32];
   // the whole table (>= 2 * max_nodes slots) is clean on entry; a scan uses a prefix sized to its own
   // point count so that the slots all resident CTAs touch stay inside the L2
   const CloudScratch sc = carve(scratch, per_cta, max_nodes, hash_size_for(max_nodes));
   const uint32_t tid = threadIdx.x, lane = tid & 31;
-  for (uint32_t s = blockIdx.x; s < n_scans; s += gridDim.x) {
+  const uint32_t n_work = list ? min(*list_count, n_scans) : n_scans;
+  for (uint32_t sj = blockIdx.x; sj < n_work; sj += gridDim.x) {
+    const uint32_t s = list ? list[sj] : sj;
     float4* pts = xyzi + (size_t)s * stride;
     const uint32_t m = point_counts[s];
     if (m == 0 || m > max_nodes) continue;
@@ -347,13 +354,15 @@ __global__ void cloud_offsets_kernel(const uint32_t* counts, uint32_t n, uint32_
 }
 
 __global__ void cloud_pack_kernel(const float4* xyzi, const uint32_t* counts, const uint32_t* offsets,
-                                  uint32_t n_scans, uint32_t stride, float4* fused) {
+                                  uint32_t n_scans, uint32_t stride, float4* fused, uint32_t capacity) {
   const uint64_t pol = l2_policy_evict_first();
   for (uint32_t s = blockIdx.y; s < n_scans; s += gridDim.y) {
     const uint32_t m = counts[s], off = offsets[s];
     const float4* src = xyzi + (size_t)s * stride;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+      if (off + i >= capacity) break;  // the reader sees total > capacity and knows the slot overflowed
       st_f32x4_if(fused + off + i, src[i], pol, 1u);
+    }
   }
 }
 
@@ -446,33 +455,34 @@ void cloud_workspace_free(CloudWorkspace& ws) {
 
 cudaError_t launch_cloud_post(float4* xyzi, uint32_t* point_counts, uint32_t n_scans, uint32_t stride,
                               uint32_t sor_k, float sor_alpha, float voxel, const CloudWorkspace& ws,
-                              cudaStream_t stream, int* launched) {
-  const int grid = (int)min((uint32_t)ws.ctas, n_scans);
+                              const uint32_t* list, const uint32_t* list_count, cudaStream_t stream, int* launched) {
+  // with a list the work is a handful of scans: a small grid finds out on the device
+  const int grid = list ? (int)min((uint32_t)ws.ctas, min(n_scans, 64u)) : (int)min((uint32_t)ws.ctas, n_scans);
   if (sor_k > 0) {
     auto k = cloud_sor_kernel<32>;
     if (sor_k <= 4) k = cloud_sor_kernel<4>;
     else if (sor_k <= 8) k = cloud_sor_kernel<8>;
     else if (sor_k <= 16) k = cloud_sor_kernel<16>;
     k<<<grid, CT, 0, stream>>>(xyzi, point_counts, n_scans, stride, sor_k, sor_alpha, ws.scratch, ws.scratch_per_cta,
-                               ws.max_nodes);
+                               ws.max_nodes, list, list_count);
     if (launched) ++*launched;
   }
   if (voxel > 0.0f) {
     cloud_voxel_kernel<<<grid, CT, 0, stream>>>(xyzi, point_counts, n_scans, stride, voxel, ws.scratch,
-                                                ws.scratch_per_cta, ws.max_nodes);
+                                                ws.scratch_per_cta, ws.max_nodes, list, list_count);
     if (launched) ++*launched;
   }
   return cudaGetLastError();
 }
 
 cudaError_t launch_cloud_fuse(const float4* xyzi, const uint32_t* point_counts, uint32_t n_scans,
-                              uint32_t stride, float4* fused, uint32_t* offsets, uint32_t* total,
+                              uint32_t stride, float4* fused, uint32_t capacity, uint32_t* offsets, uint32_t* total,
                               cudaStream_t stream, int* launched) {
   if (n_scans == 0) return cudaSuccess;
   cloud_offsets_kernel<<<1, 1024, 0, stream>>>(point_counts, n_scans, offsets, total);
   const uint32_t gy = min(n_scans, 65535u);
   const uint32_t gx = max(1u, min(32u, (stride + 255u) / 256u));
-  cloud_pack_kernel<<<dim3(gx, gy), 256, 0, stream>>>(xyzi, point_counts, offsets, n_scans, stride, fused);
+  cloud_pack_kernel<<<dim3(gx, gy), 256, 0, stream>>>(xyzi, point_counts, offsets, n_scans, stride, fused, capacity);
   if (launched) *launched += 2;
   return cudaGetLastError();
 }

@@ -17,10 +17,12 @@ struct CloudWorkspace {
 cudaError_t cloud_configure();
 cudaError_t cloud_workspace_alloc(CloudWorkspace& ws, int num_sms, uint32_t max_nodes);
 void cloud_workspace_free(CloudWorkspace& ws);
-// steps 4-5 (SOR, voxel grid) over per-scan clouds already in angle order, in place
+// steps 4-5 (SOR, voxel grid) over per-scan clouds already in angle order, in place.  list / list_count
+// (device, nullable): restrict the pass to these scans (what the shared-memory kernel of scan_small.cu
+// handed to the general kernel); the general path for revolutions above 4096 nodes.
 cudaError_t launch_cloud_post(float4* xyzi, uint32_t* point_counts, uint32_t n_scans, uint32_t stride,
                               uint32_t sor_k, float sor_alpha, float voxel, const CloudWorkspace& ws,
-                              cudaStream_t stream, int* launched);
+                              const uint32_t* list, const uint32_t* list_count, cudaStream_t stream, int* launched);
 // fuse + all-gather through peer memory (NVLink P2P, CUDA IPC)
 constexpr uint32_t kMaxPeers = 16;
 constexpr uint32_t kPeerHeaderBytes = 256;
@@ -31,8 +33,9 @@ cudaError_t launch_cloud_fuse_push(const float4* xyzi, const uint32_t* point_cou
                                    uint32_t stride, const PeerBases& peers, uint32_t world, uint32_t rank,
                                    uint32_t slot_points, uint32_t* offsets, uint32_t* total, cudaStream_t stream,
                                    int* launched);
+// capacity: points `fused` can hold (points past it are dropped; *total still reports the true count)
 cudaError_t launch_cloud_fuse(const float4* xyzi, const uint32_t* point_counts, uint32_t n_scans,
-                              uint32_t stride, float4* fused, uint32_t* offsets, uint32_t* total,
+                              uint32_t stride, float4* fused, uint32_t capacity, uint32_t* offsets, uint32_t* total,
                               cudaStream_t stream, int* launched);
 
 }  // namespace rpl

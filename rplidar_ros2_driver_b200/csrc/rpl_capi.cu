@@ -26,79 +26,9 @@ cudaError_t launch_synth(uint64_t first_scan_id, uint32_t n_scans, uint32_t n, u
 
 static_assert(sizeof(rpl_node_hq) == 8, "packed node must be 8 bytes");
 
-namespace {
-
-constexpr int kLanes = 2;  // host-buffer pipeline depth (copy/compute overlap)
-
-struct Lane {
-  cudaStream_t stream = nullptr;
-  uint32_t* fallback_list = nullptr;
-  uint32_t* fallback_count = nullptr;
-  rpl::FastWorkspace fws{};
-  rpl::GeneralWorkspace gws{};
-  rpl::CloudWorkspace cws{};
-  // device staging for host-buffer calls (lazy)
-  uint2* d_nodes = nullptr;
-  uint2* d_nodes_out = nullptr;
-  uint32_t* d_counts = nullptr;
-  float* d_ranges = nullptr;
-  float* d_intens = nullptr;
-  uint32_t* d_beams = nullptr;
-  float* d_inc = nullptr;
-  uint32_t* d_status = nullptr;
-  uint32_t* d_path = nullptr;
-  float* d_xyzi = nullptr;
-  uint32_t* d_pcount = nullptr;
-  size_t staged_nodes = 0;  // capacity in nodes of the staging buffers
-  uint32_t staged_scans = 0;
-};
-
-}  // namespace
-
-struct rpl_ctx {
-  int device = 0;
-  uint32_t max_nodes = 0, max_scans = 0;
-  int num_sms = 0;
-  int fast_grid = 0, tma_grid = 0, general_grid = 0;
-  Lane lane[kLanes];
-  std::string err;
-  uint64_t launches = 0;
-  // pinned mirrors of the small per-scan arrays of the host-buffer calls: keeps every copy of
-  // the pipeline asynchronous even when the caller's small arrays are pageable
-  uint32_t* h_counts = nullptr;
-  uint32_t* h_small = nullptr;  // [4][max_scans]: beams, angle_increment bits, status, path
-  // single-scan fast lane (rpl_scan / rpl_ascend_scan / rpl_laserscan): one pinned host block
-  // and one device block laid out [nodes in][small][nodes out][ranges][intensities] so that a
-  // scan costs one H2D copy, one or two kernel launches and one D2H copy
-  unsigned char* h_one = nullptr;
-  unsigned char* d_one = nullptr;
-  size_t one_stride = 0;  // max_nodes rounded up to even
-  // scratch of rpl_assemble_scans_dev (grown on demand)
-  uint32_t* d_reset_prefix = nullptr;
-  uint2* d_desc = nullptr;
-  size_t reset_prefix_cap = 0, desc_cap = 0;
-  uint32_t* d_state_tmp = nullptr;  // dense decoder reached through the [2]-word state interface
-  size_t state_tmp_cap = 0;
-  bool profile = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_fast, prof_general;
-};
+#include "rpl_ctx.h"
 
 namespace {
-
-bool cuda_ok(rpl_ctx* c, cudaError_t e, const char* what) {
-  if (e == cudaSuccess) return true;
-  char buf[256];
-  std::snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
-  c->err = buf;
-  return false;
-}
-#define RPL_CUDA(c, call, code)                   \
-  do {                                            \
-    if (!cuda_ok((c), (call), #call)) return (code); \
-  } while (0)
-
-// device buffers of 8-byte records (nodes, 64-bit stamps) are accessed with 8-byte loads and stores
-inline bool misaligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) != 0; }
 
 template <class P>
 cudaError_t dev_alloc(P** p, size_t count) {
@@ -166,7 +96,14 @@ rpl_result ensure_staging(rpl_ctx* c, Lane& l, uint32_t scans, size_t nodes, boo
   return RPL_RESULT_OK;
 }
 
-rpl_result enqueue_args(rpl_ctx* c, Lane& l, rpl::ScanBatchArgs a, uint32_t flags, cudaStream_t stream);
+// PointCloud2 steps 4-5 a launch may fuse into the shared-memory kernel (scan_small.cu)
+struct PostParams {
+  uint32_t sor_k = 0;
+  float sor_alpha = 0.0f;
+  float voxel = 0.0f;
+};
+rpl_result enqueue_args(rpl_ctx* c, Lane& l, rpl::ScanBatchArgs a, uint32_t flags, cudaStream_t stream,
+                        const PostParams* post = nullptr, bool* post_fused = nullptr);
 
 // queue the scan kernels for one device-resident batch on `stream`
 rpl_result enqueue_scan(rpl_ctx* c, Lane& l, const rpl_node_hq* nodes, const uint32_t* counts,
@@ -218,9 +155,11 @@ rpl_result enqueue_scan(rpl_ctx* c, Lane& l, const rpl_node_hq* nodes, const uin
   return enqueue_args(c, l, a, p->flags, stream);
 }
 
-rpl_result enqueue_args(rpl_ctx* c, Lane& l, rpl::ScanBatchArgs a, uint32_t flags, cudaStream_t stream) {
+rpl_result enqueue_args(rpl_ctx* c, Lane& l, rpl::ScanBatchArgs a, uint32_t flags, cudaStream_t stream,
+                        const PostParams* post, bool* post_fused) {
   const uint32_t n_scans = a.n_scans, stride = a.stride;
   bool force_general = (flags & RPL_FLAG_FORCE_GENERAL) != 0;
+  if (post_fused) *post_fused = false;
   if (a.nodes_out && !a.apply_ascend) {
     // no geometric correction requested: the buffer passes through unchanged
     // (reference lidar_driver_wrapper.cpp:330-337); a plain device copy, not kernel work
@@ -231,8 +170,10 @@ rpl_result enqueue_args(rpl_ctx* c, Lane& l, rpl::ScanBatchArgs a, uint32_t flag
   }
   // status-only calls (no LaserScan, no ascended buffer) take the general kernel
   if (!a.ranges && !a.nodes_out && !a.xyzi) force_general = true;
-  // the PointCloud2 payload exists in the TMA kernel and the general kernel only
-  if (a.xyzi && ((reinterpret_cast<uintptr_t>(a.nodes) & 15u) != 0 || (stride & 1u) != 0)) force_general = true;
+  // revolutions that fit shared memory (what a lidar delivers) have their own kernels
+  const bool small = !force_general && rpl::scan_small_applies(stride) && (flags & RPL_FLAG_NO_SMALL) == 0;
+  // above that the PointCloud2 payload exists in the TMA kernel and the general kernel only
+  if (a.xyzi && !small && ((reinterpret_cast<uintptr_t>(a.nodes) & 15u) != 0 || (stride & 1u) != 0)) force_general = true;
   if (!force_general) {
     RPL_CUDA(c, cudaMemsetAsync(l.fallback_count, 0, sizeof(uint32_t), stream), RPL_RESULT_OPERATION_FAIL);
     // the TMA-ring kernel needs every scan base 16-byte aligned
@@ -246,10 +187,21 @@ rpl_result enqueue_args(rpl_ctx* c, Lane& l, rpl::ScanBatchArgs a, uint32_t flag
       cudaEventCreate(&e1);
       cudaEventRecord(e0, stream);
     }
-    if (use_tma)
+    if (small) {
+      // SOR / voxel grid run inside the kernel when the 32-bit cell keys and accumulators are exact:
+      // |cell index| < 32768 and voxel <= 4 m (scan_small.cu); otherwise as separate passes
+      bool fuse = false;
+      if (a.xyzi && post && (post->sor_k > 0 || post->voxel > 0.0f))
+        fuse = post->voxel == 0.0f || (post->voxel <= 4.0f && a.range_max / post->voxel < 32000.0f);
+      RPL_CUDA(c, rpl::launch_scan_small(a, l.fws.max_nodes, fuse ? post->sor_k : 0u, fuse ? post->sor_alpha : 0.0f,
+                                         fuse ? post->voxel : 0.0f, c->num_sms, stream),
+               RPL_RESULT_OPERATION_FAIL);
+      if (post_fused) *post_fused = fuse;
+    } else if (use_tma) {
       RPL_CUDA(c, rpl::launch_scan_tma(a, l.fws, grid, stream), RPL_RESULT_OPERATION_FAIL);
-    else
+    } else {
       RPL_CUDA(c, rpl::launch_scan_fast(a, l.fws, grid, stream), RPL_RESULT_OPERATION_FAIL);
+    }
     if (c->profile) {
       cudaEventRecord(e1, stream);
       c->prof_fast.emplace_back(e0, e1);
@@ -307,6 +259,7 @@ rpl_result rpl_ctx_create(int device, uint32_t max_nodes, uint32_t max_scans, rp
   c->num_sms = prop.multiProcessorCount;
   if (!cuda_ok(c, rpl::scan_fast_configure(), "scan_fast_configure") ||
       !cuda_ok(c, rpl::scan_tma_configure(), "scan_tma_configure") ||
+      !cuda_ok(c, rpl::scan_small_configure(), "scan_small_configure") ||
       !cuda_ok(c, rpl::scan_general_configure(), "scan_general_configure") ||
       !cuda_ok(c, rpl::cloud_configure(), "cloud_configure") ||
       !cuda_ok(c, rpl::decode_configure(), "decode_configure") ||
@@ -1323,14 +1276,25 @@ rpl_result rpl_cloud_batch_dev(rpl_ctx* c, const rpl_node_hq* nodes, const uint3
   a.range_min = params->range_min;
   a.range_max = params->range_max;
   a.intensity_min = params->intensity_min;
-  // steps 1-3 inside the scan kernels, steps 4-5 as in-place post passes
-  rpl_result r = enqueue_args(c, c->lane[0], a, 0u, st);
+  // Revolutions of at most 4096 nodes: the whole chain (window, xyz, SOR, voxel grid) in one kernel, in shared
+  // memory (scan_small.cu); the separate in-place post passes then only see the duplicate-key scans that kernel
+  // handed to the general kernel.  Larger revolutions: steps 1-3 inside the scan kernels, steps 4-5 as post passes.
+  PostParams pp;
+  pp.sor_k = params->sor_k;
+  pp.sor_alpha = params->sor_alpha;
+  pp.voxel = params->voxel_size;
+  bool fused = false;
+  const uint32_t flags = (params->flags & RPL_CLOUD_NO_FUSED) ? RPL_FLAG_NO_SMALL : 0u;
+  rpl_result r = enqueue_args(c, c->lane[0], a, flags, st, &pp, &fused);
   if (r != RPL_RESULT_OK) return r;
-  int launched = 0;
-  RPL_CUDA(c, rpl::launch_cloud_post(a.xyzi, point_counts, n_scans, stride, params->sor_k, params->sor_alpha,
-                                     params->voxel_size, c->lane[0].cws, st, &launched),
-           RPL_RESULT_OPERATION_FAIL);
-  c->launches += launched;
+  if (params->sor_k > 0 || params->voxel_size > 0.0f) {
+    int launched = 0;
+    RPL_CUDA(c, rpl::launch_cloud_post(a.xyzi, point_counts, n_scans, stride, params->sor_k, params->sor_alpha,
+                                       params->voxel_size, c->lane[0].cws, fused ? a.fallback_list : nullptr,
+                                       fused ? a.fallback_count : nullptr, st, &launched),
+             RPL_RESULT_OPERATION_FAIL);
+    c->launches += launched;
+  }
   return RPL_RESULT_OK;
 }
 
@@ -1368,7 +1332,7 @@ rpl_result rpl_cloud_fuse_dev(rpl_ctx* c, const float* xyzi, const uint32_t* poi
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
   int launched = 0;
   RPL_CUDA(c, rpl::launch_cloud_fuse(reinterpret_cast<const float4*>(xyzi), point_counts, n_scans, stride,
-                                     reinterpret_cast<float4*>(fused), offsets, total, st, &launched),
+                                     reinterpret_cast<float4*>(fused), 0xFFFFFFFFu, offsets, total, st, &launched),
            RPL_RESULT_OPERATION_FAIL);
   c->launches += launched;
   return RPL_RESULT_OK;

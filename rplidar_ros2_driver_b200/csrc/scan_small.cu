@@ -1,0 +1,785 @@
+// scan_small.cu -- the scan kernels for revolutions that fit shared memory (stride <= 4096 nodes:
+// what a spinning lidar delivers; the SDK's own holder caps a revolution at 8192, the S2/S3 produce
+// 3200 at 10 Hz).
+//
+// Same contract as scan_tma.cu / scan_fast.cu (ascendScanData_ + publish_scan, reference
+// src/sdk/src/sl_lidar_driver.cpp:128-184 and src/rplidar_node.cpp:581-677; the PointCloud2 steps of
+// oracle/cloud_oracle.cpp), different cost structure.  The big-scan kernels pay a fixed 128 KB of
+// shared-memory traffic per scan (clearing and folding a 64 KB byte map) and stream the tile twice;
+// at 3200 nodes that fixed work costs as much as the nodes themselves (round 1: 42 % of the HBM
+// roofline against 74 % at 32768 nodes).  Here
+//   * the whole revolution is staged ONCE into shared memory by one bulk-TMA copy (cp.async.bulk +
+//     mbarrier; plain loads when the scan base is not 16-byte aligned), and both passes read it there;
+//   * keys are marked straight into the 8 KB presence BITMAP with shared-memory atomicOr -- at
+//     <= 4096 nodes per revolution neighbouring keys are >= 16 apart, so lanes rarely share a word
+//     (the reason the 32768-node kernel uses a byte map instead) -- which removes the byte map, its
+//     clear and its fold; the rank table is the bitmap + a 4 KB u16 prefix;
+//   * Mode A resolves its bins from the shared-memory copy, the ascended buffer is a second bitmap
+//     over the final keys, and the PointCloud2 chain runs to the end in shared memory: the kept
+//     points are placed in angle order as (x, y) + intensity, statistical outlier removal and the
+//     voxel grid (open-addressing table of cell leaders in the dead tile buffer, 32-bit integer
+//     accumulators relative to the leader) work on them there, and only the final cloud -- rho x 16 B
+//     per input node -- is written to HBM.  The three HBM round trips and the global hash tables of
+//     the round-1 post kernels are gone.
+// Duplicate keys (popcount != count) go to the general kernel through the device-side list, as before.
+#include <algorithm>
+#include <type_traits>
+
+#include "rpl_device.cuh"
+#include "scan_args.h"
+#include "scan_common.cuh"
+
+namespace rpl {
+
+namespace {
+
+struct SmallCtl {
+  unsigned long long full;  // mbarrier of the tile copy
+  long long s1;
+  unsigned long long s2;
+  double thr;
+  uint32_t red[3 * 32];
+  uint32_t totV, totA, first_valid, front_key, fallback, count_out;
+  uint32_t chunk_base[128];  // voxel ordering: per (chunk, warp) counts -> exclusive bases
+};
+static_assert(sizeof(SmallCtl) <= 1024, "control block");
+constexpr uint32_t kCtl = 1024;
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void s_mbar_init(void* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void s_mbar_wait(void* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(s_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void s_mbar_expect_tx(void* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void s_tma_load_1d(void* dst, const void* src, uint32_t bytes, void* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+          "r"(s_u32(dst)),
+      "l"(src), "r"(bytes), "r"(s_u32(bar)), "l"(policy)
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t rank2(const uint32_t* bits, const uint16_t* pref, uint32_t key) {
+  return (uint32_t)pref[key >> 5] + __popc(bits[key >> 5] & ((1u << (key & 31)) - 1u));
+}
+
+// ---- statistical outlier removal: mean of the k smallest neighbour distances (cloud_oracle.cpp step 4) ----
+// The k smallest d are the square roots of the k smallest d^2 (sqrt is monotonic and correctly rounded), and
+// they are added in ascending order either way -- so the selection runs on d^2 and only k square roots are taken.
+template <int K>
+struct TopK {
+  float v[K];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int t = 0; t < K; ++t) v[t] = __int_as_float(0x7f800000);
+  }
+  __device__ __forceinline__ void insert(float x) {  // branch-free insertion into the ascending array
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+      const float lo = fminf(v[t], x), hi = fmaxf(v[t], x);
+      v[t] = lo;
+      x = hi;
+    }
+  }
+};
+__device__ __forceinline__ float dist2(float2 o, float2 me) {
+  const float dx = __fsub_rn(o.x, me.x), dy = __fsub_rn(o.y, me.y);
+  return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+}
+__device__ __forceinline__ void cswap(float& a, float& b) {
+  const float lo = fminf(a, b), hi = fmaxf(a, b);
+  a = lo;
+  b = hi;
+}
+// optimal 19-exchange sorting network for 8 values (ascending)
+__device__ __forceinline__ void sort8(float* v) {
+  cswap(v[0], v[2]); cswap(v[1], v[3]); cswap(v[4], v[6]); cswap(v[5], v[7]);
+  cswap(v[0], v[4]); cswap(v[1], v[5]); cswap(v[2], v[6]); cswap(v[3], v[7]);
+  cswap(v[0], v[1]); cswap(v[2], v[3]); cswap(v[4], v[5]); cswap(v[6], v[7]);
+  cswap(v[2], v[4]); cswap(v[3], v[5]);
+  cswap(v[1], v[4]); cswap(v[3], v[6]);
+  cswap(v[1], v[2]); cswap(v[3], v[4]); cswap(v[5], v[6]);
+}
+// a[0..8) and b[0..8) ascending -> a = the 8 smallest of the 16, ascending
+__device__ __forceinline__ void merge_low8(float* a, const float* b) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = fminf(a[i], b[7 - i]);  // bitonic
+  cswap(a[0], a[4]); cswap(a[1], a[5]); cswap(a[2], a[6]); cswap(a[3], a[7]);
+  cswap(a[0], a[2]); cswap(a[1], a[3]); cswap(a[4], a[6]); cswap(a[5], a[7]);
+  cswap(a[0], a[1]); cswap(a[2], a[3]); cswap(a[4], a[5]); cswap(a[6], a[7]);
+}
+__device__ __forceinline__ float mean_of_smallest(const float* d2_sorted, int kmax, uint32_t k) {
+  float sum = 0.0f;
+#pragma unroll
+  for (int t = 0; t < 32; ++t)
+    if (t < kmax && (uint32_t)t < k) sum = __fadd_rn(sum, __fsqrt_rn(d2_sorted[t]));
+  return __fdiv_rn(sum, __uint2float_rn(k));
+}
+// window form (more than 33 points), sor_k <= 8: sorting networks over the 32 candidates, 8 at a time
+__device__ __forceinline__ float sor_mean_win8(const float2* px, uint32_t m, uint32_t i, uint32_t k) {
+  const float2 me = px[i];
+  float best[8], cur[8];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float* dst = g == 0 ? best : cur;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const uint32_t o = (uint32_t)(g * 4 + t + 1);
+      uint32_t jm = i + m - o, jp = i + o;  // (i - o) mod m, (i + o) mod m with o <= 16 < m
+      if (jm >= m) jm -= m;
+      if (jp >= m) jp -= m;
+      dst[2 * t] = dist2(px[jm], me);
+      dst[2 * t + 1] = dist2(px[jp], me);
+    }
+    sort8(dst);
+    if (g != 0) merge_low8(best, cur);
+  }
+  return mean_of_smallest(best, 8, k);
+}
+// any k <= 32, window or all-others form
+__device__ __noinline__ float sor_mean_generic(const float2* px, uint32_t m, uint32_t i, uint32_t sor_k, bool all_others) {
+  const float2 me = px[i];
+  TopK<32> top;
+  top.init();
+  uint32_t nd = 0;
+  if (all_others) {
+    for (uint32_t j = 0; j < m; ++j)
+      if (j != i) {
+        top.insert(dist2(px[j], me));
+        ++nd;
+      }
+  } else {
+    for (uint32_t o = 1; o <= 16u; ++o) {
+      uint32_t jm = i + m - o, jp = i + o;
+      if (jm >= m) jm -= m;
+      if (jp >= m) jp -= m;
+      top.insert(dist2(px[jm], me));
+      top.insert(dist2(px[jp], me));
+    }
+    nd = 32;
+  }
+  return mean_of_smallest(top.v, 32, min(sor_k, nd));
+}
+
+// voxel cell of a point (cloud_oracle.cpp step 5): (floorf(x / voxel), floorf(y / voxel)) packed into 32 bits;
+// the host admits this kernel only when |cell index| < 32768 (range_max / voxel < 32000)
+__device__ __forceinline__ uint32_t cell_key(float2 p, float voxel) {
+  const int ix = __float2int_rd(__fdiv_rn(p.x, voxel));
+  const int iy = __float2int_rd(__fdiv_rn(p.y, voxel));
+  return ((uint32_t)ix << 16) | ((uint32_t)iy & 0xFFFFu);
+}
+
+// MODE: 0 LaserScan Mode B, 1 LaserScan Mode A, 2 PointCloud2.  EMIT: also write the ascended node buffer
+// (MODE 0/1).  POST: (MODE 2) SOR and/or voxel grid in shared memory before anything is written.
+template <int MODE, bool EMIT, bool POST, int TS>
+__global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchArgs a, SmallArgs p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr bool MODE_A = (MODE == 1);
+  constexpr bool CLOUD = (MODE == 2);
+  constexpr int NW = TS / 32;
+  constexpr uint32_t WPT = kWords / TS;  // bitmap words per thread in the prefix step
+  static_assert(!(EMIT && CLOUD) && !(POST && !CLOUD), "variant");
+  static_assert(kWords % TS == 0 && WPT % 4 == 0, "prefix layout");
+  SmallCtl& ctl = *reinterpret_cast<SmallCtl*>(smem_raw);
+  const uint32_t cap = p.cap;
+  uint2* tile = reinterpret_cast<uint2*>(smem_raw + kCtl);
+  unsigned char* q = smem_raw + kCtl + (size_t)cap * 8;
+  float2* px = nullptr;
+  uint8_t* pi = nullptr;
+  uint32_t* bitsV;
+  uint16_t* prefV;
+  uint32_t* bitsA = nullptr;
+  uint16_t* prefA = nullptr;
+  uint16_t* sidx = nullptr;
+  unsigned char* acc = nullptr;
+  if (POST) {
+    px = reinterpret_cast<float2*>(q); q += (size_t)cap * 8;
+    pi = q; q += cap;
+    acc = q;  // 16 * cap bytes; the rank table lives at its start until the place pass is over
+  }
+  bitsV = reinterpret_cast<uint32_t*>(q); q += kWords * 4;
+  prefV = reinterpret_cast<uint16_t*>(q); q += kWords * 2;
+  if (EMIT) {
+    bitsA = reinterpret_cast<uint32_t*>(q); q += kWords * 4;
+    prefA = reinterpret_cast<uint16_t*>(q); q += kWords * 2;
+  }
+  if (MODE_A) sidx = reinterpret_cast<uint16_t*>(q);
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool new_proto = a.is_new_protocol != 0;
+  const bool inverted = a.inverted != 0;
+  const uint64_t pol_stream = l2_policy_evict_first();
+  const uint32_t q_shift = new_proto ? 16u : 18u, q_mask = new_proto ? 0xFFu : 0x3Fu;
+  const float w_rmin = a.range_min, w_rmax = a.range_max, w_imin = a.intensity_min;
+  auto intensity_of = [&](uint32_t y) {
+    return __fsub_rn(__uint_as_float(((y >> q_shift) & q_mask) | 0x4B000000u), 8388608.0f);
+  };
+  const bool want_scan = CLOUD ? false : (EMIT ? (a.ranges != nullptr) : true);
+
+  if (tid == 0) {
+    s_mbar_init(&ctl.full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+
+  for (uint32_t s = blockIdx.x; s < a.n_scans; s += gridDim.x) {
+    const uint32_t n = a.counts[s];
+    if (n > a.stride || n > p.max_nodes) {  // caller error: report, touch nothing
+      if (tid == 0) {
+        if (a.status) a.status[s] = 0x80008000u;  // SL_RESULT_INVALID_DATA
+        if (a.path) a.path[s] = 0u;
+        if (a.beam_counts) a.beam_counts[s] = 0u;
+        if (a.angle_inc) a.angle_inc[s] = 0.0f;
+      }
+      continue;
+    }
+    if (n == 0) {  // ascendScanData: OPERATION_FAIL; publish_scan: nodes.empty() -> return
+      if (tid == 0) {
+        if (a.status) a.status[s] = a.apply_ascend ? kResultOperationFail : kResultOk;
+        if (a.path) a.path[s] = 0u;
+        if (a.beam_counts) a.beam_counts[s] = 0u;
+        if (a.angle_inc) a.angle_inc[s] = 0.0f;
+      }
+      continue;
+    }
+    const uint2* base = a.nodes + (size_t)s * a.stride;
+
+    // ---- stage the revolution (every thread is past the previous scan: its last barrier) -----------
+    if (p.use_tma) {
+      if (tid == 0) {
+        // the tile region may have been written with ordinary stores (voxel table): order them before the
+        // asynchronous-proxy write of the copy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // an odd count is rounded up to whole 16 bytes; the extra node lies inside the scan's (even) stride
+        const uint32_t bytes = ((n + 1u) & ~1u) * 8u;
+        s_mbar_expect_tx(&ctl.full, bytes);
+        s_tma_load_1d(tile, base, bytes, &ctl.full, pol_stream);
+      }
+    } else {
+      for (uint32_t i = tid; i < n; i += TS) tile[i] = ld_stream_v2(base + i);
+    }
+    {
+      uint4* b4 = reinterpret_cast<uint4*>(bitsV);
+      for (uint32_t w = tid; w < kWords / 4; w += TS) b4[w] = make_uint4(0, 0, 0, 0);
+      if (EMIT) {
+        uint4* a4 = reinterpret_cast<uint4*>(bitsA);
+        for (uint32_t w = tid; w < kWords / 4; w += TS) a4[w] = make_uint4(0, 0, 0, 0);
+      }
+      if (tid == 0) {
+        ctl.first_valid = 0xFFFFFFFFu;
+        ctl.fallback = 0;
+      }
+    }
+    __syncthreads();
+    if (p.use_tma) {
+      s_mbar_wait(&ctl.full, parity);
+      parity ^= 1u;
+    }
+
+    // ---- mark: one shared-memory atomicOr per kept key -----------------------------------------------
+    uint32_t cnt = 0, fmin = 0xFFFFFFFFu;
+#pragma unroll 4
+    for (uint32_t i = tid; i < n; i += TS) {
+      const uint2 nd = tile[i];
+      const uint32_t dist = __funnelshift_r(nd.x, nd.y, 16);
+      bool valid = dist != 0;
+      if (CLOUD) valid = valid && cloud_keep(dist_to_m(dist), intensity_of(nd.y), w_rmin, w_rmax, w_imin);
+      if (valid) {
+        const uint32_t k = nd.x & 0xFFFFu;
+        atomicOr(&bitsV[k >> 5], 1u << (k & 31));
+        ++cnt;
+        if (EMIT) fmin = min(fmin, i);
+      }
+    }
+    cnt = warp_sum(cnt);
+    if (lane == 0) ctl.red[warp] = cnt;
+    if (EMIT) {
+      fmin = warp_min(fmin);
+      if (lane == 0 && fmin != 0xFFFFFFFFu) atomicMin(&ctl.first_valid, fmin);
+    }
+    __syncthreads();
+    uint32_t M = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) M += ctl.red[w];
+
+    if (M == 0) {
+      // ascendScanData: OPERATION_FAIL, buffer untouched; publish_scan: nothing to publish
+      if (tid == 0) {
+        if (a.status) a.status[s] = a.apply_ascend ? kResultOperationFail : kResultOk;
+        if (a.path) a.path[s] = 0u;
+        if (a.beam_counts) a.beam_counts[s] = 0u;
+        if (a.angle_inc) a.angle_inc[s] = 0.0f;
+      }
+      if (EMIT) {
+        uint2* out = a.nodes_out + (size_t)s * a.stride;
+        for (uint32_t i = tid; i < n; i += TS) out[i] = tile[i];
+      }
+      __syncthreads();
+      continue;
+    }
+
+    // ---- ascended buffer: final keys of ALL nodes into the second bitmap --------------------------------
+    const float step = ascend_step(n);
+    uint32_t front_key = 0;
+    float front_deg = 0.0f;
+    if (EMIT) {
+      if (tid == 0) {
+        // head tune: serial, only node 0's result survives (reference sl_lidar_driver.cpp:133-147)
+        const uint32_t f = ctl.first_valid;
+        ctl.front_key = ascend_head_key(node_key(tile[f]), f, step);
+      }
+      __syncthreads();
+      front_key = ctl.front_key;
+      front_deg = key_to_deg(front_key);
+#pragma unroll 2
+      for (uint32_t i = tid; i < n; i += TS) {
+        const uint2 nd = tile[i];
+        const uint32_t dist = __funnelshift_r(nd.x, nd.y, 16);
+        const uint32_t fk = dist != 0 ? (nd.x & 0xFFFFu) : (i == 0 ? front_key : ascend_fill_key(front_deg, i, step));
+        atomicOr(&bitsA[fk >> 5], 1u << (fk & 31));
+      }
+      __syncthreads();
+    }
+
+    // ---- exclusive popcount prefix over the bitmap words ------------------------------------------------
+    {
+      uint32_t wv[WPT], wa[WPT];
+      uint32_t sv = 0, sa = 0;
+#pragma unroll
+      for (uint32_t j = 0; j < WPT / 4; ++j) {
+        const uint4 t = reinterpret_cast<const uint4*>(bitsV)[tid * (WPT / 4) + j];
+        wv[4 * j] = t.x; wv[4 * j + 1] = t.y; wv[4 * j + 2] = t.z; wv[4 * j + 3] = t.w;
+        if (EMIT) {
+          const uint4 u = reinterpret_cast<const uint4*>(bitsA)[tid * (WPT / 4) + j];
+          wa[4 * j] = u.x; wa[4 * j + 1] = u.y; wa[4 * j + 2] = u.z; wa[4 * j + 3] = u.w;
+        }
+      }
+#pragma unroll
+      for (uint32_t j = 0; j < WPT; ++j) {
+        sv += __popc(wv[j]);
+        if (EMIT) sa += __popc(wa[j]);
+      }
+      const uint32_t iv = warp_inclusive_scan(sv);
+      const uint32_t ia = EMIT ? warp_inclusive_scan(sa) : 0u;
+      if (lane == 31) {
+        ctl.red[32 + warp] = iv;
+        ctl.red[64 + warp] = ia;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        const uint32_t tv = lane < NW ? ctl.red[32 + lane] : 0u;
+        const uint32_t ta = lane < NW ? ctl.red[64 + lane] : 0u;
+        const uint32_t cv = warp_inclusive_scan(tv), ca = warp_inclusive_scan(ta);
+        if (lane < NW) {
+          ctl.red[32 + lane] = cv - tv;
+          ctl.red[64 + lane] = ca - ta;
+        }
+        if (lane == 31) {
+          ctl.totV = cv;
+          ctl.totA = ca;
+        }
+      }
+      __syncthreads();
+      uint32_t pv = ctl.red[32 + warp] + iv - sv;
+      uint32_t pa = ctl.red[64 + warp] + ia - sa;
+#pragma unroll
+      for (uint32_t j = 0; j < WPT; ++j) {
+        prefV[tid * WPT + j] = (uint16_t)pv;
+        pv += __popc(wv[j]);
+        if (EMIT) {
+          prefA[tid * WPT + j] = (uint16_t)pa;
+          pa += __popc(wa[j]);
+        }
+      }
+    }
+    __syncthreads();
+
+    // duplicate keys (fewer distinct keys than kept nodes) -> general kernel (stable tie rule)
+    if (ctl.totV != M || (EMIT && ctl.totA != n)) {
+      if (tid == 0) a.fallback_list[atomicAdd(a.fallback_count, 1u)] = s;
+      __syncthreads();
+      continue;
+    }
+
+    // ---- place ------------------------------------------------------------------------------------------
+    float* ranges = want_scan ? a.ranges + (size_t)s * a.stride : nullptr;
+    float* intens = want_scan ? a.intensities + (size_t)s * a.stride : nullptr;
+    float4* cloud = CLOUD ? a.xyzi + (size_t)s * a.stride : nullptr;
+    uint2* nodes_out = EMIT ? a.nodes_out + (size_t)s * a.stride : nullptr;
+    const float inc = angle_increment(M, MODE_A);
+    const bool has0 = (bitsV[0] & 1u) != 0;
+    // Mode B output slot = ob + os * rank in wrapping u32 arithmetic (reference rplidar_node.cpp:673)
+    const uint32_t ob = inverted ? M - 1u : 0u, os = inverted ? 0xFFFFFFFFu : 1u;
+    const ptrdiff_t i_minus_r = reinterpret_cast<char*>(intens) - reinterpret_cast<char*>(ranges);
+#pragma unroll 4
+    for (uint32_t i = tid; i < n; i += TS) {
+      const uint2 nd = tile[i];
+      const uint32_t k = nd.x & 0xFFFFu;
+      const uint32_t dist = __funnelshift_r(nd.x, nd.y, 16);
+      uint32_t measured = dist != 0 ? 1u : 0u;
+      if (EMIT) {
+        const uint32_t fk = measured ? k : (i == 0 ? front_key : ascend_fill_key(front_deg, i, step));
+        st_hint_v2(nodes_out + rank2(bitsA, prefA, fk), node_with_key(nd, fk), pol_stream);
+      }
+      if (!CLOUD && !want_scan) continue;
+      const uint32_t rk = rank2(bitsV, prefV, k);
+      const float dm = dist_to_m(dist);
+      if (CLOUD) {  // polar -> xyz at the rank among kept points (oracle/cloud_oracle.cpp steps 1-3)
+        const float it = intensity_of(nd.y);
+        if (!cloud_keep(dm, it, w_rmin, w_rmax, w_imin)) measured = 0;
+        const float2 cs = __ldg(a.trig + k);
+        const float x = __fmul_rn(dm, cs.x), y = __fmul_rn(dm, cs.y);
+        if (POST) {
+          if (measured) {
+            px[rk] = make_float2(x, y);
+            pi[rk] = (uint8_t)((nd.y >> q_shift) & q_mask);
+          }
+        } else {
+          st_f32x4_if(cloud + rk, make_float4(x, y, 0.0f, it), pol_stream, measured);
+        }
+      } else if (!MODE_A) {  // Mode B: reference rplidar_node.cpp:661-677
+        const uint32_t o = ob + os * rk;
+        const float it = intensity_of(nd.y);
+        float* pr = ranges + o;
+        st_f32_if(pr, dm, pol_stream, measured);
+        st_f32_if(reinterpret_cast<float*>(reinterpret_cast<char*>(pr) + i_minus_r), it, pol_stream, measured);
+      } else if (measured) {  // Mode A: remember which node sits at this u-rank (mode_a_emit_smem)
+        sidx[mode_a_urank(k, rk, M, inverted, has0)] = (uint16_t)i;
+      }
+    }
+    __syncthreads();
+
+    // ---- Mode A: resolve bins that hold several points (reads the nodes from shared memory) ------------
+    if constexpr (MODE_A) if (want_scan) {
+      ModeAOut mo;
+      mo.ranges = ranges;
+      mo.intens = intens;
+      mo.angle = a.angle;
+      mo.M = M;
+      mo.inc = inc;
+      mo.inverted = inverted;
+      mo.new_proto = new_proto;
+      mo.policy = pol_stream;
+      // the bitmap is dead by now: each warp stages a batch of bins in its own slice of it
+      static_assert(((kEmit2Stage + 7u) & ~7u) * 2 * NW <= kWords * 4, "bin staging must fit the bitmap");
+      mode_a_emit_smem(mo, sidx, tile, warp, NW, reinterpret_cast<uint16_t*>(bitsV) + warp * ((kEmit2Stage + 7u) & ~7u));
+    }
+
+    uint32_t m_out = M;
+    if constexpr (POST) {
+      uint32_t m = M;
+      // ---- step 4: statistical outlier removal over the +-16 angular neighbours --------------------------
+      if (p.sor_k > 0 && m >= 2) {
+        unsigned long long* qv = reinterpret_cast<unsigned long long*>(acc);  // [cap] (rank table is dead)
+        const bool all_others = (m - 1) <= 32u;
+        long long s1 = 0;
+        unsigned long long s2 = 0;
+        for (uint32_t i = tid; i < m; i += TS) {
+          const float mean = (all_others || p.sor_k > 8u) ? sor_mean_generic(px, m, i, p.sor_k, all_others)
+                                                         : sor_mean_win8(px, m, i, p.sor_k);
+          const long long qq = __float2ll_rn(__fmul_rn(mean, 65536.0f));  // llrintf
+          qv[i] = (unsigned long long)qq;
+          s1 += qq;
+          s2 += (unsigned long long)qq * (unsigned long long)qq;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (tid == 0) {
+          ctl.s1 = 0;
+          ctl.s2 = 0;
+        }
+        __syncthreads();
+        if (lane == 0) {  // exact integer sums: the order of the atomics cannot change them
+          atomicAdd(reinterpret_cast<unsigned long long*>(&ctl.s1), (unsigned long long)s1);
+          atomicAdd(&ctl.s2, s2);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          const double dn = (double)m;
+          const double t1 = (double)ctl.s1, t2 = (double)ctl.s2;
+          const double mean = __ddiv_rn(t1, dn);
+          const double sq = __ddiv_rn(__dmul_rn(t1, t1), dn);
+          double var = __ddiv_rn(__dsub_rn(t2, sq), __dsub_rn(dn, 1.0));
+          if (!(var > 0.0)) var = 0.0;
+          ctl.thr = __dadd_rn(mean, __dmul_rn((double)p.sor_alpha, __dsqrt_rn(var)));
+        }
+        __syncthreads();
+        const double thr = ctl.thr;
+        // stable in-place compaction: every thread owns a contiguous run of at most 8 points
+        constexpr uint32_t PMAX = kSmallMaxNodes / TS;
+        const uint32_t P = (m + TS - 1) / TS;
+        const uint32_t lo = tid * P;
+        float2 kx[PMAX];
+        uint8_t ki[PMAX];
+        uint32_t mask = 0, nk = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < PMAX; ++j) {
+          const uint32_t i = lo + j;
+          kx[j] = make_float2(0.f, 0.f);
+          ki[j] = 0;
+          if (j < P && i < m) {
+            kx[j] = px[i];
+            ki[j] = pi[i];
+            if ((double)(long long)qv[i] <= thr) {
+              mask |= 1u << j;
+              ++nk;
+            }
+          }
+        }
+        const uint32_t inc_w = warp_inclusive_scan(nk);
+        if (lane == 31) ctl.red[warp] = inc_w;
+        __syncthreads();  // all reads of px/pi/qv are done
+        uint32_t wbase = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          const uint32_t t = ctl.red[w];
+          if ((uint32_t)w < warp) wbase += t;
+          tot += t;
+        }
+        uint32_t pos = wbase + inc_w - nk;
+#pragma unroll
+        for (uint32_t j = 0; j < PMAX; ++j)
+          if (mask & (1u << j)) {
+            px[pos] = kx[j];
+            pi[pos] = ki[j];
+            ++pos;
+          }
+        m = tot;
+        __syncthreads();
+      }
+      m_out = m;
+
+      if (p.voxel > 0.0f && m > 0) {
+        // ---- step 5: voxel grid -------------------------------------------------------------------------
+        // acc: key32[cap] | dx[cap] | dy[cap] | cs[cap]; table of cell leaders in the (dead) tile buffer
+        uint32_t* key32 = reinterpret_cast<uint32_t*>(acc);
+        int* dxs = reinterpret_cast<int*>(acc + (size_t)cap * 4);
+        int* dys = reinterpret_cast<int*>(acc + (size_t)cap * 8);
+        uint32_t* cs = reinterpret_cast<uint32_t*>(acc + (size_t)cap * 12);
+        uint32_t* table = reinterpret_cast<uint32_t*>(tile);
+        const uint32_t nslots = 2u * cap;
+        constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+        constexpr uint32_t PMAX = kSmallMaxNodes / TS;
+        {
+          uint4* t4 = reinterpret_cast<uint4*>(table);
+          const uint4 e = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+          for (uint32_t w = tid; w < nslots / 4; w += TS) t4[w] = e;
+        }
+        for (uint32_t i = tid; i < m; i += TS) {
+          key32[i] = cell_key(px[i], p.voxel);
+          dxs[i] = 0;
+          dys[i] = 0;
+          cs[i] = 0;
+        }
+        __syncthreads();
+        // insert: a slot holds the smallest point index seen so far of ONE cell (the key of a slot never
+        // changes once it is taken: atomicMin only swaps members of the same cell)
+        uint32_t myslot[PMAX];
+#pragma unroll
+        for (uint32_t j = 0; j < PMAX; ++j) {
+          const uint32_t i = tid + j * TS;
+          myslot[j] = 0;
+          if (i < m) {
+            const uint32_t key = key32[i];
+            uint32_t h = __umulhi(key * 0x9E3779B1u, nslots);
+            for (;;) {
+              uint32_t v = *reinterpret_cast<volatile uint32_t*>(&table[h]);
+              if (v == kEmpty) {
+                v = atomicCAS(&table[h], kEmpty, i);
+                if (v == kEmpty) break;
+              }
+              if (key32[v] == key) {
+                atomicMin(&table[h], i);
+                break;
+              }
+              if (++h == nslots) h = 0;
+            }
+            myslot[j] = h;
+          }
+        }
+        __syncthreads();
+        // accumulate relative to the cell leader (32-bit integers: |delta| <= voxel * 65536 + 2 and the host
+        // admits voxel <= 4 m, so 4096 members cannot overflow), leaders flagged for the ordering
+        uint32_t leadflag = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < PMAX; ++j) {
+          const uint32_t i = tid + j * TS;
+          bool is_lead = false;
+          if (i < m) {
+            const uint32_t lead = table[myslot[j]];
+            const uint32_t inten = pi[i];
+            if (lead == i) {
+              is_lead = true;
+              atomicAdd(&cs[i], inten);
+            } else {
+              const float2 me = px[i], ld = px[lead];
+              const long long ddx = __float2ll_rn(__fmul_rn(me.x, 65536.0f)) - __float2ll_rn(__fmul_rn(ld.x, 65536.0f));
+              const long long ddy = __float2ll_rn(__fmul_rn(me.y, 65536.0f)) - __float2ll_rn(__fmul_rn(ld.y, 65536.0f));
+              atomicAdd(&dxs[lead], (int)ddx);
+              atomicAdd(&dys[lead], (int)ddy);
+              atomicAdd(&cs[lead], (1u << 20) + inten);
+            }
+          }
+          const uint32_t bal = __ballot_sync(0xffffffffu, is_lead);
+          if (is_lead) leadflag |= 1u << j;
+          if (lane == 0) ctl.chunk_base[j * NW + warp] = __popc(bal);
+          // position of this leader among the leaders of its (chunk, warp) group
+          myslot[j] = __popc(bal & ((1u << lane) - 1u));
+        }
+        __syncthreads();
+        // cells are emitted in the order of their first member = index order of the leaders: exclusive scan
+        // over the (chunk, warp) counts, chunk-major
+        if (warp == 0) {
+          constexpr uint32_t G = PMAX * NW;          // groups
+          constexpr uint32_t GPL = (G + 31) / 32;     // per lane
+          uint32_t v[GPL], sum = 0;
+#pragma unroll
+          for (uint32_t t = 0; t < GPL; ++t) {
+            const uint32_t g = lane * GPL + t;
+            v[t] = g < G ? ctl.chunk_base[g] : 0u;
+            sum += v[t];
+          }
+          const uint32_t incl = warp_inclusive_scan(sum);
+          uint32_t run = incl - sum;
+#pragma unroll
+          for (uint32_t t = 0; t < GPL; ++t) {
+            const uint32_t g = lane * GPL + t;
+            if (g < G) ctl.chunk_base[g] = run;
+            run += v[t];
+          }
+          if (lane == 31) ctl.count_out = incl;
+        }
+        __syncthreads();
+#pragma unroll
+        for (uint32_t j = 0; j < PMAX; ++j) {
+          if (leadflag & (1u << j)) {
+            const uint32_t i = tid + j * TS;
+            const uint32_t pos = ctl.chunk_base[j * NW + warp] + myslot[j];
+            const float2 ld = px[i];
+            const uint32_t c = cs[i];
+            const uint32_t members = (c >> 20) + 1u;
+            const long long sx = (long long)members * __float2ll_rn(__fmul_rn(ld.x, 65536.0f)) + (long long)dxs[i];
+            const long long sy = (long long)members * __float2ll_rn(__fmul_rn(ld.y, 65536.0f)) + (long long)dys[i];
+            const double cntd = (double)members;
+            const double den = __dmul_rn(65536.0, cntd);
+            float4 o;
+            o.x = __double2float_rn(__ddiv_rn((double)sx, den));
+            o.y = __double2float_rn(__ddiv_rn((double)sy, den));
+            o.z = 0.0f;
+            o.w = __double2float_rn(__ddiv_rn((double)(c & 0xFFFFFu), cntd));
+            st_f32x4_if(cloud + pos, o, pol_stream, 1u);
+          }
+        }
+        m_out = ctl.count_out;
+        // the table was written with ordinary stores and the next scan's bulk copy lands on it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      } else {
+        // SOR only: the surviving points, in angle order
+        for (uint32_t i = tid; i < m; i += TS) {
+          const float2 v = px[i];
+          st_f32x4_if(cloud + i, make_float4(v.x, v.y, 0.0f, small_uint_to_float(pi[i])), pol_stream, 1u);
+        }
+      }
+    }
+
+    __syncthreads();
+    if (tid == 0) {
+      if (a.status) a.status[s] = kResultOk;
+      if (a.path) a.path[s] = 0u;
+      if (a.beam_counts) a.beam_counts[s] = m_out;
+      if (a.angle_inc) a.angle_inc[s] = inc;
+    }
+    // (the barrier at the top of the next scan's mark phase orders ctl reuse; the tile is not touched
+    // before every thread has passed the barrier above)
+  }
+}
+
+template <int MODE, bool EMIT, bool POST, int TS>
+cudaError_t configure_one() {
+  return cudaFuncSetAttribute(scan_small_kernel<MODE, EMIT, POST, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              227 * 1024);
+}
+
+template <int MODE, bool EMIT, bool POST, int TS>
+cudaError_t launch_one(const ScanBatchArgs& a, const SmallArgs& p, size_t smem, int num_sms, cudaStream_t stream) {
+  int occ = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_small_kernel<MODE, EMIT, POST, TS>, TS, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorLaunchOutOfResources;
+  const int grid = (int)std::min<uint32_t>((uint32_t)(occ * num_sms), a.n_scans);
+  scan_small_kernel<MODE, EMIT, POST, TS><<<grid, TS, smem, stream>>>(a, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+constexpr int kSmallThreads = 256;      // LaserScan variants
+constexpr int kSmallPostThreads = 512;  // PointCloud2 chain
+
+size_t scan_small_smem_bytes(uint32_t cap, int mode, bool emit, bool post) {
+  size_t b = kCtl + (size_t)cap * 8;  // control block + tile
+  if (post)  // (x, y) + intensity + accumulators (the rank table sits at their start during the place pass)
+    return b + (size_t)cap * 8 + cap + std::max<size_t>((size_t)cap * 16, kWords * 6);
+  b += kWords * 6;
+  if (emit) b += kWords * 6;
+  if (mode == 1) b += (size_t)cap * 2;
+  return b;
+}
+
+bool scan_small_applies(uint32_t stride) { return stride != 0 && stride <= kSmallMaxNodes; }
+
+cudaError_t scan_small_configure() {
+  cudaError_t e;
+  if ((e = configure_one<0, false, false, kSmallThreads>()) != cudaSuccess) return e;
+  if ((e = configure_one<0, true, false, kSmallThreads>()) != cudaSuccess) return e;
+  if ((e = configure_one<1, false, false, kSmallThreads>()) != cudaSuccess) return e;
+  if ((e = configure_one<1, true, false, kSmallThreads>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, false, false, kSmallThreads>()) != cudaSuccess) return e;
+  return configure_one<2, false, true, kSmallPostThreads>();
+}
+
+cudaError_t launch_scan_small(const ScanBatchArgs& a, uint32_t max_nodes, uint32_t sor_k, float sor_alpha, float voxel,
+                              int num_sms, cudaStream_t stream) {
+  SmallArgs p{};
+  p.cap = (a.stride + 63u) & ~63u;
+  p.max_nodes = max_nodes;
+  p.use_tma = ((reinterpret_cast<uintptr_t>(a.nodes) & 15u) == 0 && (a.stride & 1u) == 0) ? 1u : 0u;
+  p.sor_k = sor_k;
+  p.sor_alpha = sor_alpha;
+  p.voxel = voxel;
+  const bool cloud = a.xyzi != nullptr;
+  const bool emit = !cloud && a.nodes_out != nullptr && a.apply_ascend != 0;
+  const bool post = cloud && (sor_k > 0 || voxel > 0.0f);
+  const int mode = cloud ? 2 : (a.mode_a ? 1 : 0);
+  const size_t sh = scan_small_smem_bytes(p.cap, mode, emit, post);
+  if (cloud) {
+    if (post) return launch_one<2, false, true, kSmallPostThreads>(a, p, sh, num_sms, stream);
+    return launch_one<2, false, false, kSmallThreads>(a, p, sh, num_sms, stream);
+  }
+  if (mode == 1) {
+    if (emit) return launch_one<1, true, false, kSmallThreads>(a, p, sh, num_sms, stream);
+    return launch_one<1, false, false, kSmallThreads>(a, p, sh, num_sms, stream);
+  }
+  if (emit) return launch_one<0, true, false, kSmallThreads>(a, p, sh, num_sms, stream);
+  return launch_one<0, false, false, kSmallThreads>(a, p, sh, num_sms, stream);
+}
+
+}  // namespace rpl

@@ -43,12 +43,16 @@ def room_scans(oracle, n_scans, n, seed, ties=False):
 
 
 def check_cloud(R, O, ctx, nodes, counts, **kw):
+    """Both implementations against the definition: flags 0 = the shared-memory kernel with SOR / voxel grid
+    fused (revolutions of at most 4096 nodes; larger ones take the TMA kernel + post passes either way),
+    CLOUD_NO_FUSED = scan kernel + separate post passes."""
     counts = np.asarray(counts, np.uint32)
-    xyzi, pc = ctx.cloud_batch(nodes.view(R.NODE_DTYPE), counts, R.cloud_params(**kw))
-    for s in range(nodes.shape[0]):
-        exp = O.cloud(nodes[s, : counts[s]], O.cloud_params(**kw))
-        assert pc[s] == exp.shape[0], (s, kw, pc[s], exp.shape[0])
-        assert (xyzi[s, : pc[s]].view(np.uint32) == exp.view(np.uint32)).all(), (s, kw)
+    exp = [O.cloud(nodes[s, : counts[s]], O.cloud_params(**kw)) for s in range(nodes.shape[0])]
+    for flags in (0, R.CLOUD_NO_FUSED):
+        xyzi, pc = ctx.cloud_batch(nodes.view(R.NODE_DTYPE), counts, R.cloud_params(flags=flags, **kw))
+        for s in range(nodes.shape[0]):
+            assert pc[s] == exp[s].shape[0], (s, kw, flags, pc[s], exp[s].shape[0])
+            assert (xyzi[s, : pc[s]].view(np.uint32) == exp[s].view(np.uint32)).all(), (s, kw, flags)
     return xyzi, pc
 
 
@@ -142,3 +146,56 @@ def test_fuse_packs_per_scan_clouds(R, oracle, ctx):
                           for s in range(n_scans)])
     got = fused[: int(total.item())].cpu().numpy()
     assert (got.view(np.uint32) == exp.view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("stride,n", [(64, 64), (65, 61), (1000, 999), (3200, 3200), (4096, 4096), (4095, 4001)])
+def test_shared_memory_chain_strides(R, oracle, ctx, stride, n):
+    """The fused chain at the edges of its range: smallest and largest capacity, odd strides (no TMA staging:
+    scan bases are only 8-byte aligned), counts below the stride."""
+    src = room_scans(oracle, 5, n, 1000 + stride)
+    nodes = np.zeros((5, stride), oracle.NODE_DTYPE)
+    nodes[:, :n] = src
+    counts = np.array([n, n - 1, n, max(n // 2, 1), n], np.uint32)
+    for kw in (dict(), dict(voxel_size=0.05), dict(sor_k=8, sor_alpha=1.0), dict(sor_k=8, sor_alpha=1.0, voxel_size=0.05),
+               dict(sor_k=20, sor_alpha=0.5, voxel_size=0.3)):
+        check_cloud(R, oracle, ctx, nodes, counts, range_min=0.15, range_max=40.0, **kw)
+
+
+def test_shared_memory_chain_ties_and_dense_cells(R, oracle, ctx):
+    """Duplicate keys inside a batch (those scans go through the general kernel and the list-restricted post
+    passes), every point in one voxel, every point its own voxel."""
+    n = 2048
+    nodes = room_scans(oracle, 6, n, 4242)
+    nodes[1] = room_scans(oracle, 1, n, 4243, ties=True)[0]
+    nodes[4] = room_scans(oracle, 1, n, 4244, ties=True)[0]
+    counts = np.full(6, n, np.uint32)
+    check_cloud(R, oracle, ctx, nodes, counts, range_min=0.15, range_max=40.0, sor_k=8, sor_alpha=1.0, voxel_size=0.05)
+    one = oracle.synth_batch(77, 3, 4096, 0)
+    one["dist_mm_q2"] = np.where(one["dist_mm_q2"] != 0, 2 + (one["dist_mm_q2"] % 30), 0)  # 0.5 .. 8 mm from the sensor
+    check_cloud(R, oracle, ctx, one, np.full(3, 4096, np.uint32), range_min=0.0, range_max=40.0, voxel_size=3.9)
+    far = oracle.synth_batch(78, 3, 4096, 0)
+    far["dist_mm_q2"] = np.where(far["dist_mm_q2"] != 0, 150000 + (far["dist_mm_q2"] % 8000), 0)  # 37.5 .. 39.5 m
+    _, pc = check_cloud(R, oracle, ctx, far, np.full(3, 4096, np.uint32), range_min=0.15, range_max=40.0, voxel_size=0.002)
+    assert (pc > 3500).all()
+
+
+def test_large_voxels_take_the_separate_passes(R, oracle, ctx):
+    """voxel > 4 m or more than 32000 cells per axis: the 32-bit cell keys / accumulators of the fused kernel
+    are not exact any more, the library must fall back to the separate passes (same results)."""
+    nodes = room_scans(oracle, 4, 3200, 99)
+    counts = np.full(4, 3200, np.uint32)
+    check_cloud(R, oracle, ctx, nodes, counts, range_min=0.15, range_max=40.0, voxel_size=6.0)
+    check_cloud(R, oracle, ctx, nodes, counts, range_min=0.15, range_max=900.0, voxel_size=0.001)
+
+
+@pytest.mark.parametrize("variant,n", [(0, 3200), (4, 3200), (1, 32768)])
+def test_cuda_projection_within_1e6_of_float64(R, oracle, ctx, variant, n):
+    """The CUDA path against float64 numpy directly (no oracle in between): BASELINE.json's 1e-6 relative
+    tolerance on the polar -> Cartesian path, laser_geometry::projectLaser semantics (tests/test_cloud_semantics.py)."""
+    from test_cloud_semantics import check_projection
+
+    nodes = oracle.synth_batch(9100 + variant, 3, n, variant)
+    counts = np.full(3, n, np.uint32)
+    xyzi, pc = ctx.cloud_batch(nodes.view(R.NODE_DTYPE), counts, R.cloud_params(range_min=0.15, range_max=40.0))
+    for s in range(3):
+        assert check_projection(xyzi[s, : pc[s]], nodes[s], range_min=0.15, range_max=40.0) < 1e-6

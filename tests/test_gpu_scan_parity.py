@@ -38,12 +38,18 @@ def oracle_batch(O, nodes, counts, newp, mode_a, inv, ascend, stable=True):
     return res
 
 
-def check_batch(R, O, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=0, stable=True, expect_path=None):
+def check_batch(R, O, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=0, stable=True, expect_path=None,
+                emit=True):
+    """Which kernel runs (rpl_capi.cu enqueue_args): flags & 1 general radix kernel; stride <= 4096 and not
+    flags & 4: the shared-memory kernels (scan_small.cu); else with the ascended buffer (emit and ascend) or
+    flags & 2 or unaligned scans: scan_fast.cu, otherwise the TMA ring (scan_tma.cu)."""
     counts = np.asarray(counts, dtype=np.uint32)
     exp = oracle_batch(O, nodes, counts, newp, mode_a, inv, ascend, stable)
     got = ctx.scan_batch(nodes.view(R.NODE_DTYPE), counts, R.scan_params(newp, mode_a, inv, ascend, flags),
-                         emit_nodes=True)
-    tag = (newp, mode_a, inv, ascend, flags)
+                         emit_nodes=emit)
+    if not emit:
+        got["nodes"] = exp["nodes"]
+    tag = (newp, mode_a, inv, ascend, flags, emit)
     assert (got["beam_counts"] == exp["beam_counts"]).all(), tag
     assert (got["status"] == exp["status"]).all(), tag
     assert (bits(got["angle_increment"]) == bits(exp["angle_increment"])).all(), tag
@@ -116,9 +122,10 @@ def test_tie_free_synthetic_both_kernels(R, oracle, ctx, n, variant):
     for newp, mode_a, inv in modes:
         for ascend in (0, 1):
             # tie-free measured keys: the reference's std::sort and the stable rule coincide
-            # flags 0: TMA-ring kernel, 2: register-streamed kernel, 1: general radix kernel
-            check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=0, stable=True)
-            check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=2, stable=True)
+            for flags in ((0, 2, 4, 6) if n <= 4096 else (0, 2)):
+                for emit in (True, False):
+                    check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=flags, stable=True,
+                                emit=emit, expect_path=0)
             check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=1, stable=True,
                         expect_path=1)
 
@@ -129,8 +136,9 @@ def test_tie_variant_follows_stable_rule(R, oracle, ctx, n):
     counts = np.full(4, n, np.uint32)
     for newp, mode_a, inv in [(0, 0, 0), (0, 1, 0), (1, 1, 1), (1, 0, 1)]:
         for ascend in (0, 1):
-            check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, stable=True)
-            check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=2, stable=True)
+            for flags in (0, 2, 4, 6):
+                check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=flags, stable=True)
+            check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, stable=True, emit=False)
     # the reference itself (unstable sort) agrees wherever order is defined: Mode A ranges
     exp = oracle_batch(oracle, nodes, counts, 0, 1, 0, 1, stable=False)
     got = ctx.scan_batch(nodes.view(R.NODE_DTYPE), counts, R.scan_params(0, 1, 0, 1))
@@ -157,7 +165,10 @@ def test_mixed_batch_ragged_counts_and_paths(R, oracle, ctx):
     for newp, mode_a, inv in ALL_MODES:
         for ascend in (0, 1):
             got = check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend)
-            check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=2)
+            for flags in (2, 4, 6):
+                check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=flags)
+            for flags in (0, 4):
+                check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=flags, emit=False)
     assert got["status"][3] == R.RESULT_OPERATION_FAIL and got["beam_counts"][3] == 0
     assert got["path"][8] == R.PATH_GENERAL
 
@@ -180,7 +191,9 @@ def test_extreme_values(R, oracle, ctx):
     counts = np.array([n, 1000], np.uint32)
     for newp, mode_a, inv in ALL_MODES:
         check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, 1)
-        check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, 1, flags=2)
+        check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, 1, emit=False)
+        check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, 1, flags=4, emit=False)
+        check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, 1, flags=6)
         check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, 0, flags=1)
     big = oracle.synth_batch(1, 1, 70000, 0)
     check_batch(R, oracle, ctx, big, np.array([70000], np.uint32), 0, 1, 0, 1, expect_path=1)
@@ -276,4 +289,6 @@ def test_odd_stride_takes_unaligned_path(R, oracle, ctx):
     nodes[:, :n] = oracle.synth_batch(321, 6, n, 1)
     counts = np.full(6, n, np.uint32)
     for newp, mode_a, inv in ALL_MODES:
-        check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, 1, expect_path=0)
+        for flags in (0, 4):  # shared-memory kernel without TMA staging / register-streamed kernel
+            for emit in (True, False):
+                check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, 1, flags=flags, emit=emit, expect_path=0)
