@@ -98,3 +98,53 @@ def test_pointcloud2_batch_from_the_cloud_path(R, oracle, frame_id):
         assert (ho[s, hs[s]:] == 0xEE).all()
         assert cdr.parse_pointcloud2(ho[s, : hs[s]].tobytes())["width"] == n
     ctx.close()
+
+
+def test_device_writer_matches_the_hand_derived_bytes(R):
+    """tests/golden/cdr_*.bin are laid out by hand from the XCDR1 rules (tests/golden/make_golden_cdr.py)."""
+    import os
+
+    import torch
+
+    from test_cdr_golden import GOLD, _load
+
+    m = _load()
+    dev = torch.device("cuda")
+    ctx = R.Context(0, 64, 4)
+    g = m.LASERSCAN
+    stride = 8
+    ranges = torch.zeros((1, stride), dtype=torch.float32, device=dev)
+    intens = torch.zeros((1, stride), dtype=torch.float32, device=dev)
+    ranges[0, :3] = torch.tensor(g["ranges"], dtype=torch.float32)
+    intens[0, :3] = torch.tensor(g["intensities"], dtype=torch.float32)
+    beams = torch.tensor([3], dtype=torch.int32, device=dev)
+    meta_h = np.zeros(1, R.capi.LASERSCAN_META_DTYPE)
+    meta_h["stamp_sec"], meta_h["stamp_nanosec"] = g["sec"], g["nanosec"]
+    for k, v in zip(("angle_min", "angle_max", "angle_increment", "time_increment", "scan_time", "range_min", "range_max"),
+                    g["scalars"]):
+        meta_h[k] = np.float32(v)
+    meta = torch.from_numpy(meta_h.view(np.uint8)).to(dev)
+    cdr_stride = (R.lib().rpl_laserscan_cdr_size(len(g["frame_id"]), stride) + 15) & ~15
+    out = torch.full((1, cdr_stride), 0xEE, dtype=torch.uint8, device=dev)
+    sizes = torch.zeros(1, dtype=torch.int32, device=dev)
+    ctx.laserscan_cdr_batch_dev(meta.data_ptr(), g["frame_id"], ranges.data_ptr(), intens.data_ptr(), beams.data_ptr(), 1,
+                                stride, out.data_ptr(), cdr_stride, cdr_sizes=sizes.data_ptr())
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    gold = open(os.path.join(GOLD, "cdr_laserscan.bin"), "rb").read()
+    assert int(sizes[0]) == len(gold) and out[0, : len(gold)].cpu().numpy().tobytes() == gold
+
+    g = m.PC2
+    xyzi = torch.zeros((1, stride, 4), dtype=torch.float32, device=dev)
+    xyzi[0, :2] = torch.tensor(g["points"], dtype=torch.float32)
+    pcount = torch.tensor([2], dtype=torch.int32, device=dev)
+    stamps = torch.from_numpy(np.array([[g["sec"], g["nanosec"]]], np.uint32).view(np.int32)).to(dev)
+    cdr_stride = (R.lib().rpl_pointcloud2_cdr_size(len(g["frame_id"]), stride) + 15) & ~15
+    out = torch.full((1, cdr_stride), 0xEE, dtype=torch.uint8, device=dev)
+    ctx.pointcloud2_cdr_batch_dev(stamps.data_ptr(), g["frame_id"], xyzi.data_ptr(), pcount.data_ptr(), 1, stride,
+                                  out.data_ptr(), cdr_stride, cdr_sizes=sizes.data_ptr())
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    gold = open(os.path.join(GOLD, "cdr_pointcloud2.bin"), "rb").read()
+    assert int(sizes[0]) == len(gold) and out[0, : len(gold)].cpu().numpy().tobytes() == gold
+    ctx.close()
