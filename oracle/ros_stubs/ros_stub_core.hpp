@@ -43,6 +43,22 @@ struct LaserScan {
         range_max = 0;
   std::vector<float> ranges, intensities;
 };
+struct PointField {
+  static constexpr uint8_t INT8 = 1, UINT8 = 2, INT16 = 3, UINT16 = 4, INT32 = 5, UINT32 = 6, FLOAT32 = 7, FLOAT64 = 8;
+  std::string name;
+  uint32_t offset = 0;
+  uint8_t datatype = 0;
+  uint32_t count = 0;
+};
+struct PointCloud2 {
+  std_msgs::msg::Header header;
+  uint32_t height = 0, width = 0;
+  std::vector<PointField> fields;
+  bool is_bigendian = false;
+  uint32_t point_step = 0, row_step = 0;
+  std::vector<uint8_t> data;
+  bool is_dense = false;
+};
 }  // namespace sensor_msgs::msg
 namespace geometry_msgs::msg {
 struct Vector3 {
@@ -189,10 +205,17 @@ inline std::function<void(const sensor_msgs::msg::LaserScan&)>& laserscan_sink()
   static thread_local std::function<void(const sensor_msgs::msg::LaserScan&)> f;  // one per worker thread
   return f;
 }
+inline std::function<void(const sensor_msgs::msg::PointCloud2&)>& pointcloud2_sink() {
+  static thread_local std::function<void(const sensor_msgs::msg::PointCloud2&)> f;
+  return f;
+}
 template <class Msg>
 inline void deliver(const Msg&) {}
 inline void deliver(const sensor_msgs::msg::LaserScan& m) {
   if (laserscan_sink()) laserscan_sink()(m);
+}
+inline void deliver(const sensor_msgs::msg::PointCloud2& m) {
+  if (pointcloud2_sink()) pointcloud2_sink()(m);
 }
 }  // namespace ros_stub
 
@@ -246,9 +269,18 @@ class LifecycleNode : public node_interfaces::LifecycleNodeInterface {
 
   template <class T>
   T declare_parameter(const std::string& name, const T& def) {
+    if (overridden_.count(name)) {  // an override given before the declaration wins, as in ROS
+      T v{};
+      get_parameter(name, v);
+      return v;
+    }
     set_default(name, def);
     return def;
   }
+  bool has_parameter(const std::string& name) const { return params_.count(name) != 0; }
+  // test hook (not ROS API): what a launch file / `ros2 param set` would do before the node reads the value
+  template <class T>
+  void stub_override_parameter(const std::string& name, const T& v) { set_default(name, v); overridden_[name] = true; }
   template <class T>
   bool get_parameter(const std::string& name, T& out) const {
     auto it = params_.find(name);
@@ -298,6 +330,7 @@ class LifecycleNode : public node_interfaces::LifecycleNodeInterface {
   static void convert(const Stored& s, std::string& o) { o = std::get<std::string>(s); }
   std::string name_;
   std::map<std::string, Stored> params_;
+  std::map<std::string, bool> overridden_;
 };
 }  // namespace rclcpp_lifecycle
 

@@ -10,6 +10,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -118,11 +119,31 @@ class CudaScanPipeline {
     return true;
   }
 
+  // PointCloud2 extension (north star; no reference line): one revolution -> [n][x, y, z, intensity] through
+  // rpl_cloud_batch (window, polar->xyz, optional SOR and voxel grid; oracle/cloud_oracle.cpp is the definition).
+  bool cloud(const std::vector<sl_lidar_response_measurement_node_hq_t>& nodes, const rpl_cloud_params& params,
+             std::vector<float>& xyzi, uint32_t& n_points) {
+    n_points = 0;
+    xyzi.clear();
+    if (nodes.empty()) return true;
+    // rpl_cloud_batch moves [n_scans][stride] blocks; an even stride keeps the scan on the bulk-copy path
+    const uint32_t n = static_cast<uint32_t>(nodes.size()), stride = (n + 1u) & ~1u;
+    staging_.assign(stride, rpl_node_hq{});
+    std::memcpy(staging_.data(), nodes.data(), nodes.size() * sizeof(rpl_node_hq));
+    xyzi.resize(static_cast<size_t>(stride) * 4);
+    uint32_t count = n, pts = 0;
+    if (rpl_cloud_batch(ctx_, staging_.data(), &count, 1, stride, &params, xyzi.data(), &pts) != RPL_RESULT_OK) return false;
+    n_points = pts;
+    xyzi.resize(static_cast<size_t>(pts) * 4);
+    return true;
+  }
+
   const char* last_error() const { return rpl_last_error(ctx_); }
   rpl_ctx* raw() { return ctx_; }
 
  private:
   rpl_ctx* ctx_ = nullptr;
+  std::vector<rpl_node_hq> staging_;
 };
 
 }  // namespace rplidar_b200
