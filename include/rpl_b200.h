@@ -353,6 +353,31 @@ rpl_result rpl_assemble_scans_dev(rpl_ctx* ctx, const rpl_node_hq* nodes, const 
                                   uint32_t* scans_per_stream, const uint64_t* node_ts_us,
                                   uint64_t* scan_begin_ts_us, void* stream);
 
+/* The same cut WITHOUT the copy: a published scan is returned as a view {first node, count} into the node buffer
+ * itself (first counts from the start of `nodes`, across streams), and rpl_scan_views_dev reads the revolutions
+ * where the decoder left them -- the capsule -> LaserScan chain then moves every node through HBM once less in
+ * each direction.  views_out / scan_len: [n_streams][max_scans], unused entries are {0, 0}.  The holder's capacity
+ * rule (a scan longer than max_nodes keeps overwriting its last entry) is applied IN PLACE: node first+max_nodes-1
+ * of such a scan is overwritten with the scan's last node (the nodes behind it are dropped either way), which is
+ * why `nodes` is not const here. */
+typedef struct rpl_scan_view {
+  uint32_t first; /* index of the scan's first node in the whole node buffer */
+  uint32_t count;
+} rpl_scan_view;
+rpl_result rpl_assemble_scan_views_dev(rpl_ctx* ctx, rpl_node_hq* nodes, const uint32_t* node_counts,
+                                       uint32_t n_streams, uint32_t stride_nodes, const uint32_t* capsule_status,
+                                       const uint32_t* capsule_node_offset, const uint32_t* capsule_counts,
+                                       uint32_t stride_capsules, uint32_t max_nodes, uint32_t max_scans,
+                                       rpl_scan_view* views_out, uint32_t* scan_len, uint32_t* scans_per_stream,
+                                       const uint64_t* node_ts_us, uint64_t* scan_begin_ts_us, void* stream);
+/* rpl_scan_batch_dev over views: scan s = views[s].count nodes from nodes[views[s].first]; nodes_total = nodes in
+ * the buffer; outputs laid out [n_scans][stride] as before (stride >= every count, stride <= 4096: the views are
+ * served by the shared-memory kernels).  `nodes` must be 16-byte aligned. */
+rpl_result rpl_scan_views_dev(rpl_ctx* ctx, const rpl_node_hq* nodes, uint64_t nodes_total, const rpl_scan_view* views,
+                              uint32_t n_scans, uint32_t stride, const rpl_scan_params* params, rpl_node_hq* nodes_out,
+                              float* ranges, float* intensities, uint32_t* beam_counts, float* angle_increment,
+                              uint32_t* status, uint32_t* path, void* stream);
+
 /* ---- LaserScan / PointCloud2 -> wire ---------------------------- */
 /* The serialised message the RMW layer would produce from the message the reference publishes
  * (scan_pub_->publish, reference src/rplidar_node.cpp:679): XCDR1 little endian, 4-byte

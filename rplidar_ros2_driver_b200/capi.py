@@ -44,7 +44,8 @@ EXPORTS = [
     "rpl_host_alloc", "rpl_host_free", "rpl_ctx_launch_count", "rpl_ctx_profile", "rpl_ctx_profile_read", "rpl_ascend_scan", "rpl_laserscan",
     "rpl_scan", "rpl_scan_batch", "rpl_ascend_scan_batch", "rpl_laserscan_batch", "rpl_scan_batch_dev",
     "rpl_cloud_batch_dev", "rpl_cloud_batch", "rpl_cloud_fuse_dev", "rpl_synth_batch_dev",
-    "rpl_decode_dense_batch_dev", "rpl_decode_dense", "rpl_assemble_scans_dev",
+    "rpl_decode_dense_batch_dev", "rpl_decode_dense", "rpl_assemble_scans_dev", "rpl_assemble_scan_views_dev",
+    "rpl_scan_views_dev",
     "rpl_capsule_bytes", "rpl_capsule_nodes", "rpl_decode_capsules_batch_dev", "rpl_decode_capsules",
     "rpl_decode_normal_batch_dev", "rpl_decode_normal", "rpl_node_timestamps_dev", "rpl_normal_timestamps_dev",
     "rpl_peer_gather_bytes", "rpl_peer_alloc", "rpl_peer_open", "rpl_peer_close", "rpl_peer_free",
@@ -180,6 +181,8 @@ def lib() -> C.CDLL:
         "rpl_normal_timestamps_dev": ([vp, C.POINTER(Timing), vp, vp, u32, u32, u32, vp, u32, vp, vp], u32),
         "rpl_decode_normal": ([vp, vp, u32, vp, C.POINTER(u32)], u32),
         "rpl_assemble_scans_dev": ([vp, vp, vp, u32, u32, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp, vp, vp], u32),
+        "rpl_assemble_scan_views_dev": ([vp, vp, vp, u32, u32, vp, vp, vp, u32, u32, u32, vp, vp, vp, vp, vp, vp], u32),
+        "rpl_scan_views_dev": ([vp, vp, u64, vp, u32, u32, PSP, vp, vp, vp, vp, vp, vp, vp, vp], u32),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)  # AttributeError here = the library does not export the ABI
@@ -468,6 +471,21 @@ class Context:
             self._h, _p(nodes), _p(node_counts), n_streams, stride_nodes, _p(capsule_status), _p(capsule_node_offset),
             _p(capsule_counts), stride_capsules, max_nodes, max_scans, scan_stride, _p(scans_out), _p(scan_len),
             _p(scans_per_stream), _p(node_ts_us), _p(scan_begin_ts_us), _p(stream)))
+
+    def assemble_scan_views_dev(self, nodes, node_counts, n_streams, stride_nodes, max_nodes, max_scans, views_out,
+                                scan_len, scans_per_stream, capsule_status=None, capsule_node_offset=None,
+                                capsule_counts=None, stride_capsules=0, node_ts_us=None, scan_begin_ts_us=None,
+                                stream=None):
+        self._check(self._L.rpl_assemble_scan_views_dev(
+            self._h, _p(nodes), _p(node_counts), n_streams, stride_nodes, _p(capsule_status), _p(capsule_node_offset),
+            _p(capsule_counts), stride_capsules, max_nodes, max_scans, _p(views_out), _p(scan_len),
+            _p(scans_per_stream), _p(node_ts_us), _p(scan_begin_ts_us), _p(stream)))
+
+    def scan_views_dev(self, nodes, nodes_total, views, n_scans, stride, params: ScanParams, nodes_out=None, ranges=None,
+                       intensities=None, beam_counts=None, angle_increment=None, status=None, path=None, stream=None):
+        self._check(self._L.rpl_scan_views_dev(
+            self._h, _p(nodes), nodes_total, _p(views), n_scans, stride, C.byref(params), _p(nodes_out), _p(ranges),
+            _p(intensities), _p(beam_counts), _p(angle_increment), _p(status), _p(path), _p(stream)))
 
     def cloud_fuse_dev(self, xyzi, point_counts, n_scans, stride, fused, offsets, total, stream=None):
         self._check(self._L.rpl_cloud_fuse_dev(self._h, _p(xyzi), _p(point_counts), n_scans, stride, _p(fused),

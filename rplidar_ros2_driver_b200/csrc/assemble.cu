@@ -212,6 +212,28 @@ __global__ void __launch_bounds__(AT) assemble_kernel(AssembleArgs a) {
     if (tid == 0) a.scans_per_stream[s] = total;
     // ---- copy the published scans (descriptors were written by this CTA: visible after the barrier) ---
     const uint32_t stored = min(total, a.max_scans);
+    if (a.views_out) {
+      // view mode: no copy.  A published scan is handed on as (first node, count) into the node buffer itself;
+      // a scan that hit the holder's capacity gets the holder's "replace the last entry" applied in place
+      // (the nodes behind the cap are dropped either way).
+      uint2* vout = a.views_out + (size_t)s * a.max_scans;
+      for (uint32_t k = tid; k < a.max_scans; k += AT) {
+        uint2 v = make_uint2(0u, 0u);
+        if (k < stored) {
+          const uint2 d = desc[k];
+          const uint32_t cnt = min(d.y, a.max_nodes);
+          if (d.y > cnt) a.nodes_mut[(size_t)s * a.stride_nodes + d.x + cnt - 1] = nodes[d.x + d.y - 1];
+          v = make_uint2((uint32_t)((size_t)s * a.stride_nodes + d.x), cnt);
+          if (a.scan_begin_ts_us)
+            a.scan_begin_ts_us[(size_t)s * a.max_scans + k] =
+                a.node_ts_us ? a.node_ts_us[(size_t)s * a.stride_nodes + d.x] : 0ull;
+        }
+        vout[k] = v;
+        out_len[k] = v.y;
+      }
+      __syncthreads();
+      continue;
+    }
     for (uint32_t k = 0; k < stored; ++k) {
       const uint2 d = desc[k];
       const uint32_t cnt = min(d.y, a.max_nodes);

@@ -81,7 +81,9 @@ struct AssembleArgs {
   uint32_t stride_capsules;
   uint32_t max_nodes;                 // ScanDataHolder capacity (8192 in the SDK)
   uint32_t max_scans, scan_stride;
-  uint2* scans_out;                   // [n_streams][max_scans][scan_stride]
+  uint2* scans_out;                   // [n_streams][max_scans][scan_stride] (copy mode)
+  uint2* views_out;                   // [n_streams][max_scans] {first node in the whole buffer, count} (view mode)
+  uint2* nodes_mut;                   // view mode: the node buffer, writable (capacity rule applied in place)
   uint32_t* scan_len;                 // [n_streams][max_scans]
   uint32_t* scans_per_stream;         // [n_streams] published scans (may exceed max_scans)
   const unsigned long long* node_ts_us;  // [n_streams][stride_nodes] nullable

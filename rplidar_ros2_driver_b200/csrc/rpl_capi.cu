@@ -109,7 +109,8 @@ rpl_result enqueue_args(rpl_ctx* c, Lane& l, rpl::ScanBatchArgs a, uint32_t flag
 rpl_result enqueue_scan(rpl_ctx* c, Lane& l, const rpl_node_hq* nodes, const uint32_t* counts,
                         uint32_t n_scans, uint32_t stride, const rpl_scan_params* p,
                         rpl_node_hq* nodes_out, float* ranges, float* intens, uint32_t* beams,
-                        float* inc, uint32_t* status, uint32_t* path, cudaStream_t stream) {
+                        float* inc, uint32_t* status, uint32_t* path, cudaStream_t stream,
+                        const uint2* views = nullptr, unsigned long long nodes_total = 0) {
   if (n_scans == 0) return RPL_RESULT_OK;
   if (!nodes || !counts || !p) {
     c->err = "null nodes/counts/params";
@@ -152,6 +153,8 @@ rpl_result enqueue_scan(rpl_ctx* c, Lane& l, const rpl_node_hq* nodes, const uin
   a.mode_a = p->scan_processing;
   a.inverted = p->inverted;
   a.apply_ascend = p->apply_ascend;
+  a.views = views;
+  a.nodes_total = nodes_total;
   return enqueue_args(c, l, a, p->flags, stream);
 }
 
@@ -969,14 +972,18 @@ rpl_result rpl_decode_normal(rpl_ctx* c, const uint8_t* bytes, uint32_t n_bytes,
 }
 
 // ---- scan assembly ------------------------------------------------------
-rpl_result rpl_assemble_scans_dev(rpl_ctx* c, const rpl_node_hq* nodes, const uint32_t* node_counts,
+}  // extern "C"
+
+namespace {
+// copy mode (scans_out) or view mode (views_out + writable nodes)
+rpl_result assemble_common(rpl_ctx* c, const rpl_node_hq* nodes, const uint32_t* node_counts,
                                   uint32_t n_streams, uint32_t stride_nodes, const uint32_t* capsule_status,
                                   const uint32_t* capsule_node_offset, const uint32_t* capsule_counts,
                                   uint32_t stride_capsules, uint32_t max_nodes, uint32_t max_scans,
-                                  uint32_t scan_stride, rpl_node_hq* scans_out, uint32_t* scan_len,
+                                  uint32_t scan_stride, rpl_node_hq* scans_out, rpl_scan_view* views_out, uint32_t* scan_len,
                                   uint32_t* scans_per_stream, const uint64_t* node_ts_us,
                                   uint64_t* scan_begin_ts_us, void* stream) {
-  if (!c || !nodes || !node_counts || !scans_out || !scan_len || !scans_per_stream) return RPL_RESULT_INVALID_DATA;
+  if (!c || !nodes || !node_counts || (!scans_out && !views_out) || !scan_len || !scans_per_stream) return RPL_RESULT_INVALID_DATA;
   const bool any = capsule_status || capsule_node_offset || capsule_counts;
   if (any && !(capsule_status && capsule_node_offset && capsule_counts)) {
     c->err = "capsule_status, capsule_node_offset and capsule_counts go together";
@@ -1020,6 +1027,8 @@ rpl_result rpl_assemble_scans_dev(rpl_ctx* c, const rpl_node_hq* nodes, const ui
   a.max_scans = max_scans;
   a.scan_stride = scan_stride;
   a.scans_out = reinterpret_cast<uint2*>(scans_out);
+  a.views_out = reinterpret_cast<uint2*>(views_out);
+  a.nodes_mut = views_out ? reinterpret_cast<uint2*>(const_cast<rpl_node_hq*>(nodes)) : nullptr;
   a.scan_len = scan_len;
   a.scans_per_stream = scans_per_stream;
   a.node_ts_us = reinterpret_cast<const unsigned long long*>(node_ts_us);
@@ -1030,6 +1039,58 @@ rpl_result rpl_assemble_scans_dev(rpl_ctx* c, const rpl_node_hq* nodes, const ui
   RPL_CUDA(c, rpl::launch_assemble(a, grid, st), RPL_RESULT_OPERATION_FAIL);
   c->launches++;
   return RPL_RESULT_OK;
+}
+}  // namespace
+
+extern "C" {
+
+rpl_result rpl_assemble_scans_dev(rpl_ctx* c, const rpl_node_hq* nodes, const uint32_t* node_counts,
+                                  uint32_t n_streams, uint32_t stride_nodes, const uint32_t* capsule_status,
+                                  const uint32_t* capsule_node_offset, const uint32_t* capsule_counts,
+                                  uint32_t stride_capsules, uint32_t max_nodes, uint32_t max_scans,
+                                  uint32_t scan_stride, rpl_node_hq* scans_out, uint32_t* scan_len,
+                                  uint32_t* scans_per_stream, const uint64_t* node_ts_us,
+                                  uint64_t* scan_begin_ts_us, void* stream) {
+  if (!scans_out) return RPL_RESULT_INVALID_DATA;
+  return assemble_common(c, nodes, node_counts, n_streams, stride_nodes, capsule_status, capsule_node_offset,
+                         capsule_counts, stride_capsules, max_nodes, max_scans, scan_stride, scans_out, nullptr, scan_len,
+                         scans_per_stream, node_ts_us, scan_begin_ts_us, stream);
+}
+
+rpl_result rpl_assemble_scan_views_dev(rpl_ctx* c, rpl_node_hq* nodes, const uint32_t* node_counts,
+                                       uint32_t n_streams, uint32_t stride_nodes, const uint32_t* capsule_status,
+                                       const uint32_t* capsule_node_offset, const uint32_t* capsule_counts,
+                                       uint32_t stride_capsules, uint32_t max_nodes, uint32_t max_scans,
+                                       rpl_scan_view* views_out, uint32_t* scan_len, uint32_t* scans_per_stream,
+                                       const uint64_t* node_ts_us, uint64_t* scan_begin_ts_us, void* stream) {
+  if (!views_out) return RPL_RESULT_INVALID_DATA;
+  if ((unsigned long long)n_streams * stride_nodes > 0xFFFFFFFFull) {
+    if (c) c->err = "view mode addresses nodes with 32 bits: n_streams * stride_nodes must stay below 2^32";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  return assemble_common(c, nodes, node_counts, n_streams, stride_nodes, capsule_status, capsule_node_offset,
+                         capsule_counts, stride_capsules, max_nodes, max_scans, max_nodes, nullptr, views_out, scan_len,
+                         scans_per_stream, node_ts_us, scan_begin_ts_us, stream);
+}
+
+rpl_result rpl_scan_views_dev(rpl_ctx* c, const rpl_node_hq* nodes, uint64_t nodes_total, const rpl_scan_view* views,
+                              uint32_t n_scans, uint32_t stride, const rpl_scan_params* params, rpl_node_hq* nodes_out,
+                              float* ranges, float* intensities, uint32_t* beam_counts, float* angle_increment,
+                              uint32_t* status, uint32_t* path, void* stream) {
+  if (!c || !views || !nodes || !params) return RPL_RESULT_INVALID_DATA;
+  if (!rpl::scan_small_applies(stride) || (params->flags & RPL_FLAG_NO_SMALL)) {
+    c->err = "scan views are served by the shared-memory kernels: stride (the longest scan) must be <= 4096 nodes";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if ((reinterpret_cast<uintptr_t>(nodes) & 15u) != 0) {
+    c->err = "the node buffer of a view batch must be 16-byte aligned";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
+  return enqueue_scan(c, c->lane[0], nodes, reinterpret_cast<const uint32_t*>(views), n_scans, stride, params, nodes_out,
+                      ranges, intensities, beam_counts, angle_increment, status, path, st,
+                      reinterpret_cast<const uint2*>(views), nodes_total);
 }
 
 // ---- LaserScan / PointCloud2 -> CDR -------------------------------------

@@ -31,6 +31,11 @@ struct ScanBatchArgs {
   const float2* trig;    // [65536] (cos, sin) of angle_rad(key)
   const float2* angle;   // [65536] (angle_rad, inverted angle): Mode A bins without FP64 on device
   float range_min, range_max, intensity_min;
+  // scan views (rpl_scan_views_dev): when set, scan s is the `count` nodes starting at node `first` of the
+  // whole `nodes` buffer -- views[s] = {first, count} -- instead of nodes[s * stride .. ) with counts[s];
+  // outputs stay at s * stride.  nodes_total = nodes in the buffer (bulk copies must not run past it).
+  const uint2* views;
+  unsigned long long nodes_total;
 };
 
 // per-CTA global workspace of the general kernel, sized for max_nodes

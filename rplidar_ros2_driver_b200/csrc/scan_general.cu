@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(GT, 1)
   const uint32_t n_work = all_scans ? a.n_scans : *a.fallback_count;
   for (uint32_t work = blockIdx.x; work < n_work; work += gridDim.x) {
     const uint32_t s = all_scans ? work : a.fallback_list[work];
-    const uint32_t n = a.counts[s];
-    const uint2* base = a.nodes + (size_t)s * a.stride;
+    const uint32_t n = a.views ? a.views[s].y : a.counts[s];
+    const uint2* base = a.views ? a.nodes + a.views[s].x : a.nodes + (size_t)s * a.stride;
     uint2* nodes_out = a.nodes_out ? a.nodes_out + (size_t)s * a.stride : nullptr;
 
     if (n > a.stride || n > ws.max_nodes) {  // caller error: report, touch nothing

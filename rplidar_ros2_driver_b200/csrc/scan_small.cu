@@ -196,8 +196,8 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
   static_assert(kWords % TS == 0 && WPT % 4 == 0, "prefix layout");
   SmallCtl& ctl = *reinterpret_cast<SmallCtl*>(smem_raw);
   const uint32_t cap = p.cap;
-  uint2* tile = reinterpret_cast<uint2*>(smem_raw + kCtl);
-  unsigned char* q = smem_raw + kCtl + (size_t)cap * 8;
+  uint2* const tile0 = reinterpret_cast<uint2*>(smem_raw + kCtl);  // cap + 2 nodes
+  unsigned char* q = smem_raw + kCtl + (size_t)cap * 8 + 16;
   float2* px = nullptr;
   uint8_t* pi = nullptr;
   uint32_t* bitsV;
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
   uint32_t parity = 0;
 
   for (uint32_t s = blockIdx.x; s < a.n_scans; s += gridDim.x) {
-    const uint32_t n = a.counts[s];
+    const uint32_t n = a.views ? a.views[s].y : a.counts[s];
     if (n > a.stride || n > p.max_nodes) {  // caller error: report, touch nothing
       if (tid == 0) {
         if (a.status) a.status[s] = 0x80008000u;  // SL_RESULT_INVALID_DATA
@@ -257,21 +257,32 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
       }
       continue;
     }
-    const uint2* base = a.nodes + (size_t)s * a.stride;
+    const uint2* base = a.views ? a.nodes + a.views[s].x : a.nodes + (size_t)s * a.stride;
 
     // ---- stage the revolution (every thread is past the previous scan: its last barrier) -----------
-    if (p.use_tma) {
+    // Bulk copies move whole 16-byte units from 16-byte aligned addresses.  A batch scan starts aligned (even
+    // stride) and an odd count is rounded up into the scan's own stride; a VIEW may start on an odd node: the
+    // copy then starts one node early and the tile is read from `shift` on.  A view whose rounded copy would run
+    // past the end of the node buffer is staged with ordinary loads instead.
+    uint32_t shift = 0;
+    bool bulk = p.use_tma != 0;
+    if (a.views) {
+      shift = (uint32_t)((reinterpret_cast<uintptr_t>(base) >> 3) & 1u);
+      const unsigned long long first = a.views[s].x;
+      bulk = bulk && (first - shift + ((n + shift + 1u) & ~1u) <= a.nodes_total);
+    }
+    const uint2* const tile = tile0 + shift;
+    if (bulk) {
       if (tid == 0) {
         // the tile region may have been written with ordinary stores (voxel table): order them before the
         // asynchronous-proxy write of the copy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        // an odd count is rounded up to whole 16 bytes; the extra node lies inside the scan's (even) stride
-        const uint32_t bytes = ((n + 1u) & ~1u) * 8u;
+        const uint32_t bytes = ((n + shift + 1u) & ~1u) * 8u;
         s_mbar_expect_tx(&ctl.full, bytes);
-        s_tma_load_1d(tile, base, bytes, &ctl.full, pol_stream);
+        s_tma_load_1d(tile0, base - shift, bytes, &ctl.full, pol_stream);
       }
     } else {
-      for (uint32_t i = tid; i < n; i += TS) tile[i] = ld_stream_v2(base + i);
+      for (uint32_t i = tid; i < n; i += TS) tile0[shift + i] = ld_stream_v2(base + i);
     }
     {
       uint4* b4 = reinterpret_cast<uint4*>(bitsV);
@@ -286,7 +297,7 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
       }
     }
     __syncthreads();
-    if (p.use_tma) {
+    if (bulk) {
       s_mbar_wait(&ctl.full, parity);
       parity ^= 1u;
     }
@@ -574,7 +585,7 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
         int* dxs = reinterpret_cast<int*>(acc + (size_t)cap * 4);
         int* dys = reinterpret_cast<int*>(acc + (size_t)cap * 8);
         uint32_t* cs = reinterpret_cast<uint32_t*>(acc + (size_t)cap * 12);
-        uint32_t* table = reinterpret_cast<uint32_t*>(tile);
+        uint32_t* table = reinterpret_cast<uint32_t*>(tile0);
         const uint32_t nslots = 2u * cap;
         constexpr uint32_t kEmpty = 0xFFFFFFFFu;
         constexpr uint32_t PMAX = kSmallMaxNodes / TS;
@@ -735,7 +746,7 @@ constexpr int kSmallThreads = 256;      // LaserScan variants
 constexpr int kSmallPostThreads = 512;  // PointCloud2 chain
 
 size_t scan_small_smem_bytes(uint32_t cap, int mode, bool emit, bool post) {
-  size_t b = kCtl + (size_t)cap * 8;  // control block + tile
+  size_t b = kCtl + (size_t)cap * 8 + 16;  // control block + tile (+ one node either side for unaligned views)
   if (post)  // (x, y) + intensity + accumulators (the rank table sits at their start during the place pass)
     return b + (size_t)cap * 8 + cap + std::max<size_t>((size_t)cap * 16, kWords * 6);
   b += kWords * 6;

@@ -183,3 +183,71 @@ def test_decode_assemble_scan_chain_stays_on_the_device(R, oracle, ctx):
             assert (hr[s, k, : hdr.beam_count].view(np.uint32) == r.view(np.uint32)).all()
             total += 1
     assert total > 2 * n_streams
+
+
+@pytest.mark.parametrize("max_nodes,mode_a,emit", [(4096, 0, False), (4096, 1, True), (2000, 0, True)])
+def test_scan_views_equal_the_copying_chain(R, oracle, max_nodes, mode_a, emit):
+    """decode -> rpl_assemble_scan_views_dev -> rpl_scan_views_dev (revolutions read where the decoder left them)
+    against decode -> rpl_assemble_scans_dev -> rpl_scan_batch_dev (revolutions copied out first): same LaserScan,
+    same ascended nodes, same counts -- including revolutions longer than the holder capacity (max_nodes = 2000 <
+    3200: the capacity rule is applied in place) and views that start on odd nodes."""
+    import torch
+
+    n_streams, n_caps, max_scans = 24, 640, 10
+    ctx = R.Context(0, max_nodes, n_streams * max_scans)
+    host = np.stack([make_stream(oracle, n_caps, 80.0 + s, seed=1900 + s, sync_every=(200 + 13 * s) if s % 4 else None)
+                     for s in range(n_streams)])
+    dev = torch.device("cuda")
+    NS = n_streams * max_scans
+
+    def run(view_mode):
+        caps = torch.from_numpy(host).to(dev)
+        ccounts = torch.full((n_streams,), n_caps, dtype=torch.int32, device=dev)
+        nodes = torch.zeros((n_streams, n_caps * 40, 8), dtype=torch.uint8, device=dev)
+        ncount = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+        status = torch.zeros((n_streams, n_caps), dtype=torch.int32, device=dev)
+        offs = torch.zeros((n_streams, n_caps), dtype=torch.int32, device=dev)
+        slen = torch.zeros((n_streams, max_scans), dtype=torch.int32, device=dev)
+        sps = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+        ranges = torch.full((NS, max_nodes), float("nan"), dtype=torch.float32, device=dev)
+        intens = torch.full((NS, max_nodes), float("nan"), dtype=torch.float32, device=dev)
+        nodes_out = torch.zeros((NS, max_nodes, 8), dtype=torch.uint8, device=dev)
+        beams = torch.zeros(NS, dtype=torch.int32, device=dev)
+        inc = torch.zeros(NS, dtype=torch.float32, device=dev)
+        st = torch.zeros(NS, dtype=torch.int32, device=dev)
+        ctx.decode_dense_batch_dev(caps.data_ptr(), ccounts.data_ptr(), n_streams, n_caps, 31, nodes.data_ptr(),
+                                   ncount.data_ptr(), capsule_status=status.data_ptr(),
+                                   capsule_node_offset=offs.data_ptr())
+        params = R.scan_params(1, mode_a, 0, 1)
+        kw = dict(ranges=ranges.data_ptr(), intensities=intens.data_ptr(), beam_counts=beams.data_ptr(),
+                  angle_increment=inc.data_ptr(), status=st.data_ptr(), nodes_out=nodes_out.data_ptr() if emit else None)
+        if view_mode:
+            views = torch.zeros((n_streams, max_scans, 2), dtype=torch.int32, device=dev)
+            ctx.assemble_scan_views_dev(nodes.data_ptr(), ncount.data_ptr(), n_streams, n_caps * 40, max_nodes, max_scans,
+                                        views.data_ptr(), slen.data_ptr(), sps.data_ptr(),
+                                        capsule_status=status.data_ptr(), capsule_node_offset=offs.data_ptr(),
+                                        capsule_counts=ccounts.data_ptr(), stride_capsules=n_caps)
+            ctx.scan_views_dev(nodes.data_ptr(), n_streams * n_caps * 40, views.data_ptr(), NS, max_nodes, params, **kw)
+        else:
+            scans = torch.zeros((n_streams, max_scans, max_nodes, 8), dtype=torch.uint8, device=dev)
+            ctx.assemble_scans_dev(nodes.data_ptr(), ncount.data_ptr(), n_streams, n_caps * 40, max_nodes, max_scans,
+                                   max_nodes, scans.data_ptr(), slen.data_ptr(), sps.data_ptr(),
+                                   capsule_status=status.data_ptr(), capsule_node_offset=offs.data_ptr(),
+                                   capsule_counts=ccounts.data_ptr(), stride_capsules=n_caps)
+            ctx.scan_batch_dev(scans.data_ptr(), slen.data_ptr(), NS, max_nodes, params, **kw)
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        return [t.cpu().numpy() for t in (slen, sps, beams, inc, st, ranges, intens, nodes_out)]
+
+    a, b = run(False), run(True)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and a[1].sum() > 2 * n_streams
+    assert (a[2] == b[2]).all() and (a[3].view(np.uint32) == b[3].view(np.uint32)).all() and (a[4] == b[4]).all()
+    for s in range(NS):
+        m, n = int(a[2][s]), int(a[0].reshape(-1)[s])
+        assert (a[5][s, :m].view(np.uint32) == b[5][s, :m].view(np.uint32)).all(), s
+        assert (a[6][s, :m].view(np.uint32) == b[6][s, :m].view(np.uint32)).all(), s
+        if emit:
+            assert (a[7][s, :n] == b[7][s, :n]).all(), s
+    if max_nodes < 3200:
+        assert (a[0] == max_nodes).any()  # capped revolutions were part of the comparison
+    ctx.close()
