@@ -65,6 +65,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--chain-copy", action="store_true",
+                    help="chain workload: copy the revolutions out of the node stream (rpl_assemble_scans_dev) instead of "
+                         "handing views to the scan kernel")
     ap.add_argument("--no-cloud", action="store_true", help="skip the PointCloud2 + exchange leg (extra.cloud)")
     return ap.parse_args()
 
@@ -1201,7 +1204,8 @@ def run_chain(args, rank, local_rank, world):
     ncount = torch.zeros(n_streams, dtype=torch.int32, device=dev)
     status = torch.zeros((n_streams, n_caps), dtype=torch.int32, device=dev)
     offs = torch.zeros((n_streams, n_caps), dtype=torch.int32, device=dev)
-    scans = torch.zeros((NS, max_nodes, 8), dtype=torch.uint8, device=dev)
+    scans = torch.zeros((NS if args.chain_copy else 1, max_nodes, 8), dtype=torch.uint8, device=dev)
+    views = torch.zeros((NS, 2), dtype=torch.int32, device=dev)
     slen = torch.zeros(NS, dtype=torch.int32, device=dev)
     sps = torch.zeros(n_streams, dtype=torch.int32, device=dev)
     ranges = torch.empty((NS, max_nodes), dtype=torch.float32, device=dev)
@@ -1219,15 +1223,26 @@ def run_chain(args, rank, local_rank, world):
                                    capsule_node_offset=offs.data_ptr(), stream=sp)
         if timed:
             ev[1].record(stream)
-        ctx.assemble_scans_dev(nodes.data_ptr(), ncount.data_ptr(), n_streams, n_caps * 40, max_nodes, max_scans,
-                               max_nodes, scans.data_ptr(), slen.data_ptr(), sps.data_ptr(),
-                               capsule_status=status.data_ptr(), capsule_node_offset=offs.data_ptr(),
-                               capsule_counts=ccounts.data_ptr(), stride_capsules=n_caps, stream=sp)
+        if args.chain_copy:
+            ctx.assemble_scans_dev(nodes.data_ptr(), ncount.data_ptr(), n_streams, n_caps * 40, max_nodes, max_scans,
+                                   max_nodes, scans.data_ptr(), slen.data_ptr(), sps.data_ptr(),
+                                   capsule_status=status.data_ptr(), capsule_node_offset=offs.data_ptr(),
+                                   capsule_counts=ccounts.data_ptr(), stride_capsules=n_caps, stream=sp)
+        else:  # no copy: the revolutions are handed on as views into the decoded stream
+            ctx.assemble_scan_views_dev(nodes.data_ptr(), ncount.data_ptr(), n_streams, n_caps * 40, max_nodes, max_scans,
+                                        views.data_ptr(), slen.data_ptr(), sps.data_ptr(),
+                                        capsule_status=status.data_ptr(), capsule_node_offset=offs.data_ptr(),
+                                        capsule_counts=ccounts.data_ptr(), stride_capsules=n_caps, stream=sp)
         if timed:
             ev[2].record(stream)
-        ctx.scan_batch_dev(scans.data_ptr(), slen.data_ptr(), NS, max_nodes, params, ranges=ranges.data_ptr(),
-                           intensities=intens.data_ptr(), beam_counts=beams.data_ptr(),
-                           angle_increment=inc.data_ptr(), stream=sp)
+        if args.chain_copy:
+            ctx.scan_batch_dev(scans.data_ptr(), slen.data_ptr(), NS, max_nodes, params, ranges=ranges.data_ptr(),
+                               intensities=intens.data_ptr(), beam_counts=beams.data_ptr(),
+                               angle_increment=inc.data_ptr(), stream=sp)
+        else:
+            ctx.scan_views_dev(nodes.data_ptr(), n_streams * n_caps * 40, views.data_ptr(), NS, max_nodes, params,
+                               ranges=ranges.data_ptr(), intensities=intens.data_ptr(), beam_counts=beams.data_ptr(),
+                               angle_increment=inc.data_ptr(), stream=sp)
         if timed:
             ev[3].record(stream)
 
@@ -1255,14 +1270,18 @@ def run_chain(args, rank, local_rank, world):
     n_scans = int(sps.sum().item())
     peak, peak_src = measured_peak()
     wire = n_streams * n_caps * 84
-    alg = wire + int(ncount.sum().item()) * 8 + pts * (8 + 8 + 8 + 8)  # decode out, assemble in+out, scan in+out
+    # decode out; assemble: flag pass in (+ copy in+out in copy mode); scan in + out
+    alg = wire + int(ncount.sum().item()) * (8 + 8) + pts * ((8 + 8 if args.chain_copy else 0) + 8 + 8)
     line = {
         "metric": "Mpoints/s wire capsules -> LaserScan (decode + scan assembly + scan kernel on the device)",
         "value": pts / (ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": W,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",
         "data": "synthetic",
         "config": {"workload": f"{n_streams} streams x {n_caps} dense capsules -> {n_scans} revolutions of ~3200 nodes, "
-                               f"Mode B, angle_compensate on", "l2": "every stage streams > 126 MB"},
+                               f"Mode B, angle_compensate on; "
+                               + ("revolutions copied out by the assembler" if args.chain_copy else
+                                  "revolutions read in place through views (rpl_assemble_scan_views_dev + rpl_scan_views_dev)"),
+                   "l2": "every stage streams > 126 MB"},
         "roofline": {"bound": "hbm", "kernel": "decode_dense + assemble + scan", "achieved": alg / (ms * 1e-3) / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg},

@@ -91,7 +91,7 @@ typedef struct rpl_scan_params {
 #define RPL_FLAG_NO_TMA 2u        /* use the register-streamed fast kernel (scan_fast.cu) even when the
                                      TMA-ring kernel (scan_tma.cu) applies; for A/B measurements */
 #define RPL_FLAG_NO_SMALL 4u      /* do not use the shared-memory-resident kernels (scan_small.cu) for
-                                     revolutions of at most 4096 nodes; for A/B measurements */
+                                     revolutions of at most 8192 nodes; for A/B measurements */
 
 /* per-scan path report (optional output) */
 #define RPL_PATH_FAST 0u    /* tie-free scan: bitmap-rank kernel */
@@ -319,6 +319,19 @@ rpl_result rpl_decode_capsules(rpl_ctx* ctx, uint32_t ans_type, const uint8_t* c
                                uint32_t sample_duration_us, uint32_t* state, rpl_node_hq* nodes_out,
                                uint32_t* node_count, uint32_t* capsule_status, uint32_t* capsule_node_offset,
                                const rpl_timing* timing, const uint64_t* capsule_rx_us, uint64_t* node_ts_us);
+/* Byte-level framing of RAW capsule streams (0x82, 0x84, 0x85, 0x86) with the SDK's resynchronisation: the hunt for
+ * the two sync nibbles of UnpackerHandler_{Capsule,UltraCapsule,DenseCapsule,UltraDenseCapsule}Node::onData
+ * (reference src/sdk/src/dataunpacker/unpacker/handler_capsules.cpp:107-135, 324-353, 639-668, 852-880).
+ * bytes [n_streams][stride_bytes] -> capsules_out [n_streams][stride_capsules][rpl_capsule_bytes(ans_type)], the
+ * input of the decoders above; every stretch of bytes the SDK would skip becomes ONE all-zero capsule (decoded as
+ * RPL_CAPSULE_BAD_FRAME: the decoders then forget the previous capsule, as the SDK does).  capsule_counts_out[s] >
+ * stride_capsules means the output overflowed (a stream of B bytes needs at most 2 * (B / frame size) + 2 slots);
+ * bytes_left_out (nullable): bytes of an unfinished frame at the end of the stream -- prepend them to the next
+ * piece of the stream. */
+rpl_result rpl_frame_capsules_dev(rpl_ctx* ctx, uint32_t ans_type, const uint8_t* bytes, const uint32_t* byte_counts,
+                                  uint32_t n_streams, uint32_t stride_bytes, uint8_t* capsules_out,
+                                  uint32_t stride_capsules, uint32_t* capsule_counts_out, uint32_t* bytes_left_out,
+                                  void* stream);
 /* 0x81 standard measurement nodes (5 bytes each) from RAW byte streams, with the byte-level
  * resynchronisation of UnpackerHandler_NormalNode::onData (handler_normalnode.cpp:88-141): exact on
  * misframed / corrupted streams.  bytes [n_streams][stride_bytes]; nodes_out
@@ -371,7 +384,7 @@ rpl_result rpl_assemble_scan_views_dev(rpl_ctx* ctx, rpl_node_hq* nodes, const u
                                        rpl_scan_view* views_out, uint32_t* scan_len, uint32_t* scans_per_stream,
                                        const uint64_t* node_ts_us, uint64_t* scan_begin_ts_us, void* stream);
 /* rpl_scan_batch_dev over views: scan s = views[s].count nodes from nodes[views[s].first]; nodes_total = nodes in
- * the buffer; outputs laid out [n_scans][stride] as before (stride >= every count, stride <= 4096: the views are
+ * the buffer; outputs laid out [n_scans][stride] as before (stride >= every count, stride <= 8192: the views are
  * served by the shared-memory kernels).  `nodes` must be 16-byte aligned. */
 rpl_result rpl_scan_views_dev(rpl_ctx* ctx, const rpl_node_hq* nodes, uint64_t nodes_total, const rpl_scan_view* views,
                               uint32_t n_scans, uint32_t stride, const rpl_scan_params* params, rpl_node_hq* nodes_out,

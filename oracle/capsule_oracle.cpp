@@ -18,6 +18,7 @@
 // LIDARSampleDataUnpacker compiled in place (oracle/_ref) and compares node for node, event for event.
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "oracle.h"
 
@@ -332,4 +333,56 @@ extern "C" uint32_t orc_decode_normal(const uint8_t* bytes, uint32_t n_bytes, or
   }
   if (fsm_pos) *fsm_pos = pos;
   return n_out;
+}
+
+
+// ---- byte-level framing (the sync-nibble hunt in front of every capsule decoder) -------------------------------
+// UnpackerHandler_CapsuleNode::onData            reference handler_capsules.cpp:107-135
+// UnpackerHandler_UltraCapsuleNode::onData       :324-353
+// UnpackerHandler_DenseCapsuleNode::onData       :639-668
+// UnpackerHandler_UltraDenseCapsuleNode::onData  :852-880
+// restated as the byte machine it is (`buf_pos` = _cached_scan_node_buf_pos): bytes are consumed one at a time;
+// a completed frame is appended to capsules_out; whenever the machine clears _is_previous_capsuledataRdy while
+// hunting, ONE all-zero capsule is appended before the next frame (the framed decoders treat it as a bad frame,
+// which clears the same flag).  Returns the number of capsules; *bytes_left = bytes buffered at the end.
+extern "C" uint32_t orc_frame_capsules(uint32_t ans_type, const uint8_t* bytes, uint32_t n, uint8_t* capsules_out,
+                                       uint32_t max_capsules, uint32_t* bytes_left) {
+  const uint32_t cb = orc_capsule_bytes(ans_type);
+  std::vector<uint8_t> buf(cb ? cb : 1);
+  uint32_t buf_pos = 0, count = 0;
+  bool lost = false;
+  if (cb == 0) return 0;
+  for (uint32_t pos = 0; pos < n; ++pos) {
+    const uint8_t cur = bytes[pos];
+    switch (buf_pos) {
+      case 0:
+        if ((cur >> 4) != 0xA) {
+          lost = true;  // _is_previous_capsuledataRdy = false; continue
+          continue;
+        }
+        break;
+      case 1:
+        if ((cur >> 4) != 0x5) {
+          buf_pos = 0;
+          lost = true;
+          continue;
+        }
+        break;
+      default:
+        break;
+    }
+    buf[buf_pos++] = cur;
+    if (buf_pos == cb) {
+      buf_pos = 0;
+      if (lost) {
+        if (count < max_capsules) std::memset(capsules_out + (size_t)count * cb, 0, cb);
+        ++count;
+        lost = false;
+      }
+      if (count < max_capsules) std::memcpy(capsules_out + (size_t)count * cb, buf.data(), cb);
+      ++count;
+    }
+  }
+  if (bytes_left) *bytes_left = buf_pos;
+  return count;
 }

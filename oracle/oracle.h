@@ -131,6 +131,8 @@ uint32_t orc_capsule_nodes(uint32_t ans_type);
 uint32_t orc_crc32_padded(const uint8_t* p, uint32_t len);
 /* Framed capsules of any capsule format.  state[2]: in/out {last node sync bit, last distance}
  * (dense / ultra-dense only).  nodes_out must hold orc_capsule_nodes * n_capsules nodes. */
+uint32_t orc_frame_capsules(uint32_t ans_type, const uint8_t* bytes, uint32_t n, uint8_t* capsules_out,
+                            uint32_t max_capsules, uint32_t* bytes_left);
 uint32_t orc_decode_capsules(uint32_t ans_type, const uint8_t* capsules, uint32_t n_capsules,
                              uint32_t sample_duration_us, uint32_t* state, orc_node_hq* nodes_out,
                              uint32_t* capsule_status, uint32_t* capsule_node_offset);

@@ -351,6 +351,20 @@ def decode_capsules(ans: int, capsules: np.ndarray, sample_duration_us: int = 31
     return nodes[:m].copy(), status[:n].copy(), offs[:n].copy(), (int(st[0]), int(st[1]))
 
 
+def frame_capsules(ans: int, stream_bytes: np.ndarray):
+    """The SDK's byte-level framing (sync-nibble hunt) as a function: raw bytes -> (framed capsules with one all-zero
+    capsule per skipped stretch, bytes left in an unfinished frame)."""
+    b = np.ascontiguousarray(stream_bytes, dtype=np.uint8).reshape(-1)
+    cb = capsule_bytes(ans)
+    cap = 2 * (b.shape[0] // cb) + 2
+    out = np.zeros((cap, cb), np.uint8)
+    left = C.c_uint32(0)
+    lib().orc_frame_capsules.restype = C.c_uint32
+    m = lib().orc_frame_capsules(C.c_uint32(ans), _ptr(b), C.c_uint32(b.shape[0]), _ptr(out), C.c_uint32(cap), C.byref(left))
+    assert m <= cap
+    return out[:m].copy(), left.value
+
+
 def decode_normal(stream_bytes: np.ndarray):
     """Returns (nodes, node_end_byte, fsm_pos)."""
     b = np.ascontiguousarray(stream_bytes, dtype=np.uint8).reshape(-1)

@@ -47,7 +47,7 @@ EXPORTS = [
     "rpl_decode_dense_batch_dev", "rpl_decode_dense", "rpl_assemble_scans_dev", "rpl_assemble_scan_views_dev",
     "rpl_scan_views_dev",
     "rpl_capsule_bytes", "rpl_capsule_nodes", "rpl_decode_capsules_batch_dev", "rpl_decode_capsules",
-    "rpl_decode_normal_batch_dev", "rpl_decode_normal", "rpl_node_timestamps_dev", "rpl_normal_timestamps_dev",
+    "rpl_decode_normal_batch_dev", "rpl_decode_normal", "rpl_frame_capsules_dev", "rpl_node_timestamps_dev", "rpl_normal_timestamps_dev",
     "rpl_peer_gather_bytes", "rpl_peer_alloc", "rpl_peer_open", "rpl_peer_close", "rpl_peer_free",
     "rpl_cloud_fuse_push_dev",
     "rpl_exchange_unique_id", "rpl_exchange_create", "rpl_exchange_destroy", "rpl_exchange_allgather",
@@ -159,6 +159,7 @@ def lib() -> C.CDLL:
         "rpl_decode_capsules_batch_dev": ([vp, u32, vp, vp, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp], u32),
         "rpl_decode_capsules": ([vp, u32, vp, u32, u32, vp, vp, C.POINTER(u32), vp, vp, vp, vp, vp], u32),
         "rpl_decode_normal_batch_dev": ([vp, vp, vp, u32, u32, vp, vp, vp, vp, vp], u32),
+        "rpl_frame_capsules_dev": ([vp, u32, vp, vp, u32, u32, vp, u32, vp, vp, vp], u32),
         "rpl_peer_gather_bytes": ([u32, u32], C.c_size_t),
         "rpl_peer_alloc": ([vp, C.c_size_t, C.POINTER(vp), vp], u32),
         "rpl_peer_open": ([vp, vp, C.POINTER(vp)], u32),
@@ -395,6 +396,12 @@ class Context:
             self._h, ans_type, _p(capsules), _p(capsule_counts), n_streams, stride_capsules, sample_duration_us,
             _p(state_in), _p(nodes_out), _p(node_counts), _p(capsule_status), _p(capsule_node_offset),
             _p(state_out), _p(stream)))
+
+    def frame_capsules_dev(self, ans_type, stream_bytes, byte_counts, n_streams, stride_bytes, capsules_out,
+                           stride_capsules, capsule_counts_out, bytes_left_out=None, stream=None):
+        self._check(self._L.rpl_frame_capsules_dev(
+            self._h, ans_type, _p(stream_bytes), _p(byte_counts), n_streams, stride_bytes, _p(capsules_out),
+            stride_capsules, _p(capsule_counts_out), _p(bytes_left_out), _p(stream)))
 
     def decode_normal(self, stream_bytes: np.ndarray):
         """Raw byte stream of 5-byte standard nodes -> nodes (byte-level resynchronisation included)."""

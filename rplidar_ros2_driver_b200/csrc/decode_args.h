@@ -92,6 +92,18 @@ struct AssembleArgs {
   uint2* desc;                        // scratch [n_streams][max_scans]
 };
 
+// byte-level framing with the SDK's resynchronisation (frame.cu)
+struct FrameArgs {
+  const uint8_t* bytes;           // [n_streams][stride_bytes] raw capsule streams
+  const uint32_t* byte_counts;    // [n_streams]
+  uint32_t n_streams, stride_bytes;
+  uint32_t capsule_bytes;         // frame size of the answer type
+  uint8_t* capsules_out;          // [n_streams][stride_capsules][capsule_bytes]
+  uint32_t stride_capsules;
+  uint32_t* capsule_counts_out;   // [n_streams]
+  uint32_t* bytes_left_out;       // [n_streams] nullable: bytes of an unfinished frame at the end
+};
+cudaError_t launch_frame_capsules(const FrameArgs& a, int grid, cudaStream_t stream);
 cudaError_t launch_assemble(const AssembleArgs& a, int grid, cudaStream_t stream);
 cudaError_t launch_decode_dense(const DecodeArgs& a, int grid, cudaStream_t stream);
 cudaError_t decode_configure();  // opt-in dynamic shared memory, once per device

@@ -194,7 +194,7 @@ rpl_result enqueue_args(rpl_ctx* c, Lane& l, rpl::ScanBatchArgs a, uint32_t flag
       // SOR / voxel grid run inside the kernel when the 32-bit cell keys and accumulators are exact:
       // |cell index| < 32768 and voxel <= 4 m (scan_small.cu); otherwise as separate passes
       bool fuse = false;
-      if (a.xyzi && post && (post->sor_k > 0 || post->voxel > 0.0f))
+      if (a.xyzi && post && (post->sor_k > 0 || post->voxel > 0.0f) && rpl::scan_small_post_applies(stride))
         fuse = post->voxel == 0.0f || (post->voxel <= 4.0f && a.range_max / post->voxel < 32000.0f);
       RPL_CUDA(c, rpl::launch_scan_small(a, l.fws.max_nodes, fuse ? post->sor_k : 0u, fuse ? post->sor_alpha : 0.0f,
                                          fuse ? post->voxel : 0.0f, c->num_sms, stream),
@@ -918,6 +918,35 @@ rpl_result rpl_decode_capsules(rpl_ctx* c, uint32_t ans_type, const uint8_t* cap
   return RPL_RESULT_OK;
 }
 
+rpl_result rpl_frame_capsules_dev(rpl_ctx* c, uint32_t ans_type, const uint8_t* bytes, const uint32_t* byte_counts,
+                                  uint32_t n_streams, uint32_t stride_bytes, uint8_t* capsules_out,
+                                  uint32_t stride_capsules, uint32_t* capsule_counts_out, uint32_t* bytes_left_out,
+                                  void* stream) {
+  if (!c || !bytes || !byte_counts || !capsules_out || !capsule_counts_out) return RPL_RESULT_INVALID_DATA;
+  const uint32_t cb = rpl_capsule_bytes(ans_type);
+  if (cb == 0 || ans_type == 0x83) {
+    c->err = "byte-level framing serves the capsule formats with sync nibbles: 0x82, 0x84, 0x85, 0x86";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  if (n_streams == 0) return RPL_RESULT_OK;
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->lane[0].stream;
+  rpl::FrameArgs a{};
+  a.bytes = bytes;
+  a.byte_counts = byte_counts;
+  a.n_streams = n_streams;
+  a.stride_bytes = stride_bytes;
+  a.capsule_bytes = cb;
+  a.capsules_out = capsules_out;
+  a.stride_capsules = stride_capsules;
+  a.capsule_counts_out = capsule_counts_out;
+  a.bytes_left_out = bytes_left_out;
+  const int grid = (int)std::min<uint32_t>(n_streams, (uint32_t)c->num_sms * 8u);
+  RPL_CUDA(c, rpl::launch_frame_capsules(a, grid, st), RPL_RESULT_OPERATION_FAIL);
+  c->launches++;
+  return RPL_RESULT_OK;
+}
+
 rpl_result rpl_decode_normal_batch_dev(rpl_ctx* c, const uint8_t* bytes, const uint32_t* byte_counts,
                                        uint32_t n_streams, uint32_t stride_bytes, rpl_node_hq* nodes_out,
                                        uint32_t* node_counts, uint32_t* fsm_state_out, uint32_t* node_end,
@@ -1079,7 +1108,7 @@ rpl_result rpl_scan_views_dev(rpl_ctx* c, const rpl_node_hq* nodes, uint64_t nod
                               uint32_t* status, uint32_t* path, void* stream) {
   if (!c || !views || !nodes || !params) return RPL_RESULT_INVALID_DATA;
   if (!rpl::scan_small_applies(stride) || (params->flags & RPL_FLAG_NO_SMALL)) {
-    c->err = "scan views are served by the shared-memory kernels: stride (the longest scan) must be <= 4096 nodes";
+    c->err = "scan views are served by the shared-memory kernels: stride (the longest scan) must be <= 8192 nodes";
     return RPL_RESULT_INVALID_DATA;
   }
   if ((reinterpret_cast<uintptr_t>(nodes) & 15u) != 0) {

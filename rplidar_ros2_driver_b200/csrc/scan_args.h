@@ -54,8 +54,12 @@ struct FastWorkspace {
   uint32_t max_nodes;
 };
 
-// shared-memory-resident kernels for revolutions of at most kSmallMaxNodes nodes (scan_small.cu)
-constexpr uint32_t kSmallMaxNodes = 4096;
+// shared-memory-resident kernels (scan_small.cu): revolutions of at most kSmallMaxNodes nodes -- the SDK's own
+// holder capacity -- for the LaserScan variants and the plain PointCloud2 projection; the PointCloud2 chain with
+// SOR / voxel grid fused keeps (x, y), intensity and the cell accumulators in shared memory as well, which fits
+// up to kSmallPostMaxNodes
+constexpr uint32_t kSmallMaxNodes = 8192;
+constexpr uint32_t kSmallPostMaxNodes = 4096;
 struct SmallArgs {
   uint32_t cap;        // stride rounded up to 64 nodes: capacity of the shared-memory arrays
   uint32_t max_nodes;  // the context's max_nodes (a larger count is a caller error)
@@ -65,6 +69,7 @@ struct SmallArgs {
   float voxel;         // 0 = no voxel grid
 };
 bool scan_small_applies(uint32_t stride);
+bool scan_small_post_applies(uint32_t stride);
 cudaError_t scan_small_configure();
 // a.xyzi set: PointCloud2 (window + xyz, then SOR / voxel grid in shared memory when asked for); else LaserScan
 // Mode A/B with the ascended buffer when a.nodes_out is set.  Duplicate-key scans land in a.fallback_list.

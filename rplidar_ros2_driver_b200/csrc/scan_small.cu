@@ -1,6 +1,6 @@
-// scan_small.cu -- the scan kernels for revolutions that fit shared memory (stride <= 4096 nodes:
-// what a spinning lidar delivers; the SDK's own holder caps a revolution at 8192, the S2/S3 produce
-// 3200 at 10 Hz).
+// scan_small.cu -- the scan kernels for revolutions that fit shared memory (stride <= 8192 nodes, the SDK's own
+// holder capacity: what a spinning lidar delivers; the S2/S3 produce 3200 at 10 Hz).  The PointCloud2 chain with
+// SOR / voxel grid fused needs more shared memory per node and serves strides up to 4096.
 //
 // Same contract as scan_tma.cu / scan_fast.cu (ascendScanData_ + publish_scan, reference
 // src/sdk/src/sl_lidar_driver.cpp:128-184 and src/rplidar_node.cpp:581-677; the PointCloud2 steps of
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
         __syncthreads();
         const double thr = ctl.thr;
         // stable in-place compaction: every thread owns a contiguous run of at most 8 points
-        constexpr uint32_t PMAX = kSmallMaxNodes / TS;
+        constexpr uint32_t PMAX = kSmallPostMaxNodes / TS;
         const uint32_t P = (m + TS - 1) / TS;
         const uint32_t lo = tid * P;
         float2 kx[PMAX];
@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
         uint32_t* table = reinterpret_cast<uint32_t*>(tile0);
         const uint32_t nslots = 2u * cap;
         constexpr uint32_t kEmpty = 0xFFFFFFFFu;
-        constexpr uint32_t PMAX = kSmallMaxNodes / TS;
+        constexpr uint32_t PMAX = kSmallPostMaxNodes / TS;
         {
           uint4* t4 = reinterpret_cast<uint4*>(table);
           const uint4 e = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
@@ -756,6 +756,7 @@ size_t scan_small_smem_bytes(uint32_t cap, int mode, bool emit, bool post) {
 }
 
 bool scan_small_applies(uint32_t stride) { return stride != 0 && stride <= kSmallMaxNodes; }
+bool scan_small_post_applies(uint32_t stride) { return stride != 0 && stride <= kSmallPostMaxNodes; }
 
 cudaError_t scan_small_configure() {
   cudaError_t e;

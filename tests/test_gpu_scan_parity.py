@@ -40,7 +40,7 @@ def oracle_batch(O, nodes, counts, newp, mode_a, inv, ascend, stable=True):
 
 def check_batch(R, O, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=0, stable=True, expect_path=None,
                 emit=True):
-    """Which kernel runs (rpl_capi.cu enqueue_args): flags & 1 general radix kernel; stride <= 4096 and not
+    """Which kernel runs (rpl_capi.cu enqueue_args): flags & 1 general radix kernel; stride <= 8192 and not
     flags & 4: the shared-memory kernels (scan_small.cu); else with the ascended buffer (emit and ascend) or
     flags & 2 or unaligned scans: scan_fast.cu, otherwise the TMA ring (scan_tma.cu)."""
     counts = np.asarray(counts, dtype=np.uint32)
@@ -122,7 +122,7 @@ def test_tie_free_synthetic_both_kernels(R, oracle, ctx, n, variant):
     for newp, mode_a, inv in modes:
         for ascend in (0, 1):
             # tie-free measured keys: the reference's std::sort and the stable rule coincide
-            for flags in ((0, 2, 4, 6) if n <= 4096 else (0, 2)):
+            for flags in ((0, 2, 4, 6) if n <= 8192 else (0, 2)):
                 for emit in (True, False):
                     check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=flags, stable=True,
                                 emit=emit, expect_path=0)
