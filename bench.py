@@ -1272,6 +1272,33 @@ def run_chain(args, rank, local_rank, world):
     wire = n_streams * n_caps * 84
     # decode out; assemble: flag pass in (+ copy in+out in copy mode); scan in + out
     alg = wire + int(ncount.sum().item()) * (8 + 8) + pts * ((8 + 8 if args.chain_copy else 0) + 8 + 8)
+    # ---- e2e: the same chain through the host-buffer call rpl_chain_dense_laserscan (pinned buffers) ---------
+    e2e = None
+    if not args.no_e2e:
+        out_nodes, out_scans = 3328, int(max(1, int(sps.max().item())))  # tight output slots: D2H is what the link carries
+        ectx = R.Context(local_rank, out_nodes, 64 * out_scans)
+        h_caps_t = torch.empty((n_streams, n_caps, 84), dtype=torch.uint8, pin_memory=True)
+        h_caps_t.copy_(caps)
+        ens = n_streams * out_scans
+        outs_t = {"ranges": torch.empty((ens, out_nodes), dtype=torch.float32, pin_memory=True),
+                  "intensities": torch.empty((ens, out_nodes), dtype=torch.float32, pin_memory=True)}
+        outs = {k: v.numpy() for k, v in outs_t.items()}
+        hcc = np.full(n_streams, n_caps, np.uint32)
+        for _ in range(2):
+            res = ectx.chain_dense_laserscan(h_caps_t.numpy(), hcc, params, out_nodes, out_scans, out=outs)
+        ke = max(3, min(args.steps, 8))
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            res = ectx.chain_dense_laserscan(h_caps_t.numpy(), hcc, params, out_nodes, out_scans, out=outs)
+        dt = time.perf_counter() - t0
+        epts = int(res["beam_counts"].sum())  # measured points that reached a LaserScan
+        same = int(res["scans_per_stream"].sum()) == n_scans
+        e2e = {"value": pts * ke / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": n_streams * n_caps * 84 + n_streams * 4,
+               "d2h_bytes_per_step": 2 * ens * out_nodes * 4 + 2 * ens * 4 + n_streams * 4, "steps": ke,
+               "ms_per_step": dt / ke * 1e3, "api": "rpl_chain_dense_laserscan (pinned host buffers)",
+               "scans_match_device_path": same, "beams_out": epts,
+               "h2d_bytes_per_point": n_streams * n_caps * 84 / pts, "d2h_bytes_per_point": 2 * ens * out_nodes * 4 / pts}
+        ectx.close()
     line = {
         "metric": "Mpoints/s wire capsules -> LaserScan (decode + scan assembly + scan kernel on the device)",
         "value": pts / (ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": W,
@@ -1285,7 +1312,7 @@ def run_chain(args, rank, local_rank, world):
         "roofline": {"bound": "hbm", "kernel": "decode_dense + assemble + scan", "achieved": alg / (ms * 1e-3) / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg},
-        "cpu_baseline": None, "e2e": None, "gpu_launches": ctx.launch_count - l0, "clocks": clocks,
+        "cpu_baseline": None, "e2e": e2e, "gpu_launches": ctx.launch_count - l0, "clocks": clocks,
         "extra": {"ms_decode": parts[0], "ms_assemble": parts[1], "ms_scan": parts[2], "scans_published": n_scans,
                   "points_decoded": int(ncount.sum().item())},
     }

@@ -391,6 +391,20 @@ rpl_result rpl_scan_views_dev(rpl_ctx* ctx, const rpl_node_hq* nodes, uint64_t n
                               float* ranges, float* intensities, uint32_t* beam_counts, float* angle_increment,
                               uint32_t* status, uint32_t* path, void* stream);
 
+/* Wire bytes -> LaserScan in ONE host call: framed dense (0x85) capsules in host memory -> H2D -> decode ->
+ * scan views -> scan kernel -> D2H, chunked over the two lanes so that copies and kernels overlap.  2.1 bytes per
+ * point cross the host link on the way in instead of the 8 of a decoded node.  capsules: host
+ * [n_streams][stride_capsules][84]; outputs: host ranges / intensities [n_streams * max_scans][max_nodes],
+ * beam_counts / angle_increment (nullable) [n_streams * max_scans] (slot k of stream s at s * max_scans + k; unused
+ * slots have beam count 0), scans_per_stream [n_streams].  max_nodes: even, <= 8192, at least the longest
+ * revolution (longer ones are cut by the holder's capacity rule); the context's max_scans must cover
+ * max_scans of at least one stream.  Pinned host memory (rpl_host_alloc) keeps the copies asynchronous. */
+rpl_result rpl_chain_dense_laserscan(rpl_ctx* ctx, const uint8_t* capsules, const uint32_t* capsule_counts,
+                                     uint32_t n_streams, uint32_t stride_capsules, uint32_t sample_duration_us,
+                                     const rpl_scan_params* params, uint32_t max_nodes, uint32_t max_scans,
+                                     float* ranges, float* intensities, uint32_t* beam_counts, float* angle_increment,
+                                     uint32_t* scans_per_stream);
+
 /* ---- LaserScan / PointCloud2 -> wire ---------------------------- */
 /* The serialised message the RMW layer would produce from the message the reference publishes
  * (scan_pub_->publish, reference src/rplidar_node.cpp:679): XCDR1 little endian, 4-byte

@@ -45,7 +45,7 @@ EXPORTS = [
     "rpl_scan", "rpl_scan_batch", "rpl_ascend_scan_batch", "rpl_laserscan_batch", "rpl_scan_batch_dev",
     "rpl_cloud_batch_dev", "rpl_cloud_batch", "rpl_cloud_fuse_dev", "rpl_synth_batch_dev",
     "rpl_decode_dense_batch_dev", "rpl_decode_dense", "rpl_assemble_scans_dev", "rpl_assemble_scan_views_dev",
-    "rpl_scan_views_dev",
+    "rpl_scan_views_dev", "rpl_chain_dense_laserscan",
     "rpl_capsule_bytes", "rpl_capsule_nodes", "rpl_decode_capsules_batch_dev", "rpl_decode_capsules",
     "rpl_decode_normal_batch_dev", "rpl_decode_normal", "rpl_frame_capsules_dev", "rpl_node_timestamps_dev", "rpl_normal_timestamps_dev",
     "rpl_peer_gather_bytes", "rpl_peer_alloc", "rpl_peer_open", "rpl_peer_close", "rpl_peer_free",
@@ -184,6 +184,7 @@ def lib() -> C.CDLL:
         "rpl_assemble_scans_dev": ([vp, vp, vp, u32, u32, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp, vp, vp], u32),
         "rpl_assemble_scan_views_dev": ([vp, vp, vp, u32, u32, vp, vp, vp, u32, u32, u32, vp, vp, vp, vp, vp, vp], u32),
         "rpl_scan_views_dev": ([vp, vp, u64, vp, u32, u32, PSP, vp, vp, vp, vp, vp, vp, vp, vp], u32),
+        "rpl_chain_dense_laserscan": ([vp, vp, vp, u32, u32, u32, PSP, u32, u32, vp, vp, vp, vp, vp], u32),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)  # AttributeError here = the library does not export the ABI
@@ -493,6 +494,26 @@ class Context:
         self._check(self._L.rpl_scan_views_dev(
             self._h, _p(nodes), nodes_total, _p(views), n_scans, stride, C.byref(params), _p(nodes_out), _p(ranges),
             _p(intensities), _p(beam_counts), _p(angle_increment), _p(status), _p(path), _p(stream)))
+
+    def chain_dense_laserscan(self, capsules, capsule_counts, params: ScanParams, max_nodes, max_scans,
+                              sample_duration_us=31, out=None):
+        """Host buffers: capsules [n_streams, stride_capsules, 84] uint8 -> dict(ranges, intensities [n_streams*max_scans,
+        max_nodes], beam_counts, angle_increment, scans_per_stream)."""
+        assert capsules.dtype == np.uint8 and capsules.ndim == 3 and capsules.shape[2] == 84 and capsules.flags.c_contiguous
+        n_streams, stride_caps = capsules.shape[:2]
+        cc = np.ascontiguousarray(capsule_counts, dtype=np.uint32)
+        out = dict(out or {})
+        ns = n_streams * max_scans
+        for k, shape, dt in (("ranges", (ns, max_nodes), np.float32), ("intensities", (ns, max_nodes), np.float32),
+                             ("beam_counts", (ns,), np.uint32), ("angle_increment", (ns,), np.float32),
+                             ("scans_per_stream", (n_streams,), np.uint32)):
+            if k not in out:
+                out[k] = np.zeros(shape, dt)
+        self._check(self._L.rpl_chain_dense_laserscan(
+            self._h, _p(capsules), _p(cc), n_streams, stride_caps, sample_duration_us, C.byref(params), max_nodes,
+            max_scans, _p(out["ranges"]), _p(out["intensities"]), _p(out["beam_counts"]), _p(out["angle_increment"]),
+            _p(out["scans_per_stream"])))
+        return out
 
     def cloud_fuse_dev(self, xyzi, point_counts, n_scans, stride, fused, offsets, total, stream=None):
         self._check(self._L.rpl_cloud_fuse_dev(self._h, _p(xyzi), _p(point_counts), n_scans, stride, _p(fused),

@@ -56,6 +56,7 @@ void free_lane(Lane& l) {
   cudaFree(l.d_path);
   cudaFree(l.d_xyzi);
   cudaFree(l.d_pcount);
+  cudaFree(l.d_chain);
   if (l.stream) cudaStreamDestroy(l.stream);
   l = Lane{};
 }
@@ -318,6 +319,7 @@ void rpl_ctx_destroy(rpl_ctx* c) {
     if (c->lane[i].stream) cudaStreamSynchronize(c->lane[i].stream);
     free_lane(c->lane[i]);
   }
+  if (c->asm_done) cudaEventDestroy(c->asm_done);
   cudaFree(c->d_state_tmp);
   cudaFree(c->d_reset_prefix);
   cudaFree(c->d_desc);
@@ -1120,6 +1122,111 @@ rpl_result rpl_scan_views_dev(rpl_ctx* c, const rpl_node_hq* nodes, uint64_t nod
   return enqueue_scan(c, c->lane[0], nodes, reinterpret_cast<const uint32_t*>(views), n_scans, stride, params, nodes_out,
                       ranges, intensities, beam_counts, angle_increment, status, path, st,
                       reinterpret_cast<const uint2*>(views), nodes_total);
+}
+
+// ---- wire bytes -> LaserScan in one host call --------------------------------------------------------------------
+rpl_result rpl_chain_dense_laserscan(rpl_ctx* c, const uint8_t* capsules, const uint32_t* capsule_counts,
+                                     uint32_t n_streams, uint32_t stride_capsules, uint32_t sample_duration_us,
+                                     const rpl_scan_params* params, uint32_t max_nodes, uint32_t max_scans,
+                                     float* ranges, float* intensities, uint32_t* beam_counts, float* angle_increment,
+                                     uint32_t* scans_per_stream) {
+  if (!c || !capsules || !capsule_counts || !params || !ranges || !intensities || !beam_counts || !scans_per_stream)
+    return RPL_RESULT_INVALID_DATA;
+  if (n_streams == 0) return RPL_RESULT_OK;
+  if (max_nodes == 0 || max_nodes > rpl::kSmallMaxNodes || (max_nodes & 1u) || max_scans == 0 || stride_capsules == 0) {
+    c->err = "need an even max_nodes in [2, 8192] (the longest revolution), max_scans > 0, stride_capsules > 0";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  for (uint32_t s = 0; s < n_streams; ++s)
+    if (capsule_counts[s] > stride_capsules) {
+      c->err = "capsule_counts[s] exceeds stride_capsules";
+      return RPL_RESULT_INVALID_DATA;
+    }
+  RPL_CUDA(c, cudaSetDevice(c->device), RPL_RESULT_OPERATION_FAIL);
+  // chunk: about 16 MiB of capsules (~64 MiB of decoded nodes), whole streams
+  const size_t cap_bytes_stream = (size_t)stride_capsules * 84;
+  uint32_t chunk = (uint32_t)std::max<size_t>(1, ((size_t)16 << 20) / cap_bytes_stream);
+  chunk = std::min(chunk, n_streams);
+  if ((size_t)chunk * max_scans > c->max_scans) chunk = c->max_scans / max_scans;
+  if (chunk == 0) {
+    c->err = "the context's max_scans is smaller than max_scans of one stream";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  const size_t nodes_stream = (size_t)stride_capsules * 40;
+  if ((size_t)chunk * nodes_stream > 0xFFFFFFFFull) {
+    c->err = "chunk too large for 32-bit views";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t NS = (size_t)chunk * max_scans;
+  const size_t o_caps = 0, o_ccnt = o_caps + up(chunk * cap_bytes_stream), o_nodes = o_ccnt + up((size_t)chunk * 4),
+               o_ncnt = o_nodes + up(chunk * nodes_stream * 8), o_st = o_ncnt + up((size_t)chunk * 4),
+               o_off = o_st + up((size_t)chunk * stride_capsules * 4), o_views = o_off + up((size_t)chunk * stride_capsules * 4),
+               o_slen = o_views + up(NS * 8), o_sps = o_slen + up(NS * 4), o_r = o_sps + up((size_t)chunk * 4),
+               o_i = o_r + up(NS * max_nodes * 4), o_b = o_i + up(NS * max_nodes * 4), o_inc = o_b + up(NS * 4),
+               total = o_inc + up(NS * 4);
+  for (int i = 0; i < kLanes; ++i) {
+    Lane& l = c->lane[i];
+    if (l.chain_bytes < total) {
+      RPL_CUDA(c, cudaStreamSynchronize(l.stream), RPL_RESULT_OPERATION_FAIL);
+      cudaFree(l.d_chain);
+      l.d_chain = nullptr;
+      l.chain_bytes = 0;
+      RPL_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&l.d_chain), total), RPL_RESULT_INSUFFICIENT_MEMORY);
+      l.chain_bytes = total;
+    }
+  }
+  const cudaMemcpyKind h2d = cudaMemcpyHostToDevice, d2h = cudaMemcpyDeviceToHost;
+  auto run_chunk = [&](Lane& l, uint32_t s0, uint32_t ns) -> rpl_result {
+    unsigned char* d = l.d_chain;
+    const size_t nsc = (size_t)ns * max_scans;
+    RPL_CUDA(c, cudaStreamSynchronize(l.stream), RPL_RESULT_OPERATION_FAIL);  // the lane's previous chunk has left
+    RPL_CUDA(c, cudaMemcpyAsync(d + o_caps, capsules + (size_t)s0 * cap_bytes_stream, ns * cap_bytes_stream, h2d, l.stream),
+             RPL_RESULT_OPERATION_FAIL);
+    RPL_CUDA(c, cudaMemcpyAsync(d + o_ccnt, capsule_counts + s0, (size_t)ns * 4, h2d, l.stream), RPL_RESULT_OPERATION_FAIL);
+    rpl_result r = rpl_decode_dense_batch_dev(c, d + o_caps, reinterpret_cast<uint32_t*>(d + o_ccnt), ns, stride_capsules,
+                                              sample_duration_us, nullptr, reinterpret_cast<rpl_node_hq*>(d + o_nodes),
+                                              reinterpret_cast<uint32_t*>(d + o_ncnt), reinterpret_cast<uint32_t*>(d + o_st),
+                                              reinterpret_cast<uint32_t*>(d + o_off), nullptr, l.stream);
+    if (r != RPL_RESULT_OK) return r;
+    // the assembler's scratch belongs to the context, not to the lane: one assemble kernel at a time
+    if (!c->asm_done) RPL_CUDA(c, cudaEventCreateWithFlags(&c->asm_done, cudaEventDisableTiming), RPL_RESULT_OPERATION_FAIL);
+    RPL_CUDA(c, cudaStreamWaitEvent(l.stream, c->asm_done, 0), RPL_RESULT_OPERATION_FAIL);
+    r = rpl_assemble_scan_views_dev(c, reinterpret_cast<rpl_node_hq*>(d + o_nodes), reinterpret_cast<uint32_t*>(d + o_ncnt), ns,
+                                    (uint32_t)nodes_stream, reinterpret_cast<uint32_t*>(d + o_st),
+                                    reinterpret_cast<uint32_t*>(d + o_off), reinterpret_cast<uint32_t*>(d + o_ccnt),
+                                    stride_capsules, max_nodes, max_scans, reinterpret_cast<rpl_scan_view*>(d + o_views),
+                                    reinterpret_cast<uint32_t*>(d + o_slen), reinterpret_cast<uint32_t*>(d + o_sps), nullptr,
+                                    nullptr, l.stream);
+    if (r != RPL_RESULT_OK) return r;
+    RPL_CUDA(c, cudaEventRecord(c->asm_done, l.stream), RPL_RESULT_OPERATION_FAIL);
+    r = enqueue_scan(c, l, reinterpret_cast<rpl_node_hq*>(d + o_nodes), reinterpret_cast<uint32_t*>(d + o_slen),
+                     (uint32_t)nsc, max_nodes, params, nullptr, reinterpret_cast<float*>(d + o_r),
+                     reinterpret_cast<float*>(d + o_i), reinterpret_cast<uint32_t*>(d + o_b),
+                     reinterpret_cast<float*>(d + o_inc), nullptr, nullptr, l.stream,
+                     reinterpret_cast<const uint2*>(d + o_views), (unsigned long long)ns * nodes_stream);
+    if (r != RPL_RESULT_OK) return r;
+    const size_t so = (size_t)s0 * max_scans;
+    RPL_CUDA(c, cudaMemcpyAsync(ranges + so * max_nodes, d + o_r, nsc * max_nodes * 4, d2h, l.stream), RPL_RESULT_OPERATION_FAIL);
+    RPL_CUDA(c, cudaMemcpyAsync(intensities + so * max_nodes, d + o_i, nsc * max_nodes * 4, d2h, l.stream),
+             RPL_RESULT_OPERATION_FAIL);
+    RPL_CUDA(c, cudaMemcpyAsync(beam_counts + so, d + o_b, nsc * 4, d2h, l.stream), RPL_RESULT_OPERATION_FAIL);
+    if (angle_increment)
+      RPL_CUDA(c, cudaMemcpyAsync(angle_increment + so, d + o_inc, nsc * 4, d2h, l.stream), RPL_RESULT_OPERATION_FAIL);
+    RPL_CUDA(c, cudaMemcpyAsync(scans_per_stream + s0, d + o_sps, (size_t)ns * 4, d2h, l.stream), RPL_RESULT_OPERATION_FAIL);
+    return RPL_RESULT_OK;
+  };
+  uint32_t ci = 0;
+  for (uint32_t s0 = 0; s0 < n_streams; s0 += chunk, ++ci) {
+    const rpl_result r = run_chunk(c->lane[ci % kLanes], s0, std::min(chunk, n_streams - s0));
+    if (r != RPL_RESULT_OK) {
+      const std::string why = c->err;
+      for (int i = 0; i < kLanes; ++i) cudaStreamSynchronize(c->lane[i].stream);
+      c->err = why;
+      return r;
+    }
+  }
+  return rpl_ctx_synchronize(c);
 }
 
 // ---- LaserScan / PointCloud2 -> CDR -------------------------------------

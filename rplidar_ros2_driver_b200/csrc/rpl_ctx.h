@@ -35,6 +35,10 @@ struct Lane {
   uint32_t* d_pcount = nullptr;
   size_t staged_nodes = 0;  // capacity in nodes of the staging buffers
   uint32_t staged_scans = 0;
+  // device staging of rpl_chain_dense_laserscan (lazy): one block carved into capsules, decoded nodes,
+  // per-capsule reports, views and the LaserScan outputs of a chunk of streams
+  unsigned char* d_chain = nullptr;
+  size_t chain_bytes = 0;
 };
 
 struct rpl_ctx {
@@ -59,6 +63,7 @@ struct rpl_ctx {
   uint32_t* d_reset_prefix = nullptr;
   uint2* d_desc = nullptr;
   size_t reset_prefix_cap = 0, desc_cap = 0;
+  cudaEvent_t asm_done = nullptr;   // rpl_chain_dense_laserscan: the assemble scratch above is shared by the lanes
   uint32_t* d_state_tmp = nullptr;  // dense decoder reached through the [2]-word state interface
   size_t state_tmp_cap = 0;
   bool profile = false;

@@ -251,3 +251,33 @@ def test_scan_views_equal_the_copying_chain(R, oracle, max_nodes, mode_a, emit):
     if max_nodes < 3200:
         assert (a[0] == max_nodes).any()  # capped revolutions were part of the comparison
     ctx.close()
+
+
+def test_wire_bytes_to_laserscan_in_one_host_call(R, oracle):
+    """rpl_chain_dense_laserscan (host buffers, chunked over both lanes) against the CPU chain
+    decode -> assemble -> ascend -> publish, for more streams than one chunk holds."""
+    n_streams, n_caps, max_nodes, max_scans = 150, 1500, 3328, 20
+    ctx = R.Context(0, max_nodes, 40 * max_scans)  # 40 streams per chunk at most
+    host = np.stack([make_stream(oracle, n_caps, 80.0 + (s % 7), seed=3000 + s, sync_every=(300 + 11 * (s % 5)) if s % 3 else None)
+                     for s in range(n_streams)])
+    counts = np.full(n_streams, n_caps, np.uint32)
+    counts[7], counts[8] = 0, 123
+    out = ctx.chain_dense_laserscan(host, counts, R.scan_params(1, 0, 0, 1), max_nodes, max_scans)
+    total = 0
+    for s in list(range(0, n_streams, 9)) + [7, 8, n_streams - 1]:
+        en, es, eo, _ = oracle.dense_decode(host[s, : counts[s]], 31, 0)
+        e, elen, ek = oracle.assemble_scans(en, oracle.resets_from_capsules(es, eo), max_nodes, max_scans)
+        assert out["scans_per_stream"][s] == ek
+        for k in range(max_scans):
+            slot = s * max_scans + k
+            if k >= min(ek, max_scans):
+                assert out["beam_counts"][slot] == 0
+                continue
+            rc, asc = oracle.ascend(e[k, : elen[k]].copy())
+            hdr, r, it = oracle.publish(asc, oracle.scan_params(1, 0, 0, 1, 40.0, 0.1))
+            assert out["beam_counts"][slot] == hdr.beam_count
+            assert (out["ranges"][slot, : hdr.beam_count].view(np.uint32) == r.view(np.uint32)).all()
+            assert (out["intensities"][slot, : hdr.beam_count].view(np.uint32) == it.view(np.uint32)).all()
+            total += 1
+    assert total > 40
+    ctx.close()
