@@ -506,8 +506,11 @@ def run_b200(args, rank, local_rank, world):
         lctx = R.Context(local_rank, 8192, 1)
         prm1 = R.scan_params(0, mode_a, 0, 1)
         for nn in (360, 3200, 8192):
+            tmp = torch.empty((1, nn, 8), dtype=torch.uint8, device=dev)
+            lctx.synth_batch_dev(rank * S, 1, nn, nn, args.variant, tmp.data_ptr(), None, stream=sptr)
+            torch.cuda.synchronize()
             one = np.zeros(nn, dtype=R.NODE_DTYPE)
-            one[:] = nodes[0, :nn].cpu().numpy().view(R.NODE_DTYPE).reshape(-1)
+            one[:] = tmp[0].cpu().numpy().view(R.NODE_DTYPE).reshape(-1)
             r1, i1 = np.zeros(nn, np.float32), np.zeros(nn, np.float32)
             b1, a1, s1 = C.c_uint32(0), C.c_float(0), C.c_uint32(0)
 

@@ -175,13 +175,24 @@ __device__ __noinline__ float sor_mean_generic(const float2* px, uint32_t m, uin
   return mean_of_smallest(top.v, 32, min(sor_k, nd));
 }
 
+// floorf(x / v) without the division for all but a handful of points: q0 = x * RN(1/v) is within 2.4e-7 |q0| of the
+// correctly rounded quotient, so both floor to the same integer unless q0 sits that close to one -- then (about 1 %
+// of the points, the exact multiples of the voxel size among them) the division is done after all.
+__device__ __forceinline__ int floor_div(float x, float v, float rv) {
+  const float q0 = __fmul_rn(x, rv);
+  const float n = rintf(q0);
+  if (fabsf(__fsub_rn(q0, n)) <= __fmul_rn(fabsf(q0), 4e-7f)) return __float2int_rd(__fdiv_rn(x, v));
+  return __float2int_rd(q0);
+}
 // voxel cell of a point (cloud_oracle.cpp step 5): (floorf(x / voxel), floorf(y / voxel)) packed into 32 bits;
 // the host admits this kernel only when |cell index| < 32768 (range_max / voxel < 32000)
-__device__ __forceinline__ uint32_t cell_key(float2 p, float voxel) {
-  const int ix = __float2int_rd(__fdiv_rn(p.x, voxel));
-  const int iy = __float2int_rd(__fdiv_rn(p.y, voxel));
+__device__ __forceinline__ uint32_t cell_key(float2 p, float voxel, float rvoxel) {
+  const int ix = floor_div(p.x, voxel, rvoxel);
+  const int iy = floor_div(p.y, voxel, rvoxel);
   return ((uint32_t)ix << 16) | ((uint32_t)iy & 0xFFFFu);
 }
+// llrintf(v * 65536) as a 32-bit integer: the host admits the fused voxel grid only for range_max < 1000 m
+__device__ __forceinline__ int fix16(float v) { return __float2int_rn(__fmul_rn(v, 65536.0f)); }
 
 // MODE: 0 LaserScan Mode B, 1 LaserScan Mode A, 2 PointCloud2.  EMIT: also write the ascended node buffer
 // (MODE 0/1).  POST: (MODE 2) SOR and/or voxel grid in shared memory before anything is written.
@@ -594,23 +605,29 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
           const uint4 e = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
           for (uint32_t w = tid; w < nslots / 4; w += TS) t4[w] = e;
         }
+        const float rvoxel = __frcp_rn(p.voxel);
         for (uint32_t i = tid; i < m; i += TS) {
-          key32[i] = cell_key(px[i], p.voxel);
+          key32[i] = cell_key(px[i], p.voxel, rvoxel);
           dxs[i] = 0;
           dys[i] = 0;
           cs[i] = 0;
         }
         __syncthreads();
         // insert: a slot holds the smallest point index seen so far of ONE cell (the key of a slot never
-        // changes once it is taken: atomicMin only swaps members of the same cell)
+        // changes once it is taken: atomicMin only swaps members of the same cell).  Points arrive in angle
+        // order, so the members of a cell are mostly neighbours: within a warp only the first point of a run of
+        // equal cells goes to the table, the others take its slot by shuffle (they cannot be the cell's leader).
         uint32_t myslot[PMAX];
 #pragma unroll
         for (uint32_t j = 0; j < PMAX; ++j) {
           const uint32_t i = tid + j * TS;
-          myslot[j] = 0;
-          if (i < m) {
-            const uint32_t key = key32[i];
-            uint32_t h = __umulhi(key * 0x9E3779B1u, nslots);
+          const bool live = i < m;
+          const uint32_t key = live ? key32[i] : 0u;
+          const uint32_t kprev = __shfl_up_sync(0xffffffffu, key, 1);
+          const bool head = live && (lane == 0 || key != kprev);
+          uint32_t h = 0;
+          if (head) {
+            h = __umulhi(key * 0x9E3779B1u, nslots);
             for (;;) {
               uint32_t v = *reinterpret_cast<volatile uint32_t*>(&table[h]);
               if (v == kEmpty) {
@@ -623,8 +640,12 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
               }
               if (++h == nslots) h = 0;
             }
-            myslot[j] = h;
           }
+          __syncwarp();
+          const uint32_t heads = __ballot_sync(0xffffffffu, head);
+          const uint32_t below = heads & (0xFFFFFFFFu >> (31u - lane));  // heads at or below this lane (lane 0 is one)
+          const int src = 31 - __clz((int)(below | 1u));
+          myslot[j] = __shfl_sync(0xffffffffu, h, src);
         }
         __syncthreads();
         // accumulate relative to the cell leader (32-bit integers: |delta| <= voxel * 65536 + 2 and the host
@@ -642,10 +663,8 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
               atomicAdd(&cs[i], inten);
             } else {
               const float2 me = px[i], ld = px[lead];
-              const long long ddx = __float2ll_rn(__fmul_rn(me.x, 65536.0f)) - __float2ll_rn(__fmul_rn(ld.x, 65536.0f));
-              const long long ddy = __float2ll_rn(__fmul_rn(me.y, 65536.0f)) - __float2ll_rn(__fmul_rn(ld.y, 65536.0f));
-              atomicAdd(&dxs[lead], (int)ddx);
-              atomicAdd(&dys[lead], (int)ddy);
+              atomicAdd(&dxs[lead], fix16(me.x) - fix16(ld.x));
+              atomicAdd(&dys[lead], fix16(me.y) - fix16(ld.y));
               atomicAdd(&cs[lead], (1u << 20) + inten);
             }
           }
@@ -686,16 +705,33 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
             const uint32_t pos = ctl.chunk_base[j * NW + warp] + myslot[j];
             const float2 ld = px[i];
             const uint32_t c = cs[i];
-            const uint32_t members = (c >> 20) + 1u;
-            const long long sx = (long long)members * __float2ll_rn(__fmul_rn(ld.x, 65536.0f)) + (long long)dxs[i];
-            const long long sy = (long long)members * __float2ll_rn(__fmul_rn(ld.y, 65536.0f)) + (long long)dys[i];
-            const double cntd = (double)members;
-            const double den = __dmul_rn(65536.0, cntd);
+            const int qx = fix16(ld.x), qy = fix16(ld.y);
             float4 o;
-            o.x = __double2float_rn(__ddiv_rn((double)sx, den));
-            o.y = __double2float_rn(__ddiv_rn((double)sy, den));
             o.z = 0.0f;
-            o.w = __double2float_rn(__ddiv_rn((double)(c & 0xFFFFFu), cntd));
+            if ((c >> 20) == 0u) {
+              // a cell of one point: sum / 65536 is exact in float (an integer below 2^24, or a float-valued integer)
+              o.x = __fmul_rn(__int2float_rn(qx), 1.52587890625e-05f);
+              o.y = __fmul_rn(__int2float_rn(qy), 1.52587890625e-05f);
+              o.w = __uint2float_rn(c);
+            } else {
+              // (float)((double)sum / (65536.0 * count)): the double quotient from the correctly rounded reciprocal
+              // and one residual step (Markstein) -- bit-identical to the division, a third of its instructions
+              const uint32_t members = (c >> 20) + 1u;
+              const double sx = (double)((long long)members * qx + (long long)dxs[i]);
+              const double sy = (double)((long long)members * qy + (long long)dys[i]);
+              const double cntd = (double)members;
+              const double den = __dmul_rn(65536.0, cntd);
+              const double rden = __drcp_rn(den);
+              const double rcnt = __dmul_rn(rden, 65536.0);  // = RN(1 / count): scaling by 2^16 is exact
+              auto quot = [](double a, double d, double r) {
+                const double q0 = __dmul_rn(a, r);
+                const double e = __fma_rn(-q0, d, a);
+                return __fma_rn(e, r, q0);
+              };
+              o.x = __double2float_rn(quot(sx, den, rden));
+              o.y = __double2float_rn(quot(sy, den, rden));
+              o.w = __double2float_rn(quot((double)(c & 0xFFFFFu), cntd, rcnt));
+            }
             st_f32x4_if(cloud + pos, o, pol_stream, 1u);
           }
         }

@@ -124,8 +124,10 @@ def test_tie_free_synthetic_both_kernels(R, oracle, ctx, n, variant):
             # tie-free measured keys: the reference's std::sort and the stable rule coincide
             for flags in ((0, 2, 4, 6) if n <= 8192 else (0, 2)):
                 for emit in (True, False):
+                    # (with the ascended buffer a fill key may collide with a measured key: that scan then takes
+                    # the general kernel, legitimately -- so the path is only pinned without it)
                     check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=flags, stable=True,
-                                emit=emit, expect_path=0)
+                                emit=emit, expect_path=None if emit else 0)
             check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, ascend, flags=1, stable=True,
                         expect_path=1)
 
@@ -291,4 +293,5 @@ def test_odd_stride_takes_unaligned_path(R, oracle, ctx):
     for newp, mode_a, inv in ALL_MODES:
         for flags in (0, 4):  # shared-memory kernel without TMA staging / register-streamed kernel
             for emit in (True, False):
-                check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, 1, flags=flags, emit=emit, expect_path=0)
+                check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, 1, flags=flags, emit=emit,
+                            expect_path=None if emit else 0)
