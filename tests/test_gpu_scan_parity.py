@@ -295,3 +295,41 @@ def test_odd_stride_takes_unaligned_path(R, oracle, ctx):
             for emit in (True, False):
                 check_batch(R, oracle, ctx, nodes, counts, newp, mode_a, inv, 1, flags=flags, emit=emit,
                             expect_path=None if emit else 0)
+
+
+def test_mode_a_sorted_revolution_detection_edge_cases(R, oracle, ctx):
+    """The TMA kernel resolves Mode A bins on the spot when the revolution is sorted up to a rotation, and goes
+    through its index map otherwise.  Shapes around that decision: sorted / rotated / two interleaved ascending runs
+    (one descent, but not a rotation) / unmeasured runs across chunk boundaries (1024 nodes) and around the wrap /
+    bins shared by many points and long empty stretches."""
+    rng = np.random.default_rng(77)
+    n = 12288
+    cases = []
+    base_keys = np.sort(rng.choice(65536, size=n, replace=False))
+    dist = rng.integers(600, 160000, n)
+    q = rng.integers(0, 256, n)
+    cases.append(oracle.make_nodes(base_keys, dist, q, 2))                                   # sorted
+    cases.append(np.roll(cases[0], -5000))                                                   # rotated
+    inter = cases[0].copy()
+    half = n // 2
+    inter["angle_z_q14"][:half] = base_keys[0::2]
+    inter["angle_z_q14"][half:] = base_keys[1::2]
+    cases.append(inter)                                                                      # one descent, no rotation
+    gaps = np.roll(cases[0], -1021).copy()
+    gaps["dist_mm_q2"][1000:1100] = 0     # unmeasured run across the first chunk boundary
+    gaps["dist_mm_q2"][n - 30:] = 0       # ... at the end of the buffer
+    gaps["dist_mm_q2"][:17] = 0           # ... and at its start
+    gaps["dist_mm_q2"][n - 1021 - 3: n - 1021 + 3] = 0  # around the wrap of the rotation
+    cases.append(gaps)
+    dense = cases[0].copy()
+    dense["angle_z_q14"] = np.sort(np.concatenate([rng.choice(np.arange(20000, 20600), 500, replace=False),
+                                                   rng.choice(np.arange(40000, 65536), n - 500, replace=False)]))
+    cases.append(np.roll(dense, -777))                                                       # crowded bins + a long gap
+    nodes = np.stack(cases)
+    counts = np.full(len(cases), n, np.uint32)
+    for newp, inv in ((0, 0), (1, 1), (1, 0)):
+        check_batch(R, oracle, ctx, nodes, counts, newp, 1, inv, 1, emit=False, expect_path=0)
+        check_batch(R, oracle, ctx, nodes, counts, newp, 1, inv, 0, emit=False, expect_path=0)
+    small = nodes[:, :8000].copy()  # the same shapes through the TMA kernel at a size the shared-memory kernels serve
+    check_batch(R, oracle, ctx, small, np.full(len(cases), 8000, np.uint32), 0, 1, 0, 1, flags=4, emit=False)
+    check_batch(R, oracle, ctx, small, np.full(len(cases), 8000, np.uint32), 0, 1, 0, 1, flags=0, emit=False)
