@@ -1,6 +1,7 @@
 """Run under torchrun with >= 2 ranks (one per GPU): the fused pack + all-gather kernel over NVLink peer
-memory (rpl_cloud_fuse_push_dev) must leave on every rank exactly what rpl_cloud_fuse_dev + one NCCL
-all-gather leave.  Started by tests/test_gpu_multi_push.py; prints PUSH_OK on success."""
+memory (rpl_cloud_fuse_push_dev) and the C++ exchange object (rpl_exchange_*: NCCL all-gather and copy-engine
+pushes, double-buffered, with a consumer stream) must leave on every rank exactly what rpl_cloud_fuse_dev + one
+torch.distributed all-gather leave.  Started by tests/test_gpu_multi_push.py; prints PUSH_OK on success."""
 import os
 import sys
 
@@ -57,8 +58,48 @@ def main():
                 ok = False
                 print(f"[rank {rank}] step {step}: slot {r} differs", flush=True)
         assert int(c_ref.sum()) > 0
+    # ---- the C++ exchange object (rpl_exchange_*): NCCL all-gather and copy-engine pushes, several steps so that
+    # both buffers are reused, a consumer on its own stream with wait / release, against the reference gather ----
+    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(R.exchange_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    torch.cuda.synchronize()
+    ex = R.Exchange(ctx, idt.cpu().numpy().tobytes(), world, rank, cap)
+    consumer = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream().cuda_stream
+
+    class View:
+        def __init__(self, ptr, shape, typestr):
+            self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+    for step in range(6):
+        mode = R.EXCHANGE_NCCL if step % 3 == 0 else R.EXCHANGE_COPY
+        ctx.synth_batch_dev(5000 * rank + 31 * step, S, N, N, 4, nodes.data_ptr(), counts.data_ptr(), stream=main_stream)
+        ctx.cloud_batch_dev(nodes.data_ptr(), counts.data_ptr(), S, N, prm, xyzi.data_ptr(), pc.data_ptr(), stream=main_stream)
+        idx = ex.allgather(xyzi.data_ptr(), pc.data_ptr(), S, N, mode, stream=main_stream)
+        # the reference for this step, from the same per-scan clouds
+        ctx.cloud_fuse_dev(xyzi.data_ptr(), pc.data_ptr(), S, N, fused.data_ptr(), offs.data_ptr(), total.data_ptr(),
+                           stream=main_stream)
+        torch.cuda.synchronize()  # (the exchange's collectives and torch's must not be in flight together)
+        ex.synchronize()
+        g_ref, c_ref = ref_gather(fused, total)
+        torch.cuda.synchronize()
+        ex.wait(idx, stream=consumer.cuda_stream)
+        with torch.cuda.stream(consumer):
+            for r in range(world):
+                p_pts, p_cnt = ex.slot(idx, r)
+                c = int(torch.as_tensor(View(p_cnt, (1,), "<i4"), device=dev)[0].item())
+                pts = torch.as_tensor(View(p_pts, (cap, 4), "<f4"), device=dev)
+                if c != int(c_ref[r]) or not torch.equal(pts[:c].view(torch.int32), g_ref[r, :c].view(torch.int32)):
+                    ok = False
+                    print(f"[rank {rank}] exchange step {step} mode {mode}: slot {r} differs ({c} vs {int(c_ref[r])})", flush=True)
+        ex.release(idx, stream=consumer.cuda_stream)
+    torch.cuda.synchronize()
+    ex.synchronize()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    ex.close()
     peer.close()
     ctx.close()
     if rank == 0:
