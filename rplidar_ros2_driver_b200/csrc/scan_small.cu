@@ -145,8 +145,17 @@ __device__ __forceinline__ float sor_mean_win8(const float2* px, uint32_t m, uin
       dst[2 * t] = dist2(px[jm], me);
       dst[2 * t + 1] = dist2(px[jp], me);
     }
-    sort8(dst);
-    if (g != 0) merge_low8(best, cur);
+    if (g == 0) {
+      sort8(best);
+    } else {
+      // the neighbours further away in angle rarely beat the eight nearest found so far: when no lane of the warp
+      // holds a candidate below its current eighth-smallest, sorting and merging the group would change nothing
+      const float lo = fminf(fminf(fminf(cur[0], cur[1]), fminf(cur[2], cur[3])), fminf(fminf(cur[4], cur[5]), fminf(cur[6], cur[7])));
+      if (__any_sync(__activemask(), lo < best[7])) {
+        sort8(cur);
+        merge_low8(best, cur);
+      }
+    }
   }
   return mean_of_smallest(best, 8, k);
 }
