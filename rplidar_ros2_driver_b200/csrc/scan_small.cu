@@ -489,13 +489,17 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
         float* pr = ranges + o;
         st_f32_if(pr, dm, pol_stream, measured);
         st_f32_if(reinterpret_cast<float*>(reinterpret_cast<char*>(pr) + i_minus_r), it, pol_stream, measured);
-      } else if (measured) {  // Mode A: remember which node sits at this u-rank (mode_a_emit_smem)
+      } else if (measured) {  // Mode A: remember which node sits at this u-rank (mode_a_emit_direct)
         sidx[mode_a_urank(k, rk, M, inverted, has0)] = (uint16_t)i;
       }
     }
     __syncthreads();
 
-    // ---- Mode A: resolve bins that hold several points (reads the nodes from shared memory) ------------
+    // ---- Mode A (reference rplidar_node.cpp:630-660): every bin keeps the smallest dist_m of its points.  Bins grow
+    // along the u-order (ascending keys; for inverted scans key 0 first, then descending keys), and the place pass
+    // left the node index of every u-rank in sidx, so the points of a bin are neighbours THERE: one thread per
+    // u-rank looks at its predecessor (is this the first point of its bin?) and, if it is, walks the few points
+    // behind it.  Everything is read from shared memory; no staging, no batches.
     if constexpr (MODE_A) if (want_scan) {
       ModeAOut mo;
       mo.ranges = ranges;
@@ -506,9 +510,7 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
       mo.inverted = inverted;
       mo.new_proto = new_proto;
       mo.policy = pol_stream;
-      // the bitmap is dead by now: each warp stages a batch of bins in its own slice of it
-      static_assert(((kEmit2Stage + 7u) & ~7u) * 2 * NW <= kWords * 4, "bin staging must fit the bitmap");
-      mode_a_emit_smem(mo, sidx, tile, warp, NW, reinterpret_cast<uint16_t*>(bitsV) + warp * ((kEmit2Stage + 7u) & ~7u));
+      mode_a_emit_direct(mo, sidx, tile, tid, TS);
     }
 
     uint32_t m_out = M;

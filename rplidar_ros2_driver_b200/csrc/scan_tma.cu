@@ -63,14 +63,7 @@ struct __align__(128) TmaSmem {
   uint32_t valid_count;
   uint32_t totV;
   uint32_t fallback;
-  // Mode A, sorted-revolution detection (mark pass): descents inside chunks, first / last measured key per chunk
-  uint32_t descents;
-  uint32_t sorted_rot;
-  uint32_t cfirst[kKeySpace / CH + 1], clast[kKeySpace / CH + 1];
 };
-
-// two CTAs per SM: 228 KB of shared memory per SM, 1 KB of it reserved per resident CTA
-static_assert(sizeof(TmaSmem) <= (233472 - 2 * 1024) / 2, "TmaSmem must leave room for two CTAs per SM");
 
 // byte-map swizzle: within the row a thread folds, the 16-byte column is XORed with row bits so
 // that the 128-bit reads of 8 neighbouring threads hit 8 different bank groups
@@ -258,18 +251,12 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
       for (uint32_t j = 0; j < kKeySpace / 16 / TC; ++j) bm[j * TC + tid] = z;
       if (tid == 0) {
         sm.fallback = 0;
-        sm.descents = 0;
       }
-      if (MODE_A)
-        for (uint32_t c = tid; c < nch; c += TC) {
-          sm.cfirst[c] = 0xFFFFFFFFu;
-          sm.clast[c] = 0xFFFFFFFFu;
-        }
     }
     consumer_sync();
 
     // ---- phase 1 (mark): one byte store per measured key ---------------------------------
-    uint32_t cnt = 0, desc = 0;
+    uint32_t cnt = 0;
     uint8_t* const bmap = sm.bytemap;
     auto mark_chunk = [&](auto checked, uint32_t c) {
       mbar_wait(&sm.full[stage], parity);
@@ -285,34 +272,6 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
         if (decltype(checked)::value && c * CH + r * TC + tid >= n) valid = false;
         if (valid) bmap[swz_x(v[r].x)] = 1;
         cnt += valid ? 1u : 0u;
-        if (MODE_A && !inverted && valid) {
-          // Is the revolution sorted (up to its rotation)?  Compare with the nearest measured node before this one
-          // in the chunk; the first / last measured key of every chunk are compared across chunks afterwards.
-          const uint32_t li = r * TC + tid;  // index in the chunk
-          const uint32_t cn = min(CH, n - c * CH);
-          uint32_t j = li, pk = 0xFFFFFFFFu;
-          while (j > 0) {
-            --j;
-            const uint2 pn = slot[j];
-            if (__funnelshift_r(pn.x, pn.y, 16) != 0) {
-              pk = pn.x & 0xFFFFu;
-              break;
-            }
-          }
-          const uint32_t k = v[r].x & 0xFFFFu;
-          if (pk == 0xFFFFFFFFu) sm.cfirst[c] = k;          // no measured node before it in the chunk
-          else if (k < pk) ++desc;
-          // last measured node of the chunk: nothing measured behind it
-          bool last = true;
-          for (uint32_t jj = li + 1; jj < cn; ++jj) {
-            const uint2 nn = slot[jj];
-            if (__funnelshift_r(nn.x, nn.y, 16) != 0) {
-              last = false;
-              break;
-            }
-          }
-          if (last) sm.clast[c] = k;
-        }
       }
       release();
       advance();
@@ -322,10 +281,6 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
     if (nfull < nch) mark_chunk(Checked{}, nfull);
     cnt = warp_sum(cnt);
     if (lane == 0) sm.red[warp] = cnt;
-    if (MODE_A && !inverted) {
-      desc = warp_sum(desc);
-      if (lane == 0 && desc) atomicAdd(&sm.descents, desc);
-    }
     consumer_sync();
 
     // ---- fold: byte map -> bitmap + exclusive popcount prefix ------------------------------
@@ -361,19 +316,6 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
           sm.totV = cv;
           sm.valid_count = cc;
         }
-        if (MODE_A && lane == 0) {
-          // sorted up to a rotation <=> at most one descent along the buffer, and if there is one the revolution's
-          // last measured key lies below its first (the keys are distinct here)
-          uint32_t D = sm.descents, first = 0xFFFFFFFFu, prev = 0xFFFFFFFFu;
-          for (uint32_t c = 0; c < nch; ++c) {
-            const uint32_t f = sm.cfirst[c];
-            if (f == 0xFFFFFFFFu) continue;
-            if (prev != 0xFFFFFFFFu && f < prev) ++D;
-            if (first == 0xFFFFFFFFu) first = f;
-            prev = sm.clast[c];
-          }
-          sm.sorted_rot = (!inverted && (D == 0 || (D == 1 && prev < first))) ? 1u : 0u;
-        }
       }
       consumer_sync();
       uint32_t pv = sm.red[2 * kCWarps + warp] + iv - sv;
@@ -400,11 +342,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
     }
     // duplicate keys (fewer distinct keys than measured nodes) -> general kernel (stable rule);
     // so do Mode A scans too large for the shared-memory index map
-    // Mode A on a revolution that is sorted up to its rotation (what a lidar delivers): the points of a bin are
-    // neighbours in the BUFFER, so the place pass resolves every bin on the spot from the chunk in shared memory
-    // -- no index map, no second gather pass
-    const bool direct = MODE_A && sm.sorted_rot != 0;
-    if (sm.totV != M || (MODE_A && !direct && M > kModeASmemMaxPoints)) {
+    if (sm.totV != M || (MODE_A && M > kModeASmemMaxPoints)) {
       if (tid == 0) a.fallback_list[atomicAdd(a.fallback_count, 1u)] = s;
       drain(nch);
       consumer_sync();
@@ -423,15 +361,6 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
     // rplidar_node.cpp:673); intensities[] sits at a fixed byte distance from ranges[]
     const uint32_t ob = inverted ? M - 1u : 0u, os = inverted ? 0xFFFFFFFFu : 1u;
     const ptrdiff_t i_minus_r = reinterpret_cast<char*>(intens) - reinterpret_cast<char*>(ranges);
-    ModeAOut mo;
-    mo.ranges = ranges;
-    mo.intens = intens;
-    mo.angle = a.angle;
-    mo.M = M;
-    mo.inc = inc;
-    mo.inverted = inverted;
-    mo.new_proto = new_proto;
-    mo.policy = pol_stream;
 
     auto place_chunk = [&](auto checked, uint32_t c) {
       mbar_wait(&sm.full[stage], parity);
@@ -460,41 +389,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
           float* pr = ranges + o;
           st_f32_if(pr, dm, pol_stream, measured);
           st_f32_if(reinterpret_cast<float*>(reinterpret_cast<char*>(pr) + i_minus_r), it, pol_stream, measured);
-        } else if (measured && direct) {  // Mode A, sorted revolution: reference rplidar_node.cpp:630-660 on the spot
-          const uint32_t c0 = c * CH, cn = min(CH, n - c0), gi = c0 + r * TC + tid;
-          auto node_at = [&](uint32_t j) { return (j - c0 < cn) ? slot[j - c0] : ld_hint_v2(base + j, pol_stream); };
-          auto entry_of = [&](uint2 x) {
-            return mode_a_entry(dist_to_m(__funnelshift_r(x.x, x.y, 16)), x.x & 0xFFFFu, (x.y >> 16) & 0xFFu);
-          };
-          const int b = mode_a_bin_fast(k, M, inc, false);
-          int bp = -1;
-          if (rk > 0) {  // the measured node before this one in the buffer (circular) is its predecessor in angle
-            uint32_t j = gi;
-            uint2 pn;
-            do {
-              j = (j == 0) ? n - 1 : j - 1;
-              pn = node_at(j);
-            } while (__funnelshift_r(pn.x, pn.y, 16) == 0);
-            bp = mode_a_bin_fast(pn.x & 0xFFFFu, M, inc, false);
-          }
-          if (b != bp) {  // first point of its bin: take the bin's minimum over the points behind it
-            unsigned long long best = entry_of(nd);
-            uint32_t left = M - 1u - rk, j = gi;
-            while (left) {
-              uint2 nn;
-              do {
-                j = (j + 1 == n) ? 0 : j + 1;
-                nn = node_at(j);
-              } while (__funnelshift_r(nn.x, nn.y, 16) == 0);
-              if (mode_a_bin_fast(nn.x & 0xFFFFu, M, inc, false) != b) break;
-              best = min(best, entry_of(nn));
-              --left;
-            }
-            mode_a_store_bin(mo, b, best, 1u);
-            if (b - bp > 1) mode_a_fill_empty(mo, bp + 1, b);  // empty bins in front of this one
-          }
-          if (rk == M - 1u) mode_a_fill_empty(mo, b + 1, (int)M);  // empty bins behind the last point
-        } else if (measured) {  // Mode A: remember which node sits at this u-rank (mode_a_emit_smem)
+        } else if (measured) {  // Mode A: remember which node sits at this u-rank (mode_a_emit_direct)
           sidx[mode_a_urank(k, rk, M, inverted, has0)] = (uint16_t)(c * CH + r * TC + tid);
         }
       }
@@ -506,13 +401,17 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
     consumer_sync();
 
     // ---- phase 3 (Mode A): resolve bins that hold several points --------------------------
-    if (MODE_A && !direct) {
-      // the rank table is dead by now: each warp stages a batch of bins in its own slice of it
-      static_assert(kEmit2Stage * 2 * kCWarps <= sizeof(sm.rankV), "bin staging must fit the rank table");
-#ifndef RPL_DBG_NO_EMIT
-      mode_a_emit_smem(mo, sidx, base, warp, kCWarps,
-                       reinterpret_cast<uint16_t*>(sm.rankV) + warp * ((kEmit2Stage + 7u) & ~7u));
-#endif
+    if (MODE_A) {
+      ModeAOut mo;
+      mo.ranges = ranges;
+      mo.intens = intens;
+      mo.angle = a.angle;
+      mo.M = M;
+      mo.inc = inc;
+      mo.inverted = inverted;
+      mo.new_proto = new_proto;
+      mo.policy = pol_stream;
+      mode_a_emit_direct(mo, sidx, base, tid, TC);
     }
     consumer_sync();
     if (tid == 0) {

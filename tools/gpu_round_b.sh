@@ -13,6 +13,9 @@ timeout 600 python bench.py --workload chain --steps 50 > gpurun_out/${T}_chain.
 timeout 600 python bench.py --workload chain --chain-copy --steps 50 --no-e2e > gpurun_out/${T}_chain_copy.json 2> gpurun_out/${T}_chain_copy.err
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_small -c 1 -f -o gpurun_out/${T}_ncu_cloud python bench.py --workload cloud --steps 1 --no-cpu > /dev/null 2> gpurun_out/${T}_ncu_cloud.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_small -c 1 -f -o gpurun_out/${T}_ncu_cloud_sor python bench.py --workload cloud --sor 8 --steps 1 --no-cpu > /dev/null 2> gpurun_out/${T}_ncu_cloud_sor.log
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:decode_capsule -c 1 -f -o gpurun_out/${T}_ncu_dec84 python bench.py --workload decode --format 0x84 --steps 1 > /dev/null 2> gpurun_out/${T}_ncu_dec84.log
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:decode_capsule -c 1 -f -o gpurun_out/${T}_ncu_dec86 python bench.py --workload decode --format 0x86 --steps 1 > /dev/null 2> gpurun_out/${T}_ncu_dec86.log
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:scan_tma -c 1 -f -o gpurun_out/${T}_ncu_modea python bench.py --mode a --steps 1 --no-cpu --no-cloud --no-e2e --no-extra > /dev/null 2> gpurun_out/${T}_ncu_modea.log
 T=$T python - <<'PY'
 import json,glob,os
 for f in sorted(glob.glob('gpurun_out/'+os.environ['T']+'_*.json')):
