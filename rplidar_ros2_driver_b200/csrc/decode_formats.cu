@@ -134,7 +134,15 @@ __device__ __forceinline__ uint2 node_ultra(const uint8_t* prev, const uint8_t* 
   // the angle correction int(off_q16 * 180 / 3.14159265) depends on the distance only through
   // k2 = 98361 / dist_q2 in [0, 491] (dist_q2 >= 200): a 493-entry table built on the host with the
   // reference's own double arithmetic (entry 492 = the short-range default)
-  const int off_deg_q16 = __ldg(&g_ultra_offset[dist_q2 >= 200 ? 98361 / dist_q2 : 492]);
+  // 98361 / dist_q2 (<= 491) without the integer division: float quotient, then an exact +-1 correction
+  uint32_t k2 = 492u;
+  if (dist_q2 >= 200) {
+    const uint32_t d = (uint32_t)dist_q2;
+    k2 = __float2uint_rz(__fdividef(98361.0f, __uint2float_rn(d)));
+    if (k2 * d > 98361u) --k2;
+    else if ((k2 + 1u) * d <= 98361u) ++k2;
+  }
+  const int off_deg_q16 = __ldg(&g_ultra_offset[k2]);
   const int angle_q6 = (a - off_deg_q16) >> 10;
   return pack_node(angle_q6, (uint32_t)dist_q2, sync, dist_q2 ? (0x2Fu << 2) : 0u);
 }
