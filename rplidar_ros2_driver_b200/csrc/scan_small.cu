@@ -631,6 +631,8 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
         uint32_t myslot[PMAX];
 #pragma unroll
         for (uint32_t j = 0; j < PMAX; ++j) {
+          myslot[j] = 0;
+          if (j * TS >= m) continue;  // (uniform) chunks past the end of the cloud: nothing to do
           const uint32_t i = tid + j * TS;
           const bool live = i < m;
           const uint32_t key = live ? key32[i] : 0u;
@@ -664,6 +666,10 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
         uint32_t leadflag = 0;
 #pragma unroll
         for (uint32_t j = 0; j < PMAX; ++j) {
+          if (j * TS >= m) {  // (uniform)
+            if (lane == 0) ctl.chunk_base[j * NW + warp] = 0u;
+            continue;
+          }
           const uint32_t i = tid + j * TS;
           bool is_lead = false;
           if (i < m) {
