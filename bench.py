@@ -1209,6 +1209,8 @@ def run_chain(args, rank, local_rank, world):
     offs = torch.zeros((n_streams, n_caps), dtype=torch.int32, device=dev)
     scans = torch.zeros((NS if args.chain_copy else 1, max_nodes, 8), dtype=torch.uint8, device=dev)
     views = torch.zeros((NS, 2), dtype=torch.int32, device=dev)
+    starts = torch.zeros((n_streams, 128), dtype=torch.int32, device=dev)
+    scnt = torch.zeros(n_streams, dtype=torch.int32, device=dev)
     slen = torch.zeros(NS, dtype=torch.int32, device=dev)
     sps = torch.zeros(n_streams, dtype=torch.int32, device=dev)
     ranges = torch.empty((NS, max_nodes), dtype=torch.float32, device=dev)
@@ -1223,7 +1225,9 @@ def run_chain(args, rank, local_rank, world):
             ev[0].record(stream)
         ctx.decode_dense_batch_dev(caps.data_ptr(), ccounts.data_ptr(), n_streams, n_caps, 31, nodes.data_ptr(),
                                    ncount.data_ptr(), capsule_status=status.data_ptr(),
-                                   capsule_node_offset=offs.data_ptr(), stream=sp)
+                                   capsule_node_offset=offs.data_ptr(), stream=sp,
+                                   scan_starts=None if args.chain_copy else starts.data_ptr(), starts_stride=128,
+                                   scan_start_counts=None if args.chain_copy else scnt.data_ptr())
         if timed:
             ev[1].record(stream)
         if args.chain_copy:
@@ -1232,10 +1236,11 @@ def run_chain(args, rank, local_rank, world):
                                    capsule_status=status.data_ptr(), capsule_node_offset=offs.data_ptr(),
                                    capsule_counts=ccounts.data_ptr(), stride_capsules=n_caps, stream=sp)
         else:  # no copy: the revolutions are handed on as views into the decoded stream
-            ctx.assemble_scan_views_dev(nodes.data_ptr(), ncount.data_ptr(), n_streams, n_caps * 40, max_nodes, max_scans,
-                                        views.data_ptr(), slen.data_ptr(), sps.data_ptr(),
-                                        capsule_status=status.data_ptr(), capsule_node_offset=offs.data_ptr(),
-                                        capsule_counts=ccounts.data_ptr(), stride_capsules=n_caps, stream=sp)
+            ctx.assemble_scan_views_starts_dev(nodes.data_ptr(), ncount.data_ptr(), n_streams, n_caps * 40,
+                                               starts.data_ptr(), 128, scnt.data_ptr(), max_nodes, max_scans,
+                                               views.data_ptr(), slen.data_ptr(), sps.data_ptr(),
+                                               capsule_status=status.data_ptr(), capsule_node_offset=offs.data_ptr(),
+                                               capsule_counts=ccounts.data_ptr(), stride_capsules=n_caps, stream=sp)
         if timed:
             ev[2].record(stream)
         if args.chain_copy:
@@ -1274,7 +1279,7 @@ def run_chain(args, rank, local_rank, world):
     peak, peak_src = measured_peak()
     wire = n_streams * n_caps * 84
     # decode out; assemble: flag pass in (+ copy in+out in copy mode); scan in + out
-    alg = wire + int(ncount.sum().item()) * (8 + 8) + pts * ((8 + 8 if args.chain_copy else 0) + 8 + 8)
+    alg = wire + int(ncount.sum().item()) * (8 + (8 if args.chain_copy else 0)) + pts * ((8 + 8 if args.chain_copy else 0) + 8 + 8)
     # ---- e2e: the same chain through the host-buffer call rpl_chain_dense_laserscan (pinned buffers) ---------
     e2e = None
     if not args.no_e2e:
@@ -1310,7 +1315,7 @@ def run_chain(args, rank, local_rank, world):
         "config": {"workload": f"{n_streams} streams x {n_caps} dense capsules -> {n_scans} revolutions of ~3200 nodes, "
                                f"Mode B, angle_compensate on; "
                                + ("revolutions copied out by the assembler" if args.chain_copy else
-                                  "revolutions read in place through views (rpl_assemble_scan_views_dev + rpl_scan_views_dev)"),
+                                  "revolutions read in place through views, scan starts handed over by the decoder (rpl_decode_dense_batch_starts_dev + rpl_assemble_scan_views_starts_dev + rpl_scan_views_dev)"),
                    "l2": "every stage streams > 126 MB"},
         "roofline": {"bound": "hbm", "kernel": "decode_dense + assemble + scan", "achieved": alg / (ms * 1e-3) / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,

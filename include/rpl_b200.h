@@ -273,6 +273,17 @@ rpl_result rpl_decode_dense_batch_dev(rpl_ctx* ctx, const uint8_t* capsules, con
                                       const uint32_t* sync_state_in, rpl_node_hq* nodes_out,
                                       uint32_t* node_counts, uint32_t* capsule_status,
                                       uint32_t* capsule_node_offset, uint32_t* sync_state_out, void* stream);
+/* The same, and the decoder also lists where the revolutions start: scan_starts [n_streams][starts_stride] = node
+ * offsets of the scan-start nodes of every stream (in no particular order), scan_start_counts[s] = how many there are
+ * (more than starts_stride: the list is incomplete and must not be used).  rpl_assemble_scan_views_starts_dev takes
+ * the list instead of reading every decoded node again. */
+rpl_result rpl_decode_dense_batch_starts_dev(rpl_ctx* ctx, const uint8_t* capsules, const uint32_t* capsule_counts,
+                                             uint32_t n_streams, uint32_t stride_capsules, uint32_t sample_duration_us,
+                                             const uint32_t* sync_state_in, rpl_node_hq* nodes_out,
+                                             uint32_t* node_counts, uint32_t* capsule_status,
+                                             uint32_t* capsule_node_offset, uint32_t* sync_state_out,
+                                             uint32_t* scan_starts, uint32_t starts_stride, uint32_t* scan_start_counts,
+                                             void* stream);
 /* One stream, host buffers.  nodes_out must hold 40 * n_capsules nodes. */
 rpl_result rpl_decode_dense(rpl_ctx* ctx, const uint8_t* capsules, uint32_t n_capsules,
                             uint32_t sample_duration_us, uint32_t* sync_state, rpl_node_hq* nodes_out,
@@ -383,6 +394,16 @@ rpl_result rpl_assemble_scan_views_dev(rpl_ctx* ctx, rpl_node_hq* nodes, const u
                                        uint32_t stride_capsules, uint32_t max_nodes, uint32_t max_scans,
                                        rpl_scan_view* views_out, uint32_t* scan_len, uint32_t* scans_per_stream,
                                        const uint64_t* node_ts_us, uint64_t* scan_begin_ts_us, void* stream);
+/* rpl_assemble_scan_views_dev with the decoder's scan-start list (rpl_decode_dense_batch_starts_dev): a stream whose
+ * list is complete is cut without touching its nodes; one whose list overflowed falls back to reading them. */
+rpl_result rpl_assemble_scan_views_starts_dev(rpl_ctx* ctx, rpl_node_hq* nodes, const uint32_t* node_counts,
+                                              uint32_t n_streams, uint32_t stride_nodes, const uint32_t* capsule_status,
+                                              const uint32_t* capsule_node_offset, const uint32_t* capsule_counts,
+                                              uint32_t stride_capsules, const uint32_t* scan_starts,
+                                              uint32_t starts_stride, const uint32_t* scan_start_counts,
+                                              uint32_t max_nodes, uint32_t max_scans, rpl_scan_view* views_out,
+                                              uint32_t* scan_len, uint32_t* scans_per_stream, const uint64_t* node_ts_us,
+                                              uint64_t* scan_begin_ts_us, void* stream);
 /* rpl_scan_batch_dev over views: scan s = views[s].count nodes from nodes[views[s].first]; nodes_total = nodes in
  * the buffer; outputs laid out [n_scans][stride] as before (stride >= every count, stride <= 8192: the views are
  * served by the shared-memory kernels).  `nodes` must be 16-byte aligned. */

@@ -45,7 +45,8 @@ EXPORTS = [
     "rpl_scan", "rpl_scan_batch", "rpl_ascend_scan_batch", "rpl_laserscan_batch", "rpl_scan_batch_dev",
     "rpl_cloud_batch_dev", "rpl_cloud_batch", "rpl_cloud_fuse_dev", "rpl_synth_batch_dev",
     "rpl_decode_dense_batch_dev", "rpl_decode_dense", "rpl_assemble_scans_dev", "rpl_assemble_scan_views_dev",
-    "rpl_scan_views_dev", "rpl_chain_dense_laserscan",
+    "rpl_scan_views_dev", "rpl_chain_dense_laserscan", "rpl_decode_dense_batch_starts_dev",
+    "rpl_assemble_scan_views_starts_dev",
     "rpl_capsule_bytes", "rpl_capsule_nodes", "rpl_decode_capsules_batch_dev", "rpl_decode_capsules",
     "rpl_decode_normal_batch_dev", "rpl_decode_normal", "rpl_frame_capsules_dev", "rpl_node_timestamps_dev", "rpl_normal_timestamps_dev",
     "rpl_peer_gather_bytes", "rpl_peer_alloc", "rpl_peer_open", "rpl_peer_close", "rpl_peer_free",
@@ -185,6 +186,8 @@ def lib() -> C.CDLL:
         "rpl_assemble_scan_views_dev": ([vp, vp, vp, u32, u32, vp, vp, vp, u32, u32, u32, vp, vp, vp, vp, vp, vp], u32),
         "rpl_scan_views_dev": ([vp, vp, u64, vp, u32, u32, PSP, vp, vp, vp, vp, vp, vp, vp, vp], u32),
         "rpl_chain_dense_laserscan": ([vp, vp, vp, u32, u32, u32, PSP, u32, u32, vp, vp, vp, vp, vp], u32),
+        "rpl_decode_dense_batch_starts_dev": ([vp, vp, vp, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, u32, vp, vp], u32),
+        "rpl_assemble_scan_views_starts_dev": ([vp, vp, vp, u32, u32, vp, vp, vp, u32, vp, u32, vp, u32, u32, vp, vp, vp, vp, vp, vp], u32),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)  # AttributeError here = the library does not export the ABI
@@ -359,7 +362,14 @@ class Context:
 
     def decode_dense_batch_dev(self, capsules, capsule_counts, n_streams, stride_capsules, sample_duration_us,
                                nodes_out, node_counts, sync_state_in=None, capsule_status=None,
-                               capsule_node_offset=None, sync_state_out=None, stream=None):
+                               capsule_node_offset=None, sync_state_out=None, stream=None, scan_starts=None,
+                               starts_stride=0, scan_start_counts=None):
+        if scan_starts is not None:
+            self._check(self._L.rpl_decode_dense_batch_starts_dev(
+                self._h, _p(capsules), _p(capsule_counts), n_streams, stride_capsules, sample_duration_us,
+                _p(sync_state_in), _p(nodes_out), _p(node_counts), _p(capsule_status), _p(capsule_node_offset),
+                _p(sync_state_out), _p(scan_starts), starts_stride, _p(scan_start_counts), _p(stream)))
+            return
         self._check(self._L.rpl_decode_dense_batch_dev(
             self._h, _p(capsules), _p(capsule_counts), n_streams, stride_capsules, sample_duration_us,
             _p(sync_state_in), _p(nodes_out), _p(node_counts), _p(capsule_status), _p(capsule_node_offset),
@@ -488,6 +498,16 @@ class Context:
             self._h, _p(nodes), _p(node_counts), n_streams, stride_nodes, _p(capsule_status), _p(capsule_node_offset),
             _p(capsule_counts), stride_capsules, max_nodes, max_scans, _p(views_out), _p(scan_len),
             _p(scans_per_stream), _p(node_ts_us), _p(scan_begin_ts_us), _p(stream)))
+
+    def assemble_scan_views_starts_dev(self, nodes, node_counts, n_streams, stride_nodes, scan_starts, starts_stride,
+                                       scan_start_counts, max_nodes, max_scans, views_out, scan_len, scans_per_stream,
+                                       capsule_status=None, capsule_node_offset=None, capsule_counts=None,
+                                       stride_capsules=0, node_ts_us=None, scan_begin_ts_us=None, stream=None):
+        self._check(self._L.rpl_assemble_scan_views_starts_dev(
+            self._h, _p(nodes), _p(node_counts), n_streams, stride_nodes, _p(capsule_status), _p(capsule_node_offset),
+            _p(capsule_counts), stride_capsules, _p(scan_starts), starts_stride, _p(scan_start_counts), max_nodes,
+            max_scans, _p(views_out), _p(scan_len), _p(scans_per_stream), _p(node_ts_us), _p(scan_begin_ts_us),
+            _p(stream)))
 
     def scan_views_dev(self, nodes, nodes_total, views, n_scans, stride, params: ScanParams, nodes_out=None, ranges=None,
                        intensities=None, beam_counts=None, angle_increment=None, status=None, path=None, stream=None):

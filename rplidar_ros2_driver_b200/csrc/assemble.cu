@@ -92,7 +92,14 @@ __global__ void __launch_bounds__(AT) assemble_kernel(AssembleArgs a) {
         if (idx < kResetCap) s_rlist[idx] = coff[j];
       }
     }
-    {
+    // the decoder may have handed the scan-start positions over (rpl_decode_dense_batch_starts_dev): then the node
+    // stream is not read again at all
+    const uint32_t n_listed = (a.scan_starts && a.scan_start_counts) ? a.scan_start_counts[s] : 0xFFFFFFFFu;
+    if (n_listed <= a.starts_stride && n_listed <= kListCap) {
+      const uint32_t* lst = a.scan_starts + (size_t)s * a.starts_stride;
+      for (uint32_t e = tid; e < n_listed; e += AT) s_list[e] = lst[e];
+      if (tid == 0) s_cnt = n_listed;
+    } else {
       const uint32_t* flags = reinterpret_cast<const uint32_t*>(nodes) + 1;  // word 1 of every node
       uint32_t i = tid;
       for (; i + 3 * AT < n; i += 4 * AT) {

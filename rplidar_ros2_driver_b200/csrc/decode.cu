@@ -46,6 +46,7 @@ struct __align__(16) DecodeSmem {
   uint32_t carry_sync;                 // lastNodeSyncBit entering the tile
   uint32_t tile_nodes;
   uint32_t red_sync;                   // lastNodeSyncBit leaving the tile
+  uint32_t n_starts;
 };
 
 // raw scan-start test of the 40 interpolated samples (reference :768) as a bit mask
@@ -96,7 +97,9 @@ __global__ void __launch_bounds__(DT) decode_dense_kernel(DecodeArgs a) {
     uint2* out = a.nodes_out + (size_t)s * a.stride_capsules * 40;
     uint32_t* st_out = a.capsule_status ? a.capsule_status + (size_t)s * a.stride_capsules : nullptr;
     uint32_t* off_out = a.capsule_node_offset ? a.capsule_node_offset + (size_t)s * a.stride_capsules : nullptr;
+    uint32_t* starts = a.scan_starts ? a.scan_starts + (size_t)s * a.starts_stride : nullptr;
     if (tid == 0) {
+      sm.n_starts = 0;
       sm.carry_nodes = 0;
       sm.carry_sync = a.sync_state_in ? (a.sync_state_in[s] & 1u) : 0u;
       sm.okflag[0] = 0;  // no previous capsule
@@ -214,6 +217,15 @@ __global__ void __launch_bounds__(DT) decode_dense_kernel(DecodeArgs a) {
         const uint32_t node_off = sm.carry_nodes + 40u * my_off;
         if (st_out) st_out[c0 + tid] = st;
         if (off_out) off_out[c0 + tid] = node_off;
+        if (starts) {  // the scan-start nodes of this capsule (at most a few per revolution), for the assembler
+          unsigned long long m = sm.smask[tid];
+          while (m) {
+            const int pos = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            const uint32_t idx = atomicAdd(&sm.n_starts, 1u);
+            if (idx < a.starts_stride) starts[idx] = node_off + (uint32_t)pos;
+          }
+        }
       }
       if (tid == DT - 1) {
         uint32_t tot = 0, st2 = sm.carry_sync;
@@ -266,6 +278,7 @@ __global__ void __launch_bounds__(DT) decode_dense_kernel(DecodeArgs a) {
     if (tid == 0) {
       if (a.node_counts) a.node_counts[s] = sm.carry_nodes;
       if (a.sync_state_out) a.sync_state_out[s] = sm.carry_sync;
+      if (a.scan_start_counts) a.scan_start_counts[s] = sm.n_starts;
     }
     __syncthreads();
   }

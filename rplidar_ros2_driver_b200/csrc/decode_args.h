@@ -19,6 +19,11 @@ struct DecodeArgs {
   uint32_t* capsule_status;       // [n_streams][stride_capsules] nullable
   uint32_t* capsule_node_offset;  // [n_streams][stride_capsules] nullable
   uint32_t* sync_state_out;       // [n_streams] nullable
+  // positions (node offsets) of the scan-start nodes of every stream, in no particular order (nullable): what
+  // rpl_assemble_scan_views_dev otherwise finds by reading every node again
+  uint32_t* scan_starts;          // [n_streams][starts_stride]
+  uint32_t* scan_start_counts;    // [n_streams] (may exceed starts_stride: the list is then incomplete)
+  uint32_t starts_stride;
 };
 
 // the other capsule formats (decode_formats.cu): 0x82 express, 0x83 HQ, 0x84 ultra, 0x86 ultra-dense
@@ -88,6 +93,9 @@ struct AssembleArgs {
   uint32_t* scans_per_stream;         // [n_streams] published scans (may exceed max_scans)
   const unsigned long long* node_ts_us;  // [n_streams][stride_nodes] nullable
   unsigned long long* scan_begin_ts_us;  // [n_streams][max_scans] nullable
+  const uint32_t* scan_starts;        // nullable: the decoder's list of scan-start node positions per stream
+  const uint32_t* scan_start_counts;
+  uint32_t starts_stride;
   uint32_t* reset_prefix;             // scratch [n_streams][stride_capsules]
   uint2* desc;                        // scratch [n_streams][max_scans]
 };

@@ -677,7 +677,23 @@ rpl_result rpl_decode_dense_batch_dev(rpl_ctx* c, const uint8_t* capsules, const
                                       const uint32_t* sync_state_in, rpl_node_hq* nodes_out,
                                       uint32_t* node_counts, uint32_t* capsule_status,
                                       uint32_t* capsule_node_offset, uint32_t* sync_state_out, void* stream) {
+  return rpl_decode_dense_batch_starts_dev(c, capsules, capsule_counts, n_streams, stride_capsules, sample_duration_us,
+                                           sync_state_in, nodes_out, node_counts, capsule_status, capsule_node_offset,
+                                           sync_state_out, nullptr, 0, nullptr, stream);
+}
+
+rpl_result rpl_decode_dense_batch_starts_dev(rpl_ctx* c, const uint8_t* capsules, const uint32_t* capsule_counts,
+                                             uint32_t n_streams, uint32_t stride_capsules, uint32_t sample_duration_us,
+                                             const uint32_t* sync_state_in, rpl_node_hq* nodes_out,
+                                             uint32_t* node_counts, uint32_t* capsule_status,
+                                             uint32_t* capsule_node_offset, uint32_t* sync_state_out,
+                                             uint32_t* scan_starts, uint32_t starts_stride, uint32_t* scan_start_counts,
+                                             void* stream) {
   if (!c || !capsules || !capsule_counts || !nodes_out) return RPL_RESULT_INVALID_DATA;
+  if ((scan_starts == nullptr) != (scan_start_counts == nullptr) || (scan_starts && starts_stride == 0)) {
+    c->err = "scan_starts and scan_start_counts go together (starts_stride > 0)";
+    return RPL_RESULT_INVALID_DATA;
+  }
   if (sample_duration_us == 0 || sample_duration_us > 1000000u) {
     c->err = "sample_duration_us must be in [1, 1000000]";
     return RPL_RESULT_INVALID_DATA;
@@ -701,6 +717,9 @@ rpl_result rpl_decode_dense_batch_dev(rpl_ctx* c, const uint8_t* capsules, const
   a.capsule_status = capsule_status;
   a.capsule_node_offset = capsule_node_offset;
   a.sync_state_out = sync_state_out;
+  a.scan_starts = scan_starts;
+  a.scan_start_counts = scan_start_counts;
+  a.starts_stride = starts_stride;
   const int grid = (int)std::min<uint32_t>(n_streams, (uint32_t)c->num_sms * 4u);
   RPL_CUDA(c, rpl::launch_decode_dense(a, grid, st), RPL_RESULT_OPERATION_FAIL);
   c->launches++;
@@ -1013,7 +1032,8 @@ rpl_result assemble_common(rpl_ctx* c, const rpl_node_hq* nodes, const uint32_t*
                                   uint32_t stride_capsules, uint32_t max_nodes, uint32_t max_scans,
                                   uint32_t scan_stride, rpl_node_hq* scans_out, rpl_scan_view* views_out, uint32_t* scan_len,
                                   uint32_t* scans_per_stream, const uint64_t* node_ts_us,
-                                  uint64_t* scan_begin_ts_us, void* stream) {
+                                  uint64_t* scan_begin_ts_us, void* stream, const uint32_t* scan_starts = nullptr,
+                                  uint32_t starts_stride = 0, const uint32_t* scan_start_counts = nullptr) {
   if (!c || !nodes || !node_counts || (!scans_out && !views_out) || !scan_len || !scans_per_stream) return RPL_RESULT_INVALID_DATA;
   const bool any = capsule_status || capsule_node_offset || capsule_counts;
   if (any && !(capsule_status && capsule_node_offset && capsule_counts)) {
@@ -1064,6 +1084,9 @@ rpl_result assemble_common(rpl_ctx* c, const rpl_node_hq* nodes, const uint32_t*
   a.scans_per_stream = scans_per_stream;
   a.node_ts_us = reinterpret_cast<const unsigned long long*>(node_ts_us);
   a.scan_begin_ts_us = reinterpret_cast<unsigned long long*>(scan_begin_ts_us);
+  a.scan_starts = scan_starts;
+  a.scan_start_counts = scan_start_counts;
+  a.starts_stride = starts_stride;
   a.reset_prefix = c->d_reset_prefix;
   a.desc = c->d_desc;
   const int grid = (int)std::min<uint32_t>(n_streams, (uint32_t)c->num_sms * 4u);
@@ -1102,6 +1125,25 @@ rpl_result rpl_assemble_scan_views_dev(rpl_ctx* c, rpl_node_hq* nodes, const uin
   return assemble_common(c, nodes, node_counts, n_streams, stride_nodes, capsule_status, capsule_node_offset,
                          capsule_counts, stride_capsules, max_nodes, max_scans, max_nodes, nullptr, views_out, scan_len,
                          scans_per_stream, node_ts_us, scan_begin_ts_us, stream);
+}
+
+rpl_result rpl_assemble_scan_views_starts_dev(rpl_ctx* c, rpl_node_hq* nodes, const uint32_t* node_counts,
+                                              uint32_t n_streams, uint32_t stride_nodes, const uint32_t* capsule_status,
+                                              const uint32_t* capsule_node_offset, const uint32_t* capsule_counts,
+                                              uint32_t stride_capsules, const uint32_t* scan_starts,
+                                              uint32_t starts_stride, const uint32_t* scan_start_counts,
+                                              uint32_t max_nodes, uint32_t max_scans, rpl_scan_view* views_out,
+                                              uint32_t* scan_len, uint32_t* scans_per_stream, const uint64_t* node_ts_us,
+                                              uint64_t* scan_begin_ts_us, void* stream) {
+  if (!views_out || !scan_starts || !scan_start_counts || starts_stride == 0) return RPL_RESULT_INVALID_DATA;
+  if ((unsigned long long)n_streams * stride_nodes > 0xFFFFFFFFull) {
+    if (c) c->err = "view mode addresses nodes with 32 bits: n_streams * stride_nodes must stay below 2^32";
+    return RPL_RESULT_INVALID_DATA;
+  }
+  return assemble_common(c, nodes, node_counts, n_streams, stride_nodes, capsule_status, capsule_node_offset,
+                         capsule_counts, stride_capsules, max_nodes, max_scans, max_nodes, nullptr, views_out, scan_len,
+                         scans_per_stream, node_ts_us, scan_begin_ts_us, stream, scan_starts, starts_stride,
+                         scan_start_counts);
 }
 
 rpl_result rpl_scan_views_dev(rpl_ctx* c, const rpl_node_hq* nodes, uint64_t nodes_total, const rpl_scan_view* views,
@@ -1159,12 +1201,14 @@ rpl_result rpl_chain_dense_laserscan(rpl_ctx* c, const uint8_t* capsules, const 
   }
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t NS = (size_t)chunk * max_scans;
+  const uint32_t starts_stride = 2 * max_scans + 64;  // scan starts per stream the decoder may list
   const size_t o_caps = 0, o_ccnt = o_caps + up(chunk * cap_bytes_stream), o_nodes = o_ccnt + up((size_t)chunk * 4),
                o_ncnt = o_nodes + up(chunk * nodes_stream * 8), o_st = o_ncnt + up((size_t)chunk * 4),
                o_off = o_st + up((size_t)chunk * stride_capsules * 4), o_views = o_off + up((size_t)chunk * stride_capsules * 4),
                o_slen = o_views + up(NS * 8), o_sps = o_slen + up(NS * 4), o_r = o_sps + up((size_t)chunk * 4),
                o_i = o_r + up(NS * max_nodes * 4), o_b = o_i + up(NS * max_nodes * 4), o_inc = o_b + up(NS * 4),
-               total = o_inc + up(NS * 4);
+               o_starts = o_inc + up(NS * 4), o_scnt = o_starts + up((size_t)chunk * starts_stride * 4),
+               total = o_scnt + up((size_t)chunk * 4);
   for (int i = 0; i < kLanes; ++i) {
     Lane& l = c->lane[i];
     if (l.chain_bytes < total) {
@@ -1184,18 +1228,21 @@ rpl_result rpl_chain_dense_laserscan(rpl_ctx* c, const uint8_t* capsules, const 
     RPL_CUDA(c, cudaMemcpyAsync(d + o_caps, capsules + (size_t)s0 * cap_bytes_stream, ns * cap_bytes_stream, h2d, l.stream),
              RPL_RESULT_OPERATION_FAIL);
     RPL_CUDA(c, cudaMemcpyAsync(d + o_ccnt, capsule_counts + s0, (size_t)ns * 4, h2d, l.stream), RPL_RESULT_OPERATION_FAIL);
-    rpl_result r = rpl_decode_dense_batch_dev(c, d + o_caps, reinterpret_cast<uint32_t*>(d + o_ccnt), ns, stride_capsules,
-                                              sample_duration_us, nullptr, reinterpret_cast<rpl_node_hq*>(d + o_nodes),
-                                              reinterpret_cast<uint32_t*>(d + o_ncnt), reinterpret_cast<uint32_t*>(d + o_st),
-                                              reinterpret_cast<uint32_t*>(d + o_off), nullptr, l.stream);
+    rpl_result r = rpl_decode_dense_batch_starts_dev(
+        c, d + o_caps, reinterpret_cast<uint32_t*>(d + o_ccnt), ns, stride_capsules, sample_duration_us, nullptr,
+        reinterpret_cast<rpl_node_hq*>(d + o_nodes), reinterpret_cast<uint32_t*>(d + o_ncnt),
+        reinterpret_cast<uint32_t*>(d + o_st), reinterpret_cast<uint32_t*>(d + o_off), nullptr,
+        reinterpret_cast<uint32_t*>(d + o_starts), starts_stride, reinterpret_cast<uint32_t*>(d + o_scnt), l.stream);
     if (r != RPL_RESULT_OK) return r;
     // the assembler's scratch belongs to the context, not to the lane: one assemble kernel at a time
     if (!c->asm_done) RPL_CUDA(c, cudaEventCreateWithFlags(&c->asm_done, cudaEventDisableTiming), RPL_RESULT_OPERATION_FAIL);
     RPL_CUDA(c, cudaStreamWaitEvent(l.stream, c->asm_done, 0), RPL_RESULT_OPERATION_FAIL);
-    r = rpl_assemble_scan_views_dev(c, reinterpret_cast<rpl_node_hq*>(d + o_nodes), reinterpret_cast<uint32_t*>(d + o_ncnt), ns,
+    r = rpl_assemble_scan_views_starts_dev(c, reinterpret_cast<rpl_node_hq*>(d + o_nodes), reinterpret_cast<uint32_t*>(d + o_ncnt), ns,
                                     (uint32_t)nodes_stream, reinterpret_cast<uint32_t*>(d + o_st),
                                     reinterpret_cast<uint32_t*>(d + o_off), reinterpret_cast<uint32_t*>(d + o_ccnt),
-                                    stride_capsules, max_nodes, max_scans, reinterpret_cast<rpl_scan_view*>(d + o_views),
+                                    stride_capsules, reinterpret_cast<uint32_t*>(d + o_starts), starts_stride,
+                                    reinterpret_cast<uint32_t*>(d + o_scnt), max_nodes, max_scans,
+                                    reinterpret_cast<rpl_scan_view*>(d + o_views),
                                     reinterpret_cast<uint32_t*>(d + o_slen), reinterpret_cast<uint32_t*>(d + o_sps), nullptr,
                                     nullptr, l.stream);
     if (r != RPL_RESULT_OK) return r;

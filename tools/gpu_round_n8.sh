@@ -5,10 +5,8 @@ set -u
 mkdir -p gpurun_out
 T=${1:-r2n8}
 nvidia-smi topo -m > gpurun_out/${T}_topo.txt 2>&1
-timeout 600 python -m pytest tests/test_gpu_multi_push.py -q 2>&1 | tail -15 > gpurun_out/${T}_pytest.txt; tail -5 gpurun_out/${T}_pytest.txt
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
 timeout 900 $RUN --master-port 29521 bench.py --gpus 8 --steps 50 > gpurun_out/${T}_default.json 2> gpurun_out/${T}_default.err; tail -c 1500 gpurun_out/${T}_default.err
-timeout 600 $RUN --master-port 29522 bench.py --gpus 8 --workload cloud --steps 30 > gpurun_out/${T}_cloud.json 2> gpurun_out/${T}_cloud.err; tail -c 800 gpurun_out/${T}_cloud.err
 
 NCCL_DEBUG=INFO timeout 600 $RUN --master-port 29524 bench.py --gpus 8 --workload cloud --steps 3 > /dev/null 2> gpurun_out/${T}_nccl_info.log; grep -iE "NVLS|via P2P|Channel 00|NCCL version|Connected all" gpurun_out/${T}_nccl_info.log | sort | uniq -c | head -12
 T=$T python - <<'PY'
