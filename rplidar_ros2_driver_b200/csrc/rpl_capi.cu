@@ -44,7 +44,7 @@ void free_lane(Lane& l) {
   cudaFree(l.gws.idx1);
   cudaFree(l.gws.vidx);
   cudaFree(l.gws.cell);
-  rpl::cloud_workspace_free(l.cws);
+  if (l.owns_cws) rpl::cloud_workspace_free(l.cws);
   cudaFree(l.d_nodes);
   cudaFree(l.d_nodes_out);
   cudaFree(l.d_counts);
@@ -291,8 +291,16 @@ rpl_result rpl_ctx_create(int device, uint32_t max_nodes, uint32_t max_scans, rp
         !cuda_ok(c, dev_alloc(&l.gws.idx1, gen_nodes), "cudaMalloc") ||
         !cuda_ok(c, dev_alloc(&l.gws.vidx, gen_nodes), "cudaMalloc") ||
         !cuda_ok(c, dev_alloc(&l.gws.cell, gen_nodes), "cudaMalloc") ||
-        !cuda_ok(c, rpl::cloud_workspace_alloc(l.cws, c->num_sms, max_nodes), "cloud workspace"))
+        false)
       return fail(oom);
+    if (i == 0) {
+      if (!cuda_ok(c, rpl::cloud_workspace_alloc(l.cws, c->num_sms, max_nodes), "cloud workspace")) return fail(oom);
+      l.owns_cws = true;
+    } else {  // read-only tables shared with lane 0; the PointCloud2 post passes run on lane 0 only
+      l.cws = rpl::CloudWorkspace{};
+      l.cws.trig = c->lane[0].cws.trig;
+      l.cws.angle = c->lane[0].cws.angle;
+    }
     if (!cuda_ok(c, cudaMemset(l.fallback_count, 0, sizeof(uint32_t)), "cudaMemset"))
       return fail(RPL_RESULT_OPERATION_FAIL);
   }

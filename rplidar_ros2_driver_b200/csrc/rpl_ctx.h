@@ -12,7 +12,7 @@
 #include "cloud_args.h"
 #include "scan_args.h"
 
-constexpr int kLanes = 2;  // host-buffer pipeline depth (copy/compute overlap)
+constexpr int kLanes = 3;  // host-buffer pipeline depth: with three chunks in flight both DMA directions stay busy
 
 struct Lane {
   cudaStream_t stream = nullptr;
@@ -20,7 +20,8 @@ struct Lane {
   uint32_t* fallback_count = nullptr;
   rpl::FastWorkspace fws{};
   rpl::GeneralWorkspace gws{};
-  rpl::CloudWorkspace cws{};
+  rpl::CloudWorkspace cws{};   // lane 0 owns the tables and the post-pass scratch; the others alias its tables
+  bool owns_cws = false;
   // device staging for host-buffer calls (lazy)
   uint2* d_nodes = nullptr;
   uint2* d_nodes_out = nullptr;
