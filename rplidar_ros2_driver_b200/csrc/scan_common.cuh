@@ -181,32 +181,135 @@ __device__ __forceinline__ void mode_a_emit(const ModeAOut& o, const unsigned lo
   }
 }
 
-constexpr uint32_t kModeASmemMaxPoints = kKeySpace / 2;  // u16 node indices in the 64 KB the dead presence map leaves free
+// ---- Mode A emit, shared-memory variant (scan_tma.cu) ----------------------------------------
+// ncu on the variant above showed the scratch doubling DRAM traffic (8 B written + 8 B read per
+// point through a 76 MB working set).  Here the place pass only records WHICH node sits at each
+// u-rank, as a u16 node index in the 64 KB the dead presence map leaves free (so M <= 32768),
+// and the emit pass gathers the nodes from the tile again (L2 hits, coalesced for a sorted
+// revolution).  Bins of a batch are staged per warp in the (equally dead) rank table.
+constexpr uint32_t kEmit2Batch = 256;
+constexpr uint32_t kEmit2Stage = kEmit2Batch + 33;  // staged bins: one entry before, 32 after
+constexpr uint32_t kModeASmemMaxPoints = kKeySpace / 2;
 
-// ---- Mode A emit, one thread per u-rank ------------------------------------------------------------------------
-// sidx[r] = index (in `nodes`) of the measured node at u-rank r.  Bins do not decrease along the u-order, so the
-// points of a bin are neighbours there: the thread of rank r compares its bin with its predecessor's and, when it is
-// the first point of its bin, walks the few points behind it, stores the bin and fills the empty bins in front of it
-// (the last rank also those behind it).  `nodes` may live in shared memory (scan_small.cu) or in global memory (the
-// TMA kernel: the tile was just streamed, the gathers hit L2 and are coalesced for a sorted revolution).
-// ~35 instructions per point instead of the ~90 of the staged variant above.
-__device__ __forceinline__ void mode_a_emit_direct(const ModeAOut& o, const uint16_t* sidx, const uint2* nodes,
-                                                   uint32_t tid, uint32_t nthreads) {
+__device__ __forceinline__ void mode_a_emit_smem(const ModeAOut& o, const uint16_t* sidx, const uint2* tile,
+                                                 uint32_t warp, uint32_t nwarps, uint16_t* sb) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t M = o.M;
+  const uint32_t len = ((M + nwarps - 1u) / nwarps + kEmit2Batch - 1u) & ~(kEmit2Batch - 1u);
+  const uint32_t r_begin = min(M, warp * len), r_end = min(M, r_begin + len);
+  if (r_begin >= r_end) return;
+  const bool inverted = o.inverted;
+  const float inc = o.inc;
+  // integer quotient where the float chain provably agrees, else the exact chain in registers
+  // (FP64, no memory access): this pass is bound by load latency, not by issue slots, so the
+  // table lookup of mode_a_emit would only add a dependent L2 access per entry
+  auto bin_of_key = [&](uint32_t key) { return (uint32_t)mode_a_bin_fast(key, M, inc, inverted); };
+  const uint32_t kNoBin = 0xFFFFu, kBeforeFirst = 0xFFFEu;  // real bins are < 32768
+  const float kInf = __int_as_float(0x7f800000);
+  auto entry_of = [&](uint2 nd) {
+    return mode_a_entry(dist_to_m(__funnelshift_r(nd.x, nd.y, 16)), nd.x & 0xFFFFu, (nd.y >> 16) & 0xFFu);
+  };
+  constexpr int kW = kEmit2Batch / 32;
+  using Checked = std::integral_constant<bool, true>;
+  using Unchecked = std::integral_constant<bool, false>;
+
+  auto batch = [&](auto checked, uint32_t base) {
+    constexpr bool CK = decltype(checked)::value;
+    __syncwarp();
+    // stage: this lane's own eight entries (kept in registers) plus one halo entry (the entry
+    // before the batch for lane 0, the 32 after it for the others); all gathers issued together
+    uint2 nd[kW];
+#pragma unroll
+    for (int w = 0; w < kW; ++w) {
+      const uint32_t r = base + w * 32 + lane;
+      nd[w] = (!CK || r < M) ? tile[sidx[r]] : make_uint2(0, 0);
+    }
+    const uint32_t th = (lane == 0) ? 0u : (kEmit2Batch + lane);  // lane 0 -> before; 1..31 -> after
+    const long long rh = (long long)base - 1 + th;
+    const bool halo_ok = !CK || (rh >= 0 && rh < (long long)M);
+    const uint2 ndh = halo_ok ? tile[sidx[halo_ok ? rh : 0]] : make_uint2(0, 0);
+    const uint32_t r2 = base - 1 + kEmit2Batch + 32;  // last look-ahead slot (lane 31)
+    const bool last_ok = (lane == 31) && (!CK || r2 < M);
+    const uint2 nd2 = last_ok ? tile[sidx[last_ok ? r2 : 0]] : make_uint2(0, 0);
+#pragma unroll
+    for (int w = 0; w < kW; ++w) {
+      const uint32_t r = base + w * 32 + lane;
+      sb[1 + w * 32 + lane] = (!CK || r < M) ? (uint16_t)bin_of_key(nd[w].x & 0xFFFFu) : (uint16_t)kNoBin;
+    }
+    {
+      uint32_t b = (CK && rh < 0) ? kBeforeFirst : kNoBin;
+      if (halo_ok) b = bin_of_key(ndh.x & 0xFFFFu);
+      sb[th] = (uint16_t)b;
+      if (lane == 31) sb[kEmit2Batch + 32] = last_ok ? (uint16_t)bin_of_key(nd2.x & 0xFFFFu) : (uint16_t)kNoBin;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int w = 0; w < kW; ++w) {
+      const uint32_t i = 1 + w * 32 + lane;
+      const uint32_t r = base + w * 32 + lane;
+      const bool live = !CK || r < M;
+      const uint32_t b = sb[i], bprev = sb[i - 1];
+      const bool head = live && (b != bprev);
+      unsigned long long v = entry_of(nd[w]);
+      // the next entry's node sits in the neighbouring lane (or lane 0 of the next window):
+      // a bin shared by two points -- the usual collision -- costs two shuffles, no memory access
+      uint2 nxt;
+      nxt.x = __shfl_down_sync(0xffffffffu, nd[w].x, 1);
+      nxt.y = __shfl_down_sync(0xffffffffu, nd[w].y, 1);
+      if (w + 1 < kW) {
+        const uint32_t fx = __shfl_sync(0xffffffffu, nd[(w + 1) % kW].x, 0);
+        const uint32_t fy = __shfl_sync(0xffffffffu, nd[(w + 1) % kW].y, 0);
+        if (lane == 31) nxt = make_uint2(fx, fy);
+      }
+      if (head && sb[i + 1] == b) {
+        if (w + 1 == kW && lane == 31) nxt = tile[sidx[r + 1]];  // first entry of the next batch
+        v = min(v, entry_of(nxt));
+        if (sb[i + 2] == b) {  // three or more points in the bin: walk on (rare: M points, M bins)
+          for (uint32_t rr = r + 2; rr < M; ++rr) {
+            const uint2 other = tile[sidx[rr]];
+            if (bin_of_key(other.x & 0xFFFFu) != b) break;
+            v = min(v, entry_of(other));
+          }
+        }
+      }
+      mode_a_store_bin(o, head ? (int)b : 0, v, head ? 1u : 0u);
+      const int gap_from = (CK && bprev == kBeforeFirst) ? 0 : (int)bprev + 1;
+      if (head && (int)b > gap_from) {  // empty bins in front of this run
+        if ((int)b - gap_from == 1) {
+          o.ranges[gap_from] = kInf;
+          o.intens[gap_from] = 0.0f;
+        } else {
+          mode_a_fill_empty(o, gap_from, (int)b);
+        }
+      }
+      if (CK && live && r == M - 1u) mode_a_fill_empty(o, (int)b + 1, (int)M);  // empty bins behind the last run
+    }
+  };
+  for (uint32_t base = r_begin; base < r_end; base += kEmit2Batch) {
+    // interior batches (entry before and all 256 + 32 look-ahead entries exist) skip every range check
+    if (base >= 1u && base + kEmit2Batch + 32u <= M) batch(Unchecked{}, base);
+    else batch(Checked{}, base);
+  }
+}
+
+// ---- Mode A emit, one thread per u-rank (scan_small.cu: everything in shared memory) ------------------------------
+// sidx[r] = index (in `nodes`) of the measured node at u-rank r, binv[r] = its bin (both written by the place pass,
+// which evaluates every bin exactly once).  Bins do not decrease along the u-order, so the points of a bin are
+// neighbours there: the thread of rank r compares its bin with its predecessor's and, when it is the first point of
+// its bin, walks the few points behind it, stores the bin and fills the empty bins in front of it (the last rank also
+// those behind it).  No staging, no batches, no barriers inside the pass.
+__device__ __forceinline__ void mode_a_emit_direct(const ModeAOut& o, const uint16_t* sidx, const uint16_t* binv,
+                                                   const uint2* nodes, uint32_t tid, uint32_t nthreads) {
   const uint32_t M = o.M;
   auto entry_of = [&](uint2 x) {
     return mode_a_entry(dist_to_m(__funnelshift_r(x.x, x.y, 16)), x.x & 0xFFFFu, (x.y >> 16) & 0xFFu);
   };
   for (uint32_t r = tid; r < M; r += nthreads) {
-    const uint2 me = nodes[sidx[r]];
-    const int b = mode_a_bin_fast(me.x & 0xFFFFu, M, o.inc, o.inverted);
-    const int bp = r > 0 ? mode_a_bin_fast(nodes[sidx[r - 1]].x & 0xFFFFu, M, o.inc, o.inverted) : -1;
+    const int b = (int)binv[r];
+    const int bp = r > 0 ? (int)binv[r - 1] : -1;
     if (b != bp) {
-      unsigned long long best = entry_of(me);
-      for (uint32_t j = r + 1; j < M; ++j) {
-        const uint2 nx = nodes[sidx[j]];
-        if (mode_a_bin_fast(nx.x & 0xFFFFu, M, o.inc, o.inverted) != b) break;
-        best = min(best, entry_of(nx));
-      }
+      unsigned long long best = entry_of(nodes[sidx[r]]);
+      for (uint32_t j = r + 1; j < M && (int)binv[j] == b; ++j) best = min(best, entry_of(nodes[sidx[j]]));
       mode_a_store_bin(o, b, best, 1u);
       if (b - bp > 1) mode_a_fill_empty(o, bp + 1, b);  // empty bins in front of this one
     }

@@ -237,7 +237,11 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
     bitsA = reinterpret_cast<uint32_t*>(q); q += kWords * 4;
     prefA = reinterpret_cast<uint16_t*>(q); q += kWords * 2;
   }
-  if (MODE_A) sidx = reinterpret_cast<uint16_t*>(q);
+  uint16_t* binv = nullptr;
+  if (MODE_A) {
+    sidx = reinterpret_cast<uint16_t*>(q);
+    binv = sidx + cap;
+  }
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool new_proto = a.is_new_protocol != 0;
@@ -381,7 +385,13 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
       for (uint32_t i = tid; i < n; i += TS) {
         const uint2 nd = tile[i];
         const uint32_t dist = __funnelshift_r(nd.x, nd.y, 16);
-        const uint32_t fk = dist != 0 ? (nd.x & 0xFFFFu) : (i == 0 ? front_key : ascend_fill_key(front_deg, i, step));
+        uint32_t fk = nd.x & 0xFFFFu;
+        if (dist == 0) {
+          // the final key of an unmeasured node is written back into the shared-memory copy: the place pass then
+          // reads every node's final key where it reads the node
+          fk = (i == 0) ? front_key : ascend_fill_key(front_deg, i, step);
+          tile0[shift + i].x = (nd.x & 0xFFFF0000u) | fk;
+        }
         atomicOr(&bitsA[fk >> 5], 1u << (fk & 31));
       }
       __syncthreads();
@@ -463,10 +473,7 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
       const uint32_t k = nd.x & 0xFFFFu;
       const uint32_t dist = __funnelshift_r(nd.x, nd.y, 16);
       uint32_t measured = dist != 0 ? 1u : 0u;
-      if (EMIT) {
-        const uint32_t fk = measured ? k : (i == 0 ? front_key : ascend_fill_key(front_deg, i, step));
-        st_hint_v2(nodes_out + rank2(bitsA, prefA, fk), node_with_key(nd, fk), pol_stream);
-      }
+      if (EMIT) st_hint_v2(nodes_out + rank2(bitsA, prefA, k), nd, pol_stream);  // k is the FINAL key here
       if (!CLOUD && !want_scan) continue;
       const uint32_t rk = rank2(bitsV, prefV, k);
       const float dm = dist_to_m(dist);
@@ -490,7 +497,9 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
         st_f32_if(pr, dm, pol_stream, measured);
         st_f32_if(reinterpret_cast<float*>(reinterpret_cast<char*>(pr) + i_minus_r), it, pol_stream, measured);
       } else if (measured) {  // Mode A: remember which node sits at this u-rank (mode_a_emit_direct)
-        sidx[mode_a_urank(k, rk, M, inverted, has0)] = (uint16_t)i;
+        const uint32_t ur = mode_a_urank(k, rk, M, inverted, has0);
+        sidx[ur] = (uint16_t)i;
+        binv[ur] = (uint16_t)mode_a_bin_fast(k, M, inc, inverted);  // bins are < M <= 8192
       }
     }
     __syncthreads();
@@ -510,7 +519,7 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
       mo.inverted = inverted;
       mo.new_proto = new_proto;
       mo.policy = pol_stream;
-      mode_a_emit_direct(mo, sidx, tile, tid, TS);
+      mode_a_emit_direct(mo, sidx, binv, tile, tid, TS);
     }
 
     uint32_t m_out = M;
@@ -804,7 +813,7 @@ size_t scan_small_smem_bytes(uint32_t cap, int mode, bool emit, bool post) {
     return b + (size_t)cap * 8 + cap + std::max<size_t>((size_t)cap * 16, kWords * 6);
   b += kWords * 6;
   if (emit) b += kWords * 6;
-  if (mode == 1) b += (size_t)cap * 2;
+  if (mode == 1) b += (size_t)cap * 4;  // node index + bin per u-rank
   return b;
 }
 

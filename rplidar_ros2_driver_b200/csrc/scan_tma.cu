@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
           float* pr = ranges + o;
           st_f32_if(pr, dm, pol_stream, measured);
           st_f32_if(reinterpret_cast<float*>(reinterpret_cast<char*>(pr) + i_minus_r), it, pol_stream, measured);
-        } else if (measured) {  // Mode A: remember which node sits at this u-rank (mode_a_emit_direct)
+        } else if (measured) {  // Mode A: remember which node sits at this u-rank (mode_a_emit_smem)
           sidx[mode_a_urank(k, rk, M, inverted, has0)] = (uint16_t)(c * CH + r * TC + tid);
         }
       }
@@ -411,7 +411,10 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) scan_tma_kernel(ScanBatchA
       mo.inverted = inverted;
       mo.new_proto = new_proto;
       mo.policy = pol_stream;
-      mode_a_emit_direct(mo, sidx, base, tid, TC);
+      // the rank table is dead by now: each warp stages a batch of bins in its own slice of it
+      static_assert(kEmit2Stage * 2 * kCWarps <= sizeof(sm.rankV), "bin staging must fit the rank table");
+      mode_a_emit_smem(mo, sidx, base, warp, kCWarps,
+                       reinterpret_cast<uint16_t*>(sm.rankV) + warp * ((kEmit2Stage + 7u) & ~7u));
     }
     consumer_sync();
     if (tid == 0) {

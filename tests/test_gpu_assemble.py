@@ -297,7 +297,17 @@ def test_wire_bytes_to_laserscan_in_one_host_call(R, oracle, n_streams, max_node
             assert out["beam_counts"][slot] == hdr.beam_count, (s, k, elen[k])
             got_r = out["ranges"][slot, : hdr.beam_count].view(np.uint32)
             bad = np.nonzero(got_r != r.view(np.uint32))[0]
-            assert bad.size == 0, (s, k, int(elen[k]), int(hdr.beam_count), bad[:8].tolist(), int(bad.size))
+            if bad.size:  # diagnostics: the same revolution through the plain batch call (no views, no chain)
+                one = np.zeros((1, max_nodes), R.NODE_DTYPE)
+                one[0, : elen[k]] = e[k, : elen[k]].view(R.NODE_DTYPE)
+                chk = R.Context(0, max_nodes, 1)
+                alt = chk.scan_batch(one, np.array([elen[k]], np.uint32), R.scan_params(1, 0, 0, 1))
+                chk.close()
+                alt_ok = bool((alt["ranges"][0, : hdr.beam_count].view(np.uint32) == r.view(np.uint32)).all())
+                where = [int(np.nonzero(got_r == v)[0][0]) if (got_r == v).any() else -1 for v in r.view(np.uint32)[bad[:4]]]
+                raise AssertionError((s, k, int(elen[k]), int(hdr.beam_count), bad[:8].tolist(), int(bad.size),
+                                      "plain batch call ok" if alt_ok else "plain batch call ALSO wrong",
+                                      out["ranges"][slot, bad[:4]].tolist(), r[bad[:4]].tolist(), where))
             assert (out["intensities"][slot, : hdr.beam_count].view(np.uint32) == it.view(np.uint32)).all(), (s, k)
             total += 1
     assert total > 20
