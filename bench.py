@@ -1307,6 +1307,43 @@ def run_chain(args, rank, local_rank, world):
                "scans_match_device_path": same, "beams_out": epts,
                "h2d_bytes_per_point": n_streams * n_caps * 84 / pts, "d2h_bytes_per_point": 2 * ens * out_nodes * 4 / pts}
         ectx.close()
+    # ---- cpu baseline: the same chain with the oracle ports (decode, assembly) and the reference's own
+    # ascendScanData + publish_scan, one stream per task ---------------------------------------------------------
+    cpu = None
+    if not args.no_cpu:
+        from concurrent.futures import ThreadPoolExecutor
+
+        from oracle import pyoracle as O
+
+        O.build(ref=False)
+        cores, cores_how = effective_cores()
+        prm = O.scan_params(1, 0, 0, 1, 40.0, 0.1)
+
+        def one_stream(i):
+            en, es, eo, _ = O.dense_decode(host[i % distinct], 31, 0)
+            e, elen, ek = O.assemble_scans(en, O.resets_from_capsules(es, eo), max_nodes, max_scans)
+            k = min(ek, max_scans)
+            if k:
+                if O.have_ref_node():
+                    O.ref_pipeline_batch(np.ascontiguousarray(e[:k]), elen[:k].astype(np.uint32), prm, threads=1, outputs=False)
+                else:
+                    O.pipeline_batch(np.ascontiguousarray(e[:k]).copy(), elen[:k].astype(np.uint32), prm, stable=False, threads=1)
+            return int(elen[:k].sum())
+
+        one_stream(0)
+        t0 = time.perf_counter()
+        p1 = one_stream(1)
+        t_one = time.perf_counter() - t0
+        reps = max(2 * cores, 32)
+        with ThreadPoolExecutor(cores) as ex:
+            t0 = time.perf_counter()
+            ptsc = sum(ex.map(one_stream, range(reps)))
+            t_all = time.perf_counter() - t0
+        cpu = {"value": ptsc / t_all / 1e6, "unit": UNIT, "cores": cores, "cores_how": cores_how,
+               "kind": "reference" if O.have_ref_node() else "port",
+               "sample": f"{reps} streams x {n_caps} capsules: oracle ports of the dense decoder and the scan holder (validated "
+                         f"against the compiled SDK), then the reference's own ascendScanData + publish_scan per revolution; "
+                         f"one stream per task, {cores} threads", "value_1thread": p1 / t_one / 1e6}
     line = {
         "metric": "Mpoints/s wire capsules -> LaserScan (decode + scan assembly + scan kernel on the device)",
         "value": pts / (ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": W,
@@ -1320,7 +1357,7 @@ def run_chain(args, rank, local_rank, world):
         "roofline": {"bound": "hbm", "kernel": "decode_dense + assemble + scan", "achieved": alg / (ms * 1e-3) / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg},
-        "cpu_baseline": None, "e2e": e2e, "gpu_launches": ctx.launch_count - l0, "clocks": clocks,
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": ctx.launch_count - l0, "clocks": clocks,
         "extra": {"ms_decode": parts[0], "ms_assemble": parts[1], "ms_scan": parts[2], "scans_published": n_scans,
                   "points_decoded": int(ncount.sum().item())},
     }
