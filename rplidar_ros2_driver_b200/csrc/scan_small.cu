@@ -238,9 +238,11 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
     prefA = reinterpret_cast<uint16_t*>(q); q += kWords * 2;
   }
   uint16_t* binv = nullptr;
+  uint16_t* firstv = nullptr;
   if (MODE_A) {
     sidx = reinterpret_cast<uint16_t*>(q);
     binv = sidx + cap;
+    firstv = binv + cap;
   }
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -314,6 +316,10 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
       if (EMIT) {
         uint4* a4 = reinterpret_cast<uint4*>(bitsA);
         for (uint32_t w = tid; w < kWords / 4; w += TS) a4[w] = make_uint4(0, 0, 0, 0);
+      }
+      if (MODE_A) {  // "no rank starts this bin" for every bin (mode_a_emit_bins); cap is a multiple of 64
+        uint4* f4 = reinterpret_cast<uint4*>(firstv);
+        for (uint32_t w = tid; w < cap / 8; w += TS) f4[w] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
       }
       if (tid == 0) {
         ctl.first_valid = 0xFFFFFFFFu;
@@ -496,7 +502,7 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
         float* pr = ranges + o;
         st_f32_if(pr, dm, pol_stream, measured);
         st_f32_if(reinterpret_cast<float*>(reinterpret_cast<char*>(pr) + i_minus_r), it, pol_stream, measured);
-      } else if (measured) {  // Mode A: remember which node sits at this u-rank (mode_a_emit_direct)
+      } else if (measured) {  // Mode A: remember which node sits at this u-rank (mode_a_emit_bins)
         const uint32_t ur = mode_a_urank(k, rk, M, inverted, has0);
         sidx[ur] = (uint16_t)i;
         binv[ur] = (uint16_t)mode_a_bin_fast(k, M, inc, inverted);  // bins are < M <= 8192
@@ -519,7 +525,7 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
       mo.inverted = inverted;
       mo.new_proto = new_proto;
       mo.policy = pol_stream;
-      mode_a_emit_direct(mo, sidx, binv, tile, tid, TS);
+      mode_a_emit_bins(mo, sidx, binv, firstv, tile, tid, TS);
     }
 
     uint32_t m_out = M;
@@ -813,7 +819,7 @@ size_t scan_small_smem_bytes(uint32_t cap, int mode, bool emit, bool post) {
     return b + (size_t)cap * 8 + cap + std::max<size_t>((size_t)cap * 16, kWords * 6);
   b += kWords * 6;
   if (emit) b += kWords * 6;
-  if (mode == 1) b += (size_t)cap * 4;  // node index + bin per u-rank
+  if (mode == 1) b += (size_t)cap * 6;  // node index + bin per u-rank, first rank per bin
   return b;
 }
 
