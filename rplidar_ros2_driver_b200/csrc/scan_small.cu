@@ -130,6 +130,7 @@ __device__ __forceinline__ float mean_of_smallest(const float* d2_sorted, int km
   return __fdiv_rn(sum, __uint2float_rn(k));
 }
 // window form (more than 33 points), sor_k <= 8: sorting networks over the 32 candidates, 8 at a time
+template <bool WRAP>
 __device__ __forceinline__ float sor_mean_win8(const float2* px, uint32_t m, uint32_t i, uint32_t k) {
   const float2 me = px[i];
   float best[8], cur[8];
@@ -139,9 +140,12 @@ __device__ __forceinline__ float sor_mean_win8(const float2* px, uint32_t m, uin
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const uint32_t o = (uint32_t)(g * 4 + t + 1);
-      uint32_t jm = i + m - o, jp = i + o;  // (i - o) mod m, (i + o) mod m with o <= 16 < m
-      if (jm >= m) jm -= m;
-      if (jp >= m) jp -= m;
+      uint32_t jm = i - o, jp = i + o;
+      if (WRAP) {  // (i - o) mod m, (i + o) mod m with o <= 16 < m; interior points (WRAP = false) need neither
+        jm = i + m - o;
+        if (jm >= m) jm -= m;
+        if (jp >= m) jp -= m;
+      }
       dst[2 * t] = dist2(px[jm], me);
       dst[2 * t + 1] = dist2(px[jp], me);
     }
@@ -538,8 +542,14 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
         long long s1 = 0;
         unsigned long long s2 = 0;
         for (uint32_t i = tid; i < m; i += TS) {
-          const float mean = (all_others || p.sor_k > 8u) ? sor_mean_generic(px, m, i, p.sor_k, all_others)
-                                                         : sor_mean_win8(px, m, i, p.sor_k);
+          float mean;
+          if (all_others || p.sor_k > 8u) {
+            mean = sor_mean_generic(px, m, i, p.sor_k, all_others);
+          } else if (__all_sync(__activemask(), i >= 16u && i + 16u < m)) {  // the whole warp is clear of both ends
+            mean = sor_mean_win8<false>(px, m, i, p.sor_k);
+          } else {
+            mean = sor_mean_win8<true>(px, m, i, p.sor_k);
+          }
           const long long qq = __float2ll_rn(__fmul_rn(mean, 65536.0f));  // llrintf
           qv[i] = (unsigned long long)qq;
           s1 += qq;
