@@ -228,7 +228,6 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
   uint16_t* prefV;
   uint32_t* bitsA = nullptr;
   uint16_t* prefA = nullptr;
-  uint16_t* sidx = nullptr;
   unsigned char* acc = nullptr;
   if (POST) {
     px = reinterpret_cast<float2*>(q); q += (size_t)cap * 8;
@@ -241,13 +240,17 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
     bitsA = reinterpret_cast<uint32_t*>(q); q += kWords * 4;
     prefA = reinterpret_cast<uint16_t*>(q); q += kWords * 2;
   }
-  uint16_t* binv = nullptr;
-  uint16_t* firstv = nullptr;
+  // Mode A: per bin the smallest dist_m (as bits) and, among the points that have it, the smallest key | quality;
+  // per node its bin
+  uint32_t* minv = nullptr;
+  uint32_t* wkey = nullptr;
+  uint16_t* binn = nullptr;
   if (MODE_A) {
-    sidx = reinterpret_cast<uint16_t*>(q);
-    binv = sidx + cap;
-    firstv = binv + cap;
+    minv = reinterpret_cast<uint32_t*>(q);
+    wkey = minv + cap;
+    binn = reinterpret_cast<uint16_t*>(wkey + cap);
   }
+
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool new_proto = a.is_new_protocol != 0;
@@ -321,9 +324,9 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
         uint4* a4 = reinterpret_cast<uint4*>(bitsA);
         for (uint32_t w = tid; w < kWords / 4; w += TS) a4[w] = make_uint4(0, 0, 0, 0);
       }
-      if (MODE_A) {  // "no rank starts this bin" for every bin (mode_a_emit_bins); cap is a multiple of 64
-        uint4* f4 = reinterpret_cast<uint4*>(firstv);
-        for (uint32_t w = tid; w < cap / 8; w += TS) f4[w] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+      if (MODE_A) {  // "nothing in this bin yet" for every bin (minv and wkey are adjacent; cap is a multiple of 64)
+        uint4* f4 = reinterpret_cast<uint4*>(minv);
+        for (uint32_t w = tid; w < cap / 2; w += TS) f4[w] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
       }
       if (tid == 0) {
         ctl.first_valid = 0xFFFFFFFFu;
@@ -473,7 +476,6 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
     float4* cloud = CLOUD ? a.xyzi + (size_t)s * a.stride : nullptr;
     uint2* nodes_out = EMIT ? a.nodes_out + (size_t)s * a.stride : nullptr;
     const float inc = angle_increment(M, MODE_A);
-    const bool has0 = (bitsV[0] & 1u) != 0;
     // Mode B output slot = ob + os * rank in wrapping u32 arithmetic (reference rplidar_node.cpp:673)
     const uint32_t ob = inverted ? M - 1u : 0u, os = inverted ? 0xFFFFFFFFu : 1u;
     const ptrdiff_t i_minus_r = reinterpret_cast<char*>(intens) - reinterpret_cast<char*>(ranges);
@@ -485,8 +487,18 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
       uint32_t measured = dist != 0 ? 1u : 0u;
       if (EMIT) st_hint_v2(nodes_out + rank2(bitsA, prefA, k), nd, pol_stream);  // k is the FINAL key here
       if (!CLOUD && !want_scan) continue;
-      const uint32_t rk = rank2(bitsV, prefV, k);
       const float dm = dist_to_m(dist);
+      if (MODE_A) {
+        // Mode A needs no order at all (reference rplidar_node.cpp:630-660): a bin keeps the smallest dist_m of the
+        // points that fall into it -- dist_m >= 0, so its bit pattern orders like the value
+        if (measured) {
+          const uint32_t b = (uint32_t)mode_a_bin_fast(k, M, inc, inverted);  // < M <= 8192
+          binn[i] = (uint16_t)b;
+          atomicMin(&minv[b], __float_as_uint(dm));
+        }
+        continue;
+      }
+      const uint32_t rk = rank2(bitsV, prefV, k);
       if (CLOUD) {  // polar -> xyz at the rank among kept points (oracle/cloud_oracle.cpp steps 1-3)
         const float it = intensity_of(nd.y);
         if (!cloud_keep(dm, it, w_rmin, w_rmax, w_imin)) measured = 0;
@@ -500,36 +512,37 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
         } else {
           st_f32x4_if(cloud + rk, make_float4(x, y, 0.0f, it), pol_stream, measured);
         }
-      } else if (!MODE_A) {  // Mode B: reference rplidar_node.cpp:661-677
+      } else {  // Mode B: reference rplidar_node.cpp:661-677
         const uint32_t o = ob + os * rk;
         const float it = intensity_of(nd.y);
         float* pr = ranges + o;
         st_f32_if(pr, dm, pol_stream, measured);
         st_f32_if(reinterpret_cast<float*>(reinterpret_cast<char*>(pr) + i_minus_r), it, pol_stream, measured);
-      } else if (measured) {  // Mode A: remember which node sits at this u-rank (mode_a_emit_bins)
-        const uint32_t ur = mode_a_urank(k, rk, M, inverted, has0);
-        sidx[ur] = (uint16_t)i;
-        binv[ur] = (uint16_t)mode_a_bin_fast(k, M, inc, inverted);  // bins are < M <= 8192
       }
     }
     __syncthreads();
 
-    // ---- Mode A (reference rplidar_node.cpp:630-660): every bin keeps the smallest dist_m of its points.  Bins grow
-    // along the u-order (ascending keys; for inverted scans key 0 first, then descending keys), and the place pass
-    // left the node index of every u-rank in sidx, so the points of a bin are neighbours THERE: one thread per
-    // u-rank looks at its predecessor (is this the first point of its bin?) and, if it is, walks the few points
-    // behind it.  Everything is read from shared memory; no staging, no batches.
+    // ---- Mode A, continued: among the points that hold their bin's minimum the first in ascending key order wins
+    // (strict '<' in the reference; keys are distinct here) -- the smallest key | quality; then one thread per bin writes
+    // (dist_m, intensity) or (+inf, 0) for a bin nothing fell into.  Lanes hold consecutive bins: coalesced stores.
     if constexpr (MODE_A) if (want_scan) {
-      ModeAOut mo;
-      mo.ranges = ranges;
-      mo.intens = intens;
-      mo.angle = a.angle;
-      mo.M = M;
-      mo.inc = inc;
-      mo.inverted = inverted;
-      mo.new_proto = new_proto;
-      mo.policy = pol_stream;
-      mode_a_emit_bins(mo, sidx, binv, firstv, tile, tid, TS);
+#pragma unroll 4
+      for (uint32_t i = tid; i < n; i += TS) {
+        const uint2 nd = tile[i];
+        const uint32_t dist = __funnelshift_r(nd.x, nd.y, 16);
+        if (dist != 0) {
+          const uint32_t b = binn[i];
+          if (__float_as_uint(dist_to_m(dist)) == minv[b]) atomicMin(&wkey[b], ((nd.x & 0xFFFFu) << 8) | ((nd.y >> 16) & 0xFFu));
+        }
+      }
+      __syncthreads();
+      const float kInf = __int_as_float(0x7f800000);
+      for (uint32_t b = tid; b < M; b += TS) {
+        const uint32_t mb = minv[b];
+        const bool hit = mb != 0xFFFFFFFFu;
+        st_f32_if(ranges + b, hit ? __uint_as_float(mb) : kInf, pol_stream, 1u);
+        st_f32_if(intens + b, hit ? quality_to_intensity(wkey[b] & 0xFFu, new_proto) : 0.0f, pol_stream, 1u);
+      }
     }
 
     uint32_t m_out = M;
@@ -829,7 +842,7 @@ size_t scan_small_smem_bytes(uint32_t cap, int mode, bool emit, bool post) {
     return b + (size_t)cap * 8 + cap + std::max<size_t>((size_t)cap * 16, kWords * 6);
   b += kWords * 6;
   if (emit) b += kWords * 6;
-  if (mode == 1) b += (size_t)cap * 6;  // node index + bin per u-rank, first rank per bin
+  if (mode == 1) b += (size_t)cap * 10;  // per bin: min dist_m bits, winner key | quality; per node: its bin
   return b;
 }
 
