@@ -32,8 +32,21 @@ __device__ __forceinline__ float key_to_deg(uint32_t key) {
   return __fmul_rn(__fmul_rn(__uint2float_rn(key), 90.0f), 1.0f / 16384.0f);
 }
 // setAngle(hq, v): angle_z_q14 = (u16)(u32)(v * 16384.f / 90.f) (reference :107-110).
+// The division by 90 is one multiply + two FMAs (Markstein's reciprocal refinement, as in dist_to_m below) for
+// every angle this path can produce (0 <= deg <= 720): oracle/check_div90.c proves the quotient bit-identical to
+// the IEEE one for EVERY float in [0, 1024], denormals included.  Anything else takes the division itself.
 __device__ __forceinline__ uint32_t deg_to_key(float deg) {
-  return __float2uint_rz(__fdiv_rn(__fmul_rn(deg, 16384.0f), 90.0f)) & 0xFFFFu;
+  const float x = __fmul_rn(deg, 16384.0f);
+  float q;
+  if (deg >= 0.0f && deg <= 1024.0f) {
+    const float r = 1.0f / 90.0f;  // RN(1/90) = 0x1.6c16c2p-7
+    const float q0 = __fmul_rn(x, r);
+    const float e = __fmaf_rn(-q0, 90.0f, x);
+    q = __fmaf_rn(e, r, q0);
+  } else {
+    q = __fdiv_rn(x, 90.0f);
+  }
+  return __float2uint_rz(q) & 0xFFFFu;
 }
 // inc_origin_angle = 360.f / count (reference :130)
 __device__ __forceinline__ float ascend_step(uint32_t count) {
@@ -101,20 +114,23 @@ __device__ __forceinline__ int mode_a_bin(uint32_t key, float inc, bool inverted
   return __float2int_rz(__fdiv_rn(__fsub_rn(a, 0.0f), inc));
 }
 
-// Mode A bin without floating point for most keys.  The reference's float chain computes
+// Mode A bin without floating point for almost all keys.  The reference's float chain computes
 // (k * 2pi/65536) / (2pi/M) with three float roundings (angle_rad, angle_increment, the
-// quotient; the double-precision steps add < 1e-14): relative error <= 3 * 2^-24, i.e. at
-// most 0.012 bins over the whole range (0.016 for inverted scans, where 2pi - angle adds an
-// absolute 2^-24 * 2pi).  So whenever the exact ratio k*M/65536 (resp. (65536-k)*M/65536) has
-// a fractional part in [1/32, 31/32], truncation of the float result equals the integer
-// quotient; only the ~6% of keys closer than 1/32 to a bin edge, and key 0 of inverted scans
-// (the reference wraps it to 1.7e-7), take the exact chain.  tests/test_device_math_proofs.py
-// checks the claim against the float chain for every key over thousands of beam counts.
+// quotient; the double-precision steps add < 1e-14): relative error <= 3 * 2^-24 of a quotient
+// < M, i.e. at most 3M * 2^-24 bins (4M * 2^-24 for inverted scans, where 2pi - angle adds an
+// absolute 2^-24 * 2pi).  In units of 2^-16 bin that is M/64, so whenever the exact ratio
+// k*M/65536 (resp. (65536-k)*M/65536) has a fractional part further than g = M/32 + 2 units (twice
+// the bound) from both bin edges, truncation of the float result equals the integer quotient; only
+// the keys closer than that (a share M / 2^20 of them: 0.3 % for a 3200-beam scan, 6 % at 65536) and
+// key 0 of inverted scans (the reference wraps it to 1.7e-7) take the exact chain.
+// tests/test_device_math_proofs.py checks the claim against the float chain for every key over
+// thousands of beam counts.
 __device__ __forceinline__ int mode_a_bin_fast(uint32_t key, uint32_t m, float inc, bool inverted) {
   const uint32_t kk = inverted ? (65536u - key) : key;
   const uint32_t t = kk * m;  // < 2^32: kk <= 65535 on this branch, m <= 65536
   const uint32_t frac = t & 0xFFFFu;
-  if ((!inverted || key != 0u) && (frac - 2048u) <= (63488u - 2048u)) return (int)(t >> 16);
+  const uint32_t g = (m >> 5) + 2u;
+  if ((!inverted || key != 0u) && (frac - g) <= (65536u - 2u * g)) return (int)(t >> 16);
   return mode_a_bin(key, inc, inverted);
 }
 

@@ -292,38 +292,5 @@ __device__ __forceinline__ void mode_a_emit_smem(const ModeAOut& o, const uint16
   }
 }
 
-// ---- Mode A emit, one thread per BIN (scan_small.cu: everything in shared memory) ---------------------------------
-// sidx[r] = index (in `nodes`) of the measured node at u-rank r, binv[r] = its bin (both written by the place pass,
-// which evaluates every bin exactly once), first[b] = 0xFFFF (set before the place pass).  Bins do not decrease along
-// the u-order, so the points of a bin are neighbours there:
-//   step 1  every rank whose bin differs from its predecessor's records itself as the first rank of that bin;
-//   step 2  one thread per bin: an empty bin gets (+inf, 0), any other the minimum (dist_m, key) over the few ranks
-//           that share it.  Lanes hold consecutive bins, so the two stores per bin are coalesced and no thread
-//           ever fills somebody else's gap.
-// One block barrier between the steps (the caller's barrier after the place pass comes first).
-__device__ __forceinline__ void mode_a_emit_bins(const ModeAOut& o, const uint16_t* sidx, const uint16_t* binv,
-                                                 uint16_t* first, const uint2* nodes, uint32_t tid, uint32_t nthreads) {
-  const uint32_t M = o.M;
-  for (uint32_t r = tid; r < M; r += nthreads)
-    if (r == 0 || binv[r] != binv[r - 1]) first[binv[r]] = (uint16_t)r;
-  __syncthreads();
-  const float kInf = __int_as_float(0x7f800000);
-  for (uint32_t b = tid; b < M; b += nthreads) {
-    const uint32_t r0 = first[b];
-    float dm = kInf, it = 0.0f;
-    if (r0 != 0xFFFFu) {
-      auto entry_of = [&](uint2 x) {
-        return mode_a_entry(dist_to_m(__funnelshift_r(x.x, x.y, 16)), x.x & 0xFFFFu, (x.y >> 16) & 0xFFu);
-      };
-      unsigned long long best = entry_of(nodes[sidx[r0]]);
-      for (uint32_t j = r0 + 1; j < M && binv[j] == b; ++j) best = min(best, entry_of(nodes[sidx[j]]));
-      dm = __uint_as_float((uint32_t)(best >> 32));
-      it = quality_to_intensity((uint32_t)best & 0xFFu, o.new_proto);
-    }
-    st_f32_if(o.ranges + b, dm, o.policy, 1u);
-    st_f32_if(o.intens + b, it, o.policy, 1u);
-  }
-}
-
 }  // namespace
 }  // namespace rpl

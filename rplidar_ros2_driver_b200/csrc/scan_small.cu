@@ -224,8 +224,8 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
   unsigned char* q = smem_raw + kCtl + (size_t)cap * 8 + 16;
   float2* px = nullptr;
   uint8_t* pi = nullptr;
-  uint32_t* bitsV;
-  uint16_t* prefV;
+  uint32_t* bitsV = nullptr;
+  uint16_t* prefV = nullptr;
   uint32_t* bitsA = nullptr;
   uint16_t* prefA = nullptr;
   unsigned char* acc = nullptr;
@@ -234,21 +234,22 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
     pi = q; q += cap;
     acc = q;  // 16 * cap bytes; the rank table lives at its start until the place pass is over
   }
-  bitsV = reinterpret_cast<uint32_t*>(q); q += kWords * 4;
-  prefV = reinterpret_cast<uint16_t*>(q); q += kWords * 2;
+  // Mode A needs no ranks among the measured points (see below): no bitmap of their keys
+  constexpr bool USE_V = !MODE_A;
+  if (USE_V) {
+    bitsV = reinterpret_cast<uint32_t*>(q); q += kWords * 4;
+    prefV = reinterpret_cast<uint16_t*>(q); q += kWords * 2;
+  }
   if (EMIT) {
     bitsA = reinterpret_cast<uint32_t*>(q); q += kWords * 4;
     prefA = reinterpret_cast<uint16_t*>(q); q += kWords * 2;
   }
-  // Mode A: per bin the smallest dist_m (as bits) and, among the points that have it, the smallest key | quality;
-  // per node its bin
+  // Mode A: per bin the smallest dist_m (as bits) and, among the points that have it, the smallest key | quality
   uint32_t* minv = nullptr;
   uint32_t* wkey = nullptr;
-  uint16_t* binn = nullptr;
   if (MODE_A) {
     minv = reinterpret_cast<uint32_t*>(q);
     wkey = minv + cap;
-    binn = reinterpret_cast<uint16_t*>(wkey + cap);
   }
 
 
@@ -318,8 +319,10 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
       for (uint32_t i = tid; i < n; i += TS) tile0[shift + i] = ld_stream_v2(base + i);
     }
     {
-      uint4* b4 = reinterpret_cast<uint4*>(bitsV);
-      for (uint32_t w = tid; w < kWords / 4; w += TS) b4[w] = make_uint4(0, 0, 0, 0);
+      if (USE_V) {
+        uint4* b4 = reinterpret_cast<uint4*>(bitsV);
+        for (uint32_t w = tid; w < kWords / 4; w += TS) b4[w] = make_uint4(0, 0, 0, 0);
+      }
       if (EMIT) {
         uint4* a4 = reinterpret_cast<uint4*>(bitsA);
         for (uint32_t w = tid; w < kWords / 4; w += TS) a4[w] = make_uint4(0, 0, 0, 0);
@@ -348,8 +351,10 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
       bool valid = dist != 0;
       if (CLOUD) valid = valid && cloud_keep(dist_to_m(dist), intensity_of(nd.y), w_rmin, w_rmax, w_imin);
       if (valid) {
-        const uint32_t k = nd.x & 0xFFFFu;
-        atomicOr(&bitsV[k >> 5], 1u << (k & 31));
+        if (USE_V) {
+          const uint32_t k = nd.x & 0xFFFFu;
+          atomicOr(&bitsV[k >> 5], 1u << (k & 31));
+        }
         ++cnt;
         if (EMIT) fmin = min(fmin, i);
       }
@@ -411,13 +416,17 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
     }
 
     // ---- exclusive popcount prefix over the bitmap words ------------------------------------------------
-    {
+    if constexpr (USE_V || EMIT) {
       uint32_t wv[WPT], wa[WPT];
       uint32_t sv = 0, sa = 0;
 #pragma unroll
       for (uint32_t j = 0; j < WPT / 4; ++j) {
-        const uint4 t = reinterpret_cast<const uint4*>(bitsV)[tid * (WPT / 4) + j];
-        wv[4 * j] = t.x; wv[4 * j + 1] = t.y; wv[4 * j + 2] = t.z; wv[4 * j + 3] = t.w;
+        if (USE_V) {
+          const uint4 t = reinterpret_cast<const uint4*>(bitsV)[tid * (WPT / 4) + j];
+          wv[4 * j] = t.x; wv[4 * j + 1] = t.y; wv[4 * j + 2] = t.z; wv[4 * j + 3] = t.w;
+        } else {
+          wv[4 * j] = wv[4 * j + 1] = wv[4 * j + 2] = wv[4 * j + 3] = 0u;
+        }
         if (EMIT) {
           const uint4 u = reinterpret_cast<const uint4*>(bitsA)[tid * (WPT / 4) + j];
           wa[4 * j] = u.x; wa[4 * j + 1] = u.y; wa[4 * j + 2] = u.z; wa[4 * j + 3] = u.w;
@@ -425,10 +434,10 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
       }
 #pragma unroll
       for (uint32_t j = 0; j < WPT; ++j) {
-        sv += __popc(wv[j]);
+        if (USE_V) sv += __popc(wv[j]);
         if (EMIT) sa += __popc(wa[j]);
       }
-      const uint32_t iv = warp_inclusive_scan(sv);
+      const uint32_t iv = USE_V ? warp_inclusive_scan(sv) : 0u;
       const uint32_t ia = EMIT ? warp_inclusive_scan(sa) : 0u;
       if (lane == 31) {
         ctl.red[32 + warp] = iv;
@@ -453,18 +462,21 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
       uint32_t pa = ctl.red[64 + warp] + ia - sa;
 #pragma unroll
       for (uint32_t j = 0; j < WPT; ++j) {
-        prefV[tid * WPT + j] = (uint16_t)pv;
-        pv += __popc(wv[j]);
+        if (USE_V) {
+          prefV[tid * WPT + j] = (uint16_t)pv;
+          pv += __popc(wv[j]);
+        }
         if (EMIT) {
           prefA[tid * WPT + j] = (uint16_t)pa;
           pa += __popc(wa[j]);
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
 
-    // duplicate keys (fewer distinct keys than kept nodes) -> general kernel (stable tie rule)
-    if (ctl.totV != M || (EMIT && ctl.totA != n)) {
+    // duplicate keys (fewer distinct keys than kept nodes) -> general kernel (stable tie rule).  Mode A without the
+    // ascended buffer looks only for the duplicates that matter to it, in its winner pass below.
+    if ((USE_V && ctl.totV != M) || (EMIT && ctl.totA != n)) {
       if (tid == 0) a.fallback_list[atomicAdd(a.fallback_count, 1u)] = s;
       __syncthreads();
       continue;
@@ -493,7 +505,6 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
         // points that fall into it -- dist_m >= 0, so its bit pattern orders like the value
         if (measured) {
           const uint32_t b = (uint32_t)mode_a_bin_fast(k, M, inc, inverted);  // < M <= 8192
-          binn[i] = (uint16_t)b;
           atomicMin(&minv[b], __float_as_uint(dm));
         }
         continue;
@@ -523,19 +534,36 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
     __syncthreads();
 
     // ---- Mode A, continued: among the points that hold their bin's minimum the first in ascending key order wins
-    // (strict '<' in the reference; keys are distinct here) -- the smallest key | quality; then one thread per bin writes
-    // (dist_m, intensity) or (+inf, 0) for a bin nothing fell into.  Lanes hold consecutive bins: coalesced stores.
+    // (strict '<' in the reference) -- the smallest key | quality; then one thread per bin writes (dist_m, intensity)
+    // or (+inf, 0) for a bin nothing fell into.  Lanes hold consecutive bins: coalesced stores.
+    // Duplicate keys: equal keys fall into the same bin, and the order among them only matters when two of them hold
+    // the bin's minimum with different qualities (the stable rule then takes the first in buffer order).  The second
+    // of two such points to arrive finds the first one's key in the value its atomicMin returns -- unless a smaller
+    // key is already there, and then neither wins.  Such a scan goes to the general kernel, like every scan with
+    // duplicate keys does in the other modes.
     if constexpr (MODE_A) if (want_scan) {
+      bool conflict = false;
 #pragma unroll 4
       for (uint32_t i = tid; i < n; i += TS) {
         const uint2 nd = tile[i];
         const uint32_t dist = __funnelshift_r(nd.x, nd.y, 16);
         if (dist != 0) {
-          const uint32_t b = binn[i];
-          if (__float_as_uint(dist_to_m(dist)) == minv[b]) atomicMin(&wkey[b], ((nd.x & 0xFFFFu) << 8) | ((nd.y >> 16) & 0xFFu));
+          const uint32_t k = nd.x & 0xFFFFu;
+          const uint32_t b = (uint32_t)mode_a_bin_fast(k, M, inc, inverted);
+          if (__float_as_uint(dist_to_m(dist)) == minv[b]) {
+            const uint32_t v = (k << 8) | ((nd.y >> 16) & 0xFFu);
+            const uint32_t old = atomicMin(&wkey[b], v);
+            if (!EMIT) conflict = conflict || ((old >> 8) == k && old != v);
+          }
         }
       }
+      if (!EMIT && conflict) ctl.fallback = 1u;
       __syncthreads();
+      if (!EMIT && ctl.fallback != 0u) {  // block-uniform: set before the barrier, cleared at the start of the next scan
+        if (tid == 0) a.fallback_list[atomicAdd(a.fallback_count, 1u)] = s;
+        __syncthreads();
+        continue;
+      }
       const float kInf = __int_as_float(0x7f800000);
       for (uint32_t b = tid; b < M; b += TS) {
         const uint32_t mb = minv[b];
@@ -842,7 +870,7 @@ size_t scan_small_smem_bytes(uint32_t cap, int mode, bool emit, bool post) {
     return b + (size_t)cap * 8 + cap + std::max<size_t>((size_t)cap * 16, kWords * 6);
   b += kWords * 6;
   if (emit) b += kWords * 6;
-  if (mode == 1) b += (size_t)cap * 10;  // per bin: min dist_m bits, winner key | quality; per node: its bin
+  if (mode == 1) b += (size_t)cap * 8 - kWords * 6;  // per bin: min dist_m bits, winner key | quality; no bitmap
   return b;
 }
 

@@ -1,8 +1,10 @@
-"""CPU proofs of the two arithmetic shortcuts the CUDA kernels take (rpl_device.cuh):
+"""CPU proofs of the arithmetic shortcuts the CUDA kernels take (rpl_device.cuh):
 
   dist_to_m        dist_mm_q2 / 4000.0f as one multiply + two FMAs  -> exhaustive C check
-  mode_a_bin_fast  Mode A bin index by integer arithmetic wherever the exact ratio is at
-                   least 1/32 away from a bin edge                   -> numpy sweep vs the
+  deg_to_key       v * 16384 / 90 with the division replaced by a reciprocal refinement
+                                                                     -> exhaustive C check
+  mode_a_bin_fast  Mode A bin index by integer arithmetic wherever the exact ratio is further
+                   than twice the float chain's error bound from a bin edge -> numpy sweep vs the
                    reference's float chain (rplidar_node.cpp:586-652) for every key
 """
 import os
@@ -28,6 +30,20 @@ def test_division_by_4000_is_exact_for_every_u32(tmp_path):
     assert "mismatches 0" in r.stdout and "checked 83886082 values" in r.stdout
 
 
+def test_division_by_90_is_exact_for_every_angle(tmp_path):
+    """deg_to_key: v * 16384 / 90 through the reciprocal, for every float in [0, 1024] (1.15e9 values, ~12 s)."""
+    src = os.path.join(ROOT, "oracle", "check_div90.c")
+    exe = str(tmp_path / "check_div90")
+    flags = ["-O2", "-ffp-contract=off"]
+    cpu = open("/proc/cpuinfo").read()
+    if " fma " in cpu or " fma\n" in cpu:
+        flags.append("-mfma")
+    subprocess.run(["gcc", *flags, src, "-o", exe, "-lm"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout
+    assert "mismatches 0, key mismatches 0" in r.stdout and "checked 1149239297 values" in r.stdout
+
+
 def exact_bins(m: int, inverted: bool) -> np.ndarray:
     k = np.arange(65536, dtype=np.float32)
     deg = (k * F32(90.0)) / F32(16384.0)
@@ -47,7 +63,8 @@ def fast_zone_bins(m: int, inverted: bool):
     kk = (65536 - k) if inverted else k
     t = kk * np.uint64(m)
     frac = (t & np.uint64(0xFFFF)).astype(np.int64)
-    ok = (frac >= 2048) & (frac <= 63488)
+    g = (m >> 5) + 2  # mode_a_bin_fast: twice the error bound M/64 of the float chain, in 2^-16 bin
+    ok = (frac >= g) & (frac <= 65536 - g)
     if inverted:
         ok &= k != 0
     return (t >> np.uint64(16)).astype(np.int64), ok
@@ -55,7 +72,8 @@ def fast_zone_bins(m: int, inverted: bool):
 
 def test_mode_a_integer_bins_match_the_float_chain():
     rng = np.random.default_rng(42)
-    ms = set(range(1, 1537)) | {65536, 65535, 65534, 32768, 32767, 31117, 31130, 49152, 360, 3200, 8192}
+    ms = set(range(1, 1537)) | {65536, 65535, 65534, 32768, 32767, 31117, 31130, 49152, 360, 3200, 8192, 8191, 4096, 4095}
+    ms |= set(range(1537, 8193, 7)) | set(range(3100, 3300))  # the sizes the shared-memory kernels see
     ms |= set(int(x) for x in rng.integers(1537, 65537, size=1200))
     worst = 0
     for m in sorted(ms):

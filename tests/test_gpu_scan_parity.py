@@ -298,10 +298,10 @@ def test_odd_stride_takes_unaligned_path(R, oracle, ctx):
 
 
 def test_mode_a_sorted_revolution_detection_edge_cases(R, oracle, ctx):
-    """The TMA kernel resolves Mode A bins on the spot when the revolution is sorted up to a rotation, and goes
-    through its index map otherwise.  Shapes around that decision: sorted / rotated / two interleaved ascending runs
-    (one descent, but not a rotation) / unmeasured runs across chunk boundaries (1024 nodes) and around the wrap /
-    bins shared by many points and long empty stretches."""
+    """Mode A on shapes that stress the order-dependent parts of its kernels (the TMA kernel's index map and run
+    detection, the shared-memory kernels' per-bin minimum): sorted / rotated / two interleaved ascending runs (one
+    descent, but not a rotation) / unmeasured runs across chunk boundaries (1024 nodes) and around the wrap / bins
+    shared by many points and long empty stretches."""
     rng = np.random.default_rng(77)
     n = 12288
     cases = []
@@ -333,3 +333,52 @@ def test_mode_a_sorted_revolution_detection_edge_cases(R, oracle, ctx):
     small = nodes[:, :8000].copy()  # the same shapes through the TMA kernel at a size the shared-memory kernels serve
     check_batch(R, oracle, ctx, small, np.full(len(cases), 8000, np.uint32), 0, 1, 0, 1, flags=4, emit=False)
     check_batch(R, oracle, ctx, small, np.full(len(cases), 8000, np.uint32), 0, 1, 0, 1, flags=0, emit=False)
+
+
+def test_mode_a_duplicate_keys_in_the_shared_memory_kernel(R, oracle, ctx):
+    """Mode A without the ascended buffer keeps no bitmap of the keys: a scan with duplicate keys stays on the
+    shared-memory kernel unless two points with the SAME key hold a bin's minimum dist_m with DIFFERENT qualities
+    (only then does the order among equal keys matter: the stable rule takes the first in buffer order).  Each of
+    the cases, checked against the oracle's stable rule, with the path each must take."""
+    rng = np.random.default_rng(5)
+    n = 3000
+    keys = np.sort(rng.choice(65536, size=n, replace=False))
+    dist = rng.integers(4000, 160000, n)
+    q = rng.integers(0, 256, n)
+    base = oracle.make_nodes(keys, dist, q, 2)
+
+    def with_dup(i, j, dist_j, q_j):  # node j gets node i's key
+        c = base.copy()
+        c["angle_z_q14"][j] = c["angle_z_q14"][i]
+        c["dist_mm_q2"][j] = dist_j
+        c["quality"][j] = q_j
+        return c
+
+    d100 = int(base["dist_mm_q2"][100])
+    q100 = int(base["quality"][100])
+    harmless = [
+        with_dup(100, 2000, d100 + 4000, q100 ^ 0x40),   # same key, the duplicate is farther: it never wins
+        with_dup(100, 2000, d100, q100),                 # same key, same distance, same quality: indistinguishable
+        with_dup(100, 50, d100 - 400, q100 ^ 0x40),      # the duplicate (earlier in the buffer) is nearer: it wins on distance
+    ]
+    conflicts = [
+        with_dup(100, 2000, d100, q100 ^ 0x40),          # same key, same distance, other quality, later in the buffer
+        with_dup(100, 50, d100, q100 ^ 0x40),            # ... earlier in the buffer: the duplicate is the first
+    ]
+    # make sure the duplicated key really holds its bin's minimum in the conflict cases (nothing nearer in the bin)
+    for c in conflicts + harmless:
+        c["dist_mm_q2"][99] = max(int(c["dist_mm_q2"][99]), d100 + 8000)
+        c["dist_mm_q2"][101] = max(int(c["dist_mm_q2"][101]), d100 + 8000)
+    for group, path in ((harmless, 0), (conflicts, R.PATH_GENERAL)):
+        nodes = np.stack(group)
+        counts = np.full(len(group), n, np.uint32)
+        for newp, inv in ((0, 0), (1, 1)):
+            for ascend in (0, 1):
+                check_batch(R, oracle, ctx, nodes, counts, newp, 1, inv, ascend, emit=False, stable=True, expect_path=path)
+                check_batch(R, oracle, ctx, nodes, counts, newp, 1, inv, ascend, emit=True, stable=True)
+                check_batch(R, oracle, ctx, nodes, counts, newp, 1, inv, ascend, flags=4, emit=False, stable=True)
+    # heavy duplication: every key four times with random distances and qualities
+    heavy = oracle.make_nodes(np.repeat(keys[: n // 4], 4), rng.integers(4000, 4100, n), rng.integers(0, 4, n) * 64, 2)
+    heavy = heavy[rng.permutation(n)]
+    for newp, inv in ((0, 0), (1, 1)):
+        check_batch(R, oracle, ctx, heavy[None], np.array([n], np.uint32), newp, 1, inv, 1, emit=False, stable=True)
