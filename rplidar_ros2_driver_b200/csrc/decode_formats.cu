@@ -20,8 +20,9 @@
 //     neighbouring short-range samples.  A capsule's effect on that value is a function of at most
 //     nine candidate inputs (the first sample either ignores the incoming value or averages with
 //     one of 17 neighbours -> 9 results), so every capsule thread tabulates its nine outcomes, one
-//     thread chains the tables across the tile, and the capsule threads then replay their 64
-//     samples from the now-known input.
+//     thread chains the tables across the tile, and the capsule threads then replay, from the now-known
+//     input, the samples before the position where their nine candidates merged (the others were final
+//     already).
 // The standard-node decoder is a 5-state byte machine with resynchronisation; each thread folds its
 // 20 bytes into a state->state map (5 x 3 bits), the maps are scanned under composition, and the
 // threads replay their bytes from the known entry state: exact on arbitrary (misframed) streams.
@@ -48,7 +49,8 @@ struct Fmt<kExpress> {
 };
 template <>
 struct Fmt<kUltra> {
-  static constexpr int CB = 132, NODES = 96, START = 2, BUFFERS = 2;
+  // one tile buffer (more CTAs per SM instead of a prefetch: the emission is instruction-bound)
+  static constexpr int CB = 132, NODES = 96, START = 2, BUFFERS = 1;
   static constexpr bool THRESHOLD = false, STATE = false;
 };
 template <>
@@ -147,6 +149,66 @@ __device__ __forceinline__ uint2 node_ultra(const uint8_t* prev, const uint8_t* 
   return pack_node(angle_q6, (uint32_t)dist_q2, sync, dist_q2 ? (0x2Fu << 2) : 0u);
 }
 
+// One warp per released capsule, one lane per cabin (3 nodes): the two cabin words (aligned 32-bit loads: capsules
+// are 132 bytes and tiles 16-byte aligned), both variable-bit-scale expansions and the base/level selection are done
+// once per cabin instead of once per node; the scan-start test needs one modulo per cabin (the other two remainders
+// follow by addition whenever the angle step is in [0, 360 deg)); the 493-entry angle-correction table is read from
+// shared memory.  The three nodes of a lane go through a per-warp staging area so that the warp stores its 96 nodes
+// as three fully coalesced 256-byte rows.  Same arithmetic as node_ultra() (kept as the definition).
+__device__ __forceinline__ uint32_t varbitscale_sel(uint32_t s, uint32_t& level) {
+  const uint32_t l = (s >= 512u) + (s >= 1280u) + (s >= 1792u) + (s >= 3328u);
+  // source bases of the five segments (12 bits each); target bases 0, 1<<9, 1<<11, 1<<12, 1<<14
+  const uint32_t src = (uint32_t)(0xD00700500200000ull >> (12u * l)) & 0xFFFu;
+  const uint32_t dst = (l ? 512u : 0u) << ((0x53200u >> (4u * l)) & 0xFu);
+  level = l;
+  return dst + ((s - src) << l);
+}
+__device__ __forceinline__ void ultra_cabin(const uint8_t* prev, const uint8_t* cur, int prev_q8, int diff_q8,
+                                            uint32_t cabin, const int* off_table, uint2* stage) {
+  const int inc = (diff_q8 << 3) / 3;
+  const uint32_t x3 = *reinterpret_cast<const uint32_t*>(prev + 4 + 4 * cabin);
+  const uint32_t nx = (cabin == 31u) ? *reinterpret_cast<const uint32_t*>(cur + 4)
+                                     : *reinterpret_cast<const uint32_t*>(prev + 8 + 4 * cabin);
+  uint32_t lvl1, lvl2;
+  const uint32_t major = varbitscale_sel(x3 & 0xFFFu, lvl1);
+  const uint32_t major2 = varbitscale_sel(nx & 0xFFFu, lvl2);
+  uint32_t base1 = major;
+  if (!major && major2) {
+    base1 = major2;
+    lvl1 = lvl2;
+  }
+  const int p1 = (int)(x3 << 10) >> 22, p2 = (int)x3 >> 22;
+  int dist[3];
+  dist[0] = (int)(major << 2);
+  dist[1] = (p1 == -512 || p1 == 511) ? 0 : (int)((((uint32_t)p1 << lvl1) + base1) << 2);
+  dist[2] = (p2 == -512 || p2 == 511) ? 0 : (int)((((uint32_t)p2 << lvl2) + major2) << 2);
+  const int a0 = (prev_q8 << 8) + (int)(3u * cabin) * inc;
+  const bool step_ok = inc >= 0 && inc < kFull;  // warp-uniform
+  int rem = (a0 + inc) % kFull;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int a = a0 + c * inc;
+    if (c > 0) {
+      if (step_ok) {
+        rem += inc;
+        if (rem >= kFull) rem -= kFull;
+      } else {
+        rem = (a + inc) % kFull;
+      }
+    }
+    const uint32_t sync = (rem < inc) ? 1u : 0u;
+    uint32_t k2 = 492u;
+    if (dist[c] >= 200) {  // 98361 / dist_q2 (<= 491) without the integer division: float quotient, exact +-1 correction
+      const uint32_t d = (uint32_t)dist[c];
+      k2 = __float2uint_rz(__fdividef(98361.0f, __uint2float_rn(d)));
+      if (k2 * d > 98361u) --k2;
+      else if ((k2 + 1u) * d <= 98361u) ++k2;
+    }
+    const int angle_q6 = (a - off_table[k2]) >> 10;
+    stage[3u * cabin + c] = pack_node(angle_q6, (uint32_t)dist[c], sync, dist[c] ? (0x2Fu << 2) : 0u);
+  }
+}
+
 // ---- ultra-dense (handler_capsules.cpp:951-1047) -------------------------------------------------------
 // raw sample: distance before smoothing, scale code, quality
 __device__ __forceinline__ int ud_sample(const uint8_t* cap, uint32_t pos, uint32_t& scale, uint32_t& quality) {
@@ -154,12 +216,11 @@ __device__ __forceinline__ int ud_sample(const uint8_t* cap, uint32_t pos, uint3
   const uint32_t hi = cab[4];
   const uint32_t qds = ld16(cab + 2 * (pos & 1u)) | (((pos & 1u) ? (hi >> 4) : (hi & 0xFu)) << 16);
   scale = qds & 3u;
-  switch (scale) {
-    case 0: quality = (qds >> 12) & 0xFFu; return (int)(qds & 0xFFCu) * 2;
-    case 1: quality = ((qds >> 13) << 1) & 0xFFu; return (int)(qds & 0x1FFCu) * 3 + (2046 << 2);
-    case 2: quality = ((qds >> 14) << 2) & 0xFFu; return (int)(qds & 0x3FFCu) * 4 + (8187 << 2);
-    default: quality = ((qds >> 15) << 3) & 0xFFu; return (int)(qds & 0x7FFCu) * 5 + (24567 << 2);
-  }
+  // the four ranges without a branch (scales differ from lane to lane): field mask 0xFFC / 0x1FFC / 0x3FFC / 0x7FFC,
+  // factor 2..5, base (0, 2046, 8187, 24567) << 2, quality (qds >> (12 + scale)) << scale
+  const uint32_t base = (uint32_t)(((24567ull << 45) | (8187ull << 30) | (2046ull << 15)) >> (15u * scale)) & 0x7FFFu;
+  quality = ((qds >> (12u + scale)) << scale) & 0xFFu;
+  return (int)((qds & ((0x1000u << scale) - 4u)) * (scale + 2u) + (base << 2));
 }
 __device__ __forceinline__ int ud_smooth(int raw, uint32_t scale, int last) {
   if (scale == 0 && last && abs(raw - last) <= 8) return (raw + last) >> 1;
@@ -208,6 +269,9 @@ struct CapsuleSmem {
   uint32_t ud_last_in[Fmt<F>::STATE ? DT : 1];
   uint16_t ud_dist[Fmt<F>::STATE ? DT : 1][64];  // smoothed short-range distances
   uint32_t carry_sync, red_sync, carry_last, red_last;
+  // ultra only: angle-correction table and the per-warp staging rows of the emission
+  int ultra_off[F == kUltra ? 496 : 1];
+  uint2 wstage[F == kUltra ? DT / 32 : 1][F == kUltra ? 96 : 1];
 };
 
 template <int F>
@@ -219,6 +283,10 @@ __global__ void __launch_bounds__(DT) decode_capsule_kernel(CapsuleDecodeArgs a)
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int thr_q8 = 0;
   if (T::THRESHOLD) thr_q8 = (360 * 100 * 32 / (int)(1000000u / a.sample_duration_us)) << 8;
+  if constexpr (F == kUltra) {
+    for (uint32_t i = tid; i < 493u; i += DT) sm.ultra_off[i] = g_ultra_offset[i];
+    __syncthreads();
+  }
 
   for (uint32_t s = blockIdx.x; s < a.n_streams; s += gridDim.x) {
     const uint32_t n = a.counts[s];
@@ -352,6 +420,10 @@ __global__ void __launch_bounds__(DT) decode_capsule_kernel(CapsuleDecodeArgs a)
         sm.tile_nodes = (uint32_t)NODES * tot;
         if (T::STATE) sm.red_sync = st2;
       }
+      // first sample position from which this capsule's smoothed distances no longer depend on the value that
+      // enters the capsule (the nine candidates have merged): step 1 stores those directly, step 3 replays only
+      // the positions before it
+      uint32_t ud_pm = 64;
       if constexpr (T::STATE) {
         // ---- smoothing chain, step 1: the nine outcomes of this capsule's 64 samples ------------------
         if (emit) {
@@ -363,10 +435,15 @@ __global__ void __launch_bounds__(DT) decode_capsule_kernel(CapsuleDecodeArgs a)
 #pragma unroll
           for (int k = 0; k < 9; ++k) cand[k] = (sc == 0) ? (r0 - 4 + k) : r0;
           bool merged = (sc != 0);
+          if (merged) {
+            ud_pm = 0;
+            sm.ud_dist[tid][0] = (uint16_t)r0;
+          }
           for (uint32_t pos = 1; pos < 64; ++pos) {
             const int r = ud_sample(pc, pos, sc, q);
             if (merged) {
               cand[0] = ud_smooth(r, sc, cand[0]);
+              sm.ud_dist[tid][pos] = (uint16_t)cand[0];  // only read back for scale-0 samples (< 8192)
             } else {
               int lo = 0x7fffffff, hi = -0x7fffffff;
 #pragma unroll
@@ -376,6 +453,10 @@ __global__ void __launch_bounds__(DT) decode_capsule_kernel(CapsuleDecodeArgs a)
                 hi = max(hi, cand[k]);
               }
               merged = (lo == hi);
+              if (merged) {
+                ud_pm = pos;
+                sm.ud_dist[tid][pos] = (uint16_t)cand[0];
+              }
             }
           }
 #pragma unroll
@@ -411,11 +492,11 @@ __global__ void __launch_bounds__(DT) decode_capsule_kernel(CapsuleDecodeArgs a)
           if (tid == 0 && E > 0) sm.carry_last = sm.red_last;
         }
         __syncthreads();
-        // ---- step 3: replay the samples from the known input, keep the smoothed distances ------------
+        // ---- step 3: replay the samples that do depend on the input, keep the smoothed distances ------
         if (emit) {
           const uint8_t* pc = (tid == 0) ? sm.carry : tile + (tid - 1) * CB;
           int last = (int)sm.ud_last_in[tid];
-          for (uint32_t pos = 0; pos < 64; ++pos) {
+          for (uint32_t pos = 0; pos < ud_pm; ++pos) {
             uint32_t sc, q;
             const int r = ud_sample(pc, pos, sc, q);
             last = ud_smooth(r, sc, last);
@@ -425,7 +506,23 @@ __global__ void __launch_bounds__(DT) decode_capsule_kernel(CapsuleDecodeArgs a)
         __syncthreads();
       }
       // ---- node-parallel emission: one contiguous run of NODES * E nodes -------------------------------
-      {
+      if constexpr (F == kUltra) {
+        const uint32_t E = sm.tile_nodes / (uint32_t)NODES;
+        uint2* o = out + sm.carry_nodes;
+        for (uint32_t e = warp; e < E; e += DT / 32) {
+          const uint32_t j = sm.emit_list[e];
+          const uint8_t* pc = (j == 0) ? sm.carry : tile + (j - 1) * CB;
+          const int pq8 = (int)sm.start_q8[j];
+          int d = (int)sm.start_q8[j + 1] - pq8;
+          if (pq8 > (int)sm.start_q8[j + 1]) d += (360 << 8);
+          ultra_cabin(pc, tile + j * CB, pq8, d, lane, sm.ultra_off, sm.wstage[warp]);
+          __syncwarp();
+          uint2* dst = o + (size_t)e * NODES;
+#pragma unroll
+          for (uint32_t k = 0; k < 3; ++k) dst[lane + 32u * k] = sm.wstage[warp][lane + 32u * k];
+          __syncwarp();
+        }
+      } else {
         const uint32_t n_nodes = sm.tile_nodes;
         uint2* o = out + sm.carry_nodes;
         for (uint32_t q = tid; q < n_nodes; q += DT) {

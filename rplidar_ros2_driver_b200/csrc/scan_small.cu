@@ -40,8 +40,16 @@ struct SmallCtl {
   double thr;
   uint32_t red[3 * 32];
   uint32_t totV, totA, first_valid, front_key, fallback, count_out;
-  uint32_t chunk_base[128];  // voxel ordering: per (chunk, warp) counts -> exclusive bases
+  union {
+    uint32_t chunk_base[128];  // PointCloud2 chain, voxel ordering: per (chunk, warp) counts -> exclusive bases
+    struct {                   // ascended buffer: the few nodes whose final key is already taken (see the place pass)
+      uint16_t dupkey[16];     // final key of every node beyond the first with that key
+      uint16_t dupnode[32];    // nodes whose key appears in dupkey: placed by the fix-up after the place pass
+      uint32_t ndup, ndupnode;
+    } d;
+  };
 };
+constexpr uint32_t kMaxDup = 16;
 static_assert(sizeof(SmallCtl) <= 1024, "control block");
 constexpr uint32_t kCtl = 1024;
 
@@ -334,6 +342,10 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
       if (tid == 0) {
         ctl.first_valid = 0xFFFFFFFFu;
         ctl.fallback = 0;
+        if (EMIT) {
+          ctl.d.ndup = 0;
+          ctl.d.ndupnode = 0;
+        }
       }
     }
     __syncthreads();
@@ -410,7 +422,11 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
           fk = (i == 0) ? front_key : ascend_fill_key(front_deg, i, step);
           tile0[shift + i].x = (nd.x & 0xFFFF0000u) | fk;
         }
-        atomicOr(&bitsA[fk >> 5], 1u << (fk & 31));
+        const uint32_t bit = 1u << (fk & 31);
+        if (atomicOr(&bitsA[fk >> 5], bit) & bit) {  // this final key is taken: one more node than distinct keys
+          const uint32_t slot = atomicAdd(&ctl.d.ndup, 1u);
+          if (slot < kMaxDup) ctl.d.dupkey[slot] = (uint16_t)fk;
+        }
       }
       __syncthreads();
     }
@@ -474,9 +490,12 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
       __syncthreads();
     }
 
-    // duplicate keys (fewer distinct keys than kept nodes) -> general kernel (stable tie rule).  Mode A without the
-    // ascended buffer looks only for the duplicates that matter to it, in its winner pass below.
-    if ((USE_V && ctl.totV != M) || (EMIT && ctl.totA != n)) {
+    // duplicate keys among the measured nodes (fewer distinct keys than kept nodes) -> general kernel (stable tie
+    // rule); Mode A looks only for the duplicates that matter to it, in its winner pass below.  Duplicates among the
+    // FINAL keys (typically the fill key of an unmeasured node landing on a measured node's key) only move entries of
+    // the ascended buffer: up to kMaxDup of them are resolved here (place pass + fix-up), more go to the general kernel.
+    const uint32_t D = EMIT ? ctl.d.ndup : 0u;  // = n - (distinct final keys)
+    if ((USE_V && ctl.totV != M) || (EMIT && D > kMaxDup)) {
       if (tid == 0) a.fallback_list[atomicAdd(a.fallback_count, 1u)] = s;
       __syncthreads();
       continue;
@@ -497,7 +516,20 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
       const uint32_t k = nd.x & 0xFFFFu;
       const uint32_t dist = __funnelshift_r(nd.x, nd.y, 16);
       uint32_t measured = dist != 0 ? 1u : 0u;
-      if (EMIT) st_hint_v2(nodes_out + rank2(bitsA, prefA, k), nd, pol_stream);  // k is the FINAL key here
+      if (EMIT) {  // k is the FINAL key here
+        uint32_t rA = rank2(bitsA, prefA, k);  // rank among the distinct final keys
+        bool defer = false;
+        if (D) {  // (block-uniform, rare) every node beyond the first of a key shifts the larger keys by one; the
+                  // nodes that share a key are ordered by buffer position (stable rule) in the fix-up below
+          for (uint32_t j = 0; j < D; ++j) {
+            const uint32_t dk = ctl.d.dupkey[j];
+            rA += (dk < k) ? 1u : 0u;
+            defer = defer || (dk == k);
+          }
+          if (defer) ctl.d.dupnode[atomicAdd(&ctl.d.ndupnode, 1u)] = (uint16_t)i;  // <= 2 * D entries
+        }
+        if (!defer) st_hint_v2(nodes_out + rA, nd, pol_stream);
+      }
       if (!CLOUD && !want_scan) continue;
       const float dm = dist_to_m(dist);
       if (MODE_A) {
@@ -533,6 +565,25 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
     }
     __syncthreads();
 
+    // ---- ascended buffer, nodes with a shared final key: position = nodes with a smaller key + nodes with the same
+    // key earlier in the buffer (stable rule); one warp per such node counts the latter over the tile
+    if (EMIT && D) {
+      const uint32_t nshared = ctl.d.ndupnode;
+      for (uint32_t e = warp; e < nshared; e += NW) {
+        const uint32_t i = ctl.d.dupnode[e];
+        const uint2 me = tile[i];
+        const uint32_t k = me.x & 0xFFFFu;
+        uint32_t before = 0;
+        for (uint32_t j = lane; j < i; j += 32) before += ((tile[j].x & 0xFFFFu) == k) ? 1u : 0u;
+        before = warp_sum(before);
+        if (lane == 0) {
+          uint32_t r = rank2(bitsA, prefA, k) + before;
+          for (uint32_t j = 0; j < D; ++j) r += (ctl.d.dupkey[j] < k) ? 1u : 0u;
+          nodes_out[r] = me;
+        }
+      }
+    }
+
     // ---- Mode A, continued: among the points that hold their bin's minimum the first in ascending key order wins
     // (strict '<' in the reference) -- the smallest key | quality; then one thread per bin writes (dist_m, intensity)
     // or (+inf, 0) for a bin nothing fell into.  Lanes hold consecutive bins: coalesced stores.
@@ -553,13 +604,13 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
           if (__float_as_uint(dist_to_m(dist)) == minv[b]) {
             const uint32_t v = (k << 8) | ((nd.y >> 16) & 0xFFu);
             const uint32_t old = atomicMin(&wkey[b], v);
-            if (!EMIT) conflict = conflict || ((old >> 8) == k && old != v);
+            conflict = conflict || ((old >> 8) == k && old != v);
           }
         }
       }
-      if (!EMIT && conflict) ctl.fallback = 1u;
+      if (conflict) ctl.fallback = 1u;
       __syncthreads();
-      if (!EMIT && ctl.fallback != 0u) {  // block-uniform: set before the barrier, cleared at the start of the next scan
+      if (ctl.fallback != 0u) {  // block-uniform: set before the barrier, cleared at the start of the next scan
         if (tid == 0) a.fallback_list[atomicAdd(a.fallback_count, 1u)] = s;
         __syncthreads();
         continue;

@@ -314,3 +314,59 @@ def test_wire_bytes_to_laserscan_in_one_host_call(R, oracle, n_streams, max_node
             total += 1
     assert total > 20
     ctx.close()
+
+
+def test_stateful_decode_and_assembly_alternate_on_one_context(R, oracle):
+    """Regression (round-1 review): the dense decoder's per-stream state scratch and the assembler's reset-prefix
+    scratch live in the same context; growing one must not free the other.  Three rounds of
+    decode (0x85, state carried from round to round) -> assemble on ONE context, stream counts growing so that both
+    scratch buffers are reallocated in between, every round compared with the oracle."""
+    import torch
+
+    dev = torch.device("cuda")
+    c = R.Context(0, 4096, 64)
+    try:
+        carried = {}
+        for rnd, n_streams in enumerate((8, 40, 24)):
+            n_caps = 160 + 16 * rnd
+            host = np.stack([make_stream(oracle, n_caps, 30.0 + s, seed=9000 + 100 * rnd + s, sync_every=40 + s)
+                             for s in range(n_streams)])
+            state_h = np.zeros((n_streams, 2), np.uint32)
+            for s in range(n_streams):
+                state_h[s] = carried.get(s, (s & 1, 0))
+            caps = torch.from_numpy(host).to(dev)
+            counts = torch.full((n_streams,), n_caps, dtype=torch.int32, device=dev)
+            state = torch.from_numpy(state_h.view(np.int32)).to(dev)
+            state_out = torch.zeros((n_streams, 2), dtype=torch.int32, device=dev)
+            nodes = torch.zeros((n_streams, n_caps * 40, 8), dtype=torch.uint8, device=dev)
+            ncount = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+            status = torch.zeros((n_streams, n_caps), dtype=torch.int32, device=dev)
+            offs = torch.zeros((n_streams, n_caps), dtype=torch.int32, device=dev)
+            c.decode_capsules_batch_dev(0x85, caps.data_ptr(), counts.data_ptr(), n_streams, n_caps, 31, nodes.data_ptr(),
+                                        ncount.data_ptr(), state_in=state.data_ptr(), capsule_status=status.data_ptr(),
+                                        capsule_node_offset=offs.data_ptr(), state_out=state_out.data_ptr())
+            max_nodes, max_scans = 700, 16
+            scans = torch.zeros((n_streams, max_scans, max_nodes, 8), dtype=torch.uint8, device=dev)
+            slen = torch.zeros((n_streams, max_scans), dtype=torch.int32, device=dev)
+            sps = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+            c.assemble_scans_dev(nodes.data_ptr(), ncount.data_ptr(), n_streams, n_caps * 40, max_nodes, max_scans, max_nodes,
+                                 scans.data_ptr(), slen.data_ptr(), sps.data_ptr(), capsule_status=status.data_ptr(),
+                                 capsule_node_offset=offs.data_ptr(), capsule_counts=counts.data_ptr(), stride_capsules=n_caps)
+            c.synchronize()
+            torch.cuda.synchronize()
+            hn = nodes.cpu().numpy().view(oracle.NODE_DTYPE).reshape(n_streams, n_caps * 40)
+            so = state_out.cpu().numpy().astype(np.uint32)
+            g = scans.cpu().numpy().view(oracle.NODE_DTYPE).reshape(n_streams, max_scans, max_nodes)
+            gl, gk = slen.cpu().numpy(), sps.cpu().numpy()
+            for s in range(n_streams):
+                en, es, eo, est = oracle.dense_decode(host[s], 31, int(state_h[s, 0]))
+                assert int(ncount[s]) == len(en), (rnd, s)
+                assert (hn[s, : len(en)].view(np.uint64) == en.view(np.uint64)).all(), (rnd, s)
+                assert int(so[s, 0]) == int(est), (rnd, s)
+                e, elen, ek = oracle.assemble_scans(en, oracle.resets_from_capsules(es, eo), max_nodes, max_scans)
+                assert int(gk[s]) == ek, (rnd, s)
+                for k in range(min(ek, max_scans)):
+                    assert int(gl[s, k]) == int(elen[k]) and (g[s, k, : elen[k]].view(np.uint64) == e[k, : elen[k]].view(np.uint64)).all()
+                carried[s] = (int(so[s, 0]), 0)
+    finally:
+        c.close()

@@ -382,3 +382,39 @@ def test_mode_a_duplicate_keys_in_the_shared_memory_kernel(R, oracle, ctx):
     heavy = heavy[rng.permutation(n)]
     for newp, inv in ((0, 0), (1, 1)):
         check_batch(R, oracle, ctx, heavy[None], np.array([n], np.uint32), newp, 1, inv, 1, emit=False, stable=True)
+
+
+def test_shared_final_keys_are_resolved_in_the_shared_memory_kernel(R, oracle, ctx):
+    """With the ascended buffer, the interpolated key of an unmeasured node can land on a measured node's key.  Up
+    to 16 such nodes per revolution are placed by the shared-memory kernel itself (stable rule: equal keys in buffer
+    order), more go to the general kernel.  Tie-free synthetic revolutions of 3200 nodes with 5 % unmeasured nodes:
+    the ones where that happens (a few per cent) must stay on the fast path and match the oracle bit for bit; then
+    hand-made cases: a key shared by three nodes, 16 and 17 shared keys."""
+    n = 3200
+    pool = oracle.synth_batch(424242, 1500, n, 0)
+    counts = np.full(pool.shape[0], n, np.uint32)
+    exp = oracle_batch(oracle, pool, counts, 0, 0, 0, 1, True)
+    keys = exp["nodes"]["angle_z_q14"]
+    shared = np.flatnonzero((np.diff(keys.astype(np.int32), axis=1) == 0).any(axis=1))
+    assert len(shared) >= 10, len(shared)  # the situation the bench meets in ~4 % of its revolutions
+    sel = pool[shared[:64]]
+    for newp, mode_a, inv in ((0, 0, 0), (1, 1, 1), (0, 1, 0), (1, 0, 1)):
+        check_batch(R, oracle, ctx, sel, np.full(len(sel), n, np.uint32), newp, mode_a, inv, 1, emit=True, expect_path=0)
+    # hand-made: measured keys 100, 200, ... ; unmeasured nodes get their keys from the fill, so put MEASURED
+    # duplicates next to them in Mode A (which keeps no bitmap of the measured keys) to reach exact counts
+    rng = np.random.default_rng(12)
+    base_keys = np.sort(rng.choice(np.arange(64, 65000), size=2000, replace=False))
+    for n_shared, path in ((1, 0), (3, 0), (16, 0), (17, R.PATH_GENERAL)):
+        k = base_keys.copy()
+        # n_shared extra nodes: the first three on ONE key (a key held by up to four nodes), the rest on distinct keys
+        src = np.concatenate([np.full(min(n_shared, 3), 500), 600 + 7 * np.arange(max(n_shared - 3, 0))]).astype(int)
+        dst = 1500 + 3 * np.arange(n_shared)
+        k[dst] = k[src]
+        dist = rng.integers(4000, 160000, len(k))
+        c = oracle.make_nodes(k, dist, rng.integers(0, 256, len(k)), 2)
+        c = c[rng.permutation(len(c))]
+        for newp, inv in ((0, 0), (1, 1)):
+            check_batch(R, oracle, ctx, c[None], np.array([len(c)], np.uint32), newp, 1, inv, 1, emit=True, stable=True,
+                        expect_path=path)
+            check_batch(R, oracle, ctx, c[None], np.array([len(c)], np.uint32), newp, 0, inv, 1, emit=True, stable=True,
+                        expect_path=R.PATH_GENERAL)  # Mode B ranks the measured keys: any duplicate among them

@@ -1,11 +1,12 @@
 #!/usr/bin/env bash
-# two GPUs: the multi-GPU parity check (push kernel + C++ exchange vs torch all-gather), the default bench line at
-# N=2 (carries extra.cloud with the three exchanges), the cloud workload on its own line, the reference arm at N=2
+# eight GPUs: the multi-GPU parity check (push kernel + C++ exchange vs torch all-gather) at world size 8, the default
+# bench line at N=8 (carries extra.cloud with the three exchanges), NCCL's transport report
 set -u
 mkdir -p gpurun_out
 T=${1:-r2n8}
 nvidia-smi topo -m > gpurun_out/${T}_topo.txt 2>&1
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
+timeout 600 $RUN --master-port 29520 tests/mgpu_push_check.py > gpurun_out/${T}_push_check.txt 2>&1; tail -3 gpurun_out/${T}_push_check.txt
 timeout 900 $RUN --master-port 29521 bench.py --gpus 8 --steps 50 > gpurun_out/${T}_default.json 2> gpurun_out/${T}_default.err; tail -c 1500 gpurun_out/${T}_default.err
 
 NCCL_DEBUG=INFO timeout 600 $RUN --master-port 29524 bench.py --gpus 8 --workload cloud --steps 3 > /dev/null 2> gpurun_out/${T}_nccl_info.log; grep -iE "NVLS|via P2P|Channel 00|NCCL version|Connected all" gpurun_out/${T}_nccl_info.log | sort | uniq -c | head -12
