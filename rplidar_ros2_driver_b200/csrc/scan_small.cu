@@ -356,19 +356,33 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
 
     // ---- mark: one shared-memory atomicOr per kept key -----------------------------------------------
     uint32_t cnt = 0, fmin = 0xFFFFFFFFu;
+    if (!USE_V && !EMIT && !CLOUD && shift == 0) {
+      // Mode A only needs the number of measured nodes here: two nodes per 128-bit load
+      const uint4* t4 = reinterpret_cast<const uint4*>(tile0);
 #pragma unroll 4
-    for (uint32_t i = tid; i < n; i += TS) {
-      const uint2 nd = tile[i];
-      const uint32_t dist = __funnelshift_r(nd.x, nd.y, 16);
-      bool valid = dist != 0;
-      if (CLOUD) valid = valid && cloud_keep(dist_to_m(dist), intensity_of(nd.y), w_rmin, w_rmax, w_imin);
-      if (valid) {
-        if (USE_V) {
-          const uint32_t k = nd.x & 0xFFFFu;
-          atomicOr(&bitsV[k >> 5], 1u << (k & 31));
+      for (uint32_t w = tid; w < n / 2; w += TS) {
+        const uint4 v = t4[w];
+        cnt += (((v.x & 0xFFFF0000u) | (v.y & 0xFFFFu)) != 0u) + (((v.z & 0xFFFF0000u) | (v.w & 0xFFFFu)) != 0u);
+      }
+      if ((n & 1u) && tid == 0) {
+        const uint2 v = tile0[n - 1];
+        cnt += ((v.x & 0xFFFF0000u) | (v.y & 0xFFFFu)) != 0u;
+      }
+    } else {
+#pragma unroll 4
+      for (uint32_t i = tid; i < n; i += TS) {
+        const uint2 nd = tile[i];
+        const uint32_t dist = __funnelshift_r(nd.x, nd.y, 16);
+        bool valid = dist != 0;
+        if (CLOUD) valid = valid && cloud_keep(dist_to_m(dist), intensity_of(nd.y), w_rmin, w_rmax, w_imin);
+        if (valid) {
+          if (USE_V) {
+            const uint32_t k = nd.x & 0xFFFFu;
+            atomicOr(&bitsV[k >> 5], 1u << (k & 31));
+          }
+          ++cnt;
+          if (EMIT) fmin = min(fmin, i);
         }
-        ++cnt;
-        if (EMIT) fmin = min(fmin, i);
       }
     }
     cnt = warp_sum(cnt);
@@ -422,11 +436,7 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
           fk = (i == 0) ? front_key : ascend_fill_key(front_deg, i, step);
           tile0[shift + i].x = (nd.x & 0xFFFF0000u) | fk;
         }
-        const uint32_t bit = 1u << (fk & 31);
-        if (atomicOr(&bitsA[fk >> 5], bit) & bit) {  // this final key is taken: one more node than distinct keys
-          const uint32_t slot = atomicAdd(&ctl.d.ndup, 1u);
-          if (slot < kMaxDup) ctl.d.dupkey[slot] = (uint16_t)fk;
-        }
+        atomicOr(&bitsA[fk >> 5], 1u << (fk & 31));
       }
       __syncthreads();
     }
@@ -494,11 +504,25 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
     // rule); Mode A looks only for the duplicates that matter to it, in its winner pass below.  Duplicates among the
     // FINAL keys (typically the fill key of an unmeasured node landing on a measured node's key) only move entries of
     // the ascended buffer: up to kMaxDup of them are resolved here (place pass + fix-up), more go to the general kernel.
-    const uint32_t D = EMIT ? ctl.d.ndup : 0u;  // = n - (distinct final keys)
+    const uint32_t D = EMIT ? n - ctl.totA : 0u;  // nodes beyond the first of their final key
     if ((USE_V && ctl.totV != M) || (EMIT && D > kMaxDup)) {
       if (tid == 0) a.fallback_list[atomicAdd(a.fallback_count, 1u)] = s;
       __syncthreads();
       continue;
+    }
+    if (EMIT && D) {
+      // (rare) which keys are they?  Every node clears its key's bit and looks at what was there: the first node of
+      // a key finds it set, every further one finds it cleared and lists the key; then the bitmap is marked again.
+      for (uint32_t i = tid; i < n; i += TS) {
+        const uint32_t fk = tile[i].x & 0xFFFFu, bit = 1u << (fk & 31);
+        if (!(atomicAnd(&bitsA[fk >> 5], ~bit) & bit)) ctl.d.dupkey[atomicAdd(&ctl.d.ndup, 1u)] = (uint16_t)fk;  // D entries
+      }
+      __syncthreads();
+      for (uint32_t i = tid; i < n; i += TS) {
+        const uint32_t fk = tile[i].x & 0xFFFFu;
+        atomicOr(&bitsA[fk >> 5], 1u << (fk & 31));
+      }
+      __syncthreads();
     }
 
     // ---- place ------------------------------------------------------------------------------------------
@@ -604,7 +628,7 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
           if (__float_as_uint(dist_to_m(dist)) == minv[b]) {
             const uint32_t v = (k << 8) | ((nd.y >> 16) & 0xFFu);
             const uint32_t old = atomicMin(&wkey[b], v);
-            conflict = conflict || ((old >> 8) == k && old != v);
+            conflict = conflict || ((old ^ v) - 1u < 255u);  // same key, another quality
           }
         }
       }
