@@ -211,10 +211,14 @@ __device__ __forceinline__ void ultra_cabin(const uint8_t* prev, const uint8_t* 
 
 // ---- ultra-dense (handler_capsules.cpp:951-1047) -------------------------------------------------------
 // raw sample: distance before smoothing, scale code, quality
+__device__ __forceinline__ int ud_decode(uint32_t qds, uint32_t& scale, uint32_t& quality);
 __device__ __forceinline__ int ud_sample(const uint8_t* cap, uint32_t pos, uint32_t& scale, uint32_t& quality) {
   const uint8_t* cab = cap + 10 + 5 * (pos >> 1);
   const uint32_t hi = cab[4];
   const uint32_t qds = ld16(cab + 2 * (pos & 1u)) | (((pos & 1u) ? (hi >> 4) : (hi & 0xFu)) << 16);
+  return ud_decode(qds, scale, quality);
+}
+__device__ __forceinline__ int ud_decode(uint32_t qds, uint32_t& scale, uint32_t& quality) {
   scale = qds & 3u;
   // the four ranges without a branch (scales differ from lane to lane): field mask 0xFFC / 0x1FFC / 0x3FFC / 0x7FFC,
   // factor 2..5, base (0, 2046, 8187, 24567) << 2, quality (qds >> (12 + scale)) << scale
@@ -521,6 +525,40 @@ __global__ void __launch_bounds__(DT) decode_capsule_kernel(CapsuleDecodeArgs a)
 #pragma unroll
           for (uint32_t k = 0; k < 3; ++k) dst[lane + 32u * k] = sm.wstage[warp][lane + 32u * k];
           __syncwarp();
+        }
+      } else if constexpr (F == kUltraDense) {
+        // one warp per released capsule, one lane per 5-byte cabin (two samples): the cabin bytes, the capsule's
+        // scan-start mask and the pair of smoothed distances are read once, and a lane stores its two nodes as
+        // one 16-byte word -- the warp writes the capsule's 64 nodes as 512 contiguous bytes
+        const uint32_t E = sm.tile_nodes / (uint32_t)NODES;
+        uint2* o = out + sm.carry_nodes;
+        const bool wide = (reinterpret_cast<uintptr_t>(o) & 15u) == 0;
+        for (uint32_t e = warp; e < E; e += DT / 32) {
+          const uint32_t j = sm.emit_list[e];
+          const uint8_t* pc = (j == 0) ? sm.carry : tile + (j - 1) * CB;
+          const int pq8 = (int)sm.start_q8[j];
+          int d = (int)sm.start_q8[j + 1] - pq8;
+          if (pq8 > (int)sm.start_q8[j + 1]) d += (360 << 8);
+          const int inc = (d << 8) / 64;
+          const uint8_t* cab = pc + 10 + 5 * lane;
+          const uint32_t hi = cab[4];
+          const uint32_t qa = ld16(cab) | ((hi & 0xFu) << 16), qb = ld16(cab + 2) | ((hi >> 4) << 16);
+          uint32_t sa, sb, qua, qub;
+          int da = ud_decode(qa, sa, qua), db = ud_decode(qb, sb, qub);
+          const uint32_t sm2 = *reinterpret_cast<const uint32_t*>(&sm.ud_dist[j][2 * lane]);  // smoothed pair
+          if (sa == 0) da = (int)(sm2 & 0xFFFFu);
+          if (sb == 0) db = (int)(sm2 >> 16);
+          const uint32_t sy = (uint32_t)(sm.smask[j] >> (2 * lane)) & 3u;
+          const int ang = (pq8 << 8) + (int)(2 * lane) * inc;
+          const uint2 na = pack_node(ang >> 10, (uint32_t)da, sy & 1u, qua);
+          const uint2 nb = pack_node((ang + inc) >> 10, (uint32_t)db, sy >> 1, qub);
+          uint2* dst = o + (size_t)e * NODES + 2 * lane;
+          if (wide) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(na.x, na.y, nb.x, nb.y);
+          } else {
+            dst[0] = na;
+            dst[1] = nb;
+          }
         }
       } else {
         const uint32_t n_nodes = sm.tile_nodes;

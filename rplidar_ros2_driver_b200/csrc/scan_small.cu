@@ -218,7 +218,7 @@ __device__ __forceinline__ int fix16(float v) { return __float2int_rn(__fmul_rn(
 // MODE: 0 LaserScan Mode B, 1 LaserScan Mode A, 2 PointCloud2.  EMIT: also write the ascended node buffer
 // (MODE 0/1).  POST: (MODE 2) SOR and/or voxel grid in shared memory before anything is written.
 template <int MODE, bool EMIT, bool POST, int TS>
-__global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchArgs a, SmallArgs p) {
+__global__ void __launch_bounds__(TS, POST ? 2 : 4) scan_small_kernel(ScanBatchArgs a, SmallArgs p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool MODE_A = (MODE == 1);
   constexpr bool CLOUD = (MODE == 2);
@@ -534,59 +534,66 @@ __global__ void __launch_bounds__(TS, POST ? 2 : 1) scan_small_kernel(ScanBatchA
     // Mode B output slot = ob + os * rank in wrapping u32 arithmetic (reference rplidar_node.cpp:673)
     const uint32_t ob = inverted ? M - 1u : 0u, os = inverted ? 0xFFFFFFFFu : 1u;
     const ptrdiff_t i_minus_r = reinterpret_cast<char*>(intens) - reinterpret_cast<char*>(ranges);
+    // (two instances: revolutions with shared final keys are rare and must not slow the loop of the others down)
+    auto place = [&](auto has_dup) {
+      constexpr bool HAS_DUP = decltype(has_dup)::value;
 #pragma unroll 4
-    for (uint32_t i = tid; i < n; i += TS) {
-      const uint2 nd = tile[i];
-      const uint32_t k = nd.x & 0xFFFFu;
-      const uint32_t dist = __funnelshift_r(nd.x, nd.y, 16);
-      uint32_t measured = dist != 0 ? 1u : 0u;
-      if (EMIT) {  // k is the FINAL key here
-        uint32_t rA = rank2(bitsA, prefA, k);  // rank among the distinct final keys
-        bool defer = false;
-        if (D) {  // (block-uniform, rare) every node beyond the first of a key shifts the larger keys by one; the
-                  // nodes that share a key are ordered by buffer position (stable rule) in the fix-up below
-          for (uint32_t j = 0; j < D; ++j) {
-            const uint32_t dk = ctl.d.dupkey[j];
-            rA += (dk < k) ? 1u : 0u;
-            defer = defer || (dk == k);
+      for (uint32_t i = tid; i < n; i += TS) {
+        const uint2 nd = tile[i];
+        const uint32_t k = nd.x & 0xFFFFu;
+        const uint32_t dist = __funnelshift_r(nd.x, nd.y, 16);
+        uint32_t measured = dist != 0 ? 1u : 0u;
+        if (EMIT) {  // k is the FINAL key here
+          uint32_t rA = rank2(bitsA, prefA, k);  // rank among the distinct final keys
+          bool defer = false;
+          if constexpr (HAS_DUP) {
+            // every node beyond the first of a key shifts the larger keys by one; the nodes that share a key are
+            // ordered by buffer position (stable rule) in the fix-up below
+            for (uint32_t j = 0; j < D; ++j) {
+              const uint32_t dk = ctl.d.dupkey[j];
+              rA += (dk < k) ? 1u : 0u;
+              defer = defer || (dk == k);
+            }
+            if (defer) ctl.d.dupnode[atomicAdd(&ctl.d.ndupnode, 1u)] = (uint16_t)i;  // <= 2 * D entries
           }
-          if (defer) ctl.d.dupnode[atomicAdd(&ctl.d.ndupnode, 1u)] = (uint16_t)i;  // <= 2 * D entries
+          if (!defer) st_hint_v2(nodes_out + rA, nd, pol_stream);
         }
-        if (!defer) st_hint_v2(nodes_out + rA, nd, pol_stream);
-      }
-      if (!CLOUD && !want_scan) continue;
-      const float dm = dist_to_m(dist);
-      if (MODE_A) {
-        // Mode A needs no order at all (reference rplidar_node.cpp:630-660): a bin keeps the smallest dist_m of the
-        // points that fall into it -- dist_m >= 0, so its bit pattern orders like the value
-        if (measured) {
-          const uint32_t b = (uint32_t)mode_a_bin_fast(k, M, inc, inverted);  // < M <= 8192
-          atomicMin(&minv[b], __float_as_uint(dm));
-        }
-        continue;
-      }
-      const uint32_t rk = rank2(bitsV, prefV, k);
-      if (CLOUD) {  // polar -> xyz at the rank among kept points (oracle/cloud_oracle.cpp steps 1-3)
-        const float it = intensity_of(nd.y);
-        if (!cloud_keep(dm, it, w_rmin, w_rmax, w_imin)) measured = 0;
-        const float2 cs = __ldg(a.trig + k);
-        const float x = __fmul_rn(dm, cs.x), y = __fmul_rn(dm, cs.y);
-        if (POST) {
+        if (!CLOUD && !want_scan) continue;
+        const float dm = dist_to_m(dist);
+        if (MODE_A) {
+          // Mode A needs no order at all (reference rplidar_node.cpp:630-660): a bin keeps the smallest dist_m of the
+          // points that fall into it -- dist_m >= 0, so its bit pattern orders like the value
           if (measured) {
-            px[rk] = make_float2(x, y);
-            pi[rk] = (uint8_t)((nd.y >> q_shift) & q_mask);
+            const uint32_t b = (uint32_t)mode_a_bin_fast(k, M, inc, inverted);  // < M <= 8192
+            atomicMin(&minv[b], __float_as_uint(dm));
           }
-        } else {
-          st_f32x4_if(cloud + rk, make_float4(x, y, 0.0f, it), pol_stream, measured);
+          continue;
         }
-      } else {  // Mode B: reference rplidar_node.cpp:661-677
-        const uint32_t o = ob + os * rk;
-        const float it = intensity_of(nd.y);
-        float* pr = ranges + o;
-        st_f32_if(pr, dm, pol_stream, measured);
-        st_f32_if(reinterpret_cast<float*>(reinterpret_cast<char*>(pr) + i_minus_r), it, pol_stream, measured);
+        const uint32_t rk = rank2(bitsV, prefV, k);
+        if (CLOUD) {  // polar -> xyz at the rank among kept points (oracle/cloud_oracle.cpp steps 1-3)
+          const float it = intensity_of(nd.y);
+          if (!cloud_keep(dm, it, w_rmin, w_rmax, w_imin)) measured = 0;
+          const float2 cs = __ldg(a.trig + k);
+          const float x = __fmul_rn(dm, cs.x), y = __fmul_rn(dm, cs.y);
+          if (POST) {
+            if (measured) {
+              px[rk] = make_float2(x, y);
+              pi[rk] = (uint8_t)((nd.y >> q_shift) & q_mask);
+            }
+          } else {
+            st_f32x4_if(cloud + rk, make_float4(x, y, 0.0f, it), pol_stream, measured);
+          }
+        } else {  // Mode B: reference rplidar_node.cpp:661-677
+          const uint32_t o = ob + os * rk;
+          const float it = intensity_of(nd.y);
+          float* pr = ranges + o;
+          st_f32_if(pr, dm, pol_stream, measured);
+          st_f32_if(reinterpret_cast<float*>(reinterpret_cast<char*>(pr) + i_minus_r), it, pol_stream, measured);
+        }
       }
-    }
+    };
+    if (EMIT && D) place(std::true_type{});
+    else place(std::false_type{});
     __syncthreads();
 
     // ---- ascended buffer, nodes with a shared final key: position = nodes with a smaller key + nodes with the same

@@ -2,7 +2,7 @@
 # quick iteration: all GPU tests, the 3200-node LaserScan line, ultra / ultra-dense decoder lines + ncu
 set -u
 mkdir -p gpurun_out
-T=${1:-r2i}
+T=${1:-r2j}
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -12 > gpurun_out/${T}_pytest.txt
 tail -4 gpurun_out/${T}_pytest.txt
 timeout 600 python bench.py --nodes 3200 --scans 40960 --steps 50 --no-cpu --no-cloud --no-e2e > gpurun_out/${T}_scan3200.json 2> gpurun_out/${T}_scan3200.err; tail -c 400 gpurun_out/${T}_scan3200.err
