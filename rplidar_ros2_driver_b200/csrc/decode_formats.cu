@@ -66,7 +66,9 @@ __device__ __forceinline__ uint32_t ld32(const uint8_t* p) { return ld16(p) | (l
 __device__ __forceinline__ uint2 pack_node(int angle_q6, uint32_t dist_q2, uint32_t sync, uint32_t quality) {
   if (angle_q6 < 0) angle_q6 += (360 << 6);
   if (angle_q6 >= (360 << 6)) angle_q6 -= (360 << 6);
-  const uint32_t key = (uint32_t)((angle_q6 << 8) / 90) & 0xFFFFu;
+  // angle_q6 >= 0 here for every wire input (start angles are 15-bit q6 values < 512 deg and the interpolated angle
+  // minus its correction stays above -360 deg), so the unsigned quotient is the reference's signed one
+  const uint32_t key = ((uint32_t)(angle_q6 << 8) / 90u) & 0xFFFFu;
   const uint32_t flag = sync | ((sync ^ 1u) << 1);
   uint2 nd;
   nd.x = key | (dist_q2 << 16);
@@ -156,7 +158,8 @@ __device__ __forceinline__ uint2 node_ultra(const uint8_t* prev, const uint8_t* 
 // shared memory.  The three nodes of a lane go through a per-warp staging area so that the warp stores its 96 nodes
 // as three fully coalesced 256-byte rows.  Same arithmetic as node_ultra() (kept as the definition).
 __device__ __forceinline__ uint32_t varbitscale_sel(uint32_t s, uint32_t& level) {
-  const uint32_t l = (s >= 512u) + (s >= 1280u) + (s >= 1792u) + (s >= 3328u);
+  // segment of s (< 4096): the bounds 512, 1280, 1792, 3328 are multiples of 256 -> 16 nibbles indexed by s >> 8
+  const uint32_t l = (uint32_t)(0x4443333332211100ull >> (4u * (s >> 8))) & 0xFu;
   // source bases of the five segments (12 bits each); target bases 0, 1<<9, 1<<11, 1<<12, 1<<14
   const uint32_t src = (uint32_t)(0xD00700500200000ull >> (12u * l)) & 0xFFFu;
   const uint32_t dst = (l ? 512u : 0u) << ((0x53200u >> (4u * l)) & 0xFu);
@@ -198,11 +201,12 @@ __device__ __forceinline__ void ultra_cabin(const uint8_t* prev, const uint8_t* 
     }
     const uint32_t sync = (rem < inc) ? 1u : 0u;
     uint32_t k2 = 492u;
-    if (dist[c] >= 200) {  // 98361 / dist_q2 (<= 491) without the integer division: float quotient, exact +-1 correction
-      const uint32_t d = (uint32_t)dist[c];
-      k2 = __float2uint_rz(__fdividef(98361.0f, __uint2float_rn(d)));
-      if (k2 * d > 98361u) --k2;
-      else if ((k2 + 1u) * d <= 98361u) ++k2;
+    if (dist[c] >= 200) {
+      // 98361 / dist_q2 (<= 491) without the integer division: both operands are exact floats (dist_q2 < 2^22) and
+      // the correctly rounded quotient cannot reach an integer the exact one stays below (it would have to be within
+      // 98361/d * 2^-24 of it, but misses it by at least 1/d): truncation gives the integer quotient.
+      // tests/test_device_math_proofs.py checks every dist_q2.
+      k2 = __float2uint_rz(__fdiv_rn(98361.0f, __uint2float_rn((uint32_t)dist[c])));
     }
     const int angle_q6 = (a - off_table[k2]) >> 10;
     stage[3u * cabin + c] = pack_node(angle_q6, (uint32_t)dist[c], sync, dist[c] ? (0x2Fu << 2) : 0u);
@@ -271,7 +275,7 @@ struct CapsuleSmem {
   uint32_t ud_out[Fmt<F>::STATE ? DT : 1][10];   // nine outcomes of the smoothing chain + first raw sample
   uint32_t ud_first_scale[Fmt<F>::STATE ? DT : 1];  // bit 31: the capsule's outcome does not depend on its input
   uint32_t ud_last_in[Fmt<F>::STATE ? DT : 1];
-  uint16_t ud_dist[Fmt<F>::STATE ? DT : 1][64];  // smoothed short-range distances
+  uint16_t ud_dist[Fmt<F>::STATE ? DT : 1][66];  // smoothed short-range distances (rows padded to 33 words: a thread per capsule walks a column)
   uint32_t carry_sync, red_sync, carry_last, red_last;
   // ultra only: angle-correction table and the per-warp staging rows of the emission
   int ultra_off[F == kUltra ? 496 : 1];

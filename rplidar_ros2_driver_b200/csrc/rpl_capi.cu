@@ -867,7 +867,8 @@ rpl_result rpl_decode_capsules_batch_dev(rpl_ctx* c, uint32_t ans_type, const ui
   a.capsule_status = capsule_status;
   a.capsule_node_offset = capsule_node_offset;
   a.state_out = state_out;
-  const int grid = (int)std::min<uint32_t>(n_streams, (uint32_t)c->num_sms * 2u);
+  // one CTA per stream while they fit (express / ultra: five CTAs per SM by shared memory, ultra-dense two)
+  const int grid = (int)std::min<uint32_t>(n_streams, (uint32_t)c->num_sms * 8u);
   RPL_CUDA(c, rpl::launch_decode_capsules(ans_type, a, grid, st), RPL_RESULT_OPERATION_FAIL);
   c->launches++;
   return RPL_RESULT_OK;

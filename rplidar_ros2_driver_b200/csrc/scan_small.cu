@@ -218,7 +218,7 @@ __device__ __forceinline__ int fix16(float v) { return __float2int_rn(__fmul_rn(
 // MODE: 0 LaserScan Mode B, 1 LaserScan Mode A, 2 PointCloud2.  EMIT: also write the ascended node buffer
 // (MODE 0/1).  POST: (MODE 2) SOR and/or voxel grid in shared memory before anything is written.
 template <int MODE, bool EMIT, bool POST, int TS>
-__global__ void __launch_bounds__(TS, POST ? 2 : 4) scan_small_kernel(ScanBatchArgs a, SmallArgs p) {
+__global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : 1)) scan_small_kernel(ScanBatchArgs a, SmallArgs p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool MODE_A = (MODE == 1);
   constexpr bool CLOUD = (MODE == 2);

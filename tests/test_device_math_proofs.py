@@ -44,6 +44,14 @@ def test_division_by_90_is_exact_for_every_angle(tmp_path):
     assert "mismatches 0, key mismatches 0" in r.stdout and "checked 1149239297 values" in r.stdout
 
 
+def test_ultra_angle_table_index_by_float_division():
+    """decode_formats.cu ultra_cabin: 98361 / dist_q2 as trunc(RN(98361.0f / (float)dist_q2)) for every distance the
+    format can carry (dist_q2 < 2^22)."""
+    d = np.arange(200, 1 << 22, dtype=np.uint32)
+    q = (F32(98361.0) / d.astype(F32)).astype(np.uint32)
+    assert (q == 98361 // d).all() and int(q.max()) == 491
+
+
 def exact_bins(m: int, inverted: bool) -> np.ndarray:
     k = np.arange(65536, dtype=np.float32)
     deg = (k * F32(90.0)) / F32(16384.0)
