@@ -63,6 +63,9 @@ def parse():
                          "0x85 dense, 0x86 ultra-dense)")
     ap.add_argument("--sor", type=int, default=0, help="cloud workload: SOR k (0 = off)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-wc", action="store_true",
+                    help="e2e leg: the host INPUT buffer is write-combined pinned memory (cudaHostAllocWriteCombined): "
+                         "the GPU's reads of it do not snoop the CPU caches")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--chain-copy", action="store_true",
@@ -580,7 +583,18 @@ def run_b200(args, rank, local_rank, world):
     e2e = None
     h_nodes = None
     if not args.no_e2e:
-        h_nodes_t = torch.empty((S, N, 8), dtype=torch.uint8, pin_memory=True)
+        if args.e2e_wc:
+            import ctypes as C
+
+            rt = C.CDLL("libcudart.so.12")
+            rt.cudaHostAlloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_uint]
+            wc_ptr = C.c_void_p()
+            rc = rt.cudaHostAlloc(C.byref(wc_ptr), S * N * 8, 0x04)  # cudaHostAllocWriteCombined
+            if rc != 0:
+                raise SystemExit(f"cudaHostAlloc(write-combined) failed: {rc}")
+            h_nodes_t = torch.from_numpy(np.ctypeslib.as_array((C.c_uint8 * (S * N * 8)).from_address(wc_ptr.value))).view(S, N, 8)
+        else:
+            h_nodes_t = torch.empty((S, N, 8), dtype=torch.uint8, pin_memory=True)
         h_nodes_t.copy_(nodes)
         h_counts = counts.cpu().numpy().astype(np.uint32)
         h_nodes = h_nodes_t.numpy().view(R.NODE_DTYPE).reshape(S, N)
@@ -591,6 +605,9 @@ def run_b200(args, rank, local_rank, world):
         # what the host link can do on this box (plain pinned copies of the same buffers)
         pc = []
         for src, dst in ((h_nodes_t, nodes), (ranges, out_t["ranges"])):
+            if args.e2e_wc and src is h_nodes_t:  # (torch would stage a buffer it did not pin itself)
+                pc.append(None)
+                continue
             torch.cuda.synchronize()
             tp0 = time.perf_counter()
             dst.copy_(src, non_blocking=True)
@@ -622,7 +639,8 @@ def run_b200(args, rank, local_rank, world):
                "h2d_bytes_per_step": S * N * 8 + S * 4, "d2h_bytes_per_step": 2 * S * N * 4 + 4 * S * 4,
                "steps": ke, "ms_per_step": dt / ke * 1e3, "api": "rpl_scan_batch (pinned host buffers)",
                "matches_device_path": same, "beam_count_scan0": int(res["beam_counts"][0]),
-               "link_h2d_gbs": pc[0], "link_d2h_gbs": pc[1]}
+               "link_h2d_gbs": pc[0], "link_d2h_gbs": pc[1],
+               "input_buffer": "write-combined pinned (cudaHostAllocWriteCombined)" if args.e2e_wc else "pinned"}
     # ---- BASELINE configs[2]/[4]: PointCloud2 path + the one exchange, at this world size --------
     if not args.no_cloud:
         try:

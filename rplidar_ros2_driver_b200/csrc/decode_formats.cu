@@ -24,7 +24,7 @@
 //     input, the samples before the position where their nine candidates merged (the others were final
 //     already).
 // The standard-node decoder is a 5-state byte machine with resynchronisation; each thread folds its
-// 20 bytes into a state->state map (5 x 3 bits), the maps are scanned under composition, and the
+// 30 bytes into a state->state map (5 x 3 bits), the maps are scanned under composition, and the
 // threads replay their bytes from the known entry state: exact on arbitrary (misframed) streams.
 #include "decode_args.h"
 #include "rpl_device.cuh"
@@ -618,7 +618,7 @@ constexpr int HT = 128;         // threads = capsules per tile
 constexpr int kHqBytes = 781;   // 1 sync + 8 timestamp + 96 * 8 nodes + 4 crc
 struct HqSmem {
   uint8_t cap[(HT * kHqBytes + 15) & ~15];
-  uint32_t table[256];
+  uint32_t table[8][256];  // slicing-by-8: table[k][b] = CRC of byte b followed by k zero bytes
   uint32_t emit_list[HT];
   uint32_t warp_a[HT / 32];
   uint32_t carry_nodes, tile_nodes;
@@ -632,8 +632,18 @@ __global__ void __launch_bounds__(HT) decode_hq_kernel(CapsuleDecodeArgs a) {
     uint32_t c = i;
 #pragma unroll
     for (int j = 0; j < 8; ++j) c = (c & 1u) ? (0xEDB88320u ^ (c >> 1)) : (c >> 1);
-    sm.table[i] = c;
+    sm.table[0][i] = c;
   }
+  __syncthreads();
+  for (uint32_t i = tid; i < 256; i += HT) {
+    uint32_t c = sm.table[0][i];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      c = (c >> 8) ^ sm.table[0][c & 0xFFu];
+      sm.table[k][i] = c;
+    }
+  }
+  __syncthreads();
   for (uint32_t s = blockIdx.x; s < a.n_streams; s += gridDim.x) {
     const uint32_t n = a.counts[s];
     const uint8_t* src = a.capsules + (size_t)s * a.stride_capsules * kHqBytes;
@@ -662,10 +672,28 @@ __global__ void __launch_bounds__(HT) decode_hq_kernel(CapsuleDecodeArgs a) {
         if (c[0] != 0xA5) {
           st = kStBadFrame;
         } else {
+          // 777 message bytes + the SDK's zero padding to 780.  One thread per capsule is a chain of dependent table
+          // look-ups; eight bytes per step (slicing-by-8: eight independent look-ups, one XOR tree) shorten it
+          // eightfold.  The capsule starts at any byte offset: message words come from aligned words by funnel shift.
           uint32_t crc = 0xFFFFFFFFu;
-          for (int i = 0; i < kHqBytes - 4; ++i) crc = (crc >> 8) ^ sm.table[(crc ^ c[i]) & 0xFFu];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) crc = (crc >> 8) ^ sm.table[crc & 0xFFu];  // zero padding to 780 bytes
+          const uintptr_t addr = reinterpret_cast<uintptr_t>(c);
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(addr & ~uintptr_t(3));
+          const uint32_t sh = (uint32_t)(addr & 3u) * 8u;
+          uint32_t w0 = w[0];
+#pragma unroll 2
+          for (int k = 0; k < 97; ++k) {  // 97 * 8 = 776 bytes
+            const uint32_t w1 = w[2 * k + 1], w2 = w[2 * k + 2];
+            const uint32_t one = __funnelshift_r(w0, w1, sh) ^ crc, two = __funnelshift_r(w1, w2, sh);
+            w0 = w2;
+            crc = sm.table[7][one & 0xFFu] ^ sm.table[6][(one >> 8) & 0xFFu] ^ sm.table[5][(one >> 16) & 0xFFu] ^
+                  sm.table[4][one >> 24] ^ sm.table[3][two & 0xFFu] ^ sm.table[2][(two >> 8) & 0xFFu] ^
+                  sm.table[1][(two >> 16) & 0xFFu] ^ sm.table[0][two >> 24];
+          }
+          {  // byte 776 and three zero bytes
+            const uint32_t one = (uint32_t)c[776] ^ crc;
+            crc = sm.table[3][one & 0xFFu] ^ sm.table[2][(one >> 8) & 0xFFu] ^ sm.table[1][(one >> 16) & 0xFFu] ^
+                  sm.table[0][one >> 24];
+          }
           crc ^= 0xFFFFFFFFu;
           if (crc == ld32(c + kHqBytes - 4)) {
             st = kStOk | kStEmit;
@@ -697,7 +725,11 @@ __global__ void __launch_bounds__(HT) decode_hq_kernel(CapsuleDecodeArgs a) {
       for (uint32_t q = tid; q < n_nodes; q += HT) {
         const uint32_t e = q / 96u, pos = q - e * 96u;
         const uint8_t* p = sm.cap + sm.emit_list[e] * kHqBytes + 9 + 8 * pos;
-        o[q] = make_uint2(ld32(p), ld32(p + 4));
+        const uintptr_t pa = reinterpret_cast<uintptr_t>(p);
+        const uint32_t* pw = reinterpret_cast<const uint32_t*>(pa & ~uintptr_t(3));  // (w2 stays inside the capsule)
+        const uint32_t psh = (uint32_t)(pa & 3u) * 8u;
+        const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2];
+        o[q] = make_uint2(__funnelshift_r(w0, w1, psh), __funnelshift_r(w1, w2, psh));
       }
       __syncthreads();
       if (tid == 0) sm.carry_nodes += sm.tile_nodes;
@@ -713,7 +745,7 @@ __global__ void __launch_bounds__(HT) decode_hq_kernel(CapsuleDecodeArgs a) {
 
 // ---- standard nodes (handler_normalnode.cpp:88-141): 5-state byte machine ----------------------------
 constexpr int NT = 256;       // threads
-constexpr int kChunk = 20;    // bytes per thread per tile
+constexpr int kChunk = 30;    // bytes per thread per tile (a multiple of 5; the replay keeps one bit per byte in a u32)
 constexpr int kNormTile = NT * kChunk;
 struct NormalSmem {
   uint8_t bytes[4 + kNormTile + 12];  // 4 bytes of the previous tile in front
@@ -737,7 +769,7 @@ __device__ __forceinline__ uint32_t compose_map(uint32_t g, uint32_t f) {
 }
 
 __global__ void __launch_bounds__(NT) decode_normal_kernel(NormalDecodeArgs a) {
-  __shared__ NormalSmem sm;
+  __shared__ __align__(16) NormalSmem sm;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (uint32_t s = blockIdx.x; s < a.n_streams; s += gridDim.x) {
     const uint32_t n = a.byte_counts[s];
@@ -752,7 +784,20 @@ __global__ void __launch_bounds__(NT) decode_normal_kernel(NormalDecodeArgs a) {
     __syncthreads();
     for (uint32_t t0 = 0; t0 < n; t0 += kNormTile) {
       const uint32_t live = min((uint32_t)kNormTile, n - t0);
-      for (uint32_t i = tid; i < live; i += NT) sm.bytes[4 + i] = __ldg(src + t0 + i);
+      {  // stage the tile: 16-byte loads where the stream is aligned (tiles are multiples of 16 bytes long)
+        uint32_t done = 0;
+        if ((reinterpret_cast<uintptr_t>(src + t0) & 15u) == 0) {
+          const uint4* g4 = reinterpret_cast<const uint4*>(src + t0);
+          uint32_t* d32 = reinterpret_cast<uint32_t*>(sm.bytes + 4);
+          const uint32_t quads = live >> 4;
+          for (uint32_t q = tid; q < quads; q += NT) {
+            const uint4 v = __ldg(g4 + q);
+            d32[4 * q] = v.x; d32[4 * q + 1] = v.y; d32[4 * q + 2] = v.z; d32[4 * q + 3] = v.w;
+          }
+          done = quads << 4;
+        }
+        for (uint32_t i = done + tid; i < live; i += NT) sm.bytes[4 + i] = __ldg(src + t0 + i);
+      }
       __syncthreads();
       // ---- fast path: the tile is entered between records and holds only whole, well-formed records.
       // Then the byte machine accepts every record where it lies (state 0 -> 1 -> 2 -> 3 -> 4 -> 0), so
