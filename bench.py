@@ -123,8 +123,9 @@ def _parse_cpulist(text):
 
 def numa_pin(dev_index):
     """Bind this process (and so the pinned host buffers it allocates from now on: first touch, local policy) to the
-    CPUs of the NUMA node the GPU hangs off.  Returns a dict for the report; never raises.  Without it the ranks of
-    one socket's GPUs stream their pinned buffers across the inter-socket link (SCALE_r01: e2e efficiency 0.54)."""
+    CPUs of the NUMA node the GPU hangs off.  Returns a dict for the report; never raises.  (Keeps host traffic off
+    the inter-socket link.  It is not what bounds the e2e figure at N >= 4 on the HGX box: four GPUs behind one
+    socket share ~187 GB/s of DMA traffic however the buffers are placed -- DESIGN.md section 7.)"""
     info = {"pinned": False}
     try:
         import torch

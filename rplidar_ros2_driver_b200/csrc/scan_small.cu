@@ -356,17 +356,26 @@ __global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : 1)) scan_small_kern
 
     // ---- mark: one shared-memory atomicOr per kept key -----------------------------------------------
     uint32_t cnt = 0, fmin = 0xFFFFFFFFu;
-    if (!USE_V && !EMIT && !CLOUD && shift == 0) {
-      // Mode A only needs the number of measured nodes here: two nodes per 128-bit load
+    // Mode A (no bitmap of the measured keys) and the ascended-buffer variants (which mark the measured keys together
+    // with the final keys, below) only need the number of measured nodes and the first of them here: two nodes per
+    // 128-bit load
+    const bool light = (!USE_V || EMIT) && !CLOUD && shift == 0;
+    if (light) {
       const uint4* t4 = reinterpret_cast<const uint4*>(tile0);
 #pragma unroll 4
       for (uint32_t w = tid; w < n / 2; w += TS) {
         const uint4 v = t4[w];
-        cnt += (((v.x & 0xFFFF0000u) | (v.y & 0xFFFFu)) != 0u) + (((v.z & 0xFFFF0000u) | (v.w & 0xFFFFu)) != 0u);
+        const uint32_t m0 = (((v.x & 0xFFFF0000u) | (v.y & 0xFFFFu)) != 0u) ? 1u : 0u;
+        const uint32_t m1 = (((v.z & 0xFFFF0000u) | (v.w & 0xFFFFu)) != 0u) ? 1u : 0u;
+        cnt += m0 + m1;
+        if (EMIT && (m0 | m1)) fmin = min(fmin, 2u * w + (m0 ^ 1u));
       }
       if ((n & 1u) && tid == 0) {
         const uint2 v = tile0[n - 1];
-        cnt += ((v.x & 0xFFFF0000u) | (v.y & 0xFFFFu)) != 0u;
+        if (((v.x & 0xFFFF0000u) | (v.y & 0xFFFFu)) != 0u) {
+          ++cnt;
+          if (EMIT) fmin = min(fmin, n - 1u);
+        }
       }
     } else {
 #pragma unroll 4
@@ -435,6 +444,8 @@ __global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : 1)) scan_small_kern
           // reads every node's final key where it reads the node
           fk = (i == 0) ? front_key : ascend_fill_key(front_deg, i, step);
           tile0[shift + i].x = (nd.x & 0xFFFF0000u) | fk;
+        } else if (USE_V && light) {
+          atomicOr(&bitsV[fk >> 5], 1u << (fk & 31));  // (the light first pass marks nothing)
         }
         atomicOr(&bitsA[fk >> 5], 1u << (fk & 31));
       }
