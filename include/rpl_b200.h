@@ -39,7 +39,10 @@
  *
  * Buffer contract of the *_dev entry points: every count array entry must be <= its stride (counts are
  * read on the device and not clamped), device pointers must belong to the context's device, and work is
- * ordered on the stream passed in (NULL = the context's own stream).
+ * ordered on the stream passed in (NULL = the context's own stream).  The context's own stream is a non-blocking
+ * stream: it does not wait for work the caller has in flight on other streams (the legacy default stream included).
+ * A caller that fills its device buffers on a stream of its own either passes that stream, or synchronises before the
+ * call and calls rpl_ctx_synchronize before it reads the results.
  *
  * Tie rule.  The reference sorts with std::sort (unstable); on equal angle_z_q14 its order
  * is whatever libstdc++'s introsort produces.  This library defines the order: equal keys

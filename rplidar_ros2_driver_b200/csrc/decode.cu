@@ -237,31 +237,42 @@ __global__ void __launch_bounds__(DT) decode_dense_kernel(DecodeArgs a) {
         sm.red_sync = st2;
       }
       __syncthreads();
-      // ---- write the nodes: the tile's 40 * E nodes are one contiguous run of the output; thread q
-      // handles node q (capsule emit_list[q / 40], sample q % 40): every lane busy, 8 bytes per lane
+      // ---- write the nodes: the tile's 40 * E nodes are one contiguous run of the output; a thread handles a PAIR of
+      // samples (one 32-bit word of the capsule): the capsule look-ups are shared and the two nodes leave as one
+      // 16-byte store (a capsule's run starts on a multiple of 320 bytes)
       {
-        const uint32_t n_nodes = sm.tile_nodes;
+        const uint32_t n_pairs = sm.tile_nodes / 2u;
         uint2* o = out + sm.carry_nodes;
-        for (uint32_t q = tid; q < n_nodes; q += DT) {
-          const uint32_t e = q / 40u, pos = q - e * 40u;
-          const uint32_t j = sm.emit_list[e];
-          const uint32_t* pc = (j == 0) ? sm.carry : &tile[(j - 1) * kCapWords];  // the predecessor capsule
-          const int pq8 = (int)sm.start_q8[j];
-          const int inc = sm.inc_q16[j];
-          const uint32_t wq = pc[1 + (pos >> 1)];
-          const int dist = (int)((pos & 1u) ? (wq >> 16) : (wq & 0xFFFFu));
-          const int dist_q2 = dist << 2;
-          int angle_q6 = ((pq8 << 8) + (int)pos * inc) >> 10;
+        const bool wide = (reinterpret_cast<uintptr_t>(o) & 15u) == 0;
+        auto node_of = [](int angle_q6, int dist_q2, uint32_t syncb) {
           if (angle_q6 < 0) angle_q6 += (360 << 6);
           if (angle_q6 >= (360 << 6)) angle_q6 -= (360 << 6);
-          const uint32_t syncb = (uint32_t)(sm.smask[j] >> pos) & 1u;
-          const uint32_t key = (uint32_t)((angle_q6 << 8) / 90) & 0xFFFFu;
+          // (angle_q6 >= 0 here for every wire input: start angles are 15-bit q6 values and steps are >= -152 deg)
+          const uint32_t key = ((uint32_t)(angle_q6 << 8) / 90u) & 0xFFFFu;
           const uint32_t quality = dist_q2 ? (0x2Fu << 2) : 0u;
           const uint32_t flag = syncb | ((syncb ^ 1u) << 1);
           uint2 nd;
           nd.x = key | ((uint32_t)dist_q2 << 16);
           nd.y = ((uint32_t)dist_q2 >> 16) | (quality << 16) | (flag << 24);
-          o[q] = nd;
+          return nd;
+        };
+        for (uint32_t p = tid; p < n_pairs; p += DT) {
+          const uint32_t e = p / 20u, pp = p - e * 20u, pos = 2u * pp;
+          const uint32_t j = sm.emit_list[e];
+          const uint32_t* pc = (j == 0) ? sm.carry : &tile[(j - 1) * kCapWords];  // the predecessor capsule
+          const int pq8 = (int)sm.start_q8[j];
+          const int inc = sm.inc_q16[j];
+          const uint32_t wq = pc[1 + pp];
+          const uint32_t sy = (uint32_t)(sm.smask[j] >> pos) & 3u;
+          const int a0 = (pq8 << 8) + (int)pos * inc;
+          const uint2 na = node_of(a0 >> 10, (int)((wq & 0xFFFFu) << 2), sy & 1u);
+          const uint2 nb = node_of((a0 + inc) >> 10, (int)((wq >> 16) << 2), sy >> 1);
+          if (wide) {
+            *reinterpret_cast<uint4*>(o + 2u * p) = make_uint4(na.x, na.y, nb.x, nb.y);
+          } else {
+            o[2u * p] = na;
+            o[2u * p + 1u] = nb;
+          }
         }
       }
       __syncthreads();

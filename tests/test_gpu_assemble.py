@@ -64,6 +64,7 @@ def run_gpu(ctx, oracle, streams, max_nodes, max_scans, with_resets=True):
     sps = torch.zeros(S, dtype=torch.int32, device=dev)
     kw = dict(capsule_status=st.data_ptr(), capsule_node_offset=of.data_ptr(), capsule_counts=cc.data_ptr(),
               stride_capsules=cstride) if with_resets else {}
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.assemble_scans_dev(nodes.data_ptr(), counts.data_ptr(), S, stride, max_nodes, max_scans, max_nodes,
                            scans.data_ptr(), slen.data_ptr(), sps.data_ptr(), **kw)
     ctx.synchronize()
@@ -155,14 +156,17 @@ def test_decode_assemble_scan_chain_stays_on_the_device(R, oracle, ctx):
     intens = torch.full((NS, max_nodes), float("nan"), dtype=torch.float32, device=dev)
     beams = torch.zeros(NS, dtype=torch.int32, device=dev)
     inc = torch.zeros(NS, dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.decode_dense_batch_dev(caps.data_ptr(), ccounts.data_ptr(), n_streams, n_caps, 31, nodes.data_ptr(),
                                ncount.data_ptr(), capsule_status=status.data_ptr(),
                                capsule_node_offset=offs.data_ptr())
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.assemble_scans_dev(nodes.data_ptr(), ncount.data_ptr(), n_streams, n_caps * 40, max_nodes, max_scans,
                            max_nodes, scans.data_ptr(), slen.data_ptr(), sps.data_ptr(),
                            capsule_status=status.data_ptr(), capsule_node_offset=offs.data_ptr(),
                            capsule_counts=ccounts.data_ptr(), stride_capsules=n_caps)
     params = R.scan_params(1, 0, 0, 1)
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.scan_batch_dev(scans.data_ptr(), slen.data_ptr(), NS, max_nodes, params, ranges=ranges.data_ptr(),
                        intensities=intens.data_ptr(), beam_counts=beams.data_ptr(), angle_increment=inc.data_ptr())
     ctx.synchronize()
@@ -218,6 +222,7 @@ def test_scan_views_equal_the_copying_chain(R, oracle, max_nodes, mode_a, emit):
         starts_stride = 8 if view_mode == 2 else 64  # 8: the list of some streams overflows (fallback to the flag pass)
         starts = torch.zeros((n_streams, starts_stride), dtype=torch.int32, device=dev)
         scnt = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
         ctx.decode_dense_batch_dev(caps.data_ptr(), ccounts.data_ptr(), n_streams, n_caps, 31, nodes.data_ptr(),
                                    ncount.data_ptr(), capsule_status=status.data_ptr(),
                                    capsule_node_offset=offs.data_ptr(),
@@ -229,23 +234,28 @@ def test_scan_views_equal_the_copying_chain(R, oracle, max_nodes, mode_a, emit):
         if view_mode:
             views = torch.zeros((n_streams, max_scans, 2), dtype=torch.int32, device=dev)
             if view_mode >= 2:  # the decoder's scan-start list instead of the flag pass
+                torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
                 ctx.assemble_scan_views_starts_dev(nodes.data_ptr(), ncount.data_ptr(), n_streams, n_caps * 40,
                                                    starts.data_ptr(), starts_stride, scnt.data_ptr(), max_nodes, max_scans,
                                                    views.data_ptr(), slen.data_ptr(), sps.data_ptr(),
                                                    capsule_status=status.data_ptr(), capsule_node_offset=offs.data_ptr(),
                                                    capsule_counts=ccounts.data_ptr(), stride_capsules=n_caps)
             else:
+                torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
                 ctx.assemble_scan_views_dev(nodes.data_ptr(), ncount.data_ptr(), n_streams, n_caps * 40, max_nodes, max_scans,
                                             views.data_ptr(), slen.data_ptr(), sps.data_ptr(),
                                             capsule_status=status.data_ptr(), capsule_node_offset=offs.data_ptr(),
                                             capsule_counts=ccounts.data_ptr(), stride_capsules=n_caps)
+            torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
             ctx.scan_views_dev(nodes.data_ptr(), n_streams * n_caps * 40, views.data_ptr(), NS, max_nodes, params, **kw)
         else:
             scans = torch.zeros((n_streams, max_scans, max_nodes, 8), dtype=torch.uint8, device=dev)
+            torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
             ctx.assemble_scans_dev(nodes.data_ptr(), ncount.data_ptr(), n_streams, n_caps * 40, max_nodes, max_scans,
                                    max_nodes, scans.data_ptr(), slen.data_ptr(), sps.data_ptr(),
                                    capsule_status=status.data_ptr(), capsule_node_offset=offs.data_ptr(),
                                    capsule_counts=ccounts.data_ptr(), stride_capsules=n_caps)
+            torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
             ctx.scan_batch_dev(scans.data_ptr(), slen.data_ptr(), NS, max_nodes, params, **kw)
         ctx.synchronize()
         torch.cuda.synchronize()
@@ -342,6 +352,7 @@ def test_stateful_decode_and_assembly_alternate_on_one_context(R, oracle):
             ncount = torch.zeros(n_streams, dtype=torch.int32, device=dev)
             status = torch.zeros((n_streams, n_caps), dtype=torch.int32, device=dev)
             offs = torch.zeros((n_streams, n_caps), dtype=torch.int32, device=dev)
+            torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
             c.decode_capsules_batch_dev(0x85, caps.data_ptr(), counts.data_ptr(), n_streams, n_caps, 31, nodes.data_ptr(),
                                         ncount.data_ptr(), state_in=state.data_ptr(), capsule_status=status.data_ptr(),
                                         capsule_node_offset=offs.data_ptr(), state_out=state_out.data_ptr())
@@ -349,6 +360,7 @@ def test_stateful_decode_and_assembly_alternate_on_one_context(R, oracle):
             scans = torch.zeros((n_streams, max_scans, max_nodes, 8), dtype=torch.uint8, device=dev)
             slen = torch.zeros((n_streams, max_scans), dtype=torch.int32, device=dev)
             sps = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+            torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
             c.assemble_scans_dev(nodes.data_ptr(), ncount.data_ptr(), n_streams, n_caps * 40, max_nodes, max_scans, max_nodes,
                                  scans.data_ptr(), slen.data_ptr(), sps.data_ptr(), capsule_status=status.data_ptr(),
                                  capsule_node_offset=offs.data_ptr(), capsule_counts=counts.data_ptr(), stride_capsules=n_caps)

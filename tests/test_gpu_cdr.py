@@ -33,6 +33,7 @@ def test_laserscan_batch_from_the_scan_kernel(R, oracle, frame_id):
     beams = torch.zeros(S, dtype=torch.int32, device=dev)
     inc = torch.zeros(S, dtype=torch.float32, device=dev)
     params = R.scan_params(0, 0, 0, 1)
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.scan_batch_dev(nodes.data_ptr(), counts.data_ptr(), S, N, params, ranges=ranges.data_ptr(),
                        intensities=intens.data_ptr(), beam_counts=beams.data_ptr(), angle_increment=inc.data_ptr())
     meta_h = np.zeros(S, R.capi.LASERSCAN_META_DTYPE)
@@ -45,6 +46,7 @@ def test_laserscan_batch_from_the_scan_kernel(R, oracle, frame_id):
     cdr_stride = (R.lib().rpl_laserscan_cdr_size(len(frame_id), N) + 15) & ~15
     out = torch.full((S, cdr_stride), 0xEE, dtype=torch.uint8, device=dev)
     sizes = torch.zeros(S, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.laserscan_cdr_batch_dev(meta.data_ptr(), frame_id, ranges.data_ptr(), intens.data_ptr(), beams.data_ptr(), S, N,
                                 out.data_ptr(), cdr_stride, cdr_sizes=sizes.data_ptr(), angle_increment=inc.data_ptr())
     ctx.synchronize()
@@ -77,6 +79,7 @@ def test_pointcloud2_batch_from_the_cloud_path(R, oracle, frame_id):
     counts = torch.full((S,), N, dtype=torch.int32, device=dev)
     xyzi = torch.zeros((S, N, 4), dtype=torch.float32, device=dev)
     pcount = torch.zeros(S, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.cloud_batch_dev(nodes.data_ptr(), counts.data_ptr(), S, N, R.cloud_params(0.15, 30.0, 0.0, 0.0, 0, 0.0, 1),
                         xyzi.data_ptr(), pcount.data_ptr())
     stamps_h = np.stack([np.arange(S) + 100, np.arange(S) * 1000], axis=1).astype(np.uint32)
@@ -84,6 +87,7 @@ def test_pointcloud2_batch_from_the_cloud_path(R, oracle, frame_id):
     cdr_stride = (R.lib().rpl_pointcloud2_cdr_size(len(frame_id), N) + 15) & ~15
     out = torch.full((S, cdr_stride), 0xEE, dtype=torch.uint8, device=dev)
     sizes = torch.zeros(S, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.pointcloud2_cdr_batch_dev(stamps.data_ptr(), frame_id, xyzi.data_ptr(), pcount.data_ptr(), S, N,
                                   out.data_ptr(), cdr_stride, cdr_sizes=sizes.data_ptr())
     ctx.synchronize()
@@ -127,6 +131,7 @@ def test_device_writer_matches_the_hand_derived_bytes(R):
     cdr_stride = (R.lib().rpl_laserscan_cdr_size(len(g["frame_id"]), stride) + 15) & ~15
     out = torch.full((1, cdr_stride), 0xEE, dtype=torch.uint8, device=dev)
     sizes = torch.zeros(1, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.laserscan_cdr_batch_dev(meta.data_ptr(), g["frame_id"], ranges.data_ptr(), intens.data_ptr(), beams.data_ptr(), 1,
                                 stride, out.data_ptr(), cdr_stride, cdr_sizes=sizes.data_ptr())
     ctx.synchronize()
@@ -141,6 +146,7 @@ def test_device_writer_matches_the_hand_derived_bytes(R):
     stamps = torch.from_numpy(np.array([[g["sec"], g["nanosec"]]], np.uint32).view(np.int32)).to(dev)
     cdr_stride = (R.lib().rpl_pointcloud2_cdr_size(len(g["frame_id"]), stride) + 15) & ~15
     out = torch.full((1, cdr_stride), 0xEE, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.pointcloud2_cdr_batch_dev(stamps.data_ptr(), g["frame_id"], xyzi.data_ptr(), pcount.data_ptr(), 1, stride,
                                   out.data_ptr(), cdr_stride, cdr_sizes=sizes.data_ptr())
     ctx.synchronize()

@@ -135,7 +135,9 @@ def test_fuse_packs_per_scan_clouds(R, oracle, ctx):
     offs = torch.zeros(n_scans, dtype=torch.int32, device=dev)
     total = torch.zeros(1, dtype=torch.int32, device=dev)
     prm = R.cloud_params(range_min=0.15, range_max=40.0, voxel_size=0.05)
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.cloud_batch_dev(nodes.data_ptr(), counts.data_ptr(), n_scans, n, prm, xyzi.data_ptr(), pc.data_ptr())
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.cloud_fuse_dev(xyzi.data_ptr(), pc.data_ptr(), n_scans, n, fused.data_ptr(), offs.data_ptr(), total.data_ptr())
     ctx.synchronize()
     torch.cuda.synchronize()

@@ -89,6 +89,7 @@ def test_batched_streams_and_chain_into_the_scan_path(R, oracle, ctx):
     nodes = torch.zeros((n_streams, n_caps * 40, 8), dtype=torch.uint8, device=dev)
     ncount = torch.zeros(n_streams, dtype=torch.int32, device=dev)
     status = torch.zeros((n_streams, n_caps), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.decode_dense_batch_dev(caps.data_ptr(), counts.data_ptr(), n_streams, n_caps, 31, nodes.data_ptr(),
                                ncount.data_ptr(), capsule_status=status.data_ptr())
     ctx.synchronize()

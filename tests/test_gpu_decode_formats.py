@@ -154,6 +154,7 @@ def test_batched_ragged_streams(oracle, ctx, ans):
     ncount = torch.zeros(n_streams, dtype=torch.int32, device=dev)
     status = torch.zeros((n_streams, n_caps), dtype=torch.int32, device=dev)
     state_out = torch.zeros((n_streams, 2), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.decode_capsules_batch_dev(ans, caps.data_ptr(), counts.data_ptr(), n_streams, n_caps, 31, nodes.data_ptr(),
                                   ncount.data_ptr(), state_in=state.data_ptr(), capsule_status=status.data_ptr(),
                                   state_out=state_out.data_ptr())

@@ -32,6 +32,7 @@ def run_framer(R, ctx, ans, streams):
     caps = torch.full((n_streams, stride_caps, cb), 0xEE, dtype=torch.uint8, device=dev)
     ccount = torch.zeros(n_streams, dtype=torch.int32, device=dev)
     left = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.frame_capsules_dev(ans, raw.data_ptr(), counts.data_ptr(), n_streams, stride_bytes, caps.data_ptr(), stride_caps,
                            ccount.data_ptr(), bytes_left_out=left.data_ptr())
     ctx.synchronize()
@@ -82,6 +83,7 @@ def test_raw_bytes_to_nodes_on_the_device_equals_the_sdk(R, oracle, ans):
     per = oracle.capsule_nodes(ans)
     nodes = torch.zeros((len(streams), stride_caps * per, 8), dtype=torch.uint8, device=dev)
     ncount = torch.zeros(len(streams), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.decode_capsules_batch_dev(ans, caps.data_ptr(), ccount.data_ptr(), len(streams), stride_caps, 31, nodes.data_ptr(),
                                   ncount.data_ptr())
     ctx.synchronize()

@@ -219,6 +219,7 @@ def test_device_synth_equals_oracle_synth(R, oracle, ctx, variant):
     for n in (1, 7, 360, 3200, 32768):
         t = torch.zeros((3, n, 8), dtype=torch.uint8, device="cuda")
         cnt = torch.zeros(3, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
         ctx.synth_batch_dev(11 + variant, 3, n, n, variant, t.data_ptr(), cnt.data_ptr())
         ctx.synchronize()
         torch.cuda.synchronize()
@@ -243,7 +244,9 @@ def test_full_size_batch_properties(R, oracle):
     inc = torch.empty(S, dtype=torch.float32, device=dev)
     status = torch.empty(S, dtype=torch.int32, device=dev)
     path = torch.empty(S, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.synth_batch_dev(0, S, N, N, 1, nodes.data_ptr(), counts.data_ptr())
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.scan_batch_dev(nodes.data_ptr(), counts.data_ptr(), S, N, R.scan_params(0, 0, 0, 1), ranges=ranges.data_ptr(),
                        intensities=intens.data_ptr(), beam_counts=beams.data_ptr(), angle_increment=inc.data_ptr(),
                        status=status.data_ptr(), path=path.data_ptr())

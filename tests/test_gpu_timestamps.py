@@ -56,11 +56,14 @@ def test_capsule_streams_decode_stamp_assemble(R, oracle, ctx, ans):
         slen = torch.zeros((n_streams, max_scans), dtype=torch.int32, device=dev)
         sps = torch.zeros(n_streams, dtype=torch.int32, device=dev)
         sts = torch.zeros((n_streams, max_scans), dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
         ctx.decode_capsules_batch_dev(ans, caps.data_ptr(), counts.data_ptr(), n_streams, n_caps, timing[0],
                                       nodes.data_ptr(), ncount.data_ptr(), capsule_status=status.data_ptr(),
                                       capsule_node_offset=offs.data_ptr())
+        torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
         ctx.node_timestamps_dev(ans, t, rx.data_ptr(), status.data_ptr(), offs.data_ptr(), counts.data_ptr(),
                                 n_streams, n_caps, ts.data_ptr())
+        torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
         ctx.assemble_scans_dev(nodes.data_ptr(), ncount.data_ptr(), n_streams, n_caps * per, max_nodes, max_scans,
                                max_nodes, scans.data_ptr(), slen.data_ptr(), sps.data_ptr(),
                                capsule_status=status.data_ptr(), capsule_node_offset=offs.data_ptr(),
@@ -116,8 +119,10 @@ def test_standard_node_stamps(R, oracle, ctx):
     rx = torch.from_numpy(rx_h.view(np.int64)).to(dev)
     ts = torch.zeros((n_streams, stride // 5), dtype=torch.int64, device=dev)
     timing = TIMINGS[3]
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.decode_normal_batch_dev(wire.data_ptr(), counts.data_ptr(), n_streams, stride, nodes.data_ptr(),
                                 ncount.data_ptr(), node_end=ends.data_ptr())
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.normal_timestamps_dev(R.Timing(*timing), ends.data_ptr(), ncount.data_ptr(), n_streams, stride // 5, chunk,
                               rx.data_ptr(), n_chunks, ts.data_ptr())
     ctx.synchronize()

@@ -32,8 +32,10 @@ def test_device_chain_reproduces_the_captured_reference_outputs(oracle, golden_d
         ncount = torch.zeros(1, dtype=torch.int32, device=dev)
         ends = torch.zeros(n_slots, dtype=torch.int32, device=dev)
         ts = torch.zeros(n_slots, dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
         ctx.decode_normal_batch_dev(wire_d.data_ptr(), counts.data_ptr(), 1, len(wire), nodes.data_ptr(),
                                     ncount.data_ptr(), node_end=ends.data_ptr())
+        torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
         ctx.normal_timestamps_dev(timing, ends.data_ptr(), ncount.data_ptr(), 1, n_slots, 64, rx.data_ptr(), len(rx_h),
                                   ts.data_ptr())
         kw = {}
@@ -48,9 +50,11 @@ def test_device_chain_reproduces_the_captured_reference_outputs(oracle, golden_d
         status = torch.zeros(n_caps, dtype=torch.int32, device=dev)
         offs = torch.zeros(n_caps, dtype=torch.int32, device=dev)
         ts = torch.zeros(n_slots, dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
         ctx.decode_capsules_batch_dev(ans, wire_d.data_ptr(), counts.data_ptr(), 1, n_caps, int(t4[0]),
                                       nodes.data_ptr(), ncount.data_ptr(), capsule_status=status.data_ptr(),
                                       capsule_node_offset=offs.data_ptr())
+        torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
         ctx.node_timestamps_dev(ans, timing, rx.data_ptr(), status.data_ptr(), offs.data_ptr(), counts.data_ptr(), 1,
                                 n_caps, ts.data_ptr())
         kw = dict(capsule_status=status.data_ptr(), capsule_node_offset=offs.data_ptr(),
@@ -60,6 +64,7 @@ def test_device_chain_reproduces_the_captured_reference_outputs(oracle, golden_d
     slen = torch.zeros(max_scans, dtype=torch.int32, device=dev)
     sps = torch.zeros(1, dtype=torch.int32, device=dev)
     sts = torch.zeros(max_scans, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()  # buffers were filled on torch's stream; the library runs on its own
     ctx.assemble_scans_dev(nodes.data_ptr(), ncount.data_ptr(), 1, stride_nodes, cap, max_scans, cap, scans.data_ptr(),
                            slen.data_ptr(), sps.data_ptr(), node_ts_us=ts.data_ptr(), scan_begin_ts_us=sts.data_ptr(),
                            **kw)
