@@ -11,9 +11,10 @@
 //
 // Capsule formats share one skeleton (one CTA per stream, tiles of 256 capsules staged through shared
 // memory, one thread per capsule for frame / checksum / "does this capsule release its predecessor",
-// an exclusive block scan for the node offsets, then node-parallel emission so that every lane
-// writes one 8-byte node of a contiguous run).  What differs is the per-node arithmetic and the
-// state that crosses capsules:
+// an exclusive block scan for the node offsets, then emission in the format's own grain -- a thread per
+// 5-byte cabin (two samples, one 16-byte store) for express, a warp per capsule with a lane per cabin
+// for ultra (3 samples) and ultra-dense (2 samples) -- into one contiguous run of the output).  What
+// differs besides is the state that crosses capsules:
 //   * express / ultra: none (the scan-start flag of a node is a function of its angle only);
 //   * ultra-dense: the last node's scan-start flag (a 2-bit transfer function per capsule, scanned
 //     under composition, as in decode.cu) and `_last_dist_q2`, a smoothing recurrence over
@@ -82,81 +83,44 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 }
 
 // ---- express (handler_capsules.cpp:206-266) ---------------------------------------------------------
-__device__ __forceinline__ uint2 node_express(const uint8_t* prev, int prev_q8, int diff_q8, uint32_t pos) {
+// both samples of one 5-byte cabin: angle interpolation in q16, per-sample offset (6 bits: 4 from the shared byte, 2 from
+// the distance word), scan start = the interpolated angle wraps within this sample's step
+__device__ __forceinline__ void cabin_express(const uint8_t* prev, int prev_q8, int diff_q8, uint32_t cabin, uint2& na,
+                                              uint2& nb) {
   const int inc = diff_q8 << 3;
-  const int a = (prev_q8 << 8) + (int)pos * inc;
-  const uint8_t* cab = prev + 4 + 5 * (pos >> 1);
-  const uint32_t da = ld16(cab + 2 * (pos & 1u));
-  const uint32_t ob = cab[4];
-  const int off_q3 = (int)(((pos & 1u) ? (ob >> 4) : (ob & 0xFu)) | ((da & 3u) << 4));
-  const uint32_t dist_q2 = da & 0xFFFCu;
-  const int angle_q6 = (a - (off_q3 << 13)) >> 10;
-  const uint32_t sync = (((a + inc) % kFull) < inc) ? 1u : 0u;
-  return pack_node(angle_q6, dist_q2, sync, dist_q2 ? (0x2Fu << 2) : 0u);
+  const int a0 = (prev_q8 << 8) + (int)(2u * cabin) * inc, a1 = a0 + inc;
+  const uint8_t* cab = prev + 4 + 5 * cabin;
+  const uint32_t d0 = ld16(cab), d1 = ld16(cab + 2), ob = cab[4];
+  const int off0 = (int)((ob & 0xFu) | ((d0 & 3u) << 4)), off1 = (int)((ob >> 4) | ((d1 & 3u) << 4));
+  int rem = a1 % kFull;  // (a0 + inc) % full
+  const uint32_t sync0 = (rem < inc) ? 1u : 0u;
+  if (inc >= 0 && inc < kFull) {
+    rem += inc;
+    if (rem >= kFull) rem -= kFull;
+  } else {
+    rem = (a1 + inc) % kFull;
+  }
+  const uint32_t sync1 = (rem < inc) ? 1u : 0u;
+  const uint32_t q0 = d0 & 0xFFFCu, q1 = d1 & 0xFFFCu;
+  na = pack_node((a0 - (off0 << 13)) >> 10, q0, sync0, q0 ? (0x2Fu << 2) : 0u);
+  nb = pack_node((a1 - (off1 << 13)) >> 10, q1, sync1, q1 ? (0x2Fu << 2) : 0u);
 }
 
 // ---- ultra (handler_capsules.cpp:422-580) --------------------------------------------------------------
 __device__ int g_ultra_offset[493];  // read through L1 (divergent index: not constant memory)
-
-__device__ __forceinline__ uint32_t varbitscale(uint32_t scaled, uint32_t& level) {
-  if (scaled >= 3328u) { level = 4; return (1u << 14) + ((scaled - 3328u) << 4); }
-  if (scaled >= 1792u) { level = 3; return (1u << 12) + ((scaled - 1792u) << 3); }
-  if (scaled >= 1280u) { level = 2; return (1u << 11) + ((scaled - 1280u) << 2); }
-  if (scaled >= 512u) { level = 1; return (1u << 9) + ((scaled - 512u) << 1); }
-  level = 0;
-  return scaled;
-}
-__device__ __forceinline__ uint2 node_ultra(const uint8_t* prev, const uint8_t* cur, int prev_q8, int diff_q8,
-                                            uint32_t pos) {
-  const int inc = (diff_q8 << 3) / 3;
-  const int a = (prev_q8 << 8) + (int)pos * inc;
-  const uint32_t cabin = pos / 3u, c = pos - cabin * 3u;
-  const uint32_t x3 = ld32(prev + 4 + 4 * cabin);
-  const uint32_t nx = (cabin == 31u) ? ld32(cur + 4) : ld32(prev + 8 + 4 * cabin);
-  uint32_t lvl1 = 0, lvl2 = 0;
-  const int major = (int)varbitscale(x3 & 0xFFFu, lvl1);
-  const int major2 = (int)varbitscale(nx & 0xFFFu, lvl2);
-  int base1 = major;
-  if (!major && major2) {
-    base1 = major2;
-    lvl1 = lvl2;
-  }
-  int dist_q2;
-  if (c == 0) {
-    dist_q2 = major << 2;
-  } else {
-    const int predict = (c == 1) ? ((int)(x3 << 10) >> 22) : ((int)x3 >> 22);
-    if ((uint32_t)predict == 0xFFFFFE00u || (uint32_t)predict == 0x1FFu) {
-      dist_q2 = 0;
-    } else {
-      const uint32_t lvl = (c == 1) ? lvl1 : lvl2;
-      const int base = (c == 1) ? base1 : major2;
-      dist_q2 = (int)(((uint32_t)predict << lvl) + (uint32_t)base) << 2;
-    }
-  }
-  const uint32_t sync = (((a + inc) % kFull) < inc) ? 1u : 0u;
-  // the angle correction int(off_q16 * 180 / 3.14159265) depends on the distance only through
-  // k2 = 98361 / dist_q2 in [0, 491] (dist_q2 >= 200): a 493-entry table built on the host with the
-  // reference's own double arithmetic (entry 492 = the short-range default)
-  // 98361 / dist_q2 (<= 491) without the integer division: float quotient, then an exact +-1 correction
-  uint32_t k2 = 492u;
-  if (dist_q2 >= 200) {
-    const uint32_t d = (uint32_t)dist_q2;
-    k2 = __float2uint_rz(__fdividef(98361.0f, __uint2float_rn(d)));
-    if (k2 * d > 98361u) --k2;
-    else if ((k2 + 1u) * d <= 98361u) ++k2;
-  }
-  const int off_deg_q16 = __ldg(&g_ultra_offset[k2]);
-  const int angle_q6 = (a - off_deg_q16) >> 10;
-  return pack_node(angle_q6, (uint32_t)dist_q2, sync, dist_q2 ? (0x2Fu << 2) : 0u);
-}
 
 // One warp per released capsule, one lane per cabin (3 nodes): the two cabin words (aligned 32-bit loads: capsules
 // are 132 bytes and tiles 16-byte aligned), both variable-bit-scale expansions and the base/level selection are done
 // once per cabin instead of once per node; the scan-start test needs one modulo per cabin (the other two remainders
 // follow by addition whenever the angle step is in [0, 360 deg)); the 493-entry angle-correction table is read from
 // shared memory.  The three nodes of a lane go through a per-warp staging area so that the warp stores its 96 nodes
-// as three fully coalesced 256-byte rows.  Same arithmetic as node_ultra() (kept as the definition).
+// as three fully coalesced 256-byte rows.
+// Per cabin (handler_capsules.cpp:470-540): major = varbitscale(x3 & 0xFFF), the next cabin's major2 likewise; the
+// two predictions are the signed 10-bit fields of x3 (-512 and 511 mean "no measurement"); sample 0 is major,
+// sample 1 = predict1 << level1 + base1 (base1/level1 fall back to the next cabin's when major is 0), sample 2 =
+// predict2 << level2 + major2; all << 2.  The angle correction depends on the distance only through
+// k2 = 98361 / dist_q2 in [0, 491] (dist_q2 >= 200): a 493-entry table built on the host with the reference's own
+// double arithmetic (entry 492 = the short-range default).
 __device__ __forceinline__ uint32_t varbitscale_sel(uint32_t s, uint32_t& level) {
   // segment of s (< 4096): the bounds 512, 1280, 1792, 3328 are multiples of 256 -> 16 nibbles indexed by s >> 8
   const uint32_t l = (uint32_t)(0x4443333332211100ull >> (4u * (s >> 8))) & 0xFu;
@@ -564,31 +528,27 @@ __global__ void __launch_bounds__(DT) decode_capsule_kernel(CapsuleDecodeArgs a)
             dst[1] = nb;
           }
         }
-      } else {
-        const uint32_t n_nodes = sm.tile_nodes;
+      } else if constexpr (F == kExpress) {
+        // a thread handles one 5-byte cabin (two samples): the capsule look-ups and the cabin bytes are shared and
+        // the two nodes leave as one 16-byte store (a capsule's run starts on a multiple of 256 bytes)
+        const uint32_t n_pairs = sm.tile_nodes / 2u;
         uint2* o = out + sm.carry_nodes;
-        for (uint32_t q = tid; q < n_nodes; q += DT) {
-          const uint32_t e = q / (uint32_t)NODES, pos = q - e * (uint32_t)NODES;
+        const bool wide = (reinterpret_cast<uintptr_t>(o) & 15u) == 0;
+        for (uint32_t p = tid; p < n_pairs; p += DT) {
+          const uint32_t e = p >> 4, cabin = p & 15u;
           const uint32_t j = sm.emit_list[e];
           const uint8_t* pc = (j == 0) ? sm.carry : tile + (j - 1) * CB;
           const int pq8 = (int)sm.start_q8[j];
           int d = (int)sm.start_q8[j + 1] - pq8;
           if (pq8 > (int)sm.start_q8[j + 1]) d += (360 << 8);
-          uint2 nd;
-          if constexpr (F == kExpress) {
-            nd = node_express(pc, pq8, d, pos);
-          } else if constexpr (F == kUltra) {
-            nd = node_ultra(pc, tile + j * CB, pq8, d, pos);
+          uint2 na, nb;
+          cabin_express(pc, pq8, d, cabin, na, nb);
+          if (wide) {
+            *reinterpret_cast<uint4*>(o + 2u * p) = make_uint4(na.x, na.y, nb.x, nb.y);
           } else {
-            const int inc = (d << 8) / 64;
-            const int ang = (pq8 << 8) + (int)pos * inc;
-            uint32_t sc, quality;
-            int dist = ud_sample(pc, pos, sc, quality);
-            if (sc == 0) dist = (int)sm.ud_dist[j][pos];
-            const uint32_t syncb = (uint32_t)(sm.smask[j] >> pos) & 1u;
-            nd = pack_node(ang >> 10, (uint32_t)dist, syncb, quality);
+            o[2u * p] = na;
+            o[2u * p + 1u] = nb;
           }
-          o[q] = nd;
         }
       }
       __syncthreads();
