@@ -400,16 +400,22 @@ __global__ void __launch_bounds__(DT) decode_capsule_kernel(CapsuleDecodeArgs a)
         // ---- smoothing chain, step 1: the nine outcomes of this capsule's 64 samples ------------------
         if (emit) {
           const uint8_t* pc = (tid == 0) ? sm.carry : tile + (tid - 1) * CB;
-          // cabin by cabin (5 bytes = two samples): the shared byte is loaded once and the two smoothed values are
-          // stored as one word.  Values stored for positions before the merge point are placeholders: step 3
-          // rewrites exactly those.
+          uint32_t sc, q;
+          const int r0 = ud_sample(pc, 0, sc, q);
+          const uint32_t sc_first = sc;
           int cand[9];
-          bool merged = false;
-          int r0 = 0;
-          uint32_t sc_first = 0;
-          auto feed = [&](int r, uint32_t sc, uint32_t pos) -> int {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) cand[k] = (sc == 0) ? (r0 - 4 + k) : r0;
+          bool merged = (sc != 0);
+          if (merged) {
+            ud_pm = 0;
+            sm.ud_dist[tid][0] = (uint16_t)r0;
+          }
+          for (uint32_t pos = 1; pos < 64; ++pos) {
+            const int r = ud_sample(pc, pos, sc, q);
             if (merged) {
               cand[0] = ud_smooth(r, sc, cand[0]);
+              sm.ud_dist[tid][pos] = (uint16_t)cand[0];  // only read back for scale-0 samples (< 8192)
             } else {
               int lo = 0x7fffffff, hi = -0x7fffffff;
 #pragma unroll
@@ -419,31 +425,11 @@ __global__ void __launch_bounds__(DT) decode_capsule_kernel(CapsuleDecodeArgs a)
                 hi = max(hi, cand[k]);
               }
               merged = (lo == hi);
-              if (merged) ud_pm = pos;
+              if (merged) {
+                ud_pm = pos;
+                sm.ud_dist[tid][pos] = (uint16_t)cand[0];
+              }
             }
-            return cand[0];
-          };
-          uint32_t* row = reinterpret_cast<uint32_t*>(&sm.ud_dist[tid][0]);
-          for (uint32_t c = 0; c < 32; ++c) {
-            const uint8_t* cab = pc + 10 + 5 * c;
-            const uint32_t hb = cab[4];
-            const uint32_t qa = ld16(cab) | ((hb & 0xFu) << 16), qb = ld16(cab + 2) | ((hb >> 4) << 16);
-            uint32_t sa, sb, qq;
-            const int ra = ud_decode(qa, sa, qq), rb = ud_decode(qb, sb, qq);
-            int va;
-            if (c == 0) {  // the first sample either ignores the incoming value or averages with one of 17 neighbours
-              r0 = ra;
-              sc_first = sa;
-#pragma unroll
-              for (int k = 0; k < 9; ++k) cand[k] = (sa == 0) ? (ra - 4 + k) : ra;
-              merged = (sa != 0);
-              if (merged) ud_pm = 0;
-              va = ra;
-            } else {
-              va = feed(ra, sa, 2 * c);
-            }
-            const int vb = feed(rb, sb, 2 * c + 1);
-            row[c] = ((uint32_t)va & 0xFFFFu) | ((uint32_t)vb << 16);  // only read back for scale-0 samples (< 8192)
           }
 #pragma unroll
           for (int k = 0; k < 9; ++k) sm.ud_out[tid][k] = (uint32_t)(merged ? cand[0] : cand[k]);
