@@ -574,13 +574,25 @@ __global__ void __launch_bounds__(DT) decode_capsule_kernel(CapsuleDecodeArgs a)
 }
 
 // ---- HQ capsules (handler_hqnode.cpp:93-172): CRC32 + pass-through -----------------------------------
-constexpr int HT = 128;         // threads = capsules per tile
+// The CRC (reflected 0x04C11DB7 over the 777 message bytes + the SDK's zero padding to 780, sl_crc.cpp:52-69) is a
+// chain of dependent table look-ups.  Two things shorten it: eight bytes per step (slicing-by-8: eight independent
+// look-ups + one XOR tree), and FOUR threads per capsule -- the register of a table-driven CRC is linear in (state,
+// message), so  raw(s, A || B) = advance_|B|(raw(s, A)) ^ raw(0, B):  the threads take the byte ranges [0,192),
+// [192,384), [384,576), [576,780), the first with the initial value 0xFFFFFFFF and the others with 0, and one of them
+// combines  advance_204(advance_192(advance_192(r0) ^ r1) ^ r2) ^ r3.  "Advance by N zero bytes" is four look-ups in
+// a 4 x 256 table per N, built on the host (hq_tables_init).  A capsule starts at any byte offset (781 bytes apart):
+// message words come from aligned words by funnel shift.
+constexpr int HC = 64;          // capsules per tile
+constexpr int HT = 4 * HC;      // threads: four per capsule
 constexpr int kHqBytes = 781;   // 1 sync + 8 timestamp + 96 * 8 nodes + 4 crc
+__device__ uint32_t g_hq_advance[2][4][256];  // [0]: 192 zero bytes, [1]: 204
 struct HqSmem {
-  uint8_t cap[(HT * kHqBytes + 15) & ~15];
-  uint32_t table[8][256];  // slicing-by-8: table[k][b] = CRC of byte b followed by k zero bytes
-  uint32_t emit_list[HT];
-  uint32_t warp_a[HT / 32];
+  uint8_t cap[(HC * kHqBytes + 15) & ~15];
+  uint32_t table[8][256];    // slicing-by-8: table[k][b] = CRC register after byte b and k zero bytes
+  uint32_t advance[2][4][256];
+  uint32_t emit_list[HC];
+  uint32_t status[HC], emit[HC];
+  uint32_t warp_a[HC / 32];
   uint32_t carry_nodes, tile_nodes;
 };
 
@@ -588,12 +600,13 @@ __global__ void __launch_bounds__(HT) decode_hq_kernel(CapsuleDecodeArgs a) {
   extern __shared__ __align__(16) unsigned char capsule_smem_raw[];
   HqSmem& sm = *reinterpret_cast<HqSmem*>(capsule_smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (uint32_t i = tid; i < 256; i += HT) {  // reflected 0x04C11DB7 (sl_crc.cpp:52-69)
+  for (uint32_t i = tid; i < 256; i += HT) {
     uint32_t c = i;
 #pragma unroll
     for (int j = 0; j < 8; ++j) c = (c & 1u) ? (0xEDB88320u ^ (c >> 1)) : (c >> 1);
     sm.table[0][i] = c;
   }
+  for (uint32_t i = tid; i < 2 * 4 * 256; i += HT) (&sm.advance[0][0][0])[i] = (&g_hq_advance[0][0][0])[i];
   __syncthreads();
   for (uint32_t i = tid; i < 256; i += HT) {
     uint32_t c = sm.table[0][i];
@@ -604,6 +617,10 @@ __global__ void __launch_bounds__(HT) decode_hq_kernel(CapsuleDecodeArgs a) {
     }
   }
   __syncthreads();
+  auto advance = [&](uint32_t which, uint32_t v) {
+    return sm.advance[which][0][v & 0xFFu] ^ sm.advance[which][1][(v >> 8) & 0xFFu] ^ sm.advance[which][2][(v >> 16) & 0xFFu] ^
+           sm.advance[which][3][v >> 24];
+  };
   for (uint32_t s = blockIdx.x; s < a.n_streams; s += gridDim.x) {
     const uint32_t n = a.counts[s];
     const uint8_t* src = a.capsules + (size_t)s * a.stride_capsules * kHqBytes;
@@ -612,8 +629,8 @@ __global__ void __launch_bounds__(HT) decode_hq_kernel(CapsuleDecodeArgs a) {
     uint32_t* off_out = a.capsule_node_offset ? a.capsule_node_offset + (size_t)s * a.stride_capsules : nullptr;
     if (tid == 0) sm.carry_nodes = 0;
     __syncthreads();
-    for (uint32_t c0 = 0; c0 < n; c0 += HT) {
-      const uint32_t live = min((uint32_t)HT, n - c0);
+    for (uint32_t c0 = 0; c0 < n; c0 += HC) {
+      const uint32_t live = min((uint32_t)HC, n - c0);
       const uint32_t bytes = live * kHqBytes;
       const uint8_t* g = src + (size_t)c0 * kHqBytes;
       uint32_t done = 0;
@@ -626,22 +643,22 @@ __global__ void __launch_bounds__(HT) decode_hq_kernel(CapsuleDecodeArgs a) {
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();
-      uint32_t st = 0, emit = 0;
-      if (tid < live) {
-        const uint8_t* c = sm.cap + tid * kHqBytes;
-        if (c[0] != 0xA5) {
-          st = kStBadFrame;
-        } else {
-          // 777 message bytes + the SDK's zero padding to 780.  One thread per capsule is a chain of dependent table
-          // look-ups; eight bytes per step (slicing-by-8: eight independent look-ups, one XOR tree) shorten it
-          // eightfold.  The capsule starts at any byte offset: message words come from aligned words by funnel shift.
-          uint32_t crc = 0xFFFFFFFFu;
-          const uintptr_t addr = reinterpret_cast<uintptr_t>(c);
+      // ---- CRC: thread (capsule cj, range seg) ---------------------------------------------------------------
+      const uint32_t cj = tid >> 2, seg = tid & 3u;
+      const uint8_t* c = sm.cap + cj * kHqBytes;
+      uint32_t part = 0;
+      bool framed = false;
+      if (cj < live) {
+        framed = (c[0] == 0xA5);
+        if (framed) {
+          uint32_t crc = (seg == 0) ? 0xFFFFFFFFu : 0u;
+          const uintptr_t addr = reinterpret_cast<uintptr_t>(c + 192u * seg);
           const uint32_t* w = reinterpret_cast<const uint32_t*>(addr & ~uintptr_t(3));
           const uint32_t sh = (uint32_t)(addr & 3u) * 8u;
+          const int steps = (seg == 3) ? 25 : 24;  // 8 bytes each: 192 bytes, the last range 200 + the tail below
           uint32_t w0 = w[0];
 #pragma unroll 2
-          for (int k = 0; k < 97; ++k) {  // 97 * 8 = 776 bytes
+          for (int k = 0; k < steps; ++k) {
             const uint32_t w1 = w[2 * k + 1], w2 = w[2 * k + 2];
             const uint32_t one = __funnelshift_r(w0, w1, sh) ^ crc, two = __funnelshift_r(w1, w2, sh);
             w0 = w2;
@@ -649,11 +666,24 @@ __global__ void __launch_bounds__(HT) decode_hq_kernel(CapsuleDecodeArgs a) {
                   sm.table[4][one >> 24] ^ sm.table[3][two & 0xFFu] ^ sm.table[2][(two >> 8) & 0xFFu] ^
                   sm.table[1][(two >> 16) & 0xFFu] ^ sm.table[0][two >> 24];
           }
-          {  // byte 776 and three zero bytes
+          if (seg == 3) {  // byte 776 and three zero bytes
             const uint32_t one = (uint32_t)c[776] ^ crc;
             crc = sm.table[3][one & 0xFFu] ^ sm.table[2][(one >> 8) & 0xFFu] ^ sm.table[1][(one >> 16) & 0xFFu] ^
                   sm.table[0][one >> 24];
           }
+          part = crc;
+        }
+      }
+      // the four ranges of a capsule sit in neighbouring lanes
+      const uint32_t l0 = lane & ~3u;
+      const uint32_t r1 = __shfl_sync(0xffffffffu, part, l0 + 1), r2 = __shfl_sync(0xffffffffu, part, l0 + 2),
+                     r3 = __shfl_sync(0xffffffffu, part, l0 + 3);
+      if (seg == 0 && cj < live) {
+        uint32_t st = kStBadFrame, emit = 0;
+        if (framed) {
+          uint32_t crc = advance(0, part) ^ r1;
+          crc = advance(0, crc) ^ r2;
+          crc = advance(1, crc) ^ r3;
           crc ^= 0xFFFFFFFFu;
           if (crc == ld32(c + kHqBytes - 4)) {
             st = kStOk | kStEmit;
@@ -662,22 +692,28 @@ __global__ void __launch_bounds__(HT) decode_hq_kernel(CapsuleDecodeArgs a) {
             st = kStChecksum;
           }
         }
+        sm.status[cj] = st;
+        sm.emit[cj] = emit;
       }
-      const uint32_t inc_scan = warp_inclusive_scan(emit);
-      if (lane == 31) sm.warp_a[warp] = inc_scan;
       __syncthreads();
-      uint32_t base_off = 0;
-      for (uint32_t w = 0; w < warp; ++w) base_off += sm.warp_a[w];
-      const uint32_t my_off = base_off + inc_scan - emit;
-      if (tid < live) {
-        if (emit) sm.emit_list[my_off] = tid;
-        if (st_out) st_out[c0 + tid] = st;
-        if (off_out) off_out[c0 + tid] = sm.carry_nodes + 96u * my_off;
+      // ---- node offsets: exclusive scan of the release flags over the tile's capsules (the first two warps) ----
+      uint32_t emit = 0, inc_scan = 0;
+      if (tid < HC) {
+        emit = (tid < live) ? sm.emit[tid] : 0u;
+        inc_scan = warp_inclusive_scan(emit);
+        if (lane == 31) sm.warp_a[warp] = inc_scan;
       }
-      if (tid == HT - 1) {
-        uint32_t tot = 0;
-        for (uint32_t w = 0; w < HT / 32; ++w) tot += sm.warp_a[w];
-        sm.tile_nodes = 96u * tot;
+      __syncthreads();
+      if (tid < HC) {
+        uint32_t base_off = 0;
+        for (uint32_t w = 0; w < warp; ++w) base_off += sm.warp_a[w];
+        const uint32_t my_off = base_off + inc_scan - emit;
+        if (tid < live) {
+          if (emit) sm.emit_list[my_off] = tid;
+          if (st_out) st_out[c0 + tid] = sm.status[tid];
+          if (off_out) off_out[c0 + tid] = sm.carry_nodes + 96u * my_off;
+        }
+        if (tid == HC - 1) sm.tile_nodes = 96u * (base_off + inc_scan);
       }
       __syncthreads();
       const uint32_t n_nodes = sm.tile_nodes;
@@ -904,6 +940,25 @@ cudaError_t decode_formats_configure() {
     const int off_default = (int)(7.5 * 3.1415926535 * (1 << 16) / 180.0);
     table[492] = int(off_default * 180 / 3.14159265);
     e = cudaMemcpyToSymbol(g_ultra_offset, table, sizeof(table));
+    if (e != cudaSuccess) return e;
+  }
+  {  // HQ: "advance the CRC register by N zero bytes" as 4 x 256 tables, N = 192 and 204 (decode_hq_kernel)
+    static uint32_t t0[256];
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int j = 0; j < 8; ++j) c = (c & 1u) ? (0xEDB88320u ^ (c >> 1)) : (c >> 1);
+      t0[i] = c;
+    }
+    static uint32_t adv[2][4][256];
+    const int nbytes[2] = {192, 204};
+    for (int w = 0; w < 2; ++w)
+      for (int k = 0; k < 4; ++k)
+        for (uint32_t b = 0; b < 256; ++b) {
+          uint32_t v = b << (8 * k);
+          for (int i = 0; i < nbytes[w]; ++i) v = (v >> 8) ^ t0[v & 0xFFu];
+          adv[w][k][b] = v;
+        }
+    e = cudaMemcpyToSymbol(g_hq_advance, adv, sizeof(adv));
     if (e != cudaSuccess) return e;
   }
   e = cudaFuncSetAttribute(decode_capsule_kernel<kExpress>, cudaFuncAttributeMaxDynamicSharedMemorySize,
