@@ -34,7 +34,8 @@ namespace rpl {
 
 namespace {
 
-constexpr int DT = 256;  // threads = capsules per tile
+// threads = capsules per tile: Fmt<F>::DT (smaller tiles where the per-capsule state is large: more CTAs per SM, so a
+// few hundred streams are all in flight at once instead of queueing for a second wave)
 constexpr uint32_t kStOk = 1, kStSync = 2, kStEmit = 4, kStDiscard = 8, kStChecksum = 16, kStEncReset = 32,
                    kStBadFrame = 64;
 constexpr int kFull = 360 << 16;
@@ -45,19 +46,19 @@ template <int F>
 struct Fmt;
 template <>
 struct Fmt<kExpress> {
-  static constexpr int CB = 84, NODES = 32, START = 2, BUFFERS = 2;
+  static constexpr int CB = 84, NODES = 32, START = 2, BUFFERS = 2, DT = 256;
   static constexpr bool THRESHOLD = false, STATE = false;
 };
 template <>
 struct Fmt<kUltra> {
   // one tile buffer (more CTAs per SM instead of a prefetch: the emission is instruction-bound)
-  static constexpr int CB = 132, NODES = 96, START = 2, BUFFERS = 1;
+  static constexpr int CB = 132, NODES = 96, START = 2, BUFFERS = 1, DT = 256;
   static constexpr bool THRESHOLD = false, STATE = false;
 };
 template <>
 struct Fmt<kUltraDense> {
   // one tile buffer: with the smoothing tables a second one would leave a single CTA (8 warps) per SM
-  static constexpr int CB = 170, NODES = 64, START = 8, BUFFERS = 1;
+  static constexpr int CB = 170, NODES = 64, START = 8, BUFFERS = 1, DT = 128;
   static constexpr bool THRESHOLD = true, STATE = true;
 };
 
@@ -225,7 +226,7 @@ __device__ __forceinline__ unsigned long long resolve_sync64(unsigned long long 
 
 template <int F>
 struct CapsuleSmem {
-  static constexpr int CB = Fmt<F>::CB;
+  static constexpr int CB = Fmt<F>::CB, DT = Fmt<F>::DT;
   static constexpr int kTileBytes = (DT * CB + 15) & ~15;
   uint8_t cap[Fmt<F>::BUFFERS][kTileBytes];  // tiles (double-buffered: cp.async prefetch of the next one)
   uint8_t carry[(CB + 15) & ~15];      // last capsule of the previous tile
@@ -247,9 +248,9 @@ struct CapsuleSmem {
 };
 
 template <int F>
-__global__ void __launch_bounds__(DT) decode_capsule_kernel(CapsuleDecodeArgs a) {
+__global__ void __launch_bounds__(Fmt<F>::DT) decode_capsule_kernel(CapsuleDecodeArgs a) {
   using T = Fmt<F>;
-  constexpr int CB = T::CB, NODES = T::NODES;
+  constexpr int CB = T::CB, NODES = T::NODES, DT = T::DT;
   extern __shared__ __align__(16) unsigned char capsule_smem_raw[];
   CapsuleSmem<F>& sm = *reinterpret_cast<CapsuleSmem<F>*>(capsule_smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -582,7 +583,7 @@ __global__ void __launch_bounds__(DT) decode_capsule_kernel(CapsuleDecodeArgs a)
 // combines  advance_204(advance_192(advance_192(r0) ^ r1) ^ r2) ^ r3.  "Advance by N zero bytes" is four look-ups in
 // a 4 x 256 table per N, built on the host (hq_tables_init).  A capsule starts at any byte offset (781 bytes apart):
 // message words come from aligned words by funnel shift.
-constexpr int HC = 64;          // capsules per tile
+constexpr int HC = 32;          // capsules per tile (small tiles: five CTAs per SM, so a few hundred streams are all in flight at once)
 constexpr int HT = 4 * HC;      // threads: four per capsule
 constexpr int kHqBytes = 781;   // 1 sync + 8 timestamp + 96 * 8 nodes + 4 crc
 __device__ uint32_t g_hq_advance[2][4][256];  // [0]: 192 zero bytes, [1]: 204
@@ -904,7 +905,7 @@ __global__ void __launch_bounds__(NT) decode_normal_kernel(NormalDecodeArgs a) {
 
 template <int F>
 cudaError_t launch_fmt(const CapsuleDecodeArgs& a, int grid, cudaStream_t stream) {
-  decode_capsule_kernel<F><<<grid, DT, sizeof(CapsuleSmem<F>), stream>>>(a);
+  decode_capsule_kernel<F><<<grid, Fmt<F>::DT, sizeof(CapsuleSmem<F>), stream>>>(a);
   return cudaGetLastError();
 }
 
