@@ -745,7 +745,7 @@ constexpr int NT = 256;       // threads
 constexpr int kChunk = 30;    // bytes per thread per tile (a multiple of 5; the replay keeps one bit per byte in a u32)
 constexpr int kNormTile = NT * kChunk;
 struct NormalSmem {
-  uint8_t bytes[4 + kNormTile + 12];  // 4 bytes of the previous tile in front
+  uint8_t raw[12 + 4 + kNormTile + 12];  // [12 pad][4 bytes of the previous tile][tile]: the tile starts 16-byte aligned
   uint32_t warp_f[NT / 32], warp_c[NT / 32];
   uint16_t ends[kNormTile / 5 + 8];   // tile-relative index of each record's last byte
   uint32_t carry_state, carry_nodes, tile_nodes, red_state;
@@ -767,6 +767,7 @@ __device__ __forceinline__ uint32_t compose_map(uint32_t g, uint32_t f) {
 
 __global__ void __launch_bounds__(NT) decode_normal_kernel(NormalDecodeArgs a) {
   __shared__ __align__(16) NormalSmem sm;
+  uint8_t* const sm_bytes = sm.raw + 12;  // bytes[0..3] = halo, bytes + 4 = the tile
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (uint32_t s = blockIdx.x; s < a.n_streams; s += gridDim.x) {
     const uint32_t n = a.byte_counts[s];
@@ -777,7 +778,7 @@ __global__ void __launch_bounds__(NT) decode_normal_kernel(NormalDecodeArgs a) {
       sm.carry_state = 0;
       sm.carry_nodes = 0;
     }
-    if (tid < 4) sm.bytes[tid] = 0;
+    if (tid < 4) sm_bytes[tid] = 0;
     __syncthreads();
     for (uint32_t t0 = 0; t0 < n; t0 += kNormTile) {
       const uint32_t live = min((uint32_t)kNormTile, n - t0);
@@ -785,15 +786,12 @@ __global__ void __launch_bounds__(NT) decode_normal_kernel(NormalDecodeArgs a) {
         uint32_t done = 0;
         if ((reinterpret_cast<uintptr_t>(src + t0) & 15u) == 0) {
           const uint4* g4 = reinterpret_cast<const uint4*>(src + t0);
-          uint32_t* d32 = reinterpret_cast<uint32_t*>(sm.bytes + 4);
+          uint4* d128 = reinterpret_cast<uint4*>(sm_bytes + 4);
           const uint32_t quads = live >> 4;
-          for (uint32_t q = tid; q < quads; q += NT) {
-            const uint4 v = __ldg(g4 + q);
-            d32[4 * q] = v.x; d32[4 * q + 1] = v.y; d32[4 * q + 2] = v.z; d32[4 * q + 3] = v.w;
-          }
+          for (uint32_t q = tid; q < quads; q += NT) d128[q] = __ldg(g4 + q);
           done = quads << 4;
         }
-        for (uint32_t i = done + tid; i < live; i += NT) sm.bytes[4 + i] = __ldg(src + t0 + i);
+        for (uint32_t i = done + tid; i < live; i += NT) sm_bytes[4 + i] = __ldg(src + t0 + i);
       }
       __syncthreads();
       // ---- fast path: the tile is entered between records and holds only whole, well-formed records.
@@ -803,13 +801,13 @@ __global__ void __launch_bounds__(NT) decode_normal_kernel(NormalDecodeArgs a) {
         const uint32_t n_rec = live / 5u;
         int ok = (sm.carry_state == 0 && n_rec * 5u == live) ? 1 : 0;
         for (uint32_t q = tid; q < n_rec; q += NT) {
-          const uint32_t c0 = sm.bytes[4 + 5 * q], c1 = sm.bytes[5 + 5 * q];
+          const uint32_t c0 = sm_bytes[4 + 5 * q], c1 = sm_bytes[5 + 5 * q];
           ok &= (int)(((c0 >> 1) ^ c0) & c1 & 1u);
         }
         if (__syncthreads_and(ok)) {
           uint2* o = out + sm.carry_nodes;
           for (uint32_t q = tid; q < n_rec; q += NT) {
-            const uint8_t* r = sm.bytes + 4 + 5 * q;
+            const uint8_t* r = sm_bytes + 4 + 5 * q;
             const uint32_t sq = r[0];
             const uint32_t angle_chk = ld16(r + 1), dist = ld16(r + 3);
             uint2 nd;
@@ -819,7 +817,7 @@ __global__ void __launch_bounds__(NT) decode_normal_kernel(NormalDecodeArgs a) {
             if (end_out) end_out[sm.carry_nodes + q] = t0 + 5 * q + 4;
           }
           __syncthreads();
-          if (tid < 4) sm.bytes[tid] = sm.bytes[live + tid];
+          if (tid < 4) sm_bytes[tid] = sm_bytes[live + tid];
           if (tid == 0) sm.carry_nodes += n_rec;
           __syncthreads();
           continue;
@@ -829,7 +827,7 @@ __global__ void __launch_bounds__(NT) decode_normal_kernel(NormalDecodeArgs a) {
       const uint32_t b0 = tid * kChunk;
       uint32_t f = kIdentityMap;
       for (uint32_t i = 0; i < (uint32_t)kChunk; ++i) {
-        if (b0 + i < live) f = compose_map(byte_map(sm.bytes[4 + b0 + i]), f);
+        if (b0 + i < live) f = compose_map(byte_map(sm_bytes[4 + b0 + i]), f);
       }
       uint32_t Fm = f;
 #pragma unroll
@@ -851,7 +849,7 @@ __global__ void __launch_bounds__(NT) decode_normal_kernel(NormalDecodeArgs a) {
             ends |= 1u << i;
             ++cnt;
           }
-          st = (byte_map(sm.bytes[4 + b0 + i]) >> (3u * st)) & 7u;
+          st = (byte_map(sm_bytes[4 + b0 + i]) >> (3u * st)) & 7u;
         }
       }
       const uint32_t inc_scan = warp_inclusive_scan(cnt);
@@ -877,7 +875,7 @@ __global__ void __launch_bounds__(NT) decode_normal_kernel(NormalDecodeArgs a) {
       const uint32_t n_nodes = sm.tile_nodes;
       uint2* o = out + sm.carry_nodes;
       for (uint32_t q = tid; q < n_nodes; q += NT) {
-        const uint8_t* r = sm.bytes + sm.ends[q];  // record = bytes[end-4 .. end], shifted by the 4-byte halo
+        const uint8_t* r = sm_bytes + sm.ends[q];  // record = bytes[end-4 .. end], shifted by the 4-byte halo
         const uint32_t sq = r[0];
         const uint32_t angle_chk = ld16(r + 1), dist = ld16(r + 3);
         const uint32_t key = (((angle_chk >> 1) << 8) / 90u) & 0xFFFFu;
@@ -888,7 +886,7 @@ __global__ void __launch_bounds__(NT) decode_normal_kernel(NormalDecodeArgs a) {
         if (end_out) end_out[sm.carry_nodes + q] = t0 + sm.ends[q];
       }
       __syncthreads();
-      if (tid < 4) sm.bytes[tid] = sm.bytes[live + tid];  // last four bytes of this tile (live >= 4 or stream ends)
+      if (tid < 4) sm_bytes[tid] = sm_bytes[live + tid];  // last four bytes of this tile (live >= 4 or stream ends)
       if (tid == 0) {
         sm.carry_nodes += sm.tile_nodes;
         sm.carry_state = sm.red_state;
