@@ -874,42 +874,48 @@ __global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : 1)) scan_small_kern
           if (lane == 31) ctl.count_out = incl;
         }
         __syncthreads();
+        // The leaders are a third of the points, scattered over the lanes: writing their cells from where they sit
+        // would run the (double-precision) body for every warp with a third of its lanes.  So the leaders are first
+        // listed densely in output order (the cell keys are dead: their array holds the list), then one thread per
+        // CELL does the arithmetic -- full warps, and the stores of a warp are 512 contiguous bytes.
+        uint16_t* lead16 = reinterpret_cast<uint16_t*>(key32);
 #pragma unroll
-        for (uint32_t j = 0; j < PMAX; ++j) {
-          if (leadflag & (1u << j)) {
-            const uint32_t i = tid + j * TS;
-            const uint32_t pos = ctl.chunk_base[j * NW + warp] + myslot[j];
-            const float2 ld = px[i];
-            const uint32_t c = cs[i];
-            const int qx = fix16(ld.x), qy = fix16(ld.y);
-            float4 o;
-            o.z = 0.0f;
-            if ((c >> 20) == 0u) {
-              // a cell of one point: sum / 65536 is exact in float (an integer below 2^24, or a float-valued integer)
-              o.x = __fmul_rn(__int2float_rn(qx), 1.52587890625e-05f);
-              o.y = __fmul_rn(__int2float_rn(qy), 1.52587890625e-05f);
-              o.w = __uint2float_rn(c);
-            } else {
-              // (float)((double)sum / (65536.0 * count)): the double quotient from the correctly rounded reciprocal
-              // and one residual step (Markstein) -- bit-identical to the division, a third of its instructions
-              const uint32_t members = (c >> 20) + 1u;
-              const double sx = (double)((long long)members * qx + (long long)dxs[i]);
-              const double sy = (double)((long long)members * qy + (long long)dys[i]);
-              const double cntd = (double)members;
-              const double den = __dmul_rn(65536.0, cntd);
-              const double rden = __drcp_rn(den);
-              const double rcnt = __dmul_rn(rden, 65536.0);  // = RN(1 / count): scaling by 2^16 is exact
-              auto quot = [](double a, double d, double r) {
-                const double q0 = __dmul_rn(a, r);
-                const double e = __fma_rn(-q0, d, a);
-                return __fma_rn(e, r, q0);
-              };
-              o.x = __double2float_rn(quot(sx, den, rden));
-              o.y = __double2float_rn(quot(sy, den, rden));
-              o.w = __double2float_rn(quot((double)(c & 0xFFFFFu), cntd, rcnt));
-            }
-            st_f32x4_if(cloud + pos, o, pol_stream, 1u);
+        for (uint32_t j = 0; j < PMAX; ++j)
+          if (leadflag & (1u << j)) lead16[ctl.chunk_base[j * NW + warp] + myslot[j]] = (uint16_t)(tid + j * TS);
+        __syncthreads();
+        const uint32_t n_cells = ctl.count_out;
+        for (uint32_t pos = tid; pos < n_cells; pos += TS) {
+          const uint32_t i = lead16[pos];
+          const float2 ld = px[i];
+          const uint32_t c = cs[i];
+          const int qx = fix16(ld.x), qy = fix16(ld.y);
+          float4 o;
+          o.z = 0.0f;
+          if ((c >> 20) == 0u) {
+            // a cell of one point: sum / 65536 is exact in float (an integer below 2^24, or a float-valued integer)
+            o.x = __fmul_rn(__int2float_rn(qx), 1.52587890625e-05f);
+            o.y = __fmul_rn(__int2float_rn(qy), 1.52587890625e-05f);
+            o.w = __uint2float_rn(c);
+          } else {
+            // (float)((double)sum / (65536.0 * count)): the double quotient from the correctly rounded reciprocal
+            // and one residual step (Markstein) -- bit-identical to the division, a third of its instructions
+            const uint32_t members = (c >> 20) + 1u;
+            const double sx = (double)((long long)members * qx + (long long)dxs[i]);
+            const double sy = (double)((long long)members * qy + (long long)dys[i]);
+            const double cntd = (double)members;
+            const double den = __dmul_rn(65536.0, cntd);
+            const double rden = __drcp_rn(den);
+            const double rcnt = __dmul_rn(rden, 65536.0);  // = RN(1 / count): scaling by 2^16 is exact
+            auto quot = [](double a, double d, double r) {
+              const double q0 = __dmul_rn(a, r);
+              const double e = __fma_rn(-q0, d, a);
+              return __fma_rn(e, r, q0);
+            };
+            o.x = __double2float_rn(quot(sx, den, rden));
+            o.y = __double2float_rn(quot(sy, den, rden));
+            o.w = __double2float_rn(quot((double)(c & 0xFFFFFu), cntd, rcnt));
           }
+          st_f32x4_if(cloud + pos, o, pol_stream, 1u);
         }
         m_out = ctl.count_out;
         // the table was written with ordinary stores and the next scan's bulk copy lands on it
