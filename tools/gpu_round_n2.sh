@@ -3,7 +3,7 @@
 # N=2 (carries extra.cloud with the three exchanges), the cloud workload on its own line, the reference arm at N=2
 set -u
 mkdir -p gpurun_out
-T=${1:-r2n2}
+T=${1:-r2n2final}
 nvidia-smi topo -m > gpurun_out/${T}_topo.txt 2>&1
 timeout 600 python -m pytest tests/test_gpu_multi_push.py -q 2>&1 | tail -15 > gpurun_out/${T}_pytest.txt; tail -5 gpurun_out/${T}_pytest.txt
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
