@@ -546,12 +546,6 @@ __global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : 1)) scan_small_kern
     const uint32_t ob = inverted ? M - 1u : 0u, os = inverted ? 0xFFFFFFFFu : 1u;
     const ptrdiff_t i_minus_r = reinterpret_cast<char*>(intens) - reinterpret_cast<char*>(ranges);
     // (two instances: revolutions with shared final keys are rare and must not slow the loop of the others down)
-    // Mode A without the ascended buffer, M >= 272: the place pass leaves (dist_m, bin, quality, key position within
-    // the bin) in the tile and the winner pass needs neither the conversion nor the bin again (8-bit positions need
-    // 65536 / M + 7 < 256; with the ascended buffer the tile is still needed as it is)
-    const bool packed = MODE_A && !EMIT && want_scan && M >= 272u;
-    const float keys_per_bin = __fdiv_rn(65536.0f, __uint2float_rn(M));
-    const uint32_t span_up = __float2uint_rz(keys_per_bin) + 2u;  // >= ceil(65536 / M)
     auto place = [&](auto has_dup) {
       constexpr bool HAS_DUP = decltype(has_dup)::value;
 #pragma unroll 4
@@ -582,21 +576,7 @@ __global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : 1)) scan_small_kern
           // points that fall into it -- dist_m >= 0, so its bit pattern orders like the value
           if (measured) {
             const uint32_t b = (uint32_t)mode_a_bin_fast(k, M, inc, inverted);  // < M <= 8192
-            const uint32_t dmb = __float_as_uint(dm);
-            atomicMin(&minv[b], dmb);
-            if (packed) {
-              // Leave what the winner pass needs in the shared-memory copy of the node: dist_m, the bin, the quality
-              // and the key's position WITHIN the bin in 8 bits (only the order among the keys of one bin matters).
-              // The keys of bin b lie within 1/64 key of [B, B + S], B = b * 65536 / M, S = 65536 / M (the float
-              // chain's error bound, rpl_device.cuh); `fb` is floor(B) give or take one.
-              const int fb = (int)__float2uint_rz(__fmul_rn(__uint2float_rn(b), keys_per_bin));
-              int koff = inverted ? (fb + (int)span_up + 4) - (int)(65536u - k)   // ascending key = descending 65536 - key
-                                  : (int)k - (fb - 2);
-              koff = max(koff, 0);  // (key 0 of an inverted scan: the reference wraps it into bin 0, where it is the first)
-              tile0[shift + i] = make_uint2(dmb, b | (((nd.y >> 16) & 0xFFu) << 13) | ((uint32_t)koff << 21) | 0x80000000u);
-            }
-          } else if (packed && (nd.y & 0x80000000u)) {
-            tile0[shift + i].y = nd.y & 0x7FFFFFFFu;  // bit 31 says "measured, packed" to the winner pass
+            atomicMin(&minv[b], __float_as_uint(dm));
           }
           continue;
         }
@@ -659,17 +639,6 @@ __global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : 1)) scan_small_kern
 #pragma unroll 4
       for (uint32_t i = tid; i < n; i += TS) {
         const uint2 nd = tile[i];
-        if (packed) {
-          if ((int)nd.y < 0) {
-            const uint32_t b = nd.y & 0x1FFFu;
-            if (nd.x == minv[b]) {
-              const uint32_t v = (nd.y >> 13) & 0xFFFFu;  // (position of the key within the bin) << 8 | quality
-              const uint32_t old = atomicMin(&wkey[b], v);
-              conflict = conflict || ((old ^ v) - 1u < 255u);  // same key, another quality
-            }
-          }
-          continue;
-        }
         const uint32_t dist = __funnelshift_r(nd.x, nd.y, 16);
         if (dist != 0) {
           const uint32_t k = nd.x & 0xFFFFu;
