@@ -14,14 +14,18 @@
 //     <= 4096 nodes per revolution neighbouring keys are >= 16 apart, so lanes rarely share a word
 //     (the reason the 32768-node kernel uses a byte map instead) -- which removes the byte map, its
 //     clear and its fold; the rank table is the bitmap + a 4 KB u16 prefix;
-//   * Mode A resolves its bins from the shared-memory copy, the ascended buffer is a second bitmap
-//     over the final keys, and the PointCloud2 chain runs to the end in shared memory: the kept
+//   * Mode A is a scatter-min over its bins (per bin the smallest dist_m, then the smallest key among the
+//     points that hold it: two shared atomics per point, no ranks, no bitmap of the measured keys), the
+//     ascended buffer is a second bitmap over the final keys, and the PointCloud2 chain runs to the end
+//     in shared memory: the kept
 //     points are placed in angle order as (x, y) + intensity, statistical outlier removal and the
 //     voxel grid (open-addressing table of cell leaders in the dead tile buffer, 32-bit integer
 //     accumulators relative to the leader) work on them there, and only the final cloud -- rho x 16 B
 //     per input node -- is written to HBM.  The three HBM round trips and the global hash tables of
 //     the round-1 post kernels are gone.
-// Duplicate keys (popcount != count) go to the general kernel through the device-side list, as before.
+// Duplicate keys among the measured nodes (popcount != count) go to the general kernel through the device-side
+// list; Mode A only does so when a duplicate would change its result, and up to 16 shared FINAL keys per
+// revolution (a fill key landing on a measured key) are placed here, in buffer order (stable rule).
 #include <algorithm>
 #include <type_traits>
 
