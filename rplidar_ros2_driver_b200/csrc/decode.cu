@@ -18,7 +18,8 @@
 //   * the one genuinely sequential piece of state, the reference's function-static
 //     lastNodeSyncBit (sync_i = raw_i & ~sync_{i-1}), is carried across capsules by scanning
 //     2-bit transfer functions (out(0), out(1)) under composition,
-//   * nodes are written 8 bytes per lane, 40 consecutive nodes per capsule: fully coalesced.
+//   * nodes are written by a thread per PAIR of samples (one 32-bit word of the capsule, shared look-ups, one
+//     16-byte store), 40 consecutive nodes per capsule: fully coalesced.
 //
 // Wire bytes in: 84 per capsule (2.1 B per point); nodes out: 320 per released capsule.
 #include "decode_args.h"
