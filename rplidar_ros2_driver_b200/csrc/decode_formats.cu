@@ -412,26 +412,33 @@ __global__ void __launch_bounds__(Fmt<F>::DT) decode_capsule_kernel(CapsuleDecod
             ud_pm = 0;
             sm.ud_dist[tid][0] = (uint16_t)r0;
           }
-          for (uint32_t pos = 1; pos < 64; ++pos) {
+          // two loops: with nine candidates until they merge (usually at once), then the plain recurrence, unrolled
+          // so that the decodes of the next samples overlap the dependent smoothing steps
+          uint32_t pos = 1;
+          for (; pos < 64 && !merged; ++pos) {
             const int r = ud_sample(pc, pos, sc, q);
-            if (merged) {
-              cand[0] = ud_smooth(r, sc, cand[0]);
-              sm.ud_dist[tid][pos] = (uint16_t)cand[0];  // only read back for scale-0 samples (< 8192)
-            } else {
-              int lo = 0x7fffffff, hi = -0x7fffffff;
+            int lo = 0x7fffffff, hi = -0x7fffffff;
 #pragma unroll
-              for (int k = 0; k < 9; ++k) {
-                cand[k] = ud_smooth(r, sc, cand[k]);
-                lo = min(lo, cand[k]);
-                hi = max(hi, cand[k]);
-              }
-              merged = (lo == hi);
-              if (merged) {
-                ud_pm = pos;
-                sm.ud_dist[tid][pos] = (uint16_t)cand[0];
-              }
+            for (int k = 0; k < 9; ++k) {
+              cand[k] = ud_smooth(r, sc, cand[k]);
+              lo = min(lo, cand[k]);
+              hi = max(hi, cand[k]);
+            }
+            merged = (lo == hi);
+            if (merged) {
+              ud_pm = pos;
+              sm.ud_dist[tid][pos] = (uint16_t)cand[0];
             }
           }
+          int last = cand[0];
+#pragma unroll 4
+          for (; pos < 64; ++pos) {
+            uint32_t s2, q2;
+            const int r = ud_sample(pc, pos, s2, q2);
+            last = ud_smooth(r, s2, last);
+            sm.ud_dist[tid][pos] = (uint16_t)last;  // only read back for scale-0 samples (< 8192)
+          }
+          if (merged) cand[0] = last;
 #pragma unroll
           for (int k = 0; k < 9; ++k) sm.ud_out[tid][k] = (uint32_t)(merged ? cand[0] : cand[k]);
           sm.ud_out[tid][9] = (uint32_t)r0;
