@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(Fmt<F>::DT) decode_capsule_kernel(CapsuleDecod
             }
           }
           int last = cand[0];
-#pragma unroll 4
+#pragma unroll 8
           for (; pos < 64; ++pos) {
             uint32_t s2, q2;
             const int r = ud_sample(pc, pos, s2, q2);
