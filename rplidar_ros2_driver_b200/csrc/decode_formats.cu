@@ -772,7 +772,7 @@ __device__ __forceinline__ uint32_t compose_map(uint32_t g, uint32_t f) {
   return r;
 }
 
-__global__ void __launch_bounds__(NT) decode_normal_kernel(NormalDecodeArgs a) {
+__global__ void __launch_bounds__(NT, 5) decode_normal_kernel(NormalDecodeArgs a) {
   __shared__ __align__(16) NormalSmem sm;
   uint8_t* const sm_bytes = sm.raw + 12;  // bytes[0..3] = halo, bytes + 4 = the tile
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -807,21 +807,35 @@ __global__ void __launch_bounds__(NT) decode_normal_kernel(NormalDecodeArgs a) {
       {
         const uint32_t n_rec = live / 5u;
         int ok = (sm.carry_state == 0 && n_rec * 5u == live) ? 1 : 0;
-        for (uint32_t q = tid; q < n_rec; q += NT) {
-          const uint32_t c0 = sm_bytes[4 + 5 * q], c1 = sm_bytes[5 + 5 * q];
-          ok &= (int)(((c0 >> 1) ^ c0) & c1 & 1u);
+        // one sweep: every record is read as two aligned words (5 bytes never span three), checked and turned into
+        // its node in registers; the nodes are written once the whole block agrees that the tile is clean
+        constexpr uint32_t kRecPerThread = (kNormTile / 5 + NT - 1) / NT;
+        const uint32_t* W = reinterpret_cast<const uint32_t*>(sm_bytes + 4);  // 16-byte aligned
+        uint2 nd[kRecPerThread];
+#pragma unroll
+        for (uint32_t j = 0; j < kRecPerThread; ++j) {
+          const uint32_t q = tid + j * NT;
+          nd[j] = make_uint2(0u, 0u);
+          if (q < n_rec) {
+            const uint32_t off = 5u * q, w = off >> 2, sh = (off & 3u) * 8u;
+            const uint32_t w0 = W[w], w1 = W[w + 1];
+            const uint32_t lo = __funnelshift_r(w0, w1, sh);  // bytes 0..3 of the record
+            const uint32_t b4 = (w1 >> sh) & 0xFFu;           // byte 4
+            const uint32_t sq = lo & 0xFFu, angle_chk = (lo >> 8) & 0xFFFFu, dist = (lo >> 24) | (b4 << 8);
+            ok &= (int)(((sq >> 1) ^ sq) & angle_chk & 1u);
+            nd[j].x = ((((angle_chk >> 1) << 8) / 90u) & 0xFFFFu) | (dist << 16);
+            nd[j].y = (((sq >> 2) << 2) << 16) | ((sq & 1u) << 24);
+          }
         }
         if (__syncthreads_and(ok)) {
           uint2* o = out + sm.carry_nodes;
-          for (uint32_t q = tid; q < n_rec; q += NT) {
-            const uint8_t* r = sm_bytes + 4 + 5 * q;
-            const uint32_t sq = r[0];
-            const uint32_t angle_chk = ld16(r + 1), dist = ld16(r + 3);
-            uint2 nd;
-            nd.x = ((((angle_chk >> 1) << 8) / 90u) & 0xFFFFu) | (dist << 16);
-            nd.y = (((sq >> 2) << 2) << 16) | ((sq & 1u) << 24);
-            o[q] = nd;
-            if (end_out) end_out[sm.carry_nodes + q] = t0 + 5 * q + 4;
+#pragma unroll
+          for (uint32_t j = 0; j < kRecPerThread; ++j) {
+            const uint32_t q = tid + j * NT;
+            if (q < n_rec) {
+              o[q] = nd[j];
+              if (end_out) end_out[sm.carry_nodes + q] = t0 + 5 * q + 4;
+            }
           }
           __syncthreads();
           if (tid < 4) sm_bytes[tid] = sm_bytes[live + tid];
