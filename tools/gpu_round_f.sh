@@ -2,7 +2,7 @@
 # all GPU tests + the six decoder lines + the chain line
 set -u
 mkdir -p gpurun_out
-T=${1:-r2v}
+T=${1:-r2x}
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -6
 for f in 0x81 0x82 0x83 0x84 0x85 0x86; do
   timeout 300 python bench.py --workload decode --format $f --steps 30 > gpurun_out/${T}_dec_${f}.json 2> gpurun_out/${T}_dec_${f}.err; tail -c 200 gpurun_out/${T}_dec_${f}.err
