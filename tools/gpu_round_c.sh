@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 set -u
 mkdir -p gpurun_out
-T=${1:-r2final}
+T=${1:-r2final2}
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/${T}_pytest.txt
 tail -12 gpurun_out/${T}_pytest.txt
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
