@@ -250,3 +250,123 @@ def test_rank_lookup_equals_the_sort_for_tie_free_scans(oracle, n):
         b2 = np.zeros(65536, np.uint8)
         b2[k2] = 1
         assert b2.sum() == valid.sum() - 1
+
+
+# ---- round 2: shared final keys, Mode A as a scatter-min, CRC over byte ranges --------------------------------------
+@pytest.mark.parametrize("seed", range(8))
+def test_ranks_with_shared_keys_follow_the_stable_rule(seed):
+    """scan_small.cu, ascended buffer: position of a node = (distinct keys below its key, from the bitmap)
+    + (listed keys below its key: one entry per node beyond the first of a key) + (nodes with the same key earlier in
+    the buffer) -- equals the stable sort."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(2, 400))
+    keys = rng.choice(65536, size=n, replace=False)
+    for _ in range(int(rng.integers(0, 6))):  # a few shared keys, some shared by three
+        i, j = rng.integers(0, n, 2)
+        keys[j] = keys[i]
+    distinct = np.unique(keys)
+    listed = []  # what the rare-path sweep collects: every node beyond the first (in ANY order) of its key
+    seen = set()
+    for i in rng.permutation(n):
+        if int(keys[i]) in seen:
+            listed.append(int(keys[i]))
+        seen.add(int(keys[i]))
+    assert len(listed) == n - len(distinct)
+    pos = np.empty(n, np.int64)
+    for i in range(n):
+        k = int(keys[i])
+        pos[i] = np.searchsorted(distinct, k) + sum(1 for d in listed if d < k) + int((keys[:i] == k).sum())
+    assert (pos[np.argsort(keys, kind="stable")] == np.arange(n)).all()
+
+
+def mode_a_scatter_min_model(keys, dm_bits, quality, bins, m):
+    """What the shared-memory Mode A kernel computes (two atomicMin sweeps), plus its conflict flag."""
+    minv = np.full(m, 0xFFFFFFFF, np.uint64)
+    for b, d in zip(bins, dm_bits):
+        minv[b] = min(minv[b], d)
+    wkey = np.full(m, 0xFFFFFFFF, np.uint64)
+    conflict = False
+    for k, d, q, b in zip(keys, dm_bits, quality, bins):
+        if d == minv[b]:
+            v = (int(k) << 8) | int(q)
+            old = int(wkey[b])
+            wkey[b] = min(old, v)
+            conflict = conflict or ((old >> 8) == int(k) and old != v)
+    return minv, wkey, conflict
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_mode_a_scatter_min_equals_the_sorted_walk(oracle, seed):
+    """Mode A (reference rplidar_node.cpp:630-660) walks the measured points in ascending key order and keeps, per
+    bin, the first point with the smallest dist_m.  Without any ordering: per bin min(dist_m bits), then min(key) among
+    the points that hold it.  Equal keys only matter when two of them hold a bin's minimum with different qualities:
+    that is the one case the kernel hands to the general kernel (conflict flag)."""
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(3, 500))
+    keys = rng.integers(0, 65536, n) if seed % 2 else rng.choice(65536, size=n, replace=False)
+    dist = rng.integers(1, 40, n) * 400  # few distinct distances: many ties in dist_m
+    quality = rng.integers(0, 256, n)
+    nodes = oracle.make_nodes(keys, dist, quality, 2)
+    inv = seed % 3 == 0
+    prm = oracle.scan_params(1, 1, int(inv), 0, 40.0, 0.1)
+    order = np.argsort(keys, kind="stable")
+    hdr, ranges, inten = oracle.publish(nodes[order], prm, stable=True)  # the serial walk over the sorted buffer
+    m = hdr.beam_count
+    assert m == n
+    # bins exactly as the reference computes them (float chain), from the device-math proof helpers
+    from test_device_math_proofs import exact_bins
+
+    bins_of_key = exact_bins(m, inv)
+    bins = bins_of_key[keys]
+    dm_bits = (dist.astype(np.float32) / np.float32(4000.0)).view(np.uint32).astype(np.uint64)
+    minv, wkey, conflict = mode_a_scatter_min_model(keys, dm_bits, quality, bins, m)
+    dup_conflict = False  # the definition of the conflict: same key, same (minimal) dist_m, different quality
+    for b in range(m):
+        idx = [i for i in range(n) if bins[i] == b and dm_bits[i] == minv[b]]
+        for x in idx:
+            for y in idx:
+                if keys[x] == keys[y] and quality[x] != quality[y]:
+                    dup_conflict = True
+    assert dup_conflict or not conflict  # the flag is only ever raised for a real one ...
+    if not conflict:  # ... and without it the result is the serial walk's, even if an unflagged pair exists (a
+        hit = minv != 0xFFFFFFFF  # smaller key of the same bin and distance took the bin from both)
+        got_r = np.full(m, np.inf, np.float32)
+        got_r[hit] = minv[hit].astype(np.uint32).view(np.float32)
+        got_i = np.zeros(m, np.float32)
+        got_i[hit] = (wkey[hit] & 0xFF).astype(np.float32)  # new protocol: intensity = quality
+        assert (got_r.view(np.uint32) == ranges[:m].view(np.uint32)).all()
+        assert (got_i.view(np.uint32) == inten[:m].view(np.uint32)).all()
+
+
+def test_crc32_over_four_byte_ranges_combines_to_the_whole():
+    """decode_formats.cu decode_hq_kernel: raw(s, A || B) = advance_|B|(raw(s, A)) ^ raw(0, B) for the table-driven
+    reflected CRC-32; four ranges (192, 192, 192, 204 bytes incl. the SDK's zero padding) against zlib."""
+    import zlib
+
+    t0 = np.zeros(256, np.uint64)
+    for i in range(256):
+        c = i
+        for _ in range(8):
+            c = (0xEDB88320 ^ (c >> 1)) if (c & 1) else (c >> 1)
+        t0[i] = c
+
+    def raw(s, data):
+        for x in data:
+            s = (s >> 8) ^ int(t0[(s ^ x) & 0xFF])
+        return s
+
+    def advance(s, nbytes):
+        for _ in range(nbytes):
+            s = (s >> 8) ^ int(t0[s & 0xFF])
+        return s
+
+    rng = np.random.default_rng(9)
+    for _ in range(20):
+        msg = bytes(rng.integers(0, 256, 777).astype(np.uint8)) + b"\0\0\0"
+        r = [raw(0xFFFFFFFF, msg[0:192]), raw(0, msg[192:384]), raw(0, msg[384:576]), raw(0, msg[576:780])]
+        crc = advance(advance(advance(r[0], 192) ^ r[1], 192) ^ r[2], 204) ^ r[3]
+        assert (crc ^ 0xFFFFFFFF) == zlib.crc32(msg)
+    # "advance" is linear, so it is four byte-indexed look-ups (what the kernel's tables hold)
+    s = int(rng.integers(0, 1 << 32))
+    parts = [advance(((s >> (8 * k)) & 0xFF) << (8 * k), 192) for k in range(4)]
+    assert advance(s, 192) == parts[0] ^ parts[1] ^ parts[2] ^ parts[3]
