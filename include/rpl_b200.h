@@ -416,7 +416,11 @@ rpl_result rpl_scan_views_dev(rpl_ctx* ctx, const rpl_node_hq* nodes, uint64_t n
                               uint32_t* status, uint32_t* path, void* stream);
 
 /* Wire bytes -> LaserScan in ONE host call: framed dense (0x85) capsules in host memory -> H2D -> decode ->
- * scan views -> scan kernel -> D2H, chunked over the two lanes so that copies and kernels overlap.  2.1 bytes per
+ * scan views -> scan kernel -> D2H, chunked over the two lanes so that copies and kernels overlap.  Per stream this is
+ * the reference's whole data path after the protocol codec: UnpackerHandler_DenseCapsuleNode::onData
+ * (src/sdk/src/dataunpacker/unpacker/handler_capsules.cpp:639-791) -> ScanDataHolder::pushScanNodeData
+ * (src/sdk/src/sl_lidar_driver.cpp:272-315) -> grab_scan_data with ascendScanData (src/lidar_driver_wrapper.cpp:307-342,
+ * src/sdk/src/sl_lidar_driver.cpp:128-184) -> publish_scan (src/rplidar_node.cpp:556-680).  2.1 bytes per
  * point cross the host link on the way in instead of the 8 of a decoded node.  capsules: host
  * [n_streams][stride_capsules][84]; outputs: host ranges / intensities [n_streams * max_scans][max_nodes],
  * beam_counts / angle_increment (nullable) [n_streams * max_scans] (slot k of stream s at s * max_scans + k; unused
