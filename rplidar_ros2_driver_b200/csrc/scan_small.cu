@@ -222,7 +222,7 @@ __device__ __forceinline__ int fix16(float v) { return __float2int_rn(__fmul_rn(
 // MODE: 0 LaserScan Mode B, 1 LaserScan Mode A, 2 PointCloud2.  EMIT: also write the ascended node buffer
 // (MODE 0/1).  POST: (MODE 2) SOR and/or voxel grid in shared memory before anything is written.
 template <int MODE, bool EMIT, bool POST, int TS>
-__global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : 1)) scan_small_kernel(ScanBatchArgs a, SmallArgs p) {
+__global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : (MODE == 0 ? 5 : 1))) scan_small_kernel(ScanBatchArgs a, SmallArgs p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool MODE_A = (MODE == 1);
   constexpr bool CLOUD = (MODE == 2);
@@ -248,6 +248,8 @@ __global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : 1)) scan_small_kern
   }
   // Mode A needs no ranks among the measured points (see below): no bitmap of their keys
   constexpr bool USE_V = !MODE_A;
+  // Mode B without the ascended buffer places a few duplicate MEASURED keys itself (see the place pass)
+  constexpr bool VDUP = (MODE == 0) && !EMIT;
   if (USE_V) {
     bitsV = reinterpret_cast<uint32_t*>(q); q += kWords * 4;
     prefV = reinterpret_cast<uint16_t*>(q); q += kWords * 2;
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : 1)) scan_small_kern
       if (tid == 0) {
         ctl.first_valid = 0xFFFFFFFFu;
         ctl.fallback = 0;
-        if (EMIT) {
+        if (EMIT || VDUP) {
           ctl.d.ndup = 0;
           ctl.d.ndupnode = 0;
         }
@@ -519,8 +521,11 @@ __global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : 1)) scan_small_kern
     // rule); Mode A looks only for the duplicates that matter to it, in its winner pass below.  Duplicates among the
     // FINAL keys (typically the fill key of an unmeasured node landing on a measured node's key) only move entries of
     // the ascended buffer: up to kMaxDup of them are resolved here (place pass + fix-up), more go to the general kernel.
+    // The same goes for duplicate MEASURED keys in Mode B without the ascended buffer (e.g. the first and the last
+    // node of a revolution meeting on one key: ~1 % of the revolutions of the capsule -> LaserScan chain).
     const uint32_t D = EMIT ? n - ctl.totA : 0u;  // nodes beyond the first of their final key
-    if ((USE_V && ctl.totV != M) || (EMIT && D > kMaxDup)) {
+    const uint32_t DV = VDUP ? M - ctl.totV : 0u;  // measured nodes beyond the first of their key
+    if ((USE_V && !VDUP && ctl.totV != M) || (VDUP && DV > kMaxDup) || (EMIT && D > kMaxDup)) {
       if (tid == 0) a.fallback_list[atomicAdd(a.fallback_count, 1u)] = s;
       __syncthreads();
       continue;
@@ -536,6 +541,22 @@ __global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : 1)) scan_small_kern
       for (uint32_t i = tid; i < n; i += TS) {
         const uint32_t fk = tile[i].x & 0xFFFFu;
         atomicOr(&bitsA[fk >> 5], 1u << (fk & 31));
+      }
+      __syncthreads();
+    }
+
+    if (VDUP && DV) {  // (rare) the same sweep over the measured keys
+      for (uint32_t i = tid; i < n; i += TS) {
+        const uint2 nd = tile[i];
+        if (__funnelshift_r(nd.x, nd.y, 16) != 0) {
+          const uint32_t k = nd.x & 0xFFFFu, bit = 1u << (k & 31);
+          if (!(atomicAnd(&bitsV[k >> 5], ~bit) & bit)) ctl.d.dupkey[atomicAdd(&ctl.d.ndup, 1u)] = (uint16_t)k;  // DV entries
+        }
+      }
+      __syncthreads();
+      for (uint32_t i = tid; i < n; i += TS) {
+        const uint2 nd = tile[i];
+        if (__funnelshift_r(nd.x, nd.y, 16) != 0) atomicOr(&bitsV[(nd.x & 0xFFFFu) >> 5], 1u << (nd.x & 31u));
       }
       __syncthreads();
     }
@@ -584,7 +605,21 @@ __global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : 1)) scan_small_kern
           }
           continue;
         }
-        const uint32_t rk = rank2(bitsV, prefV, k);
+        uint32_t rk = rank2(bitsV, prefV, k);
+        if constexpr (HAS_DUP && VDUP) {
+          // every measured node beyond the first of a key shifts the larger keys by one; the measured nodes that share
+          // a key are ordered by buffer position (stable rule) in the fix-up below
+          bool shared = false;
+          for (uint32_t j = 0; j < DV; ++j) {
+            const uint32_t dk = ctl.d.dupkey[j];
+            rk += (dk < k) ? 1u : 0u;
+            shared = shared || (dk == k);
+          }
+          if (shared && measured) {
+            ctl.d.dupnode[atomicAdd(&ctl.d.ndupnode, 1u)] = (uint16_t)i;  // <= 2 * DV entries
+            measured = 0;  // (its stores are left to the fix-up)
+          }
+        }
         if (CLOUD) {  // polar -> xyz at the rank among kept points (oracle/cloud_oracle.cpp steps 1-3)
           const float it = intensity_of(nd.y);
           if (!cloud_keep(dm, it, w_rmin, w_rmax, w_imin)) measured = 0;
@@ -607,7 +642,7 @@ __global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : 1)) scan_small_kern
         }
       }
     };
-    if (EMIT && D) place(std::true_type{});
+    if ((EMIT && D) || (VDUP && DV)) place(std::true_type{});
     else place(std::false_type{});
     __syncthreads();
 
@@ -626,6 +661,30 @@ __global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : 1)) scan_small_kern
           uint32_t r = rank2(bitsA, prefA, k) + before;
           for (uint32_t j = 0; j < D; ++j) r += (ctl.d.dupkey[j] < k) ? 1u : 0u;
           nodes_out[r] = me;
+        }
+      }
+    }
+
+    // ---- Mode B, measured nodes with a shared key: slot = measured nodes with a smaller key + measured nodes with the
+    // same key earlier in the buffer (stable rule)
+    if (VDUP && DV) {
+      const uint32_t nshared = ctl.d.ndupnode;
+      for (uint32_t e = warp; e < nshared; e += NW) {
+        const uint32_t i = ctl.d.dupnode[e];
+        const uint2 me = tile[i];
+        const uint32_t k = me.x & 0xFFFFu;
+        uint32_t before = 0;
+        for (uint32_t j = lane; j < i; j += 32) {
+          const uint2 o2 = tile[j];
+          before += ((o2.x & 0xFFFFu) == k && __funnelshift_r(o2.x, o2.y, 16) != 0) ? 1u : 0u;
+        }
+        before = warp_sum(before);
+        if (lane == 0) {
+          uint32_t r = rank2(bitsV, prefV, k) + before;
+          for (uint32_t j = 0; j < DV; ++j) r += (ctl.d.dupkey[j] < k) ? 1u : 0u;
+          const uint32_t o = ob + os * r;
+          ranges[o] = dist_to_m(__funnelshift_r(me.x, me.y, 16));
+          intens[o] = intensity_of(me.y);
         }
       }
     }

@@ -421,3 +421,40 @@ def test_shared_final_keys_are_resolved_in_the_shared_memory_kernel(R, oracle, c
                         expect_path=path)
             check_batch(R, oracle, ctx, c[None], np.array([len(c)], np.uint32), newp, 0, inv, 1, emit=True, stable=True,
                         expect_path=R.PATH_GENERAL)  # Mode B ranks the measured keys: any duplicate among them
+
+
+def test_mode_b_duplicate_measured_keys_in_the_shared_memory_kernel(R, oracle, ctx):
+    """Mode B without the ascended buffer: up to 16 measured nodes beyond the first of their key are placed by the
+    shared-memory kernel itself (stable rule: equal keys in buffer order), more go to the general kernel.  The pattern
+    the capsule -> LaserScan chain produces (first and last node of a revolution on one key), a key held by four
+    nodes, unmeasured nodes on a shared key (they do not count), exactly 16 and 17."""
+    rng = np.random.default_rng(21)
+    n = 3201
+    keys = np.sort(rng.choice(np.arange(8, 65500), size=n, replace=False))
+    dist = rng.integers(4000, 160000, n)
+    q = rng.integers(0, 256, n)
+
+    def make(n_shared, unmeasured_twin=False):
+        k = keys.copy()
+        if n_shared == 1:
+            k[-1] = k[0]                       # first and last node of the revolution meet
+        else:
+            src = np.concatenate([np.full(min(n_shared, 3), 700), 900 + 5 * np.arange(max(n_shared - 3, 0))]).astype(int)
+            k[2000 + 3 * np.arange(n_shared)] = k[src]
+        c = oracle.make_nodes(k, dist, q, 2)
+        if unmeasured_twin:
+            c["dist_mm_q2"][1234] = 0
+            c["angle_z_q14"][1234] = c["angle_z_q14"][50]   # an unmeasured node on a measured node's key: no duplicate
+        return c
+
+    for n_shared, path in ((1, 0), (3, 0), (16, 0), (17, R.PATH_GENERAL)):
+        for twin in (False, True):
+            c = make(n_shared, twin)
+            for rot in (0, 1500):
+                scan = np.roll(c, -rot)[None]
+                for newp, inv in ((0, 0), (1, 1)):
+                    for ascend in (0, 1):
+                        check_batch(R, oracle, ctx, scan, np.array([n], np.uint32), newp, 0, inv, ascend, emit=False,
+                                    stable=True, expect_path=path)
+                        check_batch(R, oracle, ctx, scan, np.array([n], np.uint32), newp, 0, inv, ascend, flags=4,
+                                    emit=False, stable=True)
