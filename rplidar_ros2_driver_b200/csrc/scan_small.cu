@@ -221,6 +221,81 @@ __device__ __forceinline__ int fix16(float v) { return __float2int_rn(__fmul_rn(
 
 // MODE: 0 LaserScan Mode B, 1 LaserScan Mode A, 2 PointCloud2.  EMIT: also write the ascended node buffer
 // (MODE 0/1).  POST: (MODE 2) SOR and/or voxel grid in shared memory before anything is written.
+// ---- rare paths of Mode B with duplicate measured keys, kept out of line so that they do not set the kernel's
+// register count ---------------------------------------------------------------------------------------------------
+// Which keys are held by more than one measured node?  Every measured node clears its key's bit and looks at what was
+// there: the first node of a key finds it set, every further one finds it cleared and lists the key; then the bitmap is
+// marked again.  Called by the whole block.
+__device__ __noinline__ void vdup_list_keys(const uint2* tile, uint32_t n, uint32_t* bitsV, uint32_t* ndup,
+                                            uint16_t* dupkey, uint32_t tid, uint32_t nthreads) {
+  for (uint32_t i = tid; i < n; i += nthreads) {
+    const uint2 nd = tile[i];
+    if (__funnelshift_r(nd.x, nd.y, 16) != 0) {
+      const uint32_t k = nd.x & 0xFFFFu, bit = 1u << (k & 31);
+      if (!(atomicAnd(&bitsV[k >> 5], ~bit) & bit)) dupkey[atomicAdd(ndup, 1u)] = (uint16_t)k;
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < n; i += nthreads) {
+    const uint2 nd = tile[i];
+    if (__funnelshift_r(nd.x, nd.y, 16) != 0) atomicOr(&bitsV[(nd.x & 0xFFFFu) >> 5], 1u << (nd.x & 31u));
+  }
+  __syncthreads();
+}
+// Place pass of such a revolution (Mode B): every measured node beyond the first of a key shifts the larger keys by
+// one; the measured nodes that share a key are set aside for vdup_place_shared.
+__device__ __noinline__ void vdup_place_all(const uint2* tile, uint32_t n, const uint32_t* bitsV, const uint16_t* prefV,
+                                            const uint16_t* dupkey, uint32_t n_listed, uint16_t* dupnode, uint32_t* n_shared,
+                                            float* ranges, float* intens, uint32_t ob, uint32_t os, uint32_t q_shift,
+                                            uint32_t q_mask, uint32_t tid, uint32_t nthreads) {
+  for (uint32_t i = tid; i < n; i += nthreads) {
+    const uint2 nd = tile[i];
+    const uint32_t dist = __funnelshift_r(nd.x, nd.y, 16);
+    if (dist == 0) continue;
+    const uint32_t k = nd.x & 0xFFFFu;
+    uint32_t rk = rank2(bitsV, prefV, k);
+    bool shared = false;
+    for (uint32_t j = 0; j < n_listed; ++j) {
+      const uint32_t dk = dupkey[j];
+      rk += (dk < k) ? 1u : 0u;
+      shared = shared || (dk == k);
+    }
+    if (shared) {
+      dupnode[atomicAdd(n_shared, 1u)] = (uint16_t)i;  // <= 2 * n_listed entries
+    } else {
+      const uint32_t o = ob + os * rk;
+      ranges[o] = dist_to_m(dist);
+      intens[o] = __fsub_rn(__uint_as_float(((nd.y >> q_shift) & q_mask) | 0x4B000000u), 8388608.0f);
+    }
+  }
+}
+// The measured nodes whose key is listed: one warp per node counts the measured nodes with the same key earlier in the
+// buffer and stores the node's range and intensity at its slot.
+__device__ __noinline__ void vdup_place_shared(const uint2* tile, const uint32_t* bitsV, const uint16_t* prefV,
+                                               const uint16_t* dupkey, uint32_t n_listed, const uint16_t* dupnode,
+                                               uint32_t n_shared, float* ranges, float* intens, uint32_t ob, uint32_t os,
+                                               uint32_t q_shift, uint32_t q_mask, uint32_t warp, uint32_t lane,
+                                               uint32_t nwarps) {
+  for (uint32_t e = warp; e < n_shared; e += nwarps) {
+    const uint32_t i = dupnode[e];
+    const uint2 me = tile[i];
+    const uint32_t k = me.x & 0xFFFFu;
+    uint32_t before = 0;
+    for (uint32_t j = lane; j < i; j += 32) {
+      const uint2 o2 = tile[j];
+      before += ((o2.x & 0xFFFFu) == k && __funnelshift_r(o2.x, o2.y, 16) != 0) ? 1u : 0u;
+    }
+    before = warp_sum(before);
+    if (lane == 0) {
+      uint32_t r = rank2(bitsV, prefV, k) + before;
+      for (uint32_t j = 0; j < n_listed; ++j) r += (dupkey[j] < k) ? 1u : 0u;
+      const uint32_t o = ob + os * r;
+      ranges[o] = dist_to_m(__funnelshift_r(me.x, me.y, 16));
+      intens[o] = __fsub_rn(__uint_as_float(((me.y >> q_shift) & q_mask) | 0x4B000000u), 8388608.0f);
+    }
+  }
+}
+
 template <int MODE, bool EMIT, bool POST, int TS>
 __global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : (MODE == 0 ? 5 : 1))) scan_small_kernel(ScanBatchArgs a, SmallArgs p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -545,22 +620,6 @@ __global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : (MODE == 0 ? 5 : 1)
       __syncthreads();
     }
 
-    if (VDUP && DV) {  // (rare) the same sweep over the measured keys
-      for (uint32_t i = tid; i < n; i += TS) {
-        const uint2 nd = tile[i];
-        if (__funnelshift_r(nd.x, nd.y, 16) != 0) {
-          const uint32_t k = nd.x & 0xFFFFu, bit = 1u << (k & 31);
-          if (!(atomicAnd(&bitsV[k >> 5], ~bit) & bit)) ctl.d.dupkey[atomicAdd(&ctl.d.ndup, 1u)] = (uint16_t)k;  // DV entries
-        }
-      }
-      __syncthreads();
-      for (uint32_t i = tid; i < n; i += TS) {
-        const uint2 nd = tile[i];
-        if (__funnelshift_r(nd.x, nd.y, 16) != 0) atomicOr(&bitsV[(nd.x & 0xFFFFu) >> 5], 1u << (nd.x & 31u));
-      }
-      __syncthreads();
-    }
-
     // ---- place ------------------------------------------------------------------------------------------
     float* ranges = want_scan ? a.ranges + (size_t)s * a.stride : nullptr;
     float* intens = want_scan ? a.intensities + (size_t)s * a.stride : nullptr;
@@ -573,7 +632,8 @@ __global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : (MODE == 0 ? 5 : 1)
     // (two instances: revolutions with shared final keys are rare and must not slow the loop of the others down)
     auto place = [&](auto has_dup) {
       constexpr bool HAS_DUP = decltype(has_dup)::value;
-#pragma unroll 4
+      constexpr int kUnroll = HAS_DUP ? 1 : 4;  // (the rare instance must not set the kernel's register count)
+#pragma unroll kUnroll
       for (uint32_t i = tid; i < n; i += TS) {
         const uint2 nd = tile[i];
         const uint32_t k = nd.x & 0xFFFFu;
@@ -605,21 +665,7 @@ __global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : (MODE == 0 ? 5 : 1)
           }
           continue;
         }
-        uint32_t rk = rank2(bitsV, prefV, k);
-        if constexpr (HAS_DUP && VDUP) {
-          // every measured node beyond the first of a key shifts the larger keys by one; the measured nodes that share
-          // a key are ordered by buffer position (stable rule) in the fix-up below
-          bool shared = false;
-          for (uint32_t j = 0; j < DV; ++j) {
-            const uint32_t dk = ctl.d.dupkey[j];
-            rk += (dk < k) ? 1u : 0u;
-            shared = shared || (dk == k);
-          }
-          if (shared && measured) {
-            ctl.d.dupnode[atomicAdd(&ctl.d.ndupnode, 1u)] = (uint16_t)i;  // <= 2 * DV entries
-            measured = 0;  // (its stores are left to the fix-up)
-          }
-        }
+        const uint32_t rk = rank2(bitsV, prefV, k);
         if (CLOUD) {  // polar -> xyz at the rank among kept points (oracle/cloud_oracle.cpp steps 1-3)
           const float it = intensity_of(nd.y);
           if (!cloud_keep(dm, it, w_rmin, w_rmax, w_imin)) measured = 0;
@@ -642,8 +688,15 @@ __global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : (MODE == 0 ? 5 : 1)
         }
       }
     };
-    if ((EMIT && D) || (VDUP && DV)) place(std::true_type{});
-    else place(std::false_type{});
+    if (VDUP && DV) {  // (rare) the whole place pass of such a revolution runs out of line
+      vdup_list_keys(tile, n, bitsV, &ctl.d.ndup, ctl.d.dupkey, tid, TS);
+      vdup_place_all(tile, n, bitsV, prefV, ctl.d.dupkey, DV, ctl.d.dupnode, &ctl.d.ndupnode, ranges, intens, ob, os, q_shift, q_mask,
+                     tid, TS);
+    } else if (EMIT && D) {
+      place(std::true_type{});
+    } else {
+      place(std::false_type{});
+    }
     __syncthreads();
 
     // ---- ascended buffer, nodes with a shared final key: position = nodes with a smaller key + nodes with the same
@@ -667,27 +720,9 @@ __global__ void __launch_bounds__(TS, POST ? 2 : (EMIT ? 4 : (MODE == 0 ? 5 : 1)
 
     // ---- Mode B, measured nodes with a shared key: slot = measured nodes with a smaller key + measured nodes with the
     // same key earlier in the buffer (stable rule)
-    if (VDUP && DV) {
-      const uint32_t nshared = ctl.d.ndupnode;
-      for (uint32_t e = warp; e < nshared; e += NW) {
-        const uint32_t i = ctl.d.dupnode[e];
-        const uint2 me = tile[i];
-        const uint32_t k = me.x & 0xFFFFu;
-        uint32_t before = 0;
-        for (uint32_t j = lane; j < i; j += 32) {
-          const uint2 o2 = tile[j];
-          before += ((o2.x & 0xFFFFu) == k && __funnelshift_r(o2.x, o2.y, 16) != 0) ? 1u : 0u;
-        }
-        before = warp_sum(before);
-        if (lane == 0) {
-          uint32_t r = rank2(bitsV, prefV, k) + before;
-          for (uint32_t j = 0; j < DV; ++j) r += (ctl.d.dupkey[j] < k) ? 1u : 0u;
-          const uint32_t o = ob + os * r;
-          ranges[o] = dist_to_m(__funnelshift_r(me.x, me.y, 16));
-          intens[o] = intensity_of(me.y);
-        }
-      }
-    }
+    if (VDUP && DV)
+      vdup_place_shared(tile, bitsV, prefV, ctl.d.dupkey, DV, ctl.d.dupnode, ctl.d.ndupnode, ranges, intens, ob, os, q_shift,
+                        q_mask, warp, lane, NW);
 
     // ---- Mode A, continued: among the points that hold their bin's minimum the first in ascending key order wins
     // (strict '<' in the reference) -- the smallest key | quality; then one thread per bin writes (dist_m, intensity)
