@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 set -u
 mkdir -p gpurun_out
-T=${1:-r2aa}
+T=${1:-r2ab}
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -5
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1
 timeout 600 python bench.py --nodes 3200 --scans 40960 --steps 50 --no-cpu --no-cloud --no-e2e > gpurun_out/${T}_scan3200.json 2> gpurun_out/${T}_scan3200.err; tail -c 300 gpurun_out/${T}_scan3200.err
